@@ -1,0 +1,130 @@
+/*
+ * ptts_b200.h - C ABI of the B200 (sm_100a) engine for Pocket-TTS's per-frame generation path.
+ *
+ * Plain C, plain pointers and sizes; no CUDA / torch types.  This library replaces ptts_cuda.c
+ * (reference ptts_cuda.h:9-96) as the dispatch target of ptts_flowlm.c and ptts_mimi.c, but it is
+ * entered at whole-loop granularity: the per-op host-pointer ABI of
+ * ptts_cuda.h is itself the bottleneck (one blocking H2D/D2H round trip per GEMV).
+ *
+ * Conventions
+ *   - every function returns 0 on success and -1 on failure; the message is available from
+ *     ptts_b200_last_error() (thread-local), mirroring ptts_get_error() (ptts.h:52).
+ *   - there is NO CPU fallback: if no CUDA device / kernel image is available the call fails.
+ *   - host pointers are owned by the caller; the engine owns all device memory.
+ *   - one engine per device; an engine is single-threaded; distinct engines may be driven from
+ *     distinct host threads (utterances shard across GPUs with no collective).
+ */
+#ifndef PTTS_B200_H
+#define PTTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ptts_b200_engine ptts_b200_engine;
+
+/* Host weight table entry.  dtype follows safetensor_dtype_t (ptts_safetensors.h:20-28):
+ * 0 = F32, 1 = F16, 2 = BF16.  Names are checkpoint tensor names; lookup order is the reference's
+ * (exact, then "flow_lm." / "mimi." / "model." prefix, then suffix: ptts_flowlm.c:107-122,
+ * ptts_mimi.c:77-95). */
+typedef struct {
+    const char *name;
+    const void *data;
+    int dtype;
+    int64_t numel;
+} ptts_b200_tensor;
+
+/* Engine lifetime (replaces per-call ptts_flowlm_load / ptts_mimi_load, ptts.c:1047-1053, and the
+ * host-pointer-keyed device weight cache of ptts_cuda.c:617-644).  Weights are converted once to
+ * bf16 (FlowLM) / fp16 (Mimi) device copies. */
+int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b200_tensor *tensors, int n_tensors);
+void ptts_b200_destroy(ptts_b200_engine *e);
+const char *ptts_b200_last_error(void);
+
+/* ---- drop-in for ptts_flowlm_generate_latents (ptts_flowlm.h:43-51, ptts_flowlm.c:1138-1251).
+ * Same arguments after the engine handle, same outputs (raw latents [frames,32], frames used,
+ * optional first EOS logit / first cond[1024] / first flow[32]).  The voice prefix KV is cached
+ * per engine and reused while cond_prefix is unchanged. fp32 activations, bf16 weights. */
+int ptts_b200_flowlm_generate_latents(ptts_b200_engine *e, const int *tokens, int token_len,
+                                      const float *cond_prefix, int cond_len,
+                                      int max_frames, int lsd_steps, float temp, float noise_clamp,
+                                      int64_t seed, int eos_enabled, float eos_threshold,
+                                      int eos_min_frames, int eos_after,
+                                      float *out_latents, int *out_frames_used,
+                                      float *out_first_eos_logit, float *out_first_cond,
+                                      float *out_first_flow);
+
+/* ---- drop-in for ptts_flowlm_scale_latents (ptts_flowlm.h:54-55, ptts_flowlm.c:1253-1263). */
+int ptts_b200_flowlm_scale_latents(ptts_b200_engine *e, const float *in_latents, int frames, float *out_latents);
+
+/* ---- drop-in for ptts_mimi_decode (ptts_mimi.h:26-27, ptts_mimi.c:570-738):
+ * latents [frames,32] (already scaled) -> out_audio [frames*1920], *out_len = frames*1920. */
+int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, int frames, float *out_audio, int *out_len);
+
+/* ---- additive batched entries (the reference is single-utterance, ptts.h:75-76). */
+
+/* Mimi decode of n equal-length latent sequences: latents [n, frames, 32] (scaled) ->
+ * out_audio [n, frames*1920]. */
+int ptts_b200_mimi_decode_batch(ptts_b200_engine *e, const float *latents, int n, int frames, float *out_audio);
+
+typedef struct {
+    int lsd_steps;        /* ptts_params.num_steps (ptts.h:29) */
+    float temp;           /* ptts_params.temp */
+    float noise_clamp;
+    int eos_enabled;
+    float eos_threshold;
+    int eos_min_frames;
+    int eos_after;        /* used when per-utterance eos_after[] is NULL */
+    int precise;          /* 1: activations fed to the tensor cores as bf16 hi+lo pairs (default); 0: hi only */
+} ptts_b200_gen_params;
+
+/* Batched generation, tokens -> latents -> PCM, n utterances sharing one voice prefix.
+ *   tokens_flat / token_offsets[n+1] : concatenated token ids
+ *   max_frames[n], seeds[n]          : per utterance (seed -1 is NOT time-seeded here: caller decides)
+ *   eos_after[n]                     : optional per-utterance override (NULL = params->eos_after)
+ *   out_latents [n, frames_cap, 32]  : raw latents (optional, may be NULL)
+ *   out_frames_used [n]
+ *   out_audio [n, frames_cap*1920]   : PCM, zero beyond frames_used*1920 (optional, may be NULL)
+ * frames_cap = max over max_frames[]. Host buffers; H2D/D2H copies happen inside the call. */
+int ptts_b200_generate_batch(ptts_b200_engine *e, int n, const int *tokens_flat, const int *token_offsets,
+                             const float *cond_prefix, int cond_len, const int *max_frames,
+                             const int64_t *seeds, const int *eos_after, const ptts_b200_gen_params *params,
+                             float *out_latents, int *out_frames_used, float *out_audio);
+
+/* The same job split in three so that the middle part can be timed with all inputs already
+ * resident in HBM: stage (H2D of tokens / noise, state reset), run (kernels only, asynchronous on
+ * the engine stream), fetch (D2H). generate_batch == stage + run + fetch. */
+int ptts_b200_batch_stage(ptts_b200_engine *e, int n, const int *tokens_flat, const int *token_offsets,
+                          const float *cond_prefix, int cond_len, const int *max_frames,
+                          const int64_t *seeds, const int *eos_after, const ptts_b200_gen_params *params);
+int ptts_b200_batch_run(ptts_b200_engine *e, int with_mimi);
+int ptts_b200_batch_fetch(ptts_b200_engine *e, float *out_latents, int *out_frames_used, float *out_audio);
+
+/* ---- measurement hooks (CUDA events on the engine's own stream). */
+int ptts_b200_sync(ptts_b200_engine *e);
+int ptts_b200_timer_start(ptts_b200_engine *e);
+int ptts_b200_timer_stop(ptts_b200_engine *e, float *out_ms);      /* syncs, returns elapsed ms */
+/* Per-kernel-class profiling: when enabled, launches bypass CUDA graphs and each launch is
+ * bracketed by events. classes: see ptts_b200_profile_class_name. */
+int ptts_b200_profile_enable(ptts_b200_engine *e, int on);
+int ptts_b200_profile_read(ptts_b200_engine *e, int max_classes, float *ms_per_class, int64_t *launches_per_class,
+                           int *n_classes);
+const char *ptts_b200_profile_class_name(int cls);
+/* Total kernel launches issued by the engine since creation (graph nodes count per replay). */
+int64_t ptts_b200_launch_count(ptts_b200_engine *e);
+
+/* ---- unit-test hook: one tcgen05 GEMM  D[m,n] = sum_k A[m,k] B[n,k]  on device copies of the
+ * host arrays (A, B given as f32, rounded to bf16 (bf16 != 0) or fp16 inside).  `split`:
+ * 0 none, 1 A carried as hi+lo, 2 B carried as hi+lo.  transposed != 0 stores out[n*M + m].
+ * taps > 1 runs the implicit-GEMM conv form: A is [batches, rows, K/taps] and tap j reads row
+ * m + shift0 + j*step (zero outside [0, rows)), B is [N, K]. */
+int ptts_b200_test_gemm(ptts_b200_engine *e, const float *A, const float *B, float *out,
+                        int batches, int rows, int N, int K, int taps, int shift0, int step,
+                        int bf16, int split, int transposed, int bn, int split_k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTTS_B200_H */

@@ -1,0 +1,374 @@
+// engine.cuh - engine object: device weights, workspaces, launch bookkeeping, GEMM op builder.
+#pragma once
+#include <stdarg.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ptts_b200.h"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+
+namespace ptts {
+
+thread_local char g_last_error[512] = {0};
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+    va_end(ap);
+}
+
+// ---------------------------------------------------------------- profiling classes
+enum KClass : int {
+    KC_GEMV = 0,       // batch-1 bf16 weight-streaming GEMV
+    KC_GEMM_FLOW,      // tcgen05 GEMM, batched FlowLM transformer + flow head
+    KC_ATTN_DECODE,    // RoPE + KV append + decode attention
+    KC_ROWNORM,        // LayerNorm / adaLN / split-K fold
+    KC_FLOW_MISC,      // prepare / eos / flow init / flow update
+    KC_GEMM_MIMI,      // tcgen05 GEMM, Mimi transformer linears + SEANet implicit GEMM
+    KC_MIMI_ATTN,      // banded attention
+    KC_MIMI_MISC,      // front end, rope split, final conv
+    KC_COUNT
+};
+static const char *const KCLASS_NAMES[KC_COUNT] = {"gemv_bf16", "gemm_tc_flowlm", "attn_decode", "rownorm",
+                                                   "flow_misc", "gemm_tc_mimi", "mimi_win_attn", "mimi_misc"};
+
+struct Prof {
+    bool on = false;
+    struct Rec { int cls; cudaEvent_t a, b; };
+    std::vector<Rec> recs;
+    float ms[KC_COUNT] = {0};
+    int64_t n[KC_COUNT] = {0};
+};
+
+// ---------------------------------------------------------------- TMA host API
+TmaApi g_tma;
+int TmaApi::init() {
+    if (encode) return 0;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PTTS_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    PTTS_CHECK(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    encode = (EncodeTiled)fn;
+    return 0;
+}
+
+int make_tmap(CUtensorMap *out, const void *base, bool bf16, int k, int rows, int batches, size_t ld, size_t batch_stride,
+              int box_rows) {
+    if (g_tma.init() != 0) return -1;
+    PTTS_CHECK(((uintptr_t)base & 15) == 0 && (ld * 2) % 16 == 0 && (batch_stride * 2) % 16 == 0,
+               "make_tmap: base/strides must be 16-byte aligned");
+    PTTS_CHECK(box_rows >= 1 && box_rows <= 256, "make_tmap: box rows %d out of range", box_rows);
+    cuuint64_t dims[3] = {(cuuint64_t)k, (cuuint64_t)rows, (cuuint64_t)batches};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batches > 1 ? batch_stride : (size_t)rows * ld) * 2};
+    cuuint32_t box[3] = {(cuuint32_t)GEMM_BK, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_tma.encode(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                              const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PTTS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (k=%d rows=%d batches=%d ld=%zu)", (int)r, k, rows,
+               batches, ld);
+    return 0;
+}
+
+// ---------------------------------------------------------------- GEMM dispatch
+template <int BN, int SPLIT>
+static int gemm_launch_t(const GemmOp &op, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    gemm_tc_kernel<BN, SPLIT><<<op.grid, GEMM_THREADS, op.smem_bytes, st>>>(op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.p);
+    PTTS_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int gemm_launch(const GemmOp &op, cudaStream_t st) {
+#define GL(BN_, SP_) if (op.bn == BN_ && op.split == SP_) return gemm_launch_t<BN_, SP_>(op, st);
+    GL(32, 0) GL(64, 0) GL(128, 0) GL(256, 0)
+    GL(32, 1) GL(64, 1) GL(128, 1) GL(256, 1)
+    GL(32, 2) GL(64, 2) GL(128, 2) GL(256, 2)
+#undef GL
+    set_error("gemm_launch: unsupported tile bn=%d split=%d", op.bn, op.split);
+    return -1;
+}
+
+static int stage_bytes(int bn, int split) {
+    return GEMM_BM * GEMM_BK * 2 * (split == 1 ? 2 : 1) + bn * GEMM_BK * 2 * (split == 2 ? 2 : 1);
+}
+int gemm_pick_stages(int bn, int split, int iters, bool two_ctas_per_sm) {
+    const int budget = (two_ctas_per_sm ? 108 : 216) * 1024;
+    int s = budget / stage_bytes(bn, split);
+    if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
+    if (s > iters) s = iters;
+    if (s < 1) s = 1;
+    return s;
+}
+
+// Description of one contraction; see gemm_tc.cuh for the operand roles.
+struct GemmDesc {
+    const void *A = nullptr, *Alo = nullptr;   // [a_batches][a_rows][a_k] 16-bit, row stride a_ld
+    int a_k = 0, a_rows = 0, a_batches = 1;
+    size_t a_ld = 0, a_bstride = 0;
+    const void *B = nullptr, *Blo = nullptr;   // [b_rows][b_k] 16-bit, row stride b_ld
+    int b_k = 0, b_rows = 0;
+    size_t b_ld = 0;
+    bool bf16 = true;
+    int taps = 1, k_per_tap = 0, shift0 = 0, step = 0, a_k_step = 0, b_k_step = 0;
+    int bn = 128, split_k = 1;
+    bool two_cta = true;
+    GemmParams epi = {};                       // epilogue fields only
+};
+
+static int gemm_build(GemmOp &op, const GemmDesc &d) {
+    PTTS_CHECK(d.k_per_tap % GEMM_BK == 0 && d.k_per_tap > 0, "gemm_build: K per tap %d must be a multiple of 64", d.k_per_tap);
+    PTTS_CHECK(d.bn == 32 || d.bn == 64 || d.bn == 128 || d.bn == 256, "gemm_build: bad N tile %d", d.bn);
+    op = GemmOp{};
+    op.split = d.Alo ? 1 : (d.Blo ? 2 : 0);
+    op.bn = d.bn;
+    if (make_tmap(&op.mapA, d.A, d.bf16, d.a_k, d.a_rows, d.a_batches, d.a_ld, d.a_bstride, GEMM_BM) != 0) return -1;
+    if (make_tmap(&op.mapAlo, d.Alo ? d.Alo : d.A, d.bf16, d.a_k, d.a_rows, d.a_batches, d.a_ld, d.a_bstride, GEMM_BM) != 0) return -1;
+    if (make_tmap(&op.mapB, d.B, d.bf16, d.b_k, d.b_rows, 1, d.b_ld, 0, d.bn) != 0) return -1;
+    if (make_tmap(&op.mapBlo, d.Blo ? d.Blo : d.B, d.bf16, d.b_k, d.b_rows, 1, d.b_ld, 0, d.bn) != 0) return -1;
+    GemmParams p = d.epi;
+    p.m_tiles_per_batch = (d.a_rows + GEMM_BM - 1) / GEMM_BM;
+    p.a_rows = d.a_rows;
+    p.n_total = d.b_rows;
+    p.kblocks_per_tap = d.k_per_tap / GEMM_BK;
+    p.taps = d.taps;
+    p.a_row_shift0 = d.shift0;
+    p.a_row_step = d.step;
+    p.a_k_step = d.a_k_step;
+    p.b_k_step = d.b_k_step;
+    const int iters = p.taps * p.kblocks_per_tap;
+    int split_k = d.split_k < 1 ? 1 : d.split_k;
+    if (split_k > iters) split_k = iters;
+    const int per = (iters + split_k - 1) / split_k;
+    split_k = (iters + per - 1) / per;  // no empty slices
+    p.stages = gemm_pick_stages(d.bn, op.split, per, d.two_cta);
+    p.idesc = umma_idesc_f16(GEMM_BM, d.bn, d.bf16, d.bf16);
+    op.p = p;
+    op.grid = dim3((unsigned)(d.a_batches * p.m_tiles_per_batch), (unsigned)((d.b_rows + d.bn - 1) / d.bn), (unsigned)split_k);
+    op.smem_bytes = p.stages * stage_bytes(d.bn, op.split) + 1024 + 256;
+    return 0;
+}
+
+// ---------------------------------------------------------------- host-side weight helpers
+static inline uint16_t h_f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static inline float h_bf2f(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+static inline uint16_t h_f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
+static inline float h_h2f(uint16_t h) { return __half2float(__ushort_as_half(h)); }
+
+struct HostWeights {
+    const ptts_b200_tensor *t;
+    int n;
+    static bool ends_with(const char *s, const char *suf) {
+        size_t a = strlen(s), b = strlen(suf);
+        return a >= b && strcmp(s + a - b, suf) == 0;
+    }
+    // lookup order of the reference: exact, prefixed, suffix (ptts_flowlm.c:107-122, ptts_mimi.c:77-95)
+    const ptts_b200_tensor *find(const char *name, const char *const *prefixes) const {
+        for (int i = 0; i < n; i++) if (strcmp(t[i].name, name) == 0) return &t[i];
+        char buf[512];
+        for (int p = 0; prefixes[p]; p++) {
+            snprintf(buf, sizeof buf, "%s%s", prefixes[p], name);
+            for (int i = 0; i < n; i++) if (strcmp(t[i].name, buf) == 0) return &t[i];
+        }
+        for (int i = 0; i < n; i++) if (ends_with(t[i].name, name)) return &t[i];
+        return nullptr;
+    }
+    // f32 copy (F32 / F16 / BF16 accepted, ptts_safetensors.c:294-334)
+    int get(const char *name, const char *const *prefixes, int64_t numel, std::vector<float> &out, bool optional = false) const {
+        const ptts_b200_tensor *e = find(name, prefixes);
+        if (!e) {
+            if (optional) { out.clear(); return 1; }
+            set_error("missing tensor %s", name);
+            return -1;
+        }
+        if (e->numel != numel) {
+            set_error("tensor %s has %lld elements, expected %lld", e->name, (long long)e->numel, (long long)numel);
+            return -1;
+        }
+        out.resize((size_t)numel);
+        if (e->dtype == 0) memcpy(out.data(), e->data, sizeof(float) * (size_t)numel);
+        else if (e->dtype == 1) { const uint16_t *s = (const uint16_t *)e->data; for (int64_t i = 0; i < numel; i++) out[i] = h_h2f(s[i]); }
+        else if (e->dtype == 2) { const uint16_t *s = (const uint16_t *)e->data; for (int64_t i = 0; i < numel; i++) out[i] = h_bf2f(s[i]); }
+        else { set_error("tensor %s: unsupported dtype %d", e->name, e->dtype); return -1; }
+        return 0;
+    }
+};
+static const char *const FLOW_PFX[] = {"flow_lm.", nullptr};
+static const char *const MIMI_PFX[] = {"mimi.", "model.", nullptr};
+
+// ---------------------------------------------------------------- engine
+struct FlowLayerW { __nv_bfloat16 *inproj, *outproj, *l1, *l2; float *n1w, *n1b, *n2w, *n2b; };
+struct FlowBlockW { float *lnw, *lnb, *m0b, *m2b; __nv_bfloat16 *m0w, *m2w; };
+struct MimiLayerW { __half *inproj, *outproj, *l1, *l2; float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; };
+struct ConvW { __half *w; float *b; int cin, cout, k, stride, n_rows /*GEMM N*/, k_per_tap; bool transposed_conv; };
+
+
+}  // namespace ptts
+
+struct ptts_b200_engine {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<void *> allocs;
+    int64_t launches = 0;
+    ptts::Prof prof;
+    int num_sms = 148;
+
+    // ---- FlowLM weights
+    __nv_bfloat16 *embed = nullptr, *in_lin = nullptr;
+    float *emb_std = nullptr, *emb_mean = nullptr, *bos_proj = nullptr, *onorm_w = nullptr, *onorm_b = nullptr, *eos_w = nullptr,
+          *eos_b = nullptr;
+    float h_emb_std[32], h_emb_mean[32];
+    ptts::FlowLayerW L[ptts::FL_L];
+    __nv_bfloat16 *cond_w = nullptr, *inp_w = nullptr, *ada_w = nullptr, *fin_w = nullptr;
+    float *cond_b = nullptr, *inp_b = nullptr, *ada_b = nullptr, *fin_b = nullptr;
+    ptts::FlowBlockW FB[ptts::FN_DEPTH];
+    struct { float *l0w, *l0b, *l2w, *l2b, *alpha, *freqs; } te[2];
+    std::unordered_map<int, float *> cbias;   // lsd_steps -> [steps][512] = cond_b + (ts+tt)/2
+    float *rope_cos = nullptr, *rope_sin = nullptr;
+    int rope_len = 0;
+
+    // ---- Mimi weights
+    float *quant_w = nullptr, *ups_w = nullptr, *dec_out_w = nullptr, *dec_out_b = nullptr;
+    ptts::MimiLayerW ML[ptts::MI_L];
+    ptts::ConvW dec_in, up[3], res1[3], res2[3];
+
+    // ---- FlowLM run state (capacity-sized)
+    int capB = 0, capS = 0, capTok = 0, capF = 0, capCond = 0;
+    int curB = 0;
+    ptts::FlowCtrl *ctrl = nullptr;
+    int *d_tokens = nullptr, *d_tok_len = nullptr, *d_max_frames = nullptr, *d_eos_after = nullptr;
+    float *d_noise = nullptr, *d_latent = nullptr, *d_out_latents = nullptr;
+    int *d_eos_step = nullptr, *d_done = nullptr, *d_used = nullptr;
+    float *d_first_eos = nullptr, *d_first_cond = nullptr, *d_first_flow = nullptr;
+    float *x = nullptr, *qkv = nullptr, *att = nullptr, *ffh = nullptr, *normed = nullptr;
+    uint16_t *xn_h = nullptr, *xn_l = nullptr, *att_h = nullptr, *att_l = nullptr, *ffh_h = nullptr, *ffh_l = nullptr,
+             *normed_h = nullptr, *normed_l = nullptr;
+    float *partA = nullptr, *partB = nullptr;     // split-K partials [4][B][1024]
+    float *fx = nullptr, *ada = nullptr, *ft = nullptr, *flow = nullptr, *sc = nullptr, *fg = nullptr;
+    uint16_t *sc_h = nullptr, *sc_l = nullptr, *fh_h = nullptr, *fh_l = nullptr, *fg_h = nullptr, *fg_l = nullptr;
+    float *pk = nullptr, *pv = nullptr;           // prefix KV [L][H][capCond][64]
+    float *ok = nullptr, *ov = nullptr;           // own KV [L][capB][H][capS][64]
+    float *d_cond = nullptr;                      // voice rows on device [capCond,1024]
+    std::vector<float> voice_host;                // copy of the cached voice prefix
+    int voice_len = -1;
+    // step graphs keyed by (mode, B, lsd_steps, precise); `gen` bumps whenever device pointers change
+    std::unordered_map<uint64_t, cudaGraphExec_t> graphs;
+    std::unordered_map<uint64_t, int64_t> graph_kernels;
+    uint64_t gen = 0;
+    void invalidate_graphs() {
+        for (auto &g : graphs) cudaGraphExecDestroy(g.second);
+        graphs.clear();
+        graph_kernels.clear();
+        gen++;
+    }
+    // staged batch
+    int st_n = 0, st_steps = 0, st_capF = 0, st_lsd = 1, st_precise = 1, st_eos = 0;
+    std::vector<int> st_maxf;
+    // pinned staging
+    void *pin = nullptr;
+    size_t pin_bytes = 0;
+
+    // ---- Mimi workspace
+    void *mimi_ws = nullptr;
+    size_t mimi_ws_bytes = 0;
+    float *d_mimi_lat = nullptr, *d_pcm = nullptr;
+    size_t mimi_lat_cap = 0, pcm_cap = 0;
+
+    template <typename T>
+    int dalloc(T **p, size_t count) {
+        void *q = nullptr;
+        cudaError_t r = cudaMalloc(&q, count * sizeof(T) < 16 ? 16 : count * sizeof(T));
+        if (r != cudaSuccess) {
+            ptts::set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(r));
+            return -1;
+        }
+        allocs.push_back(q);
+        *p = (T *)q;
+        return 0;
+    }
+    void dfree(void *p) {
+        if (!p) return;
+        for (size_t i = 0; i < allocs.size(); i++)
+            if (allocs[i] == p) { allocs[i] = allocs.back(); allocs.pop_back(); break; }
+        cudaFree(p);
+    }
+    int up_f32(float **dst, const std::vector<float> &v) {
+        if (dalloc(dst, v.size()) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int up_bf16(__nv_bfloat16 **dst, const std::vector<float> &v) {
+        std::vector<uint16_t> h(v.size());
+        for (size_t i = 0; i < v.size(); i++) h[i] = ptts::h_f2bf(v[i]);
+        if (dalloc(dst, v.size()) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemcpy(*dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+        return 0;
+    }
+    int up_f16(__half **dst, const std::vector<float> &v) {
+        std::vector<uint16_t> h(v.size());
+        for (size_t i = 0; i < v.size(); i++) h[i] = ptts::h_f2h(v[i]);
+        if (dalloc(dst, v.size()) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemcpy(*dst, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+        return 0;
+    }
+};
+
+namespace ptts {
+typedef ptts_b200_engine Engine;
+
+// Launch bookkeeping: count every launch; in profile mode bracket it with events.
+struct LaunchScope {
+    Engine *e;
+    int cls;
+    cudaEvent_t a = nullptr, b = nullptr;
+    LaunchScope(Engine *e_, int cls_) : e(e_), cls(cls_) {
+        e->launches++;
+        if (e->prof.on) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, e->st);
+        }
+    }
+    ~LaunchScope() {
+        if (e->prof.on) {
+            cudaEventRecord(b, e->st);
+            e->prof.recs.push_back({cls, a, b});
+        }
+    }
+};
+
+static int launch_check(const char *what) {
+    cudaError_t r = cudaGetLastError();
+    if (r != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(r));
+        return -1;
+    }
+    return 0;
+}
+
+static int run_gemm(Engine *e, const GemmOp &op, int cls) {
+    LaunchScope ls(e, cls);
+    return gemm_launch(op, e->st);
+}
+
+}  // namespace ptts

@@ -1,0 +1,408 @@
+// flowlm.cuh - FlowLM side of the engine: weight upload, lock-step generation loop
+// (ptts_flowlm.c:1138-1251) in two data paths:
+//   * batch-1 streaming decode: fp32 activations, bf16 weight-streaming GEMV kernels;
+//   * batched decode (B >= 2, padded to 16): tcgen05 GEMMs with the batch as the N operand
+//     ("weights as A": D[feature, utterance]), activations carried as bf16 hi+lo.
+// One frame step is captured once into a CUDA graph and replayed.
+#pragma once
+#include "engine.cuh"
+
+namespace ptts {
+
+static int flow_load_weights(Engine *e, const HostWeights &hw) {
+    std::vector<float> v, v2;
+    char nm[256];
+#define GETF(name, ne) if (hw.get(name, FLOW_PFX, ne, v) != 0) return -1
+    GETF("conditioner.embed.weight", 4001 * FL_D); if (e->up_bf16(&e->embed, v) != 0) return -1;
+    GETF("emb_std", FL_LAT); memcpy(e->h_emb_std, v.data(), sizeof e->h_emb_std); if (e->up_f32(&e->emb_std, v) != 0) return -1;
+    GETF("emb_mean", FL_LAT); memcpy(e->h_emb_mean, v.data(), sizeof e->h_emb_mean); if (e->up_f32(&e->emb_mean, v) != 0) return -1;
+    GETF("input_linear.weight", FL_D * FL_LAT); if (e->up_bf16(&e->in_lin, v) != 0) return -1;
+    {   // bos_proj = input_linear . bos_emb (ptts_flowlm.c:1179-1181), input-independent -> precompute (fp32)
+        if (hw.get("bos_emb", FLOW_PFX, FL_LAT, v2) != 0) return -1;
+        std::vector<float> bp(FL_D);
+        for (int n = 0; n < FL_D; n++) {
+            float a = 0.0f;
+            for (int i = 0; i < FL_LAT; i++) a += h_bf2f(h_f2bf(v[n * FL_LAT + i])) * v2[i];
+            bp[n] = a;
+        }
+        if (e->up_f32(&e->bos_proj, bp) != 0) return -1;
+    }
+    GETF("out_norm.weight", FL_D); if (e->up_f32(&e->onorm_w, v) != 0) return -1;
+    GETF("out_norm.bias", FL_D); if (e->up_f32(&e->onorm_b, v) != 0) return -1;
+    GETF("out_eos.weight", FL_D); if (e->up_f32(&e->eos_w, v) != 0) return -1;
+    GETF("out_eos.bias", 1); if (e->up_f32(&e->eos_b, v) != 0) return -1;
+    for (int l = 0; l < FL_L; l++) {
+#define LW(field, suffix, ne, up) snprintf(nm, sizeof nm, "transformer.layers.%d." suffix, l); GETF(nm, ne); if (e->up(&e->L[l].field, v) != 0) return -1
+        LW(inproj, "self_attn.in_proj.weight", 3 * FL_D * FL_D, up_bf16);
+        LW(outproj, "self_attn.out_proj.weight", FL_D * FL_D, up_bf16);
+        LW(l1, "linear1.weight", FL_FF * FL_D, up_bf16);
+        LW(l2, "linear2.weight", FL_D * FL_FF, up_bf16);
+        LW(n1w, "norm1.weight", FL_D, up_f32); LW(n1b, "norm1.bias", FL_D, up_f32);
+        LW(n2w, "norm2.weight", FL_D, up_f32); LW(n2b, "norm2.bias", FL_D, up_f32);
+#undef LW
+    }
+    GETF("flow_net.cond_embed.weight", FN_D * FL_D); if (e->up_bf16(&e->cond_w, v) != 0) return -1;
+    GETF("flow_net.cond_embed.bias", FN_D); if (e->up_f32(&e->cond_b, v) != 0) return -1;
+    GETF("flow_net.input_proj.weight", FN_D * FL_LAT); if (e->up_bf16(&e->inp_w, v) != 0) return -1;
+    GETF("flow_net.input_proj.bias", FN_D); if (e->up_f32(&e->inp_b, v) != 0) return -1;
+    for (int t = 0; t < 2; t++) {
+#define TW(field, suffix, ne) snprintf(nm, sizeof nm, "flow_net.time_embed.%d." suffix, t); GETF(nm, ne); if (e->up_f32(&e->te[t].field, v) != 0) return -1
+        TW(l0w, "mlp.0.weight", FN_D * 256); TW(l0b, "mlp.0.bias", FN_D);
+        TW(l2w, "mlp.2.weight", FN_D * FN_D); TW(l2b, "mlp.2.bias", FN_D);
+        TW(alpha, "mlp.3.alpha", FN_D);
+#undef TW
+        snprintf(nm, sizeof nm, "flow_net.time_embed.%d.freqs", t);
+        int r = hw.get(nm, FLOW_PFX, 128, v, true);   // optional (ptts_flowlm.c:575)
+        if (r < 0) return -1;
+        e->te[t].freqs = nullptr;
+        if (r == 0 && e->up_f32(&e->te[t].freqs, v) != 0) return -1;
+    }
+    // all adaLN projections stacked: rows [b*1536, (b+1)*1536) = shift|scale|gate of block b,
+    // rows [9216, 10240) = shift|scale of the final layer. One GEMV/GEMM per flow pass instead of 7.
+    std::vector<float> adaw((size_t)FN_ADA * FN_D), adab(FN_ADA);
+    for (int b = 0; b < FN_DEPTH; b++) {
+#define BW(field, suffix, ne, up) snprintf(nm, sizeof nm, "flow_net.res_blocks.%d." suffix, b); GETF(nm, ne); if (e->up(&e->FB[b].field, v) != 0) return -1
+        BW(lnw, "in_ln.weight", FN_D, up_f32); BW(lnb, "in_ln.bias", FN_D, up_f32);
+        BW(m0w, "mlp.0.weight", FN_D * FN_D, up_bf16); BW(m0b, "mlp.0.bias", FN_D, up_f32);
+        BW(m2w, "mlp.2.weight", FN_D * FN_D, up_bf16); BW(m2b, "mlp.2.bias", FN_D, up_f32);
+#undef BW
+        snprintf(nm, sizeof nm, "flow_net.res_blocks.%d.adaLN_modulation.1.weight", b);
+        GETF(nm, 3 * FN_D * FN_D);
+        memcpy(&adaw[(size_t)b * 3 * FN_D * FN_D], v.data(), sizeof(float) * v.size());
+        snprintf(nm, sizeof nm, "flow_net.res_blocks.%d.adaLN_modulation.1.bias", b);
+        GETF(nm, 3 * FN_D);
+        memcpy(&adab[(size_t)b * 3 * FN_D], v.data(), sizeof(float) * v.size());
+    }
+    GETF("flow_net.final_layer.adaLN_modulation.1.weight", 2 * FN_D * FN_D);
+    memcpy(&adaw[(size_t)FN_DEPTH * 3 * FN_D * FN_D], v.data(), sizeof(float) * v.size());
+    GETF("flow_net.final_layer.adaLN_modulation.1.bias", 2 * FN_D);
+    memcpy(&adab[(size_t)FN_DEPTH * 3 * FN_D], v.data(), sizeof(float) * v.size());
+    if (e->up_bf16(&e->ada_w, adaw) != 0 || e->up_f32(&e->ada_b, adab) != 0) return -1;
+    GETF("flow_net.final_layer.linear.weight", FL_LAT * FN_D); if (e->up_bf16(&e->fin_w, v) != 0) return -1;
+    GETF("flow_net.final_layer.linear.bias", FL_LAT); if (e->up_f32(&e->fin_b, v) != 0) return -1;
+#undef GETF
+    return 0;
+}
+
+static int ensure_rope(Engine *e, int len) {
+    if (len <= e->rope_len) return 0;
+    int n = 1024;
+    while (n < len) n *= 2;
+    e->dfree(e->rope_cos); e->dfree(e->rope_sin);
+    if (e->dalloc(&e->rope_cos, (size_t)n * 32) != 0 || e->dalloc(&e->rope_sin, (size_t)n * 32) != 0) return -1;
+    k_rope_table<<<(n * 32 + 255) / 256, 256, 0, e->st>>>(e->rope_cos, e->rope_sin, n);
+    if (launch_check("k_rope_table") != 0) return -1;
+    e->rope_len = n;
+    e->invalidate_graphs();
+    return 0;
+}
+
+// cbias[k] = cond_embed.bias + (time_embed0(k/N) + time_embed1((k+1)/N)) / 2: input-independent
+// (ptts_flowlm.c:572-586, 715-719, 768-769), computed once per lsd_steps value.
+static int ensure_cbias(Engine *e, int steps, float **out) {
+    auto it = e->cbias.find(steps);
+    if (it != e->cbias.end()) { *out = it->second; return 0; }
+    float *buf = nullptr;
+    if (e->dalloc(&buf, (size_t)steps * FN_D) != 0) return -1;
+    for (int k = 0; k < steps; k++) {
+        PTTS_CUDA_OK(cudaMemcpyAsync(buf + (size_t)k * FN_D, e->cond_b, FN_D * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
+        const float s = (float)k / (float)steps, t = (float)(k + 1) / (float)steps;
+        k_time_embed<<<1, 512, 0, e->st>>>(e->te[0].l0w, e->te[0].l0b, e->te[0].l2w, e->te[0].l2b, e->te[0].alpha, e->te[0].freqs, s,
+                                          buf + (size_t)k * FN_D);
+        k_time_embed<<<1, 512, 0, e->st>>>(e->te[1].l0w, e->te[1].l0b, e->te[1].l2w, e->te[1].l2b, e->te[1].alpha, e->te[1].freqs, t,
+                                          buf + (size_t)k * FN_D);
+        if (launch_check("k_time_embed") != 0) return -1;
+    }
+    e->cbias[steps] = buf;
+    *out = buf;
+    return 0;
+}
+
+// (Re)allocate the run state for batch B (padded), own positions S, tokens, frames, voice length.
+static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int cond) {
+    if (B <= e->capB && S <= e->capS && tok <= e->capTok && F <= e->capF && cond <= e->capCond) return 0;
+    cudaStreamSynchronize(e->st);
+    e->invalidate_graphs();
+    const bool regrow_prefix = cond > e->capCond;
+    B = std::max(B, e->capB); S = std::max(S, e->capS); tok = std::max(tok, e->capTok); F = std::max(F, e->capF);
+    cond = std::max(cond, e->capCond);
+    void **bufs[] = {(void **)&e->d_tokens, (void **)&e->d_tok_len, (void **)&e->d_max_frames, (void **)&e->d_eos_after,
+                     (void **)&e->d_noise, (void **)&e->d_latent, (void **)&e->d_out_latents, (void **)&e->d_eos_step,
+                     (void **)&e->d_done, (void **)&e->d_used, (void **)&e->d_first_eos, (void **)&e->d_first_cond,
+                     (void **)&e->d_first_flow, (void **)&e->x, (void **)&e->qkv, (void **)&e->att, (void **)&e->ffh,
+                     (void **)&e->normed, (void **)&e->xn_h, (void **)&e->xn_l, (void **)&e->att_h, (void **)&e->att_l,
+                     (void **)&e->ffh_h, (void **)&e->ffh_l, (void **)&e->normed_h, (void **)&e->normed_l, (void **)&e->partA,
+                     (void **)&e->partB, (void **)&e->fx, (void **)&e->ada, (void **)&e->ft, (void **)&e->flow, (void **)&e->sc,
+                     (void **)&e->fg, (void **)&e->sc_h, (void **)&e->sc_l, (void **)&e->fh_h, (void **)&e->fh_l,
+                     (void **)&e->fg_h, (void **)&e->fg_l, (void **)&e->ok, (void **)&e->ov};
+    for (void **p : bufs) { e->dfree(*p); *p = nullptr; }
+    const size_t b = (size_t)B;
+#define DA(ptr, count) if (e->dalloc(&e->ptr, (count)) != 0) return -1
+    DA(d_tokens, b * tok); DA(d_tok_len, b); DA(d_max_frames, b); DA(d_eos_after, b);
+    DA(d_noise, b * F * FL_LAT); DA(d_latent, b * FL_LAT); DA(d_out_latents, b * F * FL_LAT);
+    DA(d_eos_step, b); DA(d_done, b); DA(d_used, b); DA(d_first_eos, b); DA(d_first_cond, b * FL_D); DA(d_first_flow, b * FL_LAT);
+    DA(x, b * FL_D); DA(qkv, b * 3 * FL_D); DA(att, b * FL_D); DA(ffh, b * FL_FF); DA(normed, b * FL_D);
+    DA(xn_h, b * FL_D); DA(xn_l, b * FL_D); DA(att_h, b * FL_D); DA(att_l, b * FL_D); DA(ffh_h, b * FL_FF); DA(ffh_l, b * FL_FF);
+    DA(normed_h, b * FL_D); DA(normed_l, b * FL_D); DA(partA, 4 * b * FL_D); DA(partB, 4 * b * FL_D);
+    DA(fx, b * FN_D); DA(ada, b * FN_ADA); DA(ft, b * FN_D); DA(flow, b * FL_LAT); DA(sc, b * FN_D); DA(fg, b * FN_D);
+    DA(sc_h, b * FN_D); DA(sc_l, b * FN_D); DA(fh_h, b * FN_D); DA(fh_l, b * FN_D); DA(fg_h, b * FN_D); DA(fg_l, b * FN_D);
+    DA(ok, (size_t)FL_L * b * FL_D * S); DA(ov, (size_t)FL_L * b * FL_D * S);
+    if (regrow_prefix || !e->pk) {
+        e->dfree(e->pk); e->dfree(e->pv); e->dfree(e->d_cond);
+        DA(pk, (size_t)FL_L * FL_D * cond + 16); DA(pv, (size_t)FL_L * FL_D * cond + 16); DA(d_cond, (size_t)cond * FL_D + 16);
+        e->voice_len = -1;
+    }
+    if (!e->ctrl) DA(ctrl, 1);
+#undef DA
+    // zero the 16-bit operand buffers once: padded batch rows must hold finite values
+    PTTS_CUDA_OK(cudaMemsetAsync(e->x, 0, b * FL_D * 4, e->st));
+    PTTS_CUDA_OK(cudaMemsetAsync(e->d_latent, 0, b * FL_LAT * 4, e->st));
+    PTTS_CUDA_OK(cudaMemsetAsync(e->d_noise, 0, b * F * FL_LAT * 4, e->st));
+    e->capB = B; e->capS = S; e->capTok = tok; e->capF = F; e->capCond = cond;
+    return 0;
+}
+
+static FlowState make_state(Engine *e, int B, int lsd_steps, const float *ext_in) {
+    FlowState s = {};
+    s.step = &e->ctrl->step;
+    s.B = B; s.max_tok = e->capTok; s.max_frames_cap = e->capF; s.cond_len = 0;
+    s.tokens = e->d_tokens; s.tok_len = e->d_tok_len; s.max_frames = e->d_max_frames; s.ext_in = ext_in;
+    s.noise = e->d_noise; s.latent = e->d_latent; s.out_latents = e->d_out_latents;
+    s.eos_step = e->d_eos_step; s.done = e->d_done; s.used = e->d_used;
+    s.first_eos = e->d_first_eos; s.first_cond = e->d_first_cond; s.first_flow = e->d_first_flow;
+    s.eos_log = nullptr;
+    s.lsd_steps = lsd_steps;
+    return s;
+}
+
+// ---------------------------------------------------------------- batch-1 GEMV path
+template <int K, int RPC, int PRO>
+static int gemv(Engine *e, const __nv_bfloat16 *W, int N, const float *x, GemvParams p) {
+    p.W = W; p.N = N; p.x = x;
+    constexpr int THREADS = K / 8 < 128 ? K / 8 : 128;
+    LaunchScope ls(e, KC_GEMV);
+    k_gemv<K, RPC, PRO><<<(N + RPC - 1) / RPC, THREADS, 0, e->st>>>(p);
+    return launch_check("k_gemv");
+}
+
+static int attn_decode(Engine *e, int B, int layer, bool voice_mode, bool out16) {
+    AttnDecodeParams a = {};
+    a.qkv = e->qkv;
+    a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin;
+    a.ctrl_cond_len = voice_mode ? nullptr : &e->ctrl->cond_len;
+    a.pstride = e->capCond;
+    if (voice_mode) {   // the voice prefix is prefilled into the prefix buffers themselves
+        a.pk = nullptr; a.pv = nullptr;
+        a.ok = e->pk + (size_t)layer * FL_D * e->capCond; a.ov = e->pv + (size_t)layer * FL_D * e->capCond;
+        a.max_s = e->capCond;
+    } else {
+        a.pk = e->pk + (size_t)layer * FL_D * e->capCond; a.pv = e->pv + (size_t)layer * FL_D * e->capCond;
+        a.ok = e->ok + (size_t)layer * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)layer * e->capB * FL_D * e->capS;
+        a.max_s = e->capS;
+    }
+    a.step = &e->ctrl->step;
+    if (out16) { a.out_h = e->att_h; a.out_l = e->att_l; } else a.out_f32 = e->att;
+    const size_t smem = (size_t)(e->capCond + std::max(e->capS, e->capCond) + 8) * sizeof(float);
+    PTTS_CHECK(smem <= 200 * 1024, "attention score buffer of %zu bytes exceeds shared memory (sequence too long)", smem);
+    LaunchScope ls(e, KC_ATTN_DECODE);
+    k_attn_decode<<<dim3(FL_H, B), 128, smem, e->st>>>(a);
+    return launch_check("k_attn_decode");
+}
+
+static int rownorm(Engine *e, int rows, RowNormParams p, int cls = KC_ROWNORM) {
+    LaunchScope ls(e, cls);
+    k_rownorm<<<rows, 256, 0, e->st>>>(p);
+    return launch_check("k_rownorm");
+}
+
+static int flow_step_gemv(Engine *e, const FlowState &st, bool voice_mode, const float *cbias) {
+    {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_prepare_x<<<1, 256, 0, e->st>>>(st, e->embed, e->bos_proj, e->in_lin, e->x);
+        if (launch_check("k_prepare_x") != 0) return -1;
+    }
+    for (int l = 0; l < FL_L; l++) {
+        GemvParams g = {};
+        g.ln_w = e->L[l].n1w; g.ln_b = e->L[l].n1b; g.eps = 1e-5f; g.out = e->qkv;
+        if (gemv<FL_D, 8, 1>(e, e->L[l].inproj, 3 * FL_D, e->x, g) != 0) return -1;
+        if (attn_decode(e, 1, l, voice_mode, false) != 0) return -1;
+        g = {}; g.acc_out = e->x;
+        if (gemv<FL_D, 4, 0>(e, e->L[l].outproj, FL_D, e->att, g) != 0) return -1;
+        g = {}; g.ln_w = e->L[l].n2w; g.ln_b = e->L[l].n2b; g.eps = 1e-5f; g.act = ACT_GELU_ERF; g.out = e->ffh;
+        if (gemv<FL_D, 8, 1>(e, e->L[l].l1, FL_FF, e->x, g) != 0) return -1;
+        g = {}; g.acc_out = e->x;
+        if (gemv<FL_FF, 4, 0>(e, e->L[l].l2, FL_D, e->ffh, g) != 0) return -1;
+    }
+    if (voice_mode) {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
+        return launch_check("k_advance_step");
+    }
+    RowNormParams r = {};
+    r.x = e->x; r.D = FL_D; r.w = e->onorm_w; r.b = e->onorm_b; r.eps = 1e-5f; r.do_norm = 1; r.out_f32 = e->normed;
+    if (rownorm(e, 1, r) != 0) return -1;
+    {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_eos_state<<<1, 256, 0, e->st>>>(st, e->ctrl, e->d_eos_after, e->normed, e->eos_w, e->eos_b);
+        if (launch_check("k_eos_state") != 0) return -1;
+    }
+    for (int k = 0; k < st.lsd_steps; k++) {
+        {
+            LaunchScope ls(e, KC_FLOW_MISC);
+            k_flow_init<<<1, 512, 0, e->st>>>(st, k, e->inp_w, e->inp_b, e->fx);
+            if (launch_check("k_flow_init") != 0) return -1;
+        }
+        GemvParams g = {};
+        g.bias = cbias + (size_t)k * FN_D; g.act = ACT_SILU; g.out = e->sc;      // silu(c), c = cond_embed + time
+        if (gemv<FL_D, 4, 0>(e, e->cond_w, FN_D, e->normed, g) != 0) return -1;
+        g = {}; g.bias = e->ada_b; g.out = e->ada;
+        if (gemv<FN_D, 8, 0>(e, e->ada_w, FN_ADA, e->sc, g) != 0) return -1;
+        for (int b = 0; b < FN_DEPTH; b++) {
+            const float *ad = e->ada + (size_t)b * 3 * FN_D;
+            g = {}; g.ln_w = e->FB[b].lnw; g.ln_b = e->FB[b].lnb; g.eps = 1e-6f; g.shift = ad; g.scale = ad + FN_D;
+            g.bias = e->FB[b].m0b; g.act = ACT_SILU; g.out = e->fg;
+            if (gemv<FN_D, 4, 2>(e, e->FB[b].m0w, FN_D, e->fx, g) != 0) return -1;
+            g = {}; g.bias = e->FB[b].m2b; g.gate = ad + 2 * FN_D; g.acc_out = e->fx;
+            if (gemv<FN_D, 4, 0>(e, e->FB[b].m2w, FN_D, e->fg, g) != 0) return -1;
+        }
+        const float *ad = e->ada + (size_t)FN_DEPTH * 3 * FN_D;
+        g = {}; g.eps = 1e-6f; g.shift = ad; g.scale = ad + FN_D; g.bias = e->fin_b; g.out = e->flow;
+        if (gemv<FN_D, 4, 2>(e, e->fin_w, FL_LAT, e->fx, g) != 0) return -1;
+        {
+            LaunchScope ls(e, KC_FLOW_MISC);
+            k_flow_update<<<1, 32, 0, e->st>>>(st, e->ctrl, e->d_eos_after, k, e->flow);
+            if (launch_check("k_flow_update") != 0) return -1;
+        }
+    }
+    LaunchScope ls(e, KC_FLOW_MISC);
+    k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
+    return launch_check("k_advance_step");
+}
+
+// ---------------------------------------------------------------- batched tcgen05 path
+struct FlowGemms {
+    GemmOp qkv[FL_L], outp[FL_L], ff1[FL_L], ff2[FL_L];
+    std::vector<GemmOp> cond;   // per LSD step (bias differs)
+    GemmOp ada, m0[FN_DEPTH], m2[FN_DEPTH], fin;
+    int B = 0, precise = -1, lsd = 0;
+    uint64_t gen = 0;
+};
+
+static int pick_bn(int B) { return B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 128 ? 128 : 256)); }
+
+// weights [N_w, K] bf16 as the A operand; activations [B, K] (hi, lo) as the B operand; output
+// out[b*ld + feature] (transposed store).
+static int flow_gemm_build(GemmOp &op, const __nv_bfloat16 *W, int n_w, int K, const uint16_t *xh, const uint16_t *xl, int B,
+                           int split_k, const float *bias, float *out_f32, int ldo, size_t split_stride, uint16_t *oh,
+                           uint16_t *ol, int ldh, int act) {
+    GemmDesc d;
+    d.A = W; d.a_k = K; d.a_rows = n_w; d.a_batches = 1; d.a_ld = K;
+    d.B = xh; d.Blo = xl; d.b_k = K; d.b_rows = B; d.b_ld = K;
+    d.bf16 = true; d.taps = 1; d.k_per_tap = K;
+    d.bn = std::min(pick_bn(B), 64);   // N tiles of <= 64 utterances: more CTAs pulling weights
+    d.split_k = split_k; d.two_cta = true;
+    d.epi.transposed = 1; d.epi.bias = bias; d.epi.out_f32 = out_f32; d.epi.ldo = ldo; d.epi.split_stride = split_stride;
+    d.epi.out_h = oh; d.epi.out_l = ol; d.epi.ldh = ldh; d.epi.out_bf16 = 1; d.epi.act = act;
+    return gemm_build(op, d);
+}
+
+static int flow_gemms_build(Engine *e, FlowGemms &G, int B, int precise, int lsd, const float *cbias) {
+    const size_t ps = (size_t)e->capB * FL_D;
+    const uint16_t *xl = precise ? e->xn_l : nullptr, *al = precise ? e->att_l : nullptr, *fl = precise ? e->ffh_l : nullptr;
+    for (int l = 0; l < FL_L; l++) {
+        if (flow_gemm_build(G.qkv[l], e->L[l].inproj, 3 * FL_D, FL_D, e->xn_h, xl, B, 1, nullptr, e->qkv, 3 * FL_D, 0, nullptr,
+                            nullptr, 0, ACT_NONE) != 0) return -1;
+        if (flow_gemm_build(G.outp[l], e->L[l].outproj, FL_D, FL_D, e->att_h, al, B, 4, nullptr, e->partA, FL_D, ps, nullptr,
+                            nullptr, 0, ACT_NONE) != 0) return -1;
+        if (flow_gemm_build(G.ff1[l], e->L[l].l1, FL_FF, FL_D, e->xn_h, xl, B, 1, nullptr, nullptr, 0, 0, e->ffh_h,
+                            precise ? e->ffh_l : nullptr, FL_FF, ACT_GELU_ERF) != 0) return -1;
+        if (flow_gemm_build(G.ff2[l], e->L[l].l2, FL_D, FL_FF, e->ffh_h, fl, B, 4, nullptr, e->partB, FL_D, ps, nullptr, nullptr,
+                            0, ACT_NONE) != 0) return -1;
+    }
+    G.cond.resize(lsd);
+    for (int k = 0; k < lsd; k++)
+        if (flow_gemm_build(G.cond[k], e->cond_w, FN_D, FL_D, e->normed_h, precise ? e->normed_l : nullptr, B, 1,
+                            cbias + (size_t)k * FN_D, nullptr, 0, 0, e->sc_h, precise ? e->sc_l : nullptr, FN_D, ACT_SILU) != 0)
+            return -1;
+    if (flow_gemm_build(G.ada, e->ada_w, FN_ADA, FN_D, e->sc_h, precise ? e->sc_l : nullptr, B, 1, e->ada_b, e->ada, FN_ADA, 0,
+                        nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
+    for (int b = 0; b < FN_DEPTH; b++) {
+        if (flow_gemm_build(G.m0[b], e->FB[b].m0w, FN_D, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 1, e->FB[b].m0b, nullptr, 0,
+                            0, e->fg_h, precise ? e->fg_l : nullptr, FN_D, ACT_SILU) != 0) return -1;
+        if (flow_gemm_build(G.m2[b], e->FB[b].m2w, FN_D, FN_D, e->fg_h, precise ? e->fg_l : nullptr, B, 1, e->FB[b].m2b, e->ft,
+                            FN_D, 0, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
+    }
+    if (flow_gemm_build(G.fin, e->fin_w, FL_LAT, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 1, e->fin_b, e->flow, FL_LAT, 0,
+                        nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
+    G.B = B; G.precise = precise; G.lsd = lsd; G.gen = e->gen;
+    return 0;
+}
+
+static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int precise) {
+    const int B = st.B;
+    const size_t ps = (size_t)e->capB * FL_D;
+    {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_prepare_x<<<B, 256, 0, e->st>>>(st, e->embed, e->bos_proj, e->in_lin, e->x);
+        if (launch_check("k_prepare_x") != 0) return -1;
+    }
+    for (int l = 0; l < FL_L; l++) {
+        RowNormParams r = {};
+        r.x = e->x; r.D = FL_D; r.w = e->L[l].n1w; r.b = e->L[l].n1b; r.eps = 1e-5f; r.do_norm = 1;
+        r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
+        if (l > 0) { r.part = e->partB; r.nsplit = (int)G.ff2[l - 1].grid.z; r.split_stride = ps; }
+        if (rownorm(e, B, r) != 0) return -1;
+        if (run_gemm(e, G.qkv[l], KC_GEMM_FLOW) != 0) return -1;
+        if (attn_decode(e, B, l, false, true) != 0) return -1;
+        if (run_gemm(e, G.outp[l], KC_GEMM_FLOW) != 0) return -1;
+        r = {};
+        r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
+        r.part = e->partA; r.nsplit = (int)G.outp[l].grid.z; r.split_stride = ps;
+        r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
+        if (rownorm(e, B, r) != 0) return -1;
+        if (run_gemm(e, G.ff1[l], KC_GEMM_FLOW) != 0) return -1;
+        if (run_gemm(e, G.ff2[l], KC_GEMM_FLOW) != 0) return -1;
+    }
+    {
+        RowNormParams r = {};
+        r.x = e->x; r.D = FL_D; r.w = e->onorm_w; r.b = e->onorm_b; r.eps = 1e-5f; r.do_norm = 1;
+        r.part = e->partB; r.nsplit = (int)G.ff2[FL_L - 1].grid.z; r.split_stride = ps;
+        r.out_f32 = e->normed; r.out_h = e->normed_h; r.out_l = precise ? e->normed_l : nullptr; r.out_bf16 = 1;
+        if (rownorm(e, B, r) != 0) return -1;
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_eos_state<<<B, 256, 0, e->st>>>(st, e->ctrl, e->d_eos_after, e->normed, e->eos_w, e->eos_b);
+        if (launch_check("k_eos_state") != 0) return -1;
+    }
+    for (int k = 0; k < st.lsd_steps; k++) {
+        {
+            LaunchScope ls(e, KC_FLOW_MISC);
+            k_flow_init<<<B, 512, 0, e->st>>>(st, k, e->inp_w, e->inp_b, e->fx);
+            if (launch_check("k_flow_init") != 0) return -1;
+        }
+        if (run_gemm(e, G.cond[k], KC_GEMM_FLOW) != 0) return -1;
+        if (run_gemm(e, G.ada, KC_GEMM_FLOW) != 0) return -1;
+        for (int b = 0; b <= FN_DEPTH; b++) {
+            // fold the previous block's gated MLP output, then LN + adaLN for this block / the final layer
+            RowNormParams r = {};
+            r.x = e->fx; r.D = FN_D; r.eps = 1e-6f; r.do_norm = 1; r.ldmod = FN_ADA;
+            if (b > 0) { r.part = e->ft; r.nsplit = 1; r.split_stride = 0; r.gate = e->ada + (size_t)(b - 1) * 3 * FN_D + 2 * FN_D; }
+            if (b < FN_DEPTH) { r.w = e->FB[b].lnw; r.b = e->FB[b].lnb; }
+            r.shift = e->ada + (size_t)b * 3 * FN_D; r.scale = r.shift + FN_D;
+            r.out_h = e->fh_h; r.out_l = precise ? e->fh_l : nullptr; r.out_bf16 = 1;
+            if (rownorm(e, B, r) != 0) return -1;
+            if (b < FN_DEPTH) {
+                if (run_gemm(e, G.m0[b], KC_GEMM_FLOW) != 0) return -1;
+                if (run_gemm(e, G.m2[b], KC_GEMM_FLOW) != 0) return -1;
+            }
+        }
+        if (run_gemm(e, G.fin, KC_GEMM_FLOW) != 0) return -1;
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_flow_update<<<B, 32, 0, e->st>>>(st, e->ctrl, e->d_eos_after, k, e->flow);
+        if (launch_check("k_flow_update") != 0) return -1;
+    }
+    LaunchScope ls(e, KC_FLOW_MISC);
+    k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
+    return launch_check("k_advance_step");
+}
+
+}  // namespace ptts

@@ -1,0 +1,686 @@
+// kernels.cuh - the non-GEMM kernels of the hot path: bf16-weight GEMV (batch-1 streaming decode),
+// row LayerNorm / adaLN, RoPE + KV-append + decode attention, FlowLM state machine, flow-head
+// glue, Mimi front end (quantizer proj + depthwise upsample), Mimi RoPE / banded attention,
+// final conv to PCM.
+#pragma once
+#include "common.cuh"
+
+namespace ptts {
+
+constexpr int FL_D = 1024, FL_H = 16, FL_HD = 64, FL_L = 6, FL_FF = 4096, FL_LAT = 32;
+constexpr int FN_D = 512, FN_DEPTH = 6, FN_ADA = FN_DEPTH * 3 * FN_D + 2 * FN_D;  // 10240 adaLN rows
+constexpr int MI_D = 512, MI_H = 8, MI_L = 2, MI_FF = 2048, MI_CTX = 250;
+
+// Block-wide sum for up to 1024 threads; `red` must hold 32 floats. All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = lane < nw ? red[lane] : 0.0f;
+    return warp_sum(t);
+}
+__device__ __forceinline__ float block_max(float v, float *red) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    float t = lane < nw ? red[lane] : -INFINITY;
+    return warp_max(t);
+}
+
+// =====================================================================================
+// Row kernel: optional fold of split-K partial sums (+ gate) into the fp32 residual
+// stream, LayerNorm (ptts_flowlm.c:159-181: biased variance, two-pass), optional adaLN
+// modulation (ptts_flowlm.c:735-737), outputs fp32 and/or 16-bit hi(+lo).
+// One block (256 threads) per row, D <= 1024.
+// =====================================================================================
+struct RowNormParams {
+    float *x;                  // [R, D] fp32, updated in place when nsplit > 0
+    int D;
+    const float *part;         // [nsplit][R][D] partial sums to fold: x += gate * sum_z part_z
+    int nsplit;
+    size_t split_stride;
+    const float *gate;         // optional [R, ldmod] multiplier of the folded sum (flow-head gate)
+    const float *w, *b;        // LN affine (NULL = none)
+    float eps;
+    const float *shift, *scale;  // optional adaLN rows [R, ldmod]
+    int ldmod;
+    int do_norm;               // 0 = only fold
+    float *out_f32;            // [R, D] or NULL
+    uint16_t *out_h, *out_l;   // [R, D] or NULL
+    int out_bf16;
+};
+
+__global__ void __launch_bounds__(256) k_rownorm(const RowNormParams p) {
+    __shared__ float red[32];
+    const size_t row = blockIdx.x;
+    float v[4];
+    float *xr = p.x + row * p.D;
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = threadIdx.x + j * 256;
+        v[j] = 0.0f;
+        if (i < p.D) {
+            float t = xr[i];
+            if (p.nsplit > 0) {
+                float a = 0.0f;
+                for (int z = 0; z < p.nsplit; z++) a += p.part[z * p.split_stride + row * p.D + i];
+                if (p.gate) a *= p.gate[row * p.ldmod + i];
+                t += a;
+                xr[i] = t;
+            }
+            v[j] = t;
+            s += t;
+        }
+    }
+    if (!p.do_norm) return;
+    const float mean = block_sum(s, red) / (float)p.D;
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = threadIdx.x + j * 256;
+        if (i < p.D) { const float d = v[j] - mean; q += d * d; }
+    }
+    const float var = block_sum(q, red) / (float)p.D;
+    const float inv = 1.0f / sqrtf(var + p.eps);
+    const bool bf = p.out_bf16 != 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = threadIdx.x + j * 256;
+        if (i < p.D) {
+            float y = (v[j] - mean) * inv;
+            if (p.w) y *= p.w[i];
+            if (p.b) y += p.b[i];
+            if (p.scale) y = y * (1.0f + p.scale[row * p.ldmod + i]) + p.shift[row * p.ldmod + i];
+            if (p.out_f32) p.out_f32[row * p.D + i] = y;
+            if (p.out_h) {
+                const uint16_t h = f2h16(y, bf);
+                p.out_h[row * p.D + i] = h;
+                if (p.out_l) p.out_l[row * p.D + i] = f2h16(y - h162f(h, bf), bf);
+            }
+        }
+    }
+}
+
+// =====================================================================================
+// Batch-1 GEMV: y[n] = sum_k W[n,k] x[k], bf16 weights streamed once with 128-bit loads,
+// fp32 activations and accumulation, warp-shuffle reduction. K is split across the CTA's
+// threads (one 8-element chunk per thread per pass) so a warp reads 512 contiguous bytes of
+// a weight row; each CTA owns RPC consecutive rows, giving RPC * (K/8/THREADS) independent
+// 16-byte loads in flight per thread.
+// Prologue (every CTA recomputes it; x is tiny): none | LayerNorm | LayerNorm + adaLN.
+// Epilogue: + bias (+ bias2), activation, optional gate, store or in-place residual add.
+// =====================================================================================
+struct GemvParams {
+    const __nv_bfloat16 *W;    // [N, K]
+    int N;
+    const float *x;            // [K]
+    const float *ln_w, *ln_b;  // PRO >= 1
+    float eps;
+    const float *shift, *scale;  // PRO == 2
+    const float *bias, *bias2;
+    int act;
+    const float *gate;         // y *= gate[n]
+    float *acc_out;            // acc_out[n] += y   (residual stream), or
+    float *out;                // out[n] = y
+};
+
+template <int K, int RPC, int PRO>
+__global__ void __launch_bounds__((K / 8 < 128 ? K / 8 : 128)) k_gemv(const GemvParams p) {
+    constexpr int THREADS = K / 8 < 128 ? K / 8 : 128;
+    constexpr int NCH = K / 8 / THREADS;  // chunks per thread
+    constexpr int NW = THREADS / 32;
+    __shared__ float red[32];
+    __shared__ float part[NW][RPC];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int r0 = blockIdx.x * RPC;
+
+    // issue the weight loads first: they do not depend on the prologue
+    uint4 wv[RPC][NCH];
+#pragma unroll
+    for (int r = 0; r < RPC; r++)
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const int row = min(r0 + r, p.N - 1);
+            wv[r][c] = __ldcs((const uint4 *)(p.W + (size_t)row * K) + tid + c * THREADS);
+        }
+
+    float xv[NCH][8];
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const float4 a = *(const float4 *)(p.x + (tid + c * THREADS) * 8);
+        const float4 b = *(const float4 *)(p.x + (tid + c * THREADS) * 8 + 4);
+        xv[c][0] = a.x; xv[c][1] = a.y; xv[c][2] = a.z; xv[c][3] = a.w;
+        xv[c][4] = b.x; xv[c][5] = b.y; xv[c][6] = b.z; xv[c][7] = b.w;
+    }
+    if (PRO >= 1) {
+        float s = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) s += xv[c][j];
+        const float mean = block_sum(s, red) / (float)K;
+        float q = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const float d = xv[c][j] - mean; q += d * d; }
+        const float inv = 1.0f / sqrtf(block_sum(q, red) / (float)K + p.eps);
+#pragma unroll
+        for (int c = 0; c < NCH; c++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int i = (tid + c * THREADS) * 8 + j;
+                float y = (xv[c][j] - mean) * inv;
+                if (p.ln_w) y *= p.ln_w[i];
+                if (p.ln_b) y += p.ln_b[i];
+                if (PRO == 2) y = y * (1.0f + p.scale[i]) + p.shift[i];
+                xv[c][j] = y;
+            }
+    }
+    float acc[RPC];
+#pragma unroll
+    for (int r = 0; r < RPC; r++) {
+        float a = 0.0f;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const uint4 u = wv[r][c];
+            a += bf16lo(u.x) * xv[c][0] + bf16hi(u.x) * xv[c][1] + bf16lo(u.y) * xv[c][2] + bf16hi(u.y) * xv[c][3] +
+                 bf16lo(u.z) * xv[c][4] + bf16hi(u.z) * xv[c][5] + bf16lo(u.w) * xv[c][6] + bf16hi(u.w) * xv[c][7];
+        }
+        acc[r] = warp_sum(a);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RPC; r++) part[w][r] = acc[r];
+    }
+    __syncthreads();
+    if (tid < RPC && r0 + tid < p.N) {
+        const int n = r0 + tid;
+        float y = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NW; i++) y += part[i][tid];
+        if (p.bias) y += p.bias[n];
+        if (p.bias2) y += p.bias2[n];
+        y = act_apply(p.act, y);
+        if (p.gate) y *= p.gate[n];
+        if (p.acc_out) p.acc_out[n] += y; else p.out[n] = y;
+    }
+}
+
+// =====================================================================================
+// FlowLM lock-step state machine (ptts_flowlm.c:1138-1251 restructured for a batch):
+// every utterance b consumes one input per step s after the shared voice prefix:
+//   s <  tok_len[b]          text embedding row           (prefill)
+//   s == tok_len[b]          input_linear . bos_emb
+//   s >  tok_len[b]          input_linear . latent[b]     (frame i = s - tok_len[b] - 1 fed back)
+// After the transformer step, frame index i = s - tok_len[b] is sampled when
+// 0 <= i < max_frames[b] and the utterance has not stopped.
+// =====================================================================================
+struct FlowState {
+    int *step;                 // device step counter s
+    int B, max_tok, max_frames_cap, cond_len;
+    const int *tokens;         // [B, max_tok]
+    const int *tok_len;        // [B]
+    const int *max_frames;     // [B]
+    const float *ext_in;       // optional [n, 1024] inputs used instead (voice prefill)
+    const float *noise;        // [B, max_frames_cap, 32]
+    float *latent;             // [B, 32] running latent of the current frame
+    float *out_latents;        // [B, max_frames_cap, 32]
+    int *eos_step, *done, *used;     // [B]
+    float *first_eos, *first_cond, *first_flow;  // [B], [B,1024], [B,32]
+    float *eos_log;            // optional [B, max_frames_cap]
+    int lsd_steps;
+};
+
+// Device-resident per-call scalars, so that a captured step graph stays valid across calls.
+struct FlowCtrl {
+    int step, cond_len, eos_enabled, eos_min_frames, eos_after_default;
+    float eos_threshold;
+};
+
+// x[b,:] for step s. grid B, block 256.
+__global__ void __launch_bounds__(256) k_prepare_x(const FlowState st, const __nv_bfloat16 *embed, const float *bos_proj,
+                                                   const __nv_bfloat16 *in_lin, float *x) {
+    const int b = blockIdx.x, s = *st.step;
+    float *xr = x + (size_t)b * FL_D;
+    if (st.ext_in) {
+        for (int i = threadIdx.x; i < FL_D; i += 256) xr[i] = st.ext_in[(size_t)s * FL_D + i];
+        return;
+    }
+    const int tl = st.tok_len[b];
+    if (s < tl) {
+        int id = st.tokens[(size_t)b * st.max_tok + s];
+        if (id < 0 || id > 4000) id = 0;  // ptts_flowlm.c:1170
+        for (int i = threadIdx.x; i < FL_D; i += 256) xr[i] = __bfloat162float(embed[(size_t)id * FL_D + i]);
+    } else if (s == tl) {
+        for (int i = threadIdx.x; i < FL_D; i += 256) xr[i] = bos_proj[i];
+    } else {
+        __shared__ float lat[FL_LAT];
+        if (threadIdx.x < FL_LAT) lat[threadIdx.x] = st.latent[b * FL_LAT + threadIdx.x];
+        __syncthreads();
+        for (int i = threadIdx.x; i < FL_D; i += 256) {
+            const uint4 *wr = (const uint4 *)(in_lin + (size_t)i * FL_LAT);
+            float a = 0.0f;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const uint4 u = wr[c];
+                const float *l = lat + c * 8;
+                a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] +
+                     bf16lo(u.z) * l[4] + bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
+            }
+            xr[i] = a;
+        }
+    }
+}
+
+// EOS logit + stop rule (ptts_flowlm.c:1202-1209). grid B, block 256. normed [B,1024].
+__global__ void __launch_bounds__(256) k_eos_state(const FlowState st, const FlowCtrl *ctrl, const int *eos_after, const float *normed,
+                                                   const float *eos_w, const float *eos_b) {
+    __shared__ float red[32];
+    const int b = blockIdx.x, s = *st.step;
+    const float *nr = normed + (size_t)b * FL_D;
+    float a = 0.0f;
+    for (int i = threadIdx.x; i < FL_D; i += 256) a += eos_w[i] * nr[i];
+    const float eos = block_sum(a, red) + eos_b[0];
+    const int i = s - st.tok_len[b];
+    const bool valid = i >= 0 && i < st.max_frames[b] && !st.done[b];
+    if (!valid) return;
+    if (i == 0) {
+        for (int k = threadIdx.x; k < FL_D; k += 256) st.first_cond[(size_t)b * FL_D + k] = nr[k];
+    }
+    if (threadIdx.x == 0) {
+        if (i == 0) st.first_eos[b] = eos;
+        if (st.eos_log) st.eos_log[(size_t)b * st.max_frames_cap + i] = eos;
+        if (ctrl->eos_enabled && i + 1 >= ctrl->eos_min_frames && eos >= ctrl->eos_threshold && st.eos_step[b] < 0) st.eos_step[b] = i;
+    }
+}
+
+// Flow-head entry for LSD step k: latent = noise (k == 0) and fx = input_proj . latent + b
+// (ptts_flowlm.c:710). grid B, block 512.
+__global__ void __launch_bounds__(512) k_flow_init(const FlowState st, int k, const __nv_bfloat16 *inp_w /*[512,32]*/,
+                                                   const float *inp_b, float *fx) {
+    __shared__ float lat[FL_LAT];
+    const int b = blockIdx.x, s = *st.step;
+    int i = s - st.tok_len[b];
+    if (threadIdx.x < FL_LAT) {
+        float v;
+        if (k == 0) {
+            const int fi = min(max(i, 0), st.max_frames_cap - 1);
+            v = st.noise[((size_t)b * st.max_frames_cap + fi) * FL_LAT + threadIdx.x];
+            st.latent[b * FL_LAT + threadIdx.x] = v;
+        } else {
+            v = st.latent[b * FL_LAT + threadIdx.x];
+        }
+        lat[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const int n = threadIdx.x;
+    const uint4 *wr = (const uint4 *)(inp_w + (size_t)n * FL_LAT);
+    float a = inp_b[n];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const uint4 u = wr[c];
+        const float *l = lat + c * 8;
+        a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] + bf16lo(u.z) * l[4] +
+             bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
+    }
+    fx[(size_t)b * FN_D + n] = a;
+}
+
+// Euler update latent += flow / N (ptts_flowlm.c:775-777); on the last LSD step record the frame,
+// apply the stop rule (ptts_flowlm.c:1235-1238). grid B, block 32.
+__global__ void __launch_bounds__(32) k_flow_update(const FlowState st, const FlowCtrl *ctrl, const int *eos_after, int k,
+                                                    const float *flow /*[B,32]*/) {
+    const int b = blockIdx.x, s = *st.step, d = threadIdx.x;
+    const int i = s - st.tok_len[b];
+    const bool valid = i >= 0 && i < st.max_frames[b] && !st.done[b];
+    const float f = flow[b * FL_LAT + d];
+    const float v = st.latent[b * FL_LAT + d] + f / (float)st.lsd_steps;
+    st.latent[b * FL_LAT + d] = v;
+    if (valid) {
+        if (i == 0 && k == 0) st.first_flow[b * FL_LAT + d] = f;
+        if (k == st.lsd_steps - 1) st.out_latents[((size_t)b * st.max_frames_cap + i) * FL_LAT + d] = v;
+    }
+    __syncwarp();
+    if (k == st.lsd_steps - 1 && d == 0) {
+        if (valid) {
+            st.used[b] = i + 1;
+            const int es = st.eos_step[b];
+            if ((es >= 0 && i >= es + eos_after[b]) || i + 1 >= st.max_frames[b]) st.done[b] = 1;
+        }
+    }
+}
+__global__ void k_advance_step(int *step) { *step += 1; }
+
+// =====================================================================================
+// RoPE + KV append + single-query attention over [shared voice prefix | own positions]
+// (ptts_flowlm.c:465-525).  grid (16 heads, B), block 128.
+// cache layout: prefix [H][pstride][64], own [B][H][max_s][64], fp32.
+// =====================================================================================
+struct AttnDecodeParams {
+    const float *qkv;          // [B, 3072]
+    const float *rope_cos, *rope_sin;  // [max_pos][32]
+    const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
+    float *ok, *ov;            // own cache of this layer
+    const int *ctrl_cond_len;  // device cond_len (NULL = 0: voice prefill writes the prefix buffers as "own")
+    int pstride;               // row capacity of the prefix buffers
+    int max_s;
+    const int *step;
+    float *out_f32;            // [B,1024] (GEMV path)
+    uint16_t *out_h, *out_l;   // bf16 hi/lo (tensor path)
+};
+
+__global__ void __launch_bounds__(128) k_attn_decode(const AttnDecodeParams p) {
+    extern __shared__ float sc[];  // [cond_len + max_s] scores
+    __shared__ __align__(16) float sq[FL_HD];
+    __shared__ float red[32];
+    __shared__ float so[2][FL_HD];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
+    const int s = *p.step, pos = cond_len + s, P = pos + 1;
+    const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD;
+    float *okb = p.ok + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+    float *ovb = p.ov + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+    if (tid < 32) {
+        const float c = p.rope_cos[pos * 32 + tid], sn = p.rope_sin[pos * 32 + tid];
+        const float q0 = row[2 * tid], q1 = row[2 * tid + 1];
+        const float k0 = row[FL_D + 2 * tid], k1 = row[FL_D + 2 * tid + 1];
+        // 1/sqrt(64) = 0.125 is a power of two: scaling q here equals scaling each score
+        sq[2 * tid] = (q0 * c - q1 * sn) * 0.125f;
+        sq[2 * tid + 1] = (q0 * sn + q1 * c) * 0.125f;
+        okb[(size_t)s * FL_HD + 2 * tid] = k0 * c - k1 * sn;
+        okb[(size_t)s * FL_HD + 2 * tid + 1] = k0 * sn + k1 * c;
+    } else if (tid < 96) {
+        ovb[(size_t)s * FL_HD + (tid - 32)] = row[2 * FL_D + (tid - 32)];
+    }
+    __syncthreads();
+    const float *pkh = p.pk ? p.pk + (size_t)h * p.pstride * FL_HD : nullptr;
+    const float *pvh = p.pv ? p.pv + (size_t)h * p.pstride * FL_HD : nullptr;
+    float mx = -INFINITY;
+    for (int t = tid; t < P; t += 128) {
+        const float4 *kp = (const float4 *)(t < cond_len ? pkh + (size_t)t * FL_HD : okb + (size_t)(t - cond_len) * FL_HD);
+        float a = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            const float4 kv = kp[j];
+            const float4 qv = *(const float4 *)(sq + 4 * j);
+            a += kv.x * qv.x + kv.y * qv.y + kv.z * qv.z + kv.w * qv.w;
+        }
+        sc[t] = a;
+        mx = fmaxf(mx, a);
+    }
+    mx = block_max(mx, red);
+    float sum = 0.0f;
+    for (int t = tid; t < P; t += 128) {
+        const float e = expf(sc[t] - mx);
+        sc[t] = e;
+        sum += e;
+    }
+    sum = block_sum(sum, red);  // includes __syncthreads: sc[] complete
+    const int g = tid >> 6, d = tid & 63;
+    float a0 = 0.0f, a1 = 0.0f;
+    int t = g;
+    for (; t + 2 < P; t += 4) {
+        const float *v0 = t < cond_len ? pvh + (size_t)t * FL_HD : ovb + (size_t)(t - cond_len) * FL_HD;
+        const float *v1 = (t + 2) < cond_len ? pvh + (size_t)(t + 2) * FL_HD : ovb + (size_t)(t + 2 - cond_len) * FL_HD;
+        a0 += sc[t] * v0[d];
+        a1 += sc[t + 2] * v1[d];
+    }
+    for (; t < P; t += 2) {
+        const float *v0 = t < cond_len ? pvh + (size_t)t * FL_HD : ovb + (size_t)(t - cond_len) * FL_HD;
+        a0 += sc[t] * v0[d];
+    }
+    so[g][d] = a0 + a1;
+    __syncthreads();
+    if (tid < FL_HD) {
+        const float o = (so[0][tid] + so[1][tid]) / sum;
+        const size_t oi = (size_t)b * FL_D + h * FL_HD + tid;
+        if (p.out_f32) p.out_f32[oi] = o;
+        if (p.out_h) {
+            const uint16_t hh = f2h16(o, true);
+            p.out_h[oi] = hh;
+            if (p.out_l) p.out_l[oi] = f2h16(o - h162f(hh, true), true);
+        }
+    }
+}
+
+// cos/sin table: freq_i = exp(-ln(10000) * 2i/64) (ptts_flowlm.c:361-364), angle = freq_i * pos.
+__global__ void k_rope_table(float *cs, float *sn, int max_pos) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= max_pos * 32) return;
+    const int pos = idx >> 5, i = idx & 31;
+    const float f = expf(-logf(10000.0f) * (2.0f * (float)i / 64.0f));
+    const float a = f * (float)pos;
+    cs[idx] = cosf(a);
+    sn[idx] = sinf(a);
+}
+
+// Time embedding MLP for one scalar (ptts_flowlm.c:572-586), fp32 weights, single block of 512.
+// Accumulates 0.5 * embed into out (call for s and for t), out pre-initialised with cond_embed.bias.
+__global__ void __launch_bounds__(512) k_time_embed(const float *l0w, const float *l0b, const float *l2w, const float *l2b,
+                                                    const float *alpha, const float *freqs, float tval, float *out) {
+    __shared__ float e[256], h[FN_D], red[32];
+    const int n = threadIdx.x;
+    if (n < 128) {
+        const float f = freqs ? freqs[n] : expf(-logf(10000.0f) * ((float)n / 128.0f));
+        e[n] = cosf(f * tval);
+        e[n + 128] = sinf(f * tval);
+    }
+    __syncthreads();
+    float a = l0b[n];
+    for (int i = 0; i < 256; i++) a += l0w[n * 256 + i] * e[i];
+    h[n] = a / (1.0f + expf(-a));
+    __syncthreads();
+    float y = l2b[n];
+    for (int i = 0; i < FN_D; i++) y += l2w[n * FN_D + i] * h[i];
+    // variance-style "RMSNorm": unbiased variance, x not centred (ptts_flowlm.c:183-197)
+    const float mean = block_sum(y, red) / (float)FN_D;
+    const float d = y - mean;
+    const float var = block_sum(d * d, red) / (float)(FN_D - 1);
+    out[n] += 0.5f * (y * alpha[n] * (1.0f / sqrtf(var + 1e-5f)));
+}
+
+// =====================================================================================
+// Mimi front end: latent scaling (optional), quantizer.output_proj (ptts_mimi.c:577-586) and the
+// depthwise ConvTranspose1d k=32 s=16 (ptts_mimi.c:588-593; two taps per output), written
+// time-major: x[b, t*16+r, c].  grid (F, B), block 512 (thread = channel).
+// =====================================================================================
+__global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32], item stride lat_stride*/, size_t lat_stride, int F,
+                                                    const float *emb_std, const float *emb_mean,
+                                                    int apply_scale, const float *quant_w /*[512,32]*/, const float *ups /*[512,32]*/,
+                                                    float *x /*[B,16F,512]*/) {
+    __shared__ float l0[32], l1[32];
+    const int t = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
+    if (c < 32) {
+        float v = lat[(size_t)b * lat_stride + (size_t)t * 32 + c];
+        if (apply_scale) v = v * emb_std[c] + emb_mean[c];
+        l0[c] = v;
+    } else if (c < 64) {
+        float v = 0.0f;
+        if (t > 0) {
+            v = lat[(size_t)b * lat_stride + (size_t)(t - 1) * 32 + (c - 32)];
+            if (apply_scale) v = v * emb_std[c - 32] + emb_mean[c - 32];
+        }
+        l1[c - 32] = v;
+    }
+    __syncthreads();
+    float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+        const float w = quant_w[c * 32 + i];
+        q0 += w * l0[i];
+        q1 += w * l1[i];
+    }
+    float *xo = x + ((size_t)b * F + t) * 16 * MI_D + c;
+#pragma unroll
+    for (int r = 0; r < 16; r++) {
+        float v = ups[c * 32 + r] * q0;
+        if (t > 0) v += ups[c * 32 + 16 + r] * q1;
+        xo[(size_t)r * MI_D] = v;
+    }
+}
+
+// Mimi: split qkv rows [R,1536] fp32 into per-head q (scaled by 1/8), k (both RoPE-rotated at
+// pos = t) and v, stored fp16 [B][H][T][64] (ptts_mimi.c:329-341). grid R, block 256.
+__global__ void __launch_bounds__(256) k_mimi_rope_heads(const float *qkv, int T, const float *rope_cos, const float *rope_sin,
+                                                         __half *q, __half *k, __half *v) {
+    const size_t row = blockIdx.x;
+    const int b = (int)(row / T), t = (int)(row % T);
+    const float *r = qkv + row * 3 * MI_D;
+    for (int pi = threadIdx.x; pi < 3 * MI_D / 2; pi += 256) {
+        const int which = pi / (MI_D / 2), pr = pi % (MI_D / 2);
+        const int h = pr / 32, i = pr % 32;
+        const float a0 = r[which * MI_D + 2 * pr], a1 = r[which * MI_D + 2 * pr + 1];
+        float o0 = a0, o1 = a1;
+        if (which < 2) {
+            const float c = rope_cos[t * 32 + i], s = rope_sin[t * 32 + i];
+            o0 = a0 * c - a1 * s;
+            o1 = a0 * s + a1 * c;
+            if (which == 0) { o0 *= 0.125f; o1 *= 0.125f; }
+        }
+        __half *dst = (which == 0 ? q : which == 1 ? k : v) + (((size_t)b * MI_H + h) * T + t) * 64 + 2 * i;
+        *(__half2 *)dst = __floats2half2_rn(o0, o1);
+    }
+}
+
+// Mimi banded causal attention: key tk visible to query tq iff 0 <= tq - tk < 250
+// (ptts_mimi.c:264-299). One CTA = 32 consecutive queries of one (batch, head); its <= 281 keys
+// and values are staged once in shared memory (fp16, padded rows); each warp owns 4 queries and
+// shares every K / V shared-memory load between them. fp32 math.
+// grid (ceil(T/32), H, B), block 256.
+constexpr int WA_Q = 32, WA_KEYS = WA_Q + MI_CTX - 1, WA_LD = 66;  // 281 keys, row stride 66 halves
+__global__ void __launch_bounds__(256) k_mimi_win_attn(const __half *q, const __half *k, const __half *v, int T,
+                                                       __half *out /*[B*T, 512]*/) {
+    extern __shared__ __align__(16) uint8_t wa_smem[];
+    __half *sk = (__half *)wa_smem;                 // [WA_KEYS][WA_LD]
+    __half *sv = sk + WA_KEYS * WA_LD;              // [WA_KEYS][WA_LD]
+    float *sqf = (float *)(sv + WA_KEYS * WA_LD);   // [32][64] queries fp32
+    float *sp = sqf + WA_Q * 64;                    // [8 warps][4][WA_KEYS + 7] probabilities
+    constexpr int SPLD = WA_KEYS + 7;
+    const int q0 = blockIdx.x * WA_Q, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const size_t base = ((size_t)b * MI_H + h) * T;
+    const int klo = max(0, q0 - (MI_CTX - 1));
+    const int khi = min(T - 1, q0 + WA_Q - 1);
+    const int nk = khi - klo + 1;
+    for (int idx = tid; idx < nk * 32; idx += 256) {
+        const int r = idx >> 5, c = idx & 31;
+        *(__half2 *)(sk + r * WA_LD + 2 * c) = *(const __half2 *)(k + (base + klo + r) * 64 + 2 * c);
+        *(__half2 *)(sv + r * WA_LD + 2 * c) = *(const __half2 *)(v + (base + klo + r) * 64 + 2 * c);
+    }
+    for (int idx = tid; idx < WA_Q * 64; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        sqf[idx] = (q0 + r < T) ? __half2float(q[(base + q0 + r) * 64 + c]) : 0.0f;
+    }
+    __syncthreads();
+    constexpr int NCH = (WA_KEYS + 31) / 32;  // 9 key chunks of 32
+    float s[4][NCH];
+    const float *qw = sqf + (w * 4) * 64;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int kr = c * 32 + lane;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+        if (kr < nk) {
+            const __half2 *kp = (const __half2 *)(sk + kr * WA_LD);
+#pragma unroll 8
+            for (int d2 = 0; d2 < 32; d2++) {
+                const float2 kv = __half22float2(kp[d2]);
+                const float2 x0 = *(const float2 *)(qw + 2 * d2);
+                const float2 x1 = *(const float2 *)(qw + 64 + 2 * d2);
+                const float2 x2 = *(const float2 *)(qw + 128 + 2 * d2);
+                const float2 x3 = *(const float2 *)(qw + 192 + 2 * d2);
+                a0 += kv.x * x0.x + kv.y * x0.y;
+                a1 += kv.x * x1.x + kv.y * x1.y;
+                a2 += kv.x * x2.x + kv.y * x2.y;
+                a3 += kv.x * x3.x + kv.y * x3.y;
+            }
+        }
+        const int tk = klo + kr;
+        const int tq = q0 + w * 4;
+        s[0][c] = (kr < nk && tk <= tq && tq - tk < MI_CTX) ? a0 : -INFINITY;
+        s[1][c] = (kr < nk && tk <= tq + 1 && tq + 1 - tk < MI_CTX) ? a1 : -INFINITY;
+        s[2][c] = (kr < nk && tk <= tq + 2 && tq + 2 - tk < MI_CTX) ? a2 : -INFINITY;
+        s[3][c] = (kr < nk && tk <= tq + 3 && tq + 3 - tk < MI_CTX) ? a3 : -INFINITY;
+    }
+    float inv[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) mx = fmaxf(mx, s[j][c]);
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        float *pj = sp + (w * 4 + j) * SPLD;
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const float e = (s[j][c] == -INFINITY) ? 0.0f : expf(s[j][c] - mx);
+            sum += e;
+            if (c * 32 + lane < SPLD) pj[c * 32 + lane] = e;
+        }
+        sum = warp_sum(sum);
+        inv[j] = sum > 0.0f ? 1.0f / sum : 0.0f;
+    }
+    __syncwarp();
+    float o[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+    const float *p0 = sp + (w * 4) * SPLD;
+    for (int kr = 0; kr < nk; kr++) {
+        const float2 vv = __half22float2(*(const __half2 *)(sv + kr * WA_LD + 2 * lane));
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float pw = p0[j * SPLD + kr];
+            o[j][0] += pw * vv.x;
+            o[j][1] += pw * vv.y;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int tq = q0 + w * 4 + j;
+        if (tq < T) {
+            __half *dst = out + ((size_t)b * T + tq) * MI_D + h * 64 + 2 * lane;
+            *(__half2 *)dst = __floats2half2_rn(o[j][0] * inv[j], o[j][1] * inv[j]);
+        }
+    }
+}
+constexpr int WA_SMEM = 2 * WA_KEYS * WA_LD * 2 + WA_Q * 64 * 4 + 32 * (WA_KEYS + 7) * 4;
+
+// Final Conv1d 64 -> 1, k = 3 on ELU'd fp16 activations [B, T, 64] -> pcm [B, T] fp32
+// (ptts_mimi.c:723-726 with ptts_kernels.c:128-153). Thread per sample.
+__global__ void __launch_bounds__(256) k_dec_out(const __half *e, int T, const float *w /*[64*3] as [c][kk]*/, const float *bias,
+                                                 float *pcm) {
+    __shared__ float sw[3][64];
+    if (threadIdx.x < 192) sw[threadIdx.x % 3][threadIdx.x / 3] = w[threadIdx.x];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    if (t >= T) return;
+    float a = bias[0];
+#pragma unroll
+    for (int kk = 0; kk < 3; kk++) {
+        const int tt = t - 2 + kk;
+        if (tt < 0) continue;
+        const uint4 *row = (const uint4 *)(e + ((size_t)b * T + tt) * 64);
+#pragma unroll
+        for (int c8 = 0; c8 < 8; c8++) {
+            const uint4 u = row[c8];
+            const __half2 *hp = (const __half2 *)&u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 f = __half22float2(hp[j]);
+                a += f.x * sw[kk][c8 * 8 + 2 * j] + f.y * sw[kk][c8 * 8 + 2 * j + 1];
+            }
+        }
+    }
+    pcm[(size_t)b * T + t] = a;
+}
+
+__global__ void k_f32_to_h16(const float *in, uint16_t *out, size_t n, int bf) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = f2h16(in[i], bf != 0);
+}
+
+}  // namespace ptts

@@ -1,0 +1,235 @@
+// mimi.cuh - Mimi decoder (ptts_mimi.c:570-738) on the device, time-major end to end:
+// front end -> 2-layer windowed transformer -> SEANet conv stack, every linear / Conv1d /
+// ConvTranspose1d running as a tcgen05 implicit GEMM (gemm_tc.cuh) with bias / layer-scale /
+// residual / ELU / GELU fused in the epilogue. fp16 operands, fp32 accumulation, fp32 residual
+// streams. No [C,T] <-> [T,C] transposes exist (ptts_mimi.c:134-150 eliminated by layout choice).
+#pragma once
+#include "engine.cuh"
+
+namespace ptts {
+
+// Conv1d weight [out,in,k] -> GEMM B matrix [n_rows][k*cin_pad] with column tap*cin_pad + ic
+// (tap kk reads input row t-(k-1)+kk: ptts_kernels.c:128-153 with stride 1).
+static int mimi_load_conv(Engine *e, const HostWeights &hw, const char *name, ConvW &c, int cin, int cout, int k, int cin_pad,
+                          int cout_pad) {
+    std::vector<float> w, b;
+    char nm[256];
+    snprintf(nm, sizeof nm, "%s.weight", name);
+    if (hw.get(nm, MIMI_PFX, (int64_t)cin * cout * k, w) != 0) return -1;
+    snprintf(nm, sizeof nm, "%s.bias", name);
+    if (hw.get(nm, MIMI_PFX, cout, b) != 0) return -1;
+    std::vector<float> m((size_t)cout_pad * k * cin_pad, 0.0f), bp(cout_pad, 0.0f);
+    for (int o = 0; o < cout; o++) {
+        bp[o] = b[o];
+        for (int i = 0; i < cin; i++)
+            for (int kk = 0; kk < k; kk++) m[((size_t)o * k + kk) * cin_pad + i] = w[((size_t)o * cin + i) * k + kk];
+    }
+    c.cin = cin_pad; c.cout = cout_pad; c.k = k; c.stride = 1; c.n_rows = cout_pad; c.k_per_tap = cin_pad; c.transposed_conv = false;
+    if (e->up_f16(&c.w, m) != 0 || e->up_f32(&c.b, bp) != 0) return -1;
+    return 0;
+}
+
+// ConvTranspose1d weight [in,out,k], k = 2*stride -> B matrix [stride*cout][2*cin]:
+// row r*cout+oc, column tap*cin+ic = w[ic][oc][r + tap*stride]; tap 0 reads x[t], tap 1 reads x[t-1]
+// (each output sample sees exactly two taps per input channel: ptts_kernels.c:172-204).
+static int mimi_load_convtr(Engine *e, const HostWeights &hw, const char *name, ConvW &c, int cin, int cout, int k, int stride) {
+    std::vector<float> w, b;
+    char nm[256];
+    PTTS_CHECK(k == 2 * stride, "convtr %s: kernel %d != 2*stride %d", name, k, stride);
+    snprintf(nm, sizeof nm, "%s.weight", name);
+    if (hw.get(nm, MIMI_PFX, (int64_t)cin * cout * k, w) != 0) return -1;
+    snprintf(nm, sizeof nm, "%s.bias", name);
+    if (hw.get(nm, MIMI_PFX, cout, b) != 0) return -1;
+    std::vector<float> m((size_t)stride * cout * 2 * cin);
+    for (int r = 0; r < stride; r++)
+        for (int o = 0; o < cout; o++)
+            for (int tap = 0; tap < 2; tap++)
+                for (int i = 0; i < cin; i++)
+                    m[((size_t)(r * cout + o) * 2 + tap) * cin + i] = w[((size_t)i * cout + o) * k + r + tap * stride];
+    c.cin = cin; c.cout = cout; c.k = k; c.stride = stride; c.n_rows = stride * cout; c.k_per_tap = cin; c.transposed_conv = true;
+    if (e->up_f16(&c.w, m) != 0 || e->up_f32(&c.b, b) != 0) return -1;
+    return 0;
+}
+
+static int mimi_load_weights(Engine *e, const HostWeights &hw) {
+    std::vector<float> v;
+    char nm[256];
+    if (hw.get("quantizer.output_proj.weight", MIMI_PFX, MI_D * 32, v) != 0 || e->up_f32(&e->quant_w, v) != 0) return -1;
+    int r = hw.get("upsample.convtr.weight", MIMI_PFX, MI_D * 32, v, true);   // ptts_mimi.c:385-388
+    if (r < 0) return -1;
+    if (r == 1 && hw.get("upsample.convtr.convtr.weight", MIMI_PFX, MI_D * 32, v) != 0) return -1;
+    if (e->up_f32(&e->ups_w, v) != 0) return -1;
+    for (int l = 0; l < MI_L; l++) {
+#define MW(field, suffix, ne, up) snprintf(nm, sizeof nm, "decoder_transformer.transformer.layers.%d." suffix, l); \
+        if (hw.get(nm, MIMI_PFX, ne, v) != 0 || e->up(&e->ML[l].field, v) != 0) return -1
+        MW(inproj, "self_attn.in_proj.weight", 3 * MI_D * MI_D, up_f16);
+        MW(outproj, "self_attn.out_proj.weight", MI_D * MI_D, up_f16);
+        MW(l1, "linear1.weight", MI_FF * MI_D, up_f16);
+        MW(l2, "linear2.weight", MI_D * MI_FF, up_f16);
+        MW(n1w, "norm1.weight", MI_D, up_f32); MW(n1b, "norm1.bias", MI_D, up_f32);
+        MW(n2w, "norm2.weight", MI_D, up_f32); MW(n2b, "norm2.bias", MI_D, up_f32);
+        MW(ls1, "layer_scale_1.scale", MI_D, up_f32); MW(ls2, "layer_scale_2.scale", MI_D, up_f32);
+#undef MW
+    }
+    // geometry is hard-coded in the reference (ptts_mimi.c:389-486)
+    if (mimi_load_conv(e, hw, "decoder.model.0.conv", e->dec_in, 512, 512, 7, 512, 512) != 0) return -1;
+    if (mimi_load_convtr(e, hw, "decoder.model.2.convtr", e->up[0], 512, 256, 12, 6) != 0) return -1;
+    if (mimi_load_conv(e, hw, "decoder.model.3.block.1.conv", e->res1[0], 256, 128, 3, 256, 128) != 0) return -1;
+    if (mimi_load_conv(e, hw, "decoder.model.3.block.3.conv", e->res2[0], 128, 256, 1, 128, 256) != 0) return -1;
+    if (mimi_load_convtr(e, hw, "decoder.model.5.convtr", e->up[1], 256, 128, 10, 5) != 0) return -1;
+    if (mimi_load_conv(e, hw, "decoder.model.6.block.1.conv", e->res1[1], 128, 64, 3, 128, 64) != 0) return -1;
+    if (mimi_load_conv(e, hw, "decoder.model.6.block.3.conv", e->res2[1], 64, 128, 1, 64, 128) != 0) return -1;
+    if (mimi_load_convtr(e, hw, "decoder.model.8.convtr", e->up[2], 128, 64, 8, 4) != 0) return -1;
+    // 32-channel bottleneck padded to 64 channels (zero weights) so that K stays a multiple of 64
+    if (mimi_load_conv(e, hw, "decoder.model.9.block.1.conv", e->res1[2], 64, 32, 3, 64, 64) != 0) return -1;
+    if (mimi_load_conv(e, hw, "decoder.model.9.block.3.conv", e->res2[2], 32, 64, 1, 64, 64) != 0) return -1;
+    if (hw.get("decoder.model.11.conv.weight", MIMI_PFX, 64 * 3, v) != 0 || e->up_f32(&e->dec_out_w, v) != 0) return -1;
+    if (hw.get("decoder.model.11.conv.bias", MIMI_PFX, 1, v) != 0 || e->up_f32(&e->dec_out_b, v) != 0) return -1;
+    PTTS_CUDA_OK(cudaFuncSetAttribute(k_mimi_win_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
+    return 0;
+}
+
+// Workspace bytes per latent frame (16 tokens, 96 / 480 / 1920 rows in the three SEANet stages).
+static size_t mimi_ws_per_frame() {
+    const size_t tok = 16 * (size_t)(MI_D * 4 + MI_D * 2 + 3 * MI_D * 4 + 3 * MI_D * 2 + MI_D * 2 + MI_FF * 2 + MI_D * 2);
+    const size_t s0 = 96 * (size_t)(256 * 4 + 256 * 2 + 128 * 2 + 256 * 2);
+    const size_t s1 = 480 * (size_t)(128 * 4 + 128 * 2 + 64 * 2 + 128 * 2);
+    const size_t s2 = 1920 * (size_t)(64 * 4 + 64 * 2 + 64 * 2 + 64 * 2);
+    return tok + s0 + s1 + s2 + 4096;
+}
+
+struct Bump {
+    uint8_t *base; size_t off = 0;
+    template <typename T> T *take(size_t count) {
+        off = (off + 255) & ~(size_t)255;
+        T *p = (T *)(base + off);
+        off += count * sizeof(T);
+        return p;
+    }
+};
+
+// Activations [Bc][T][C] fp16 as the A operand, weights [N][taps*K] fp16 as the B operand.
+static int mimi_gemm(Engine *e, const __half *A, int Bc, int T, int C, const __half *W, int n_rows, int taps, int shift0, int step,
+                     int bn, GemmParams epi) {
+    GemmDesc d;
+    d.A = A; d.a_k = C; d.a_rows = T; d.a_batches = Bc; d.a_ld = C; d.a_bstride = (size_t)T * C;
+    d.B = W; d.b_k = taps * C; d.b_rows = n_rows; d.b_ld = (size_t)taps * C;
+    d.bf16 = false; d.taps = taps; d.k_per_tap = C; d.shift0 = shift0; d.step = step; d.a_k_step = 0; d.b_k_step = C;
+    d.bn = bn; d.split_k = 1; d.two_cta = true;
+    d.epi = epi;
+    GemmOp op;
+    if (gemm_build(op, d) != 0) return -1;
+    return run_gemm(e, op, KC_GEMM_MIMI);
+}
+
+static int conv_gemm(Engine *e, const ConvW &c, const __half *A, int Bc, int T, int bn, GemmParams epi) {
+    epi.bias = c.b;
+    if (c.transposed_conv) {
+        epi.bias_mask = c.cout - 1;
+        return mimi_gemm(e, A, Bc, T, c.cin, c.w, c.n_rows, 2, 0, -1, bn, epi);
+    }
+    return mimi_gemm(e, A, Bc, T, c.cin, c.w, c.n_rows, c.k, -(c.k - 1), 1, bn, epi);
+}
+
+// Decode Bc equal-length items. d_lat [Bc,F,32] fp32 on the device; d_pcm [Bc, F*1920].
+static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm) {
+    const int T = 16 * F;
+    const size_t R = (size_t)Bc * T;
+    if (ensure_rope(e, T) != 0) return -1;
+    const size_t need = mimi_ws_per_frame() * (size_t)Bc * F + (1 << 20);
+    if (need > e->mimi_ws_bytes) {
+        cudaStreamSynchronize(e->st);
+        e->dfree(e->mimi_ws);
+        uint8_t *p = nullptr;
+        if (e->dalloc(&p, need) != 0) return -1;
+        e->mimi_ws = p; e->mimi_ws_bytes = need;
+    }
+    Bump ws{(uint8_t *)e->mimi_ws};
+    float *x = ws.take<float>(R * MI_D);
+    __half *xn = ws.take<__half>(R * MI_D);
+    float *qkv = ws.take<float>(R * 3 * MI_D);
+    __half *q = ws.take<__half>(R * MI_D), *k = ws.take<__half>(R * MI_D), *v = ws.take<__half>(R * MI_D);
+    __half *att = ws.take<__half>(R * MI_D);
+    __half *hb = ws.take<__half>(R * MI_FF);
+    __half *d0 = ws.take<__half>(R * MI_D);
+    {
+        LaunchScope ls(e, KC_MIMI_MISC);
+        k_mimi_front<<<dim3(F, Bc), 512, 0, e->st>>>(d_lat, lat_stride, F, e->emb_std, e->emb_mean, apply_scale, e->quant_w, e->ups_w, x);
+        if (launch_check("k_mimi_front") != 0) return -1;
+    }
+    for (int l = 0; l < MI_L; l++) {
+        RowNormParams r = {};
+        r.x = x; r.D = MI_D; r.w = e->ML[l].n1w; r.b = e->ML[l].n1b; r.eps = 1e-5f; r.do_norm = 1; r.out_h = (uint16_t *)xn;
+        if (rownorm(e, (int)R, r, KC_MIMI_MISC) != 0) return -1;
+        GemmParams g = {};
+        g.out_f32 = qkv; g.ldo = 3 * MI_D;
+        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            k_mimi_rope_heads<<<(unsigned)R, 256, 0, e->st>>>(qkv, T, e->rope_cos, e->rope_sin, q, k, v);
+            if (launch_check("k_mimi_rope_heads") != 0) return -1;
+        }
+        {
+            LaunchScope ls(e, KC_MIMI_ATTN);
+            k_mimi_win_attn<<<dim3((T + WA_Q - 1) / WA_Q, MI_H, Bc), 256, WA_SMEM, e->st>>>(q, k, v, T, att);
+            if (launch_check("k_mimi_win_attn") != 0) return -1;
+        }
+        g = {}; g.scale = e->ML[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls1 * out_proj(att)
+        if (mimi_gemm(e, att, Bc, T, MI_D, e->ML[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        r = {};
+        r.x = x; r.D = MI_D; r.w = e->ML[l].n2w; r.b = e->ML[l].n2b; r.eps = 1e-5f; r.do_norm = 1; r.out_h = (uint16_t *)xn;
+        if (rownorm(e, (int)R, r, KC_MIMI_MISC) != 0) return -1;
+        g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
+        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].l1, MI_FF, 1, 0, 0, 256, g) != 0) return -1;
+        g = {}; g.scale = e->ML[l].ls2; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls2 * linear2(h)
+        if (l == MI_L - 1) { g.out_h = (uint16_t *)xn; g.ldh = MI_D; g.act = ACT_NONE; }   // fp16 copy feeds dec_in
+        if (mimi_gemm(e, hb, Bc, T, MI_FF, e->ML[l].l2, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+    }
+    // ---- SEANet (ptts_mimi.c:676-737)
+    GemmParams g = {};
+    g.out_h = (uint16_t *)d0; g.ldh = MI_D; g.act = ACT_ELU;                               // ELU(dec_in(x))
+    if (conv_gemm(e, e->dec_in, xn, Bc, T, 256, g) != 0) return -1;
+    const __half *cur = d0;
+    int Tc = T;
+    __half *last = nullptr;
+    for (int s = 0; s < 3; s++) {
+        const ConvW &U = e->up[s];
+        const int T2 = Tc * U.stride, C2 = U.cout, Ch = e->res1[s].cout;
+        const size_t R2 = (size_t)Bc * T2;
+        float *u = ws.take<float>(R2 * C2);
+        __half *eu = ws.take<__half>(R2 * C2), *rm = ws.take<__half>(R2 * Ch), *vv = ws.take<__half>(R2 * C2);
+        g = {}; g.out_f32 = u; g.ldo = U.n_rows; g.out_h = (uint16_t *)eu; g.ldh = U.n_rows; g.act = ACT_ELU;
+        if (conv_gemm(e, U, cur, Bc, Tc, U.n_rows >= 256 ? 256 : 128, g) != 0) return -1;  // u = convT(ELU(prev)), eu = ELU(u)
+        g = {}; g.out_h = (uint16_t *)rm; g.ldh = Ch; g.act = ACT_ELU;                      // ELU(conv_k3(ELU(u)))
+        if (conv_gemm(e, e->res1[s], eu, Bc, T2, Ch >= 128 ? 128 : 64, g) != 0) return -1;
+        g = {}; g.resid = u; g.ldo = C2; g.out_h = (uint16_t *)vv; g.ldh = C2; g.act = ACT_ELU;  // ELU(u + conv_k1(.))
+        if (conv_gemm(e, e->res2[s], rm, Bc, T2, C2 >= 256 ? 256 : C2, g) != 0) return -1;
+        cur = vv; Tc = T2; last = vv;
+    }
+    {
+        LaunchScope ls(e, KC_MIMI_MISC);
+        k_dec_out<<<dim3((Tc + 255) / 256, Bc), 256, 0, e->st>>>(last, Tc, e->dec_out_w, e->dec_out_b, d_pcm);
+        if (launch_check("k_dec_out") != 0) return -1;
+    }
+    return 0;
+}
+
+// latents on the device [n,F,32] (item stride lat_stride floats) -> pcm on the device [n, F*1920], chunked over items so that the
+// workspace stays within the budget (PTTS_B200_MIMI_WS_GB, default 24 GB).
+static int mimi_run(Engine *e, int n, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm) {
+    static size_t budget = 0;
+    if (!budget) {
+        const char *s = getenv("PTTS_B200_MIMI_WS_GB");
+        budget = (size_t)((s && atof(s) > 0 ? atof(s) : 24.0) * (double)(1ull << 30));
+    }
+    int per = (int)(budget / (mimi_ws_per_frame() * (size_t)F));
+    if (per < 1) per = 1;
+    if (per > n) per = n;
+    for (int i = 0; i < n; i += per) {
+        const int bc = std::min(per, n - i);
+        if (mimi_run_chunk(e, bc, F, d_lat + (size_t)i * lat_stride, lat_stride, apply_scale, d_pcm + (size_t)i * F * 1920) != 0) return -1;
+    }
+    return 0;
+}
+
+}  // namespace ptts

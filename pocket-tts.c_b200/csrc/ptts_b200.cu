@@ -1,0 +1,498 @@
+// ptts_b200.cu - C ABI (include/ptts_b200.h) of the sm_100a engine. Single translation unit.
+#include <math.h>
+#include <stdlib.h>
+#include <time.h>
+
+#include <algorithm>
+
+#include "flowlm.cuh"
+#include "mimi.cuh"
+
+using namespace ptts;
+
+// ---------------------------------------------------------------- host RNG (ptts_flowlm.c:1013-1025, 1187-1231)
+// xorshift64* + Box-Muller. The noise is data-independent, so it is generated on the host for all
+// frames and uploaded once; temp <= 0 yields zeros without advancing the generator.
+static inline uint32_t xs64_u32(uint64_t *st) {
+    uint64_t x = *st;
+    x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+    *st = x;
+    return (uint32_t)((x * 2685821657736338717ULL) >> 32);
+}
+static inline float xs64_f01(uint64_t *st) { return (xs64_u32(st) + 1.0f) / 4294967296.0f; }
+static void host_noise(int64_t seed, float temp, float clampv, int frames, float *out) {
+    uint64_t st = (uint64_t)seed;
+    const float sd = temp > 0.0f ? sqrtf(temp) : 0.0f;
+    for (int f = 0; f < frames; f++)
+        for (int d = 0; d < FL_LAT; d += 2) {
+            float z0 = 0.0f, z1 = 0.0f;
+            if (sd > 0.0f) {
+                const float u1 = xs64_f01(&st), u2 = xs64_f01(&st);
+                const float r = sqrtf(-2.0f * logf(u1)), th = 2.0f * (float)M_PI * u2;
+                z0 = r * cosf(th) * sd;
+                z1 = r * sinf(th) * sd;
+            }
+            if (clampv > 0.0f) {
+                z0 = fminf(fmaxf(z0, -clampv), clampv);
+                z1 = fminf(fmaxf(z1, -clampv), clampv);
+            }
+            out[f * FL_LAT + d] = z0;
+            out[f * FL_LAT + d + 1] = z1;
+        }
+}
+
+// ---------------------------------------------------------------- lifetime
+static std::unordered_map<Engine *, std::unordered_map<uint64_t, FlowGemms>> g_gemms;
+extern "C" const char *ptts_b200_last_error(void) { return g_last_error; }
+
+static int gemm_set_attrs() {
+#define SA(bn, sp) PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<bn, sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SA(32, 0) SA(64, 0) SA(128, 0) SA(256, 0) SA(32, 1) SA(64, 1) SA(128, 1) SA(256, 1) SA(32, 2) SA(64, 2) SA(128, 2) SA(256, 2)
+#undef SA
+    return 0;
+}
+
+extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b200_tensor *tensors, int n_tensors) {
+    PTTS_CHECK(out && tensors && n_tensors > 0, "ptts_b200_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t r = cudaGetDeviceCount(&ndev);
+    PTTS_CHECK(r == cudaSuccess && ndev > 0, "no CUDA device available (%s): this engine has no CPU fallback",
+               cudaGetErrorString(r));
+    PTTS_CHECK(device >= 0 && device < ndev, "device %d out of range (%d devices)", device, ndev);
+    PTTS_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PTTS_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    PTTS_CHECK(prop.major == 10, "device %d is sm_%d%d; this engine is built for sm_100a only", device, prop.major, prop.minor);
+    Engine *e = new Engine();
+    e->device = device;
+    e->num_sms = prop.multiProcessorCount;
+    HostWeights hw{tensors, n_tensors};
+    if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
+        cudaEventCreate(&e->ev1) != cudaSuccess) {
+        set_error("stream/event creation failed");
+        ptts_b200_destroy(e);
+        return -1;
+    }
+    if (cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        gemm_set_attrs() != 0 || flow_load_weights(e, hw) != 0 || mimi_load_weights(e, hw) != 0 || ensure_rope(e, 1024) != 0) {
+        ptts_b200_destroy(e);
+        return -1;
+    }
+    if (cudaStreamSynchronize(e->st) != cudaSuccess) {
+        set_error("engine initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ptts_b200_destroy(e);
+        return -1;
+    }
+    *out = e;
+    return 0;
+}
+
+extern "C" void ptts_b200_destroy(ptts_b200_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->st) cudaStreamSynchronize(e->st);
+    for (auto &g : e->graphs) cudaGraphExecDestroy(g.second);
+    g_gemms.erase(e);
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->pin) cudaFreeHost(e->pin);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->st) cudaStreamDestroy(e->st);
+    delete e;
+}
+
+// ---------------------------------------------------------------- step graphs
+
+static uint64_t gkey(int mode, int B, int lsd, int precise) {
+    return ((uint64_t)mode << 48) | ((uint64_t)B << 24) | ((uint64_t)lsd << 8) | (uint64_t)precise;
+}
+
+// mode 0: voice prefill (B = 1, GEMV), 1: batch-1 GEMV decode, 2: batched tcgen05 decode
+static int step_launch(Engine *e, int mode, int B, int lsd, int precise) {
+    float *cbias = nullptr;
+    if (ensure_cbias(e, lsd, &cbias) != 0) return -1;
+    FlowState st = make_state(e, B, lsd, mode == 0 ? e->d_cond : nullptr);
+    if (mode == 0) return flow_step_gemv(e, st, true, cbias);
+    if (mode == 1) return flow_step_gemv(e, st, false, cbias);
+    const uint64_t key = gkey(mode, B, lsd, precise);
+    auto &gm = g_gemms[e];
+    auto it = gm.find(key);
+    if (it == gm.end() || it->second.gen != e->gen) {
+        FlowGemms G;
+        if (flow_gemms_build(e, G, B, precise, lsd, cbias) != 0) return -1;
+        gm[key] = G;
+        it = gm.find(key);
+    }
+    return flow_step_tc(e, st, it->second, precise);
+}
+
+static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nsteps, bool poll_done) {
+    if (nsteps <= 0) return 0;
+    const bool use_graph = !e->prof.on && getenv("PTTS_B200_NO_GRAPH") == nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int64_t gk = 0;
+    if (use_graph) {
+        const uint64_t key = gkey(mode, B, lsd, precise);
+        auto it = e->graphs.find(key);
+        if (it == e->graphs.end()) {
+            float *cb = nullptr;
+            if (ensure_cbias(e, lsd, &cb) != 0) return -1;   // allocates: must happen outside capture
+            if (mode == 2) {                                   // build tensor maps outside capture too
+                auto &gm = g_gemms[e];
+                auto gi = gm.find(key);
+                if (gi == gm.end() || gi->second.gen != e->gen) {
+                    FlowGemms G;
+                    if (flow_gemms_build(e, G, B, precise, lsd, cb) != 0) return -1;
+                    gm[key] = G;
+                }
+            }
+            cudaGraph_t graph = nullptr;
+            const int64_t before = e->launches;
+            PTTS_CUDA_OK(cudaStreamBeginCapture(e->st, cudaStreamCaptureModeThreadLocal));
+            const int rc = step_launch(e, mode, B, lsd, precise);
+            cudaError_t ce = cudaStreamEndCapture(e->st, &graph);
+            const int64_t kernels = e->launches - before;
+            e->launches = before;
+            if (rc != 0) { if (graph) cudaGraphDestroy(graph); return -1; }
+            PTTS_CUDA_OK(ce);
+            cudaGraphExec_t ex = nullptr;
+            cudaError_t ie = cudaGraphInstantiate(&ex, graph, 0);
+            cudaGraphDestroy(graph);
+            PTTS_CUDA_OK(ie);
+            e->graphs[key] = ex;
+            e->graph_kernels[key] = kernels;
+            it = e->graphs.find(key);
+        }
+        exec = it->second;
+        gk = e->graph_kernels[key];
+    }
+    int *h_done = nullptr;
+    if (poll_done) {
+        if (!e->pin || e->pin_bytes < (size_t)e->capB * sizeof(int)) {
+            if (e->pin) cudaFreeHost(e->pin);
+            e->pin_bytes = std::max((size_t)e->capB * sizeof(int), (size_t)4096);
+            PTTS_CUDA_OK(cudaMallocHost(&e->pin, e->pin_bytes));
+        }
+        h_done = (int *)e->pin;
+    }
+    for (int s = 0; s < nsteps; s++) {
+        if (use_graph) {
+            PTTS_CUDA_OK(cudaGraphLaunch(exec, e->st));
+            e->launches += gk;
+        } else if (step_launch(e, mode, B, lsd, precise) != 0) {
+            return -1;
+        }
+        if (poll_done && (s % 8) == 7 && s + 1 < nsteps) {
+            PTTS_CUDA_OK(cudaMemcpyAsync(h_done, e->d_done, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, e->st));
+            PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+            bool all = true;
+            for (int b = 0; b < B; b++) all = all && h_done[b] != 0;
+            if (all) break;
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------- voice prefix
+static int set_voice(Engine *e, const float *cond, int cond_len) {
+    if (cond_len == e->voice_len && (cond_len == 0 || memcmp(e->voice_host.data(), cond, (size_t)cond_len * FL_D * 4) == 0)) return 0;
+    e->voice_len = -1;
+    if (cond_len > 0) {
+        PTTS_CUDA_OK(cudaMemcpyAsync(e->d_cond, cond, (size_t)cond_len * FL_D * 4, cudaMemcpyHostToDevice, e->st));
+        FlowCtrl c = {0, 0, 0, 1, 0, 0.0f};
+        PTTS_CUDA_OK(cudaMemcpyAsync(e->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, e->st));
+        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));   // &c is a stack temporary
+        if (run_steps(e, 0, 1, 1, 1, cond_len, false) != 0) return -1;
+        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    }
+    e->voice_host.assign(cond, cond + (size_t)cond_len * FL_D);
+    e->voice_len = cond_len;
+    return 0;
+}
+
+// ---------------------------------------------------------------- batch stage / run / fetch
+static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token_offsets, const float *cond_prefix, int cond_len,
+                      const int *max_frames, const int64_t *seeds, const int *eos_after, const ptts_b200_gen_params *gp) {
+    PTTS_CHECK(e && n >= 1 && tokens_flat && token_offsets && max_frames && seeds && gp, "batch_stage: bad arguments");
+    PTTS_CHECK(cond_len >= 0 && (cond_len == 0 || cond_prefix), "batch_stage: cond_prefix missing");
+    PTTS_CHECK(gp->lsd_steps >= 1 && gp->lsd_steps <= 64, "batch_stage: lsd_steps %d out of range", gp->lsd_steps);
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    int max_tok = 0, cap_f = 0, steps = 0;
+    for (int i = 0; i < n; i++) {
+        const int tl = token_offsets[i + 1] - token_offsets[i];
+        PTTS_CHECK(tl > 0, "batch_stage: utterance %d has no tokens", i);
+        PTTS_CHECK(max_frames[i] >= 1, "batch_stage: utterance %d has max_frames < 1", i);
+        max_tok = std::max(max_tok, tl);
+        cap_f = std::max(cap_f, max_frames[i]);
+        steps = std::max(steps, tl + max_frames[i]);
+    }
+    const int B = n == 1 ? 1 : (n + 15) / 16 * 16;
+    PTTS_CHECK(B <= 256, "batch_stage: at most 256 utterances per call (got %d); shard larger jobs on the host", n);
+    if (flow_ensure_capacity(e, B, steps, max_tok, cap_f, std::max(cond_len, 1)) != 0) return -1;
+    if (ensure_rope(e, cond_len + steps + 1) != 0) return -1;
+    if (set_voice(e, cond_prefix, cond_len) != 0) return -1;
+    // host staging
+    const int capTok = e->capTok, capF = e->capF;
+    std::vector<int> h_tok((size_t)B * capTok, 0), h_tl(B, 1), h_mf(B, 0), h_ea(B, 0), h_done(B, 1), h_es(B, -1), h_used(B, 0);
+    std::vector<float> h_noise((size_t)n * cap_f * FL_LAT);
+    for (int i = 0; i < n; i++) {
+        const int tl = token_offsets[i + 1] - token_offsets[i];
+        memcpy(&h_tok[(size_t)i * capTok], tokens_flat + token_offsets[i], sizeof(int) * tl);
+        h_tl[i] = tl; h_mf[i] = max_frames[i]; h_done[i] = 0;
+        int ea = eos_after ? eos_after[i] : gp->eos_after;
+        h_ea[i] = ea < 0 ? 0 : ea;
+        host_noise(seeds[i], gp->temp, gp->noise_clamp, max_frames[i], &h_noise[(size_t)i * cap_f * FL_LAT]);
+        for (size_t j = (size_t)max_frames[i] * FL_LAT; j < (size_t)cap_f * FL_LAT; j++) h_noise[(size_t)i * cap_f * FL_LAT + j] = 0.0f;
+    }
+    FlowCtrl c;
+    c.step = 0; c.cond_len = cond_len; c.eos_enabled = gp->eos_enabled; c.eos_min_frames = std::max(gp->eos_min_frames, 1);
+    c.eos_after_default = std::max(gp->eos_after, 0); c.eos_threshold = gp->eos_threshold;
+    cudaStream_t st = e->st;
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_tokens, h_tok.data(), h_tok.size() * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_tok_len, h_tl.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_max_frames, h_mf.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_eos_after, h_ea.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_done, h_done.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_eos_step, h_es.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_used, h_used.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpy2DAsync(e->d_noise, (size_t)capF * FL_LAT * 4, h_noise.data(), (size_t)cap_f * FL_LAT * 4,
+                                   (size_t)cap_f * FL_LAT * 4, n, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemsetAsync(e->d_out_latents, 0, (size_t)B * capF * FL_LAT * 4, st));
+    PTTS_CUDA_OK(cudaMemsetAsync(e->d_first_eos, 0, (size_t)B * 4, st));
+    PTTS_CUDA_OK(cudaMemsetAsync(e->d_first_cond, 0, (size_t)B * FL_D * 4, st));
+    PTTS_CUDA_OK(cudaMemsetAsync(e->d_first_flow, 0, (size_t)B * FL_LAT * 4, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope
+    e->st_n = n; e->curB = B; e->st_steps = steps; e->st_capF = cap_f; e->st_lsd = gp->lsd_steps;
+    e->st_precise = gp->precise ? 1 : 0;
+    e->st_maxf.assign(max_frames, max_frames + n);
+    e->st_eos = gp->eos_enabled;
+    return 0;
+}
+
+static int ensure_pcm(Engine *e, size_t samples) {
+    if (samples <= e->pcm_cap) return 0;
+    cudaStreamSynchronize(e->st);
+    e->dfree(e->d_pcm);
+    if (e->dalloc(&e->d_pcm, samples) != 0) return -1;
+    e->pcm_cap = samples;
+    return 0;
+}
+
+static int run_impl(Engine *e, int with_mimi) {
+    PTTS_CHECK(e && e->st_n > 0, "batch_run: nothing staged");
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    // rewind the device state so that run may be repeated on the same staged batch
+    const int B = e->curB, n = e->st_n;
+    std::vector<int> h_done(B, 1), h_es(B, -1), h_used(B, 0);
+    for (int i = 0; i < n; i++) h_done[i] = 0;
+    const int zero = 0;
+    PTTS_CUDA_OK(cudaMemcpyAsync(&e->ctrl->step, &zero, 4, cudaMemcpyHostToDevice, e->st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_done, h_done.data(), B * 4, cudaMemcpyHostToDevice, e->st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_eos_step, h_es.data(), B * 4, cudaMemcpyHostToDevice, e->st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_used, h_used.data(), B * 4, cudaMemcpyHostToDevice, e->st));
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    const int mode = B == 1 ? 1 : 2;
+    if (run_steps(e, mode, B, e->st_lsd, e->st_precise, e->st_steps, e->st_eos != 0) != 0) return -1;
+    if (with_mimi) {
+        const int F = e->st_capF;
+        if (ensure_pcm(e, (size_t)n * F * 1920) != 0) return -1;
+        if (mimi_run(e, n, F, e->d_out_latents, (size_t)e->capF * FL_LAT, 1, e->d_pcm) != 0) return -1;
+    }
+    return 0;
+}
+
+static int fetch_impl(Engine *e, float *out_latents, int *out_frames_used, float *out_audio) {
+    PTTS_CHECK(e && e->st_n > 0, "batch_fetch: nothing staged");
+    const int n = e->st_n, F = e->st_capF;
+    std::vector<int> used(n);
+    PTTS_CUDA_OK(cudaMemcpyAsync(used.data(), e->d_used, n * 4, cudaMemcpyDeviceToHost, e->st));
+    if (out_latents)
+        PTTS_CUDA_OK(cudaMemcpy2DAsync(out_latents, (size_t)F * FL_LAT * 4, e->d_out_latents, (size_t)e->capF * FL_LAT * 4,
+                                       (size_t)F * FL_LAT * 4, n, cudaMemcpyDeviceToHost, e->st));
+    if (out_audio) {
+        PTTS_CHECK(e->d_pcm && e->pcm_cap >= (size_t)n * F * 1920, "batch_fetch: no PCM was produced (run with_mimi = 1)");
+        PTTS_CUDA_OK(cudaMemcpyAsync(out_audio, e->d_pcm, (size_t)n * F * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
+    }
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    if (out_frames_used) memcpy(out_frames_used, used.data(), n * sizeof(int));
+    if (out_audio)
+        for (int i = 0; i < n; i++)   // audio past the stop point is not part of the utterance
+            if (used[i] < F) memset(out_audio + ((size_t)i * F + used[i]) * 1920, 0, (size_t)(F - used[i]) * 1920 * 4);
+    return 0;
+}
+
+extern "C" int ptts_b200_batch_stage(ptts_b200_engine *e, int n, const int *tokens_flat, const int *token_offsets,
+                                     const float *cond_prefix, int cond_len, const int *max_frames, const int64_t *seeds,
+                                     const int *eos_after, const ptts_b200_gen_params *params) {
+    return stage_impl(e, n, tokens_flat, token_offsets, cond_prefix, cond_len, max_frames, seeds, eos_after, params);
+}
+extern "C" int ptts_b200_batch_run(ptts_b200_engine *e, int with_mimi) { return run_impl(e, with_mimi); }
+extern "C" int ptts_b200_batch_fetch(ptts_b200_engine *e, float *out_latents, int *out_frames_used, float *out_audio) {
+    return fetch_impl(e, out_latents, out_frames_used, out_audio);
+}
+
+extern "C" int ptts_b200_generate_batch(ptts_b200_engine *e, int n, const int *tokens_flat, const int *token_offsets,
+                                        const float *cond_prefix, int cond_len, const int *max_frames, const int64_t *seeds,
+                                        const int *eos_after, const ptts_b200_gen_params *params, float *out_latents,
+                                        int *out_frames_used, float *out_audio) {
+    if (stage_impl(e, n, tokens_flat, token_offsets, cond_prefix, cond_len, max_frames, seeds, eos_after, params) != 0) return -1;
+    if (run_impl(e, out_audio != nullptr) != 0) return -1;
+    return fetch_impl(e, out_latents, out_frames_used, out_audio);
+}
+
+// ---------------------------------------------------------------- drop-in single-utterance entries
+extern "C" int ptts_b200_flowlm_generate_latents(ptts_b200_engine *e, const int *tokens, int token_len, const float *cond_prefix,
+                                                 int cond_len, int max_frames, int lsd_steps, float temp, float noise_clamp,
+                                                 int64_t seed, int eos_enabled, float eos_threshold, int eos_min_frames,
+                                                 int eos_after, float *out_latents, int *out_frames_used,
+                                                 float *out_first_eos_logit, float *out_first_cond, float *out_first_flow) {
+    // argument checks of ptts_flowlm.c:1147-1152
+    PTTS_CHECK(e && tokens && token_len > 0 && out_latents && out_frames_used, "flowlm_generate_latents: bad arguments");
+    PTTS_CHECK(max_frames >= 1 && cond_len >= 0 && (cond_len == 0 || cond_prefix), "flowlm_generate_latents: bad arguments");
+    if (eos_min_frames < 1) eos_min_frames = 1;
+    if (eos_after < 0) eos_after = 0;
+    if (seed == -1) seed = (int64_t)time(NULL);   // ptts_flowlm.c:1188
+    if (lsd_steps < 1) {                          // lsd_decode returns immediately (ptts_flowlm.c:766): latents = noise
+        lsd_steps = 1;
+        set_error("flowlm_generate_latents: lsd_steps < 1 is not supported");
+        return -1;
+    }
+    ptts_b200_gen_params gp = {lsd_steps, temp, noise_clamp, eos_enabled, eos_threshold, eos_min_frames, eos_after, 1};
+    const int offs[2] = {0, token_len};
+    if (stage_impl(e, 1, tokens, offs, cond_prefix, cond_len, &max_frames, &seed, &eos_after, &gp) != 0) return -1;
+    if (run_impl(e, 0) != 0) return -1;
+    int used = 0;
+    if (fetch_impl(e, out_latents, &used, nullptr) != 0) return -1;
+    *out_frames_used = used;
+    if (out_first_eos_logit) PTTS_CUDA_OK(cudaMemcpy(out_first_eos_logit, e->d_first_eos, 4, cudaMemcpyDeviceToHost));
+    if (out_first_cond) PTTS_CUDA_OK(cudaMemcpy(out_first_cond, e->d_first_cond, FL_D * 4, cudaMemcpyDeviceToHost));
+    if (out_first_flow) PTTS_CUDA_OK(cudaMemcpy(out_first_flow, e->d_first_flow, FL_LAT * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int ptts_b200_flowlm_scale_latents(ptts_b200_engine *e, const float *in, int frames, float *out) {
+    PTTS_CHECK(e && in && out && frames > 0, "flowlm_scale_latents: bad arguments");
+    for (int i = 0; i < frames; i++)
+        for (int d = 0; d < FL_LAT; d++) out[i * FL_LAT + d] = in[i * FL_LAT + d] * e->h_emb_std[d] + e->h_emb_mean[d];
+    return 0;
+}
+
+extern "C" int ptts_b200_mimi_decode_batch(ptts_b200_engine *e, const float *latents, int n, int frames, float *out_audio) {
+    PTTS_CHECK(e && latents && out_audio && n >= 1 && frames >= 1, "mimi_decode_batch: bad arguments");
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    const size_t nl = (size_t)n * frames * FL_LAT;
+    if (nl > e->mimi_lat_cap) {
+        cudaStreamSynchronize(e->st);
+        e->dfree(e->d_mimi_lat);
+        if (e->dalloc(&e->d_mimi_lat, nl) != 0) return -1;
+        e->mimi_lat_cap = nl;
+    }
+    if (ensure_pcm(e, (size_t)n * frames * 1920) != 0) return -1;
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_mimi_lat, latents, nl * 4, cudaMemcpyHostToDevice, e->st));
+    if (mimi_run(e, n, frames, e->d_mimi_lat, (size_t)frames * FL_LAT, 0, e->d_pcm) != 0) return -1;
+    PTTS_CUDA_OK(cudaMemcpyAsync(out_audio, e->d_pcm, (size_t)n * frames * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+extern "C" int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, int frames, float *out_audio, int *out_len) {
+    PTTS_CHECK(e && latents && out_audio && out_len && frames >= 1, "mimi_decode: bad arguments");   // ptts_mimi.c:572
+    if (ptts_b200_mimi_decode_batch(e, latents, 1, frames, out_audio) != 0) return -1;
+    *out_len = frames * 1920;
+    return 0;
+}
+
+// ---------------------------------------------------------------- measurement hooks
+extern "C" int ptts_b200_sync(ptts_b200_engine *e) {
+    PTTS_CHECK(e, "sync: null engine");
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+extern "C" int ptts_b200_timer_start(ptts_b200_engine *e) {
+    PTTS_CHECK(e, "timer_start: null engine");
+    PTTS_CUDA_OK(cudaEventRecord(e->ev0, e->st));
+    return 0;
+}
+extern "C" int ptts_b200_timer_stop(ptts_b200_engine *e, float *out_ms) {
+    PTTS_CHECK(e && out_ms, "timer_stop: bad arguments");
+    PTTS_CUDA_OK(cudaEventRecord(e->ev1, e->st));
+    PTTS_CUDA_OK(cudaEventSynchronize(e->ev1));
+    PTTS_CUDA_OK(cudaEventElapsedTime(out_ms, e->ev0, e->ev1));
+    return 0;
+}
+extern "C" int ptts_b200_profile_enable(ptts_b200_engine *e, int on) {
+    PTTS_CHECK(e, "profile_enable: null engine");
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    for (auto &r : e->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    e->prof.recs.clear();
+    memset(e->prof.ms, 0, sizeof e->prof.ms);
+    memset(e->prof.n, 0, sizeof e->prof.n);
+    e->prof.on = on != 0;
+    return 0;
+}
+extern "C" int ptts_b200_profile_read(ptts_b200_engine *e, int max_classes, float *ms, int64_t *cnt, int *n_classes) {
+    PTTS_CHECK(e && ms && cnt && n_classes, "profile_read: bad arguments");
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    for (auto &r : e->prof.recs) {
+        float t = 0.0f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { e->prof.ms[r.cls] += t; e->prof.n[r.cls]++; }
+        cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    e->prof.recs.clear();
+    const int nc = std::min(max_classes, (int)KC_COUNT);
+    for (int i = 0; i < nc; i++) { ms[i] = e->prof.ms[i]; cnt[i] = e->prof.n[i]; }
+    *n_classes = nc;
+    return 0;
+}
+extern "C" const char *ptts_b200_profile_class_name(int cls) { return cls >= 0 && cls < KC_COUNT ? KCLASS_NAMES[cls] : ""; }
+extern "C" int64_t ptts_b200_launch_count(ptts_b200_engine *e) { return e ? e->launches : 0; }
+
+// ---------------------------------------------------------------- unit-test hook for the tcgen05 GEMM
+extern "C" int ptts_b200_test_gemm(ptts_b200_engine *e, const float *A, const float *Bm, float *out, int batches, int rows, int N,
+                                   int K, int taps, int shift0, int step, int bf16, int split, int transposed, int bn,
+                                   int split_k) {
+    PTTS_CHECK(e && A && Bm && out && taps >= 1 && K % taps == 0, "test_gemm: bad arguments");
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    const int C = K / taps;
+    const size_t na = (size_t)batches * rows * C, nb = (size_t)N * K, no = (size_t)batches * rows * N;
+    std::vector<uint16_t> ah(na), al(na), bh(nb), bl(nb);
+    auto enc = [&](float v) { return bf16 ? h_f2bf(v) : h_f2h(v); };
+    auto dec = [&](uint16_t h) { return bf16 ? h_bf2f(h) : h_h2f(h); };
+    for (size_t i = 0; i < na; i++) { ah[i] = enc(A[i]); al[i] = enc(A[i] - dec(ah[i])); }
+    for (size_t i = 0; i < nb; i++) { bh[i] = enc(Bm[i]); bl[i] = enc(Bm[i] - dec(bh[i])); }
+    uint16_t *dah = nullptr, *dal = nullptr, *dbh = nullptr, *dbl = nullptr;
+    float *dout = nullptr;
+    int rc = -1;
+    if (e->dalloc(&dah, na) == 0 && e->dalloc(&dal, na) == 0 && e->dalloc(&dbh, nb) == 0 && e->dalloc(&dbl, nb) == 0 &&
+        e->dalloc(&dout, (size_t)std::max(split_k, 1) * no) == 0) {
+        cudaMemcpy(dah, ah.data(), na * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dal, al.data(), na * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dbh, bh.data(), nb * 2, cudaMemcpyHostToDevice);
+        cudaMemcpy(dbl, bl.data(), nb * 2, cudaMemcpyHostToDevice);
+        cudaMemset(dout, 0, (size_t)std::max(split_k, 1) * no * 4);
+        GemmDesc d;
+        d.A = dah; d.Alo = split == 1 ? dal : nullptr; d.a_k = C; d.a_rows = rows; d.a_batches = batches; d.a_ld = C;
+        d.a_bstride = (size_t)rows * C;
+        d.B = dbh; d.Blo = split == 2 ? dbl : nullptr; d.b_k = K; d.b_rows = N; d.b_ld = K;
+        d.bf16 = bf16 != 0; d.taps = taps; d.k_per_tap = C; d.shift0 = shift0; d.step = step; d.a_k_step = 0; d.b_k_step = C;
+        d.bn = bn; d.split_k = split_k; d.two_cta = true;
+        d.epi.transposed = transposed; d.epi.out_f32 = dout; d.epi.ldo = transposed ? rows : N; d.epi.split_stride = no;
+        GemmOp op;
+        if (gemm_build(op, d) == 0 && run_gemm(e, op, KC_GEMM_MIMI) == 0 && cudaStreamSynchronize(e->st) == cudaSuccess) {
+            std::vector<float> tmp((size_t)op.grid.z * no);
+            cudaMemcpy(tmp.data(), dout, tmp.size() * 4, cudaMemcpyDeviceToHost);
+            for (size_t i = 0; i < no; i++) {
+                float a = 0.0f;
+                for (unsigned z = 0; z < op.grid.z; z++) a += tmp[z * no + i];
+                out[i] = a;
+            }
+            rc = 0;
+        } else if (cudaGetLastError() != cudaSuccess || g_last_error[0] == 0) {
+            set_error("test_gemm: kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+    }
+    e->dfree(dah); e->dfree(dal); e->dfree(dbh); e->dfree(dbl); e->dfree(dout);
+    return rc;
+}
