@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""bench.py - audio-seconds per second of the Pocket-TTS generation hot path on N B200s.
+
+Workload (BASELINE.json configs[2], the configuration the `metric` is quoted on): batched
+generation of 256 synthetic ~100-character prompts per GPU, voice "alba" (125-frame synthetic
+prefix), 100 frames (8 s of 24 kHz audio) per prompt, temp 0.7, EOS disabled, LSD steps 1,
+random-init weights of the named architecture (no network for the HF checkpoint).
+A "step" = tokens -> FlowLM lock-step decode -> flow head -> Mimi decoder -> PCM for one batch.
+
+  value : inputs already resident in HBM (tokens + noise staged), kernels only, CUDA events on the
+          engine stream, max over ranks.
+  e2e   : the same job through the public C-ABI call sequence with HOST buffers: stage (H2D) +
+          run + fetch (D2H of PCM into pinned memory) inside the timed region.
+  --impl reference : the UNMODIFIED reference (oracle/_ref/libptts_ref.so, built by oracle/Makefile
+          with the flags of `make cpu-opt`) through its own ptts_generate on the host cores.
+
+Multi-GPU: one process per GPU (torchrun), utterances sharded across ranks, weights replicated, no
+collective on the data path (torch.distributed is used only for the barrier and the max-reduce of
+the timings) -> "scaling": "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+BATCH = 256
+FRAMES = 100
+FRAME_SEC = 0.08
+VOICE_FRAMES = 125
+WORKLOAD = "batched generation: 256 synthetic ~100-char prompts x 100 frames per GPU, voice alba (configs[2])"
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in Path(self.f.name).read_text().splitlines() if r.count(",") >= 8]
+        os.unlink(self.f.name)
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = set()
+        for r in rows:
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if "Active" in r[col] and "Not" not in r[col]:
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+def tokenize_prompts(pkg, model_dir, prompts):
+    """Host glue kept from the reference: ptts_prepare_text + SentencePiece (token ids are bit-exact
+    with the reference tokenizer, tests/test_oracle_golden.py::test_tokenizer_ids_bit_exact)."""
+    import sentencepiece as spm
+    sp = spm.SentencePieceProcessor(model_file=str(model_dir / "tokenizer.model"))
+    return [np.asarray(sp.encode(pkg.prepare_text(t)[0]), np.int32) for t in prompts]
+
+
+def run_reference(args, rank):
+    """The reference's own CPU implementation through its own public API on all host cores."""
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import pyoracle
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    md = pkg.synth.model_dir(0, VOICE_FRAMES)
+    cores = os.cpu_count() or 1
+    ref = pyoracle.Reference(md, threads=cores)
+    prompts = pkg.synth.make_prompts(args.warmup + args.steps, seed=123)
+    frames = FRAMES if args.steps <= 20 else 25
+    for i in range(args.warmup):
+        ref.generate(prompts[i], "alba", num_frames=frames, seed=123 + i, temp=0.7)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        pcm = ref.generate(prompts[args.warmup + i], "alba", num_frames=frames, seed=123 + i, temp=0.7)
+        assert pcm.shape[0] == frames * 1920
+    dt = time.perf_counter() - t0
+    val = args.steps * frames * FRAME_SEC / dt
+    sample = f"{args.steps} prompts x {frames} frames, sequential ptts_generate (reference has no batching)"
+    print(json.dumps({
+        "impl": "reference", "metric": "audio-sec/sec", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast", type=int, default=0, help="1: activations as single bf16 (precise=0); default hi+lo pairs")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(v: float) -> float:
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if rank == 0:
+        md = pkg.synth.model_dir(0, VOICE_FRAMES)
+    barrier()
+    md = pkg.synth.model_dir(0, VOICE_FRAMES)
+    W = pkg.synth.read_safetensors(md / "tts_b6369a24.safetensors")
+    voice = pkg.synth.read_safetensors(md / "embeddings" / "alba.safetensors")["audio_prompt"].reshape(-1, 1024)
+    eng = pkg.Engine(W, local_rank)
+    del W
+
+    B, F = args.batch, args.frames
+    prompts = pkg.synth.make_prompts(B * world, seed=123)[rank * B:(rank + 1) * B]
+    toks = tokenize_prompts(pkg, md, prompts)
+    seeds = np.arange(B, dtype=np.int64) + 123 + rank * B
+    params = pkg.default_params(lsd_steps=1, temp=0.7, eos_enabled=0, precise=0 if args.fast else 1)
+    audio = torch.empty((B, F * 1920), dtype=torch.float32).pin_memory().numpy()   # pinned host PCM buffer
+    audio_sec = B * F * FRAME_SEC
+
+    # ---------------- warm-up (also builds the step graph, tensor maps and workspaces)
+    eng.stage(toks, voice, F, seeds, None, params)
+    for _ in range(args.warmup):
+        eng.run(True)
+    eng.sync()
+
+    # ---------------- timed region 1: inputs resident in HBM, kernels only
+    sampler = ClockSampler(local_rank)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = eng.launch_count()
+    eng.timer_start()
+    for _ in range(args.steps):
+        eng.run(True)
+    ms = eng.timer_stop()
+    launches = eng.launch_count() - l0
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = max_over_ranks(ms)
+    ms_per_step = ms / args.steps
+    value = world * audio_sec / (ms_per_step / 1000.0)
+
+    # ---------------- timed region 2: end to end through the host-buffer C ABI
+    eng.generate_batch(toks, voice, F, seeds, None, params, True, audio)   # warm
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = eng.generate_batch(toks, voice, F, seeds, None, params, True, audio)
+    eng.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    assert np.isfinite(out["audio"][0, :1920]).all() and int(out["frames"].min()) == F
+    e2e_val = world * audio_sec * args.steps / e2e_s
+    h2d = int(sum(len(t) for t in toks) * 4 + B * F * 32 * 4 + voice.nbytes * 0 + 8 * B * 4)
+    d2h = int(B * F * 1920 * 4 + B * F * 32 * 4 + B * 4)
+
+    line = {
+        "metric": "audio-sec/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16 weights / bf16 hi+lo or fp16 activations / f32 accumulate",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_gpu": B, "frames": F, "voice_frames": int(voice.shape[0]),
+                   "lsd_steps": 1, "temp": 0.7, "eos": "disabled", "precise": int(not args.fast),
+                   "l2": "inputs larger than L2: per-step working set (KV caches + Mimi workspace) >> 126 MB",
+                   "parallelism": f"utterance sharding x{world}, weights replicated, no collective"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "realtime_factor_per_gpu": value / world,
+    }
+
+    if rank == 0:
+        # ---------------- per-kernel-class profile of one step (events around every launch, no graphs)
+        pk = peaks()
+        eng.profile(True)
+        eng.run(True)
+        prof = eng.profile_read()
+        eng.profile(False)
+        tot = sum(v["ms"] for v in prof.values()) or 1.0
+        shares = {k: round(v["ms"] / tot, 4) for k, v in prof.items() if v["launches"]}
+        dom = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
+        d = prof[dom]
+        t_s = d["ms"] / 1000.0
+        mem_frac = d["bytes"] / t_s / 1e9 / pk["hbm"]
+        flop_frac = d["flops"] / t_s / 1e12 / pk["tf_sust"]
+        if flop_frac >= mem_frac:
+            roof = {"bound": "tensor", "achieved": d["flops"] / t_s / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": flop_frac}
+        else:
+            roof = {"bound": "hbm", "achieved": d["bytes"] / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": mem_frac}
+        roof.update({"kernel": dom, "launches_per_step": d["launches"], "avg_launch_us": 1000.0 * d["ms"] / d["launches"],
+                     "peak_source": pk["src"], "traffic": None, "share_of_step": shares.get(dom),
+                     "timing": "CUDA events around each launch on the engine stream, one un-graphed step"})
+        line["roofline"] = roof
+        line["kernel_shares"] = shares
+        line["kernel_classes"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
+                                      "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
+                                      "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in prof.items() if v["launches"]}
+
+        # ---------------- batch-1 streaming decode (configs[1]) and first-audio latency
+        one = [toks[0]]
+        eng.generate_batch(one, voice, 1, [123], None, params, True)           # warm (graph capture)
+        lat = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            eng.generate_batch(one, voice, 1, [123], None, params, True)
+            lat.append(1000 * (time.perf_counter() - t0))
+        eng.stage(one, voice, 200, [123], None, params)
+        eng.run(False)
+        eng.sync()
+        eng.timer_start()
+        eng.run(False)
+        ms1 = eng.timer_stop()
+        steps1 = len(one[0]) + 200
+        line["batch1"] = {"first_audio_ms": statistics.median(lat), "first_audio_note": "tokens on host -> first 1920 PCM samples on host, voice prefix KV cached",
+                          "decode_200_frames_ms": ms1, "us_per_step": 1000 * ms1 / steps1,
+                          "audio_s_per_s": 200 * FRAME_SEC / (ms1 / 1000), "hbm_frac": 170.6e6 / (ms1 / steps1 / 1000) / 1e9 / pk["hbm"]}
+
+        # ---------------- CPU baseline: the compiled reference on the host cores, bounded sample
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                sys.path.insert(0, str(ROOT / "oracle"))
+                import pyoracle
+                cores = os.cpu_count() or 1
+                ref = pyoracle.Reference(md, threads=cores)
+                nprompt = 2
+                t0 = time.perf_counter()
+                for i in range(nprompt):
+                    ref.generate(prompts[i], "alba", num_frames=F, seed=int(seeds[i]), temp=0.7)
+                dt = time.perf_counter() - t0
+                ref.close()
+                line["cpu_baseline"] = {"value": nprompt * F * FRAME_SEC / dt, "unit": "audio-s/s", "cores": cores, "kind": "reference",
+                                        "sample": f"{nprompt} of the {B} prompts x {F} frames, sequential ptts_generate, OpenMP {cores} threads"}
+            except Exception as ex:  # the baseline is reported, never required for the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": f"unavailable: {ex}"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

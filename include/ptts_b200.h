@@ -111,6 +111,9 @@ int ptts_b200_timer_stop(ptts_b200_engine *e, float *out_ms);      /* syncs, ret
 int ptts_b200_profile_enable(ptts_b200_engine *e, int on);
 int ptts_b200_profile_read(ptts_b200_engine *e, int max_classes, float *ms_per_class, int64_t *launches_per_class,
                            int *n_classes);
+/* Algorithmic work (FLOPs, bytes) issued per class while profiling, from launch shapes (host-side
+ * accounting): the numerators of the roofline fractions. */
+int ptts_b200_profile_work(ptts_b200_engine *e, int max_classes, double *flops, double *bytes);
 const char *ptts_b200_profile_class_name(int cls);
 /* Total kernel launches issued by the engine since creation (graph nodes count per replay). */
 int64_t ptts_b200_launch_count(ptts_b200_engine *e);

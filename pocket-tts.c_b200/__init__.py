@@ -42,7 +42,7 @@ EXPORTS = [
     "ptts_b200_flowlm_scale_latents", "ptts_b200_mimi_decode", "ptts_b200_mimi_decode_batch",
     "ptts_b200_generate_batch", "ptts_b200_batch_stage", "ptts_b200_batch_run", "ptts_b200_batch_fetch",
     "ptts_b200_sync", "ptts_b200_timer_start", "ptts_b200_timer_stop", "ptts_b200_profile_enable",
-    "ptts_b200_profile_read", "ptts_b200_profile_class_name", "ptts_b200_launch_count", "ptts_b200_test_gemm",
+    "ptts_b200_profile_read", "ptts_b200_profile_work", "ptts_b200_profile_class_name", "ptts_b200_launch_count", "ptts_b200_test_gemm",
 ]
 
 
@@ -72,6 +72,7 @@ def load_library():
     L.ptts_b200_timer_stop.argtypes = [vp, _fp]
     L.ptts_b200_profile_enable.argtypes = [vp, C.c_int]
     L.ptts_b200_profile_read.argtypes = [vp, C.c_int, _fp, _lp, _ip]
+    L.ptts_b200_profile_work.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ptts_b200_profile_class_name.argtypes = [C.c_int]
     L.ptts_b200_profile_class_name.restype = C.c_char_p
     L.ptts_b200_launch_count.argtypes = [vp]
@@ -230,7 +231,12 @@ class Engine:
         cnt = np.zeros(16, np.int64)
         nc = C.c_int(0)
         self._ck(self.lib.ptts_b200_profile_read(self.h, 16, _f(ms), cnt.ctypes.data_as(_lp), C.byref(nc)), "profile_read")
-        return {self.lib.ptts_b200_profile_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(nc.value)}
+        fl = np.zeros(16, np.float64)
+        by = np.zeros(16, np.float64)
+        dp = C.POINTER(C.c_double)
+        self._ck(self.lib.ptts_b200_profile_work(self.h, 16, fl.ctypes.data_as(dp), by.ctypes.data_as(dp)), "profile_work")
+        return {self.lib.ptts_b200_profile_class_name(i).decode():
+                dict(ms=float(ms[i]), launches=int(cnt[i]), flops=float(fl[i]), bytes=float(by[i])) for i in range(nc.value)}
 
     def launch_count(self) -> int:
         return int(self.lib.ptts_b200_launch_count(self.h))

@@ -41,6 +41,9 @@ struct Prof {
     std::vector<Rec> recs;
     float ms[KC_COUNT] = {0};
     int64_t n[KC_COUNT] = {0};
+    // algorithmic work issued per class while profiling (host-side accounting from launch shapes)
+    double flops[KC_COUNT] = {0}, bytes[KC_COUNT] = {0};
+    int cur_step = 0;   // lock-step index of the step being launched (profile mode runs without graphs)
 };
 
 // ---------------------------------------------------------------- TMA host API
@@ -367,6 +370,16 @@ static int launch_check(const char *what) {
 }
 
 static int run_gemm(Engine *e, const GemmOp &op, int cls) {
+    if (e->prof.on) {
+        // algorithmic work: every A row against every B row over the full K; operands and outputs once
+        const double rows = (double)(op.grid.x / op.p.m_tiles_per_batch) * op.p.a_rows, n = op.p.n_total;
+        const double k = (double)op.p.taps * op.p.kblocks_per_tap * GEMM_BK;
+        const double a_el = op.p.a_k_step == 0 && op.p.taps > 1 ? rows * op.p.kblocks_per_tap * GEMM_BK : rows * k;
+        e->prof.flops[cls] += 2.0 * rows * n * k;
+        e->prof.bytes[cls] += 2.0 * (a_el * (op.split == 1 ? 2 : 1) + n * k * (op.split == 2 ? 2 : 1)) +
+                              rows * n * ((op.p.out_f32 ? 4.0 : 0.0) + (op.p.resid ? 4.0 : 0.0) + (op.p.out_h ? 2.0 : 0.0) +
+                                          (op.p.out_l ? 2.0 : 0.0));
+    }
     LaunchScope ls(e, cls);
     return gemm_launch(op, e->st);
 }

@@ -180,6 +180,7 @@ template <int K, int RPC, int PRO>
 static int gemv(Engine *e, const __nv_bfloat16 *W, int N, const float *x, GemvParams p) {
     p.W = W; p.N = N; p.x = x;
     constexpr int THREADS = K / 8 < 128 ? K / 8 : 128;
+    if (e->prof.on) { e->prof.bytes[KC_GEMV] += 2.0 * N * K + 4.0 * (K + N); e->prof.flops[KC_GEMV] += 2.0 * N * K; }
     LaunchScope ls(e, KC_GEMV);
     k_gemv<K, RPC, PRO><<<(N + RPC - 1) / RPC, THREADS, 0, e->st>>>(p);
     return launch_check("k_gemv");
@@ -204,6 +205,13 @@ static int attn_decode(Engine *e, int B, int layer, bool voice_mode, bool out16)
     if (out16) { a.out_h = e->att_h; a.out_l = e->att_l; } else a.out_f32 = e->att;
     const size_t smem = (size_t)(e->capCond + std::max(e->capS, e->capCond) + 8) * sizeof(float);
     PTTS_CHECK(smem <= 200 * 1024, "attention score buffer of %zu bytes exceeds shared memory (sequence too long)", smem);
+    if (e->prof.on) {
+        // algorithmic bytes: shared prefix K/V once, each utterance's own K/V (s+1 positions) once,
+        // the new K/V row written, q/k/v read and the output written
+        const double own = voice_mode ? e->prof.cur_step + 1 : e->prof.cur_step + 1, pre = voice_mode ? 0 : e->voice_len;
+        e->prof.bytes[KC_ATTN_DECODE] += 2.0 * FL_D * 4.0 * (pre + (double)B * own) + (double)B * FL_D * 4.0 * (2 + 3 + 1);
+        e->prof.flops[KC_ATTN_DECODE] += 4.0 * FL_D * (double)B * (pre + own);
+    }
     LaunchScope ls(e, KC_ATTN_DECODE);
     k_attn_decode<<<dim3(FL_H, B), 128, smem, e->st>>>(a);
     return launch_check("k_attn_decode");

@@ -170,6 +170,12 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
             if (launch_check("k_mimi_rope_heads") != 0) return -1;
         }
         {
+            if (e->prof.on) {   // banded attention: <= 250 keys per query, QK^T and PV
+                double pairs = 0.0;
+                for (int t = 0; t < T; t++) pairs += std::min(t + 1, MI_CTX);
+                e->prof.flops[KC_MIMI_ATTN] += 4.0 * 64.0 * MI_H * pairs * Bc;
+                e->prof.bytes[KC_MIMI_ATTN] += (double)R * MI_D * 2.0 * 4.0;
+            }
             LaunchScope ls(e, KC_MIMI_ATTN);
             k_mimi_win_attn<<<dim3((T + WA_Q - 1) / WA_Q, MI_H, Bc), 256, WA_SMEM, e->st>>>(q, k, v, T, att);
             if (launch_check("k_mimi_win_attn") != 0) return -1;

