@@ -203,17 +203,23 @@ static int attn_decode(Engine *e, int B, int layer, bool voice_mode, bool out16)
     }
     a.step = &e->ctrl->step;
     if (out16) { a.out_h = e->att_h; a.out_l = e->att_l; } else a.out_f32 = e->att;
-    const size_t smem = (size_t)(e->capCond + std::max(e->capS, e->capCond) + 8) * sizeof(float);
+    const int pcap = ((e->capCond + std::max(e->capS, e->capCond) + 63) / 32) * 32;
+    const int G = B >= 128 ? 8 : (B >= 64 ? 4 : (B >= 32 ? 2 : 1));
+    const size_t smem = attn2_smem_bytes(pcap, G);
     PTTS_CHECK(smem <= 200 * 1024, "attention score buffer of %zu bytes exceeds shared memory (sequence too long)", smem);
     if (e->prof.on) {
         // algorithmic bytes: shared prefix K/V once, each utterance's own K/V (s+1 positions) once,
         // the new K/V row written, q/k/v read and the output written
-        const double own = voice_mode ? e->prof.cur_step + 1 : e->prof.cur_step + 1, pre = voice_mode ? 0 : e->voice_len;
+        const double own = e->prof.cur_step + 1, pre = voice_mode ? 0 : e->voice_len;
         e->prof.bytes[KC_ATTN_DECODE] += 2.0 * FL_D * 4.0 * (pre + (double)B * own) + (double)B * FL_D * 4.0 * (2 + 3 + 1);
         e->prof.flops[KC_ATTN_DECODE] += 4.0 * FL_D * (double)B * (pre + own);
     }
     LaunchScope ls(e, KC_ATTN_DECODE);
-    k_attn_decode<<<dim3(FL_H, B), 128, smem, e->st>>>(a);
+    const dim3 grid(FL_H, (B + G - 1) / G);
+    if (G == 8) k_attn_decode2<1><<<grid, 256, smem, e->st>>>(a, B, pcap);
+    else if (G == 4) k_attn_decode2<2><<<grid, 256, smem, e->st>>>(a, B, pcap);
+    else if (G == 2) k_attn_decode2<4><<<grid, 256, smem, e->st>>>(a, B, pcap);
+    else k_attn_decode2<8><<<grid, 256, smem, e->st>>>(a, B, pcap);
     return launch_check("k_attn_decode");
 }
 

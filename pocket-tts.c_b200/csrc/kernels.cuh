@@ -449,6 +449,194 @@ __global__ void __launch_bounds__(128) k_attn_decode(const AttnDecodeParams p) {
     }
 }
 
+// =====================================================================================
+// v2 of the decode attention (same arithmetic as k_attn_decode): one CTA = one head x G
+// utterances, 8 warps, WPU = 8/G warps per utterance.
+//   * the shared voice-prefix K / V tiles are staged ONCE per CTA in shared memory and reused
+//     by all G utterances (the prefix is utterance-independent, ptts_flowlm.c:1159-1166);
+//   * per-utterance keys are read straight from HBM with fully coalesced 256-byte rows
+//     (lane = dimension pair), 8 rows in flight per warp;
+//   * keys are dealt to the warps of an utterance in blocks of 32; partial (max, sum, acc)
+//     triples are merged flash-decoding style.
+// grid (16, ceil(B/G)), block 256. smem: tile[128][65] + scores[8][pcap] + sq[G][64] + comb[8][66].
+// =====================================================================================
+constexpr int AD_TILE = 128, AD_LD = 65;
+__host__ __device__ inline size_t attn2_smem_bytes(int pcap, int G) {
+    return (size_t)(AD_TILE * AD_LD + 8 * pcap + G * FL_HD + 8 * 66) * sizeof(float);
+}
+
+template <int WPU>
+__global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, int B, int pcap) {
+    constexpr int G = 8 / WPU;
+    extern __shared__ __align__(16) float ad_smem[];
+    float *tile = ad_smem;                       // [128][65]
+    float *scores = tile + AD_TILE * AD_LD;      // [8][pcap]
+    float *sq = scores + 8 * pcap;               // [G][64]
+    float *comb = sq + G * FL_HD;                // [8][66]
+    const int h = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int g = w / WPU, wu = w % WPU;
+    const int b = blockIdx.y * G + g;
+    const bool live = b < B;
+    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
+    const int s = *p.step, pos = cond_len + s, P = pos + 1;
+    float *okb = p.ok + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
+    float *ovb = p.ov + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
+    float *sc = scores + w * pcap;
+    float2 q = make_float2(0.0f, 0.0f);
+    if (live) {
+        const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD;
+        const float c = p.rope_cos[pos * 32 + lane], sn = p.rope_sin[pos * 32 + lane];
+        const float2 qq = *(const float2 *)(row + 2 * lane);
+        // 1/sqrt(64) = 0.125 is a power of two: scaling q equals scaling every score
+        q = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
+        if (wu == 0) {
+            const float2 kk = *(const float2 *)(row + FL_D + 2 * lane);
+            *(float2 *)(okb + (size_t)s * FL_HD + 2 * lane) = make_float2(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
+            *(float2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = *(const float2 *)(row + 2 * FL_D + 2 * lane);
+            *(float2 *)(sq + g * FL_HD + 2 * lane) = q;
+        }
+    }
+    __syncthreads();   // appended row + sq visible to every warp of the CTA
+    const float *pkh = p.pk ? p.pk + (size_t)h * p.pstride * FL_HD : nullptr;
+    const float *pvh = p.pv ? p.pv + (size_t)h * p.pstride * FL_HD : nullptr;
+    const float *qs = sq + g * FL_HD;
+
+    // ---- scores, prefix part: lane = key, K tile in shared memory (row stride 65: conflict-free)
+    for (int t0 = 0; t0 < cond_len; t0 += AD_TILE) {
+        const int nt = min(AD_TILE, cond_len - t0);
+        for (int idx = tid; idx < nt * 16; idx += 256) {
+            const int r = idx >> 4, c4 = (idx & 15) * 4;
+            const float4 v = *(const float4 *)(pkh + (size_t)(t0 + r) * FL_HD + c4);
+            float *d = tile + r * AD_LD + c4;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+        __syncthreads();
+        if (live) {
+            for (int rr = 0; rr < AD_TILE / 32; rr++) {
+                const int blk = t0 / 32 + rr;
+                if (blk % WPU != wu) continue;
+                const int r = rr * 32 + lane;
+                if (r < nt) {
+                    const float *kr = tile + r * AD_LD;
+                    float a = 0.0f;
+#pragma unroll 16
+                    for (int d = 0; d < FL_HD; d++) a += qs[d] * kr[d];
+                    sc[t0 + r] = a;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- scores, own part: lane = dimension pair, coalesced 256 B rows from HBM, 8 in flight
+    float mx = -INFINITY;
+    if (live) {
+        for (int blk = cond_len / 32; blk * 32 < P; blk++) {
+            if (blk % WPU != wu) continue;
+            const int ta = max(blk * 32, cond_len), tb = min(blk * 32 + 32, P);
+            for (int t = ta; t < tb; t += 8) {
+                float2 kv[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    kv[j] = (t + j < tb) ? *(const float2 *)(okb + (size_t)(t + j - cond_len) * FL_HD + 2 * lane) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float a = warp_sum(q.x * kv[j].x + q.y * kv[j].y);
+                    if (lane == 0 && t + j < tb) sc[t + j] = a;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- per-warp softmax partials over the blocks dealt to this warp
+        for (int blk = wu; blk * 32 < P; blk += WPU) {
+            const int t = blk * 32 + lane;
+            if (t < P) mx = fmaxf(mx, sc[t]);
+        }
+        mx = warp_max(mx);
+    }
+    float sum = 0.0f;
+    if (live) {
+        for (int blk = wu; blk * 32 < P; blk += WPU) {
+            const int t = blk * 32 + lane;
+            if (t < P) { const float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
+        }
+        sum = warp_sum(sum);
+        __syncwarp();
+    }
+    // ---- P.V, prefix part from shared memory
+    float2 acc = make_float2(0.0f, 0.0f);
+    for (int t0 = 0; t0 < cond_len; t0 += AD_TILE) {
+        const int nt = min(AD_TILE, cond_len - t0);
+        for (int idx = tid; idx < nt * 16; idx += 256) {
+            const int r = idx >> 4, c4 = (idx & 15) * 4;
+            *(float4 *)(tile + r * FL_HD + c4) = *(const float4 *)(pvh + (size_t)(t0 + r) * FL_HD + c4);
+        }
+        __syncthreads();
+        if (live) {
+            for (int rr = 0; rr < AD_TILE / 32; rr++) {
+                const int blk = t0 / 32 + rr;
+                if (blk % WPU != wu) continue;
+                const int r1 = min(rr * 32 + 32, nt);
+#pragma unroll 4
+                for (int r = rr * 32; r < r1; r++) {
+                    const float pw = sc[t0 + r];
+                    const float2 v = *(const float2 *)(tile + r * FL_HD + 2 * lane);
+                    acc.x += pw * v.x; acc.y += pw * v.y;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- P.V, own part from HBM
+    if (live) {
+        for (int blk = cond_len / 32; blk * 32 < P; blk++) {
+            if (blk % WPU != wu) continue;
+            const int ta = max(blk * 32, cond_len), tb = min(blk * 32 + 32, P);
+            for (int t = ta; t < tb; t += 8) {
+                float2 vv[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    vv[j] = (t + j < tb) ? *(const float2 *)(ovb + (size_t)(t + j - cond_len) * FL_HD + 2 * lane) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float pw = (t + j < tb) ? sc[t + j] : 0.0f;
+                    acc.x += pw * vv[j].x; acc.y += pw * vv[j].y;
+                }
+            }
+        }
+    }
+    // ---- merge the WPU partials of each utterance
+    float *cw = comb + w * 66;
+    if (lane == 0) { cw[64] = mx; cw[65] = sum; }
+    *(float2 *)(cw + 2 * lane) = acc;
+    __syncthreads();
+    if (live && wu == 0) {
+        float M = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < WPU; i++) M = fmaxf(M, comb[(g * WPU + i) * 66 + 64]);
+        float L = 0.0f;
+        float2 o = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < WPU; i++) {
+            const float *ci = comb + (g * WPU + i) * 66;
+            const float f = ci[64] == -INFINITY ? 0.0f : expf(ci[64] - M);
+            L += ci[65] * f;
+            const float2 a = *(const float2 *)(ci + 2 * lane);
+            o.x += a.x * f; o.y += a.y * f;
+        }
+        o.x /= L; o.y /= L;
+        const size_t oi = (size_t)b * FL_D + h * FL_HD + 2 * lane;
+        if (p.out_f32) *(float2 *)(p.out_f32 + oi) = o;
+        if (p.out_h) {
+            const uint16_t h0 = f2h16(o.x, true), h1 = f2h16(o.y, true);
+            *(uint32_t *)(p.out_h + oi) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            if (p.out_l) {
+                const uint16_t l0 = f2h16(o.x - h162f(h0, true), true), l1 = f2h16(o.y - h162f(h1, true), true);
+                *(uint32_t *)(p.out_l + oi) = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+        }
+    }
+}
+
 // cos/sin table: freq_i = exp(-ln(10000) * 2i/64) (ptts_flowlm.c:361-364), angle = freq_i * pos.
 __global__ void k_rope_table(float *cs, float *sn, int max_pos) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;

@@ -74,7 +74,10 @@ extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b
         ptts_b200_destroy(e);
         return -1;
     }
-    if (cudaFuncSetAttribute(k_attn_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_attn_decode2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_attn_decode2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_attn_decode2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_attn_decode2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         gemm_set_attrs() != 0 || flow_load_weights(e, hw) != 0 || mimi_load_weights(e, hw) != 0 || ensure_rope(e, 1024) != 0) {
         ptts_b200_destroy(e);
         return -1;
