@@ -160,6 +160,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Wait for outstanding tcgen05.ld and tie the destination registers to the wait, so the compiler
+// cannot hoist their uses above it (the loads are asynchronous until the wait retires).
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// Activations for 16-bit outputs (Mimi): hardware exp / tanh approximations (relative error
+// ~2^-11, the same as the fp16 rounding that follows).
+__device__ __forceinline__ float act_apply_fast(int act, float x) {
+    switch (act) {
+        case ACT_GELU_TANH: return 0.5f * x * (1.0f + tanh_fast(0.7978845608f * (x + 0.044715f * x * x * x)));
+        case ACT_ELU: return x >= 0.0f ? x : (__expf(x) - 1.0f);
+        case ACT_SILU: return __fdividef(x, 1.0f + __expf(-x));
+        case ACT_GELU_ERF: return 0.5f * x * (1.0f + erff(x * 0.7071067811865475f));
+        default: return x;
+    }
+}
 
 // Shared-memory matrix descriptor for a K-major tile whose rows are exactly 128 bytes
 // (64 16-bit elements) laid out by TMA with CU_TENSOR_MAP_SWIZZLE_128B: 8-row core groups

@@ -103,14 +103,15 @@ int gemm_launch(const GemmOp &op, cudaStream_t st) {
 static int stage_bytes(int bn, int split) {
     return GEMM_BM * GEMM_BK * 2 * (split == 1 ? 2 : 1) + bn * GEMM_BK * 2 * (split == 2 ? 2 : 1);
 }
-int gemm_pick_stages(int bn, int split, int iters, bool two_ctas_per_sm) {
-    const int budget = (two_ctas_per_sm ? 108 : 216) * 1024;
-    int s = budget / stage_bytes(bn, split);
+// one persistent CTA per SM: the whole shared memory (minus barriers) is the TMA ring
+int gemm_pick_stages(int bn, int split, int iters, bool) {
+    int s = (200 * 1024) / stage_bytes(bn, split);
     if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-    if (s > iters) s = iters;
     if (s < 1) s = 1;
+    (void)iters;
     return s;
 }
+static int g_num_sms = 148;
 
 // Description of one contraction; see gemm_tc.cuh for the operand roles.
 struct GemmDesc {
@@ -152,10 +153,17 @@ static int gemm_build(GemmOp &op, const GemmDesc &d) {
     if (split_k > iters) split_k = iters;
     const int per = (iters + split_k - 1) / split_k;
     split_k = (iters + per - 1) / per;  // no empty slices
+    p.split_k = split_k;
+    p.iters_per_split = per;
+    p.m_tiles_total = d.a_batches * p.m_tiles_per_batch;
+    p.n_tiles = (d.b_rows + d.bn - 1) / d.bn;
+    const long long tiles = (long long)p.m_tiles_total * p.n_tiles * split_k;
+    PTTS_CHECK(tiles < (1ll << 31), "gemm_build: too many tiles");
+    p.total_tiles = (int)tiles;
     p.stages = gemm_pick_stages(d.bn, op.split, per, d.two_cta);
     p.idesc = umma_idesc_f16(GEMM_BM, d.bn, d.bf16, d.bf16);
     op.p = p;
-    op.grid = dim3((unsigned)(d.a_batches * p.m_tiles_per_batch), (unsigned)((d.b_rows + d.bn - 1) / d.bn), (unsigned)split_k);
+    op.grid = dim3((unsigned)std::min<long long>(tiles, g_num_sms), 1, 1);
     op.smem_bytes = p.stages * stage_bytes(d.bn, op.split) + 1024 + 256;
     return 0;
 }
@@ -372,7 +380,7 @@ static int launch_check(const char *what) {
 static int run_gemm(Engine *e, const GemmOp &op, int cls) {
     if (e->prof.on) {
         // algorithmic work: every A row against every B row over the full K; operands and outputs once
-        const double rows = (double)(op.grid.x / op.p.m_tiles_per_batch) * op.p.a_rows, n = op.p.n_total;
+        const double rows = (double)(op.p.m_tiles_total / op.p.m_tiles_per_batch) * op.p.a_rows, n = op.p.n_total;
         const double k = (double)op.p.taps * op.p.kblocks_per_tap * GEMM_BK;
         const double a_el = op.p.a_k_step == 0 && op.p.taps > 1 ? rows * op.p.kblocks_per_tap * GEMM_BK : rows * k;
         e->prof.flops[cls] += 2.0 * rows * n * k;

@@ -144,7 +144,7 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
     DA(x, b * FL_D); DA(qkv, b * 3 * FL_D); DA(att, b * FL_D); DA(ffh, b * FL_FF); DA(normed, b * FL_D);
     DA(xn_h, b * FL_D); DA(xn_l, b * FL_D); DA(att_h, b * FL_D); DA(att_l, b * FL_D); DA(ffh_h, b * FL_FF); DA(ffh_l, b * FL_FF);
     DA(normed_h, b * FL_D); DA(normed_l, b * FL_D); DA(partA, 4 * b * FL_D); DA(partB, 4 * b * FL_D);
-    DA(fx, b * FN_D); DA(ada, b * FN_ADA); DA(ft, b * FN_D); DA(flow, b * FL_LAT); DA(sc, b * FN_D); DA(fg, b * FN_D);
+    DA(fx, b * FN_D); DA(ada, b * FN_ADA); DA(ft, 4 * b * FN_D); DA(flow, b * FL_LAT); DA(sc, b * FN_D); DA(fg, b * FN_D);
     DA(sc_h, b * FN_D); DA(sc_l, b * FN_D); DA(fh_h, b * FN_D); DA(fh_l, b * FN_D); DA(fg_h, b * FN_D); DA(fg_l, b * FN_D);
     DA(ok, (size_t)FL_L * b * FL_D * S); DA(ov, (size_t)FL_L * b * FL_D * S);
     if (regrow_prefix || !e->pk) {
@@ -343,8 +343,8 @@ static int flow_gemms_build(Engine *e, FlowGemms &G, int B, int precise, int lsd
     for (int b = 0; b < FN_DEPTH; b++) {
         if (flow_gemm_build(G.m0[b], e->FB[b].m0w, FN_D, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 1, e->FB[b].m0b, nullptr, 0,
                             0, e->fg_h, precise ? e->fg_l : nullptr, FN_D, ACT_SILU) != 0) return -1;
-        if (flow_gemm_build(G.m2[b], e->FB[b].m2w, FN_D, FN_D, e->fg_h, precise ? e->fg_l : nullptr, B, 1, e->FB[b].m2b, e->ft,
-                            FN_D, 0, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
+        if (flow_gemm_build(G.m2[b], e->FB[b].m2w, FN_D, FN_D, e->fg_h, precise ? e->fg_l : nullptr, B, 4, e->FB[b].m2b, e->ft,
+                            FN_D, (size_t)e->capB * FN_D, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
     }
     if (flow_gemm_build(G.fin, e->fin_w, FL_LAT, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 1, e->fin_b, e->flow, FL_LAT, 0,
                         nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
@@ -364,14 +364,14 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
         RowNormParams r = {};
         r.x = e->x; r.D = FL_D; r.w = e->L[l].n1w; r.b = e->L[l].n1b; r.eps = 1e-5f; r.do_norm = 1;
         r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
-        if (l > 0) { r.part = e->partB; r.nsplit = (int)G.ff2[l - 1].grid.z; r.split_stride = ps; }
+        if (l > 0) { r.part = e->partB; r.nsplit = (int)G.ff2[l - 1].p.split_k; r.split_stride = ps; }
         if (rownorm(e, B, r) != 0) return -1;
         if (run_gemm(e, G.qkv[l], KC_GEMM_FLOW) != 0) return -1;
         if (attn_decode(e, B, l, false, true) != 0) return -1;
         if (run_gemm(e, G.outp[l], KC_GEMM_FLOW) != 0) return -1;
         r = {};
         r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
-        r.part = e->partA; r.nsplit = (int)G.outp[l].grid.z; r.split_stride = ps;
+        r.part = e->partA; r.nsplit = (int)G.outp[l].p.split_k; r.split_stride = ps;
         r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
         if (rownorm(e, B, r) != 0) return -1;
         if (run_gemm(e, G.ff1[l], KC_GEMM_FLOW) != 0) return -1;
@@ -380,7 +380,7 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
     {
         RowNormParams r = {};
         r.x = e->x; r.D = FL_D; r.w = e->onorm_w; r.b = e->onorm_b; r.eps = 1e-5f; r.do_norm = 1;
-        r.part = e->partB; r.nsplit = (int)G.ff2[FL_L - 1].grid.z; r.split_stride = ps;
+        r.part = e->partB; r.nsplit = (int)G.ff2[FL_L - 1].p.split_k; r.split_stride = ps;
         r.out_f32 = e->normed; r.out_h = e->normed_h; r.out_l = precise ? e->normed_l : nullptr; r.out_bf16 = 1;
         if (rownorm(e, B, r) != 0) return -1;
         LaunchScope ls(e, KC_FLOW_MISC);
@@ -399,7 +399,7 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
             // fold the previous block's gated MLP output, then LN + adaLN for this block / the final layer
             RowNormParams r = {};
             r.x = e->fx; r.D = FN_D; r.eps = 1e-6f; r.do_norm = 1; r.ldmod = FN_ADA;
-            if (b > 0) { r.part = e->ft; r.nsplit = 1; r.split_stride = 0; r.gate = e->ada + (size_t)(b - 1) * 3 * FN_D + 2 * FN_D; }
+            if (b > 0) { r.part = e->ft; r.nsplit = G.m2[b - 1].p.split_k; r.split_stride = (size_t)e->capB * FN_D; r.gate = e->ada + (size_t)(b - 1) * 3 * FN_D + 2 * FN_D; }
             if (b < FN_DEPTH) { r.w = e->FB[b].lnw; r.b = e->FB[b].lnb; }
             r.shift = e->ada + (size_t)b * 3 * FN_D; r.scale = r.shift + FN_D;
             r.out_h = e->fh_h; r.out_l = precise ? e->fh_l : nullptr; r.out_bf16 = 1;

@@ -20,11 +20,17 @@ namespace ptts {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;        // 64 x 16-bit = 128 B = one swizzle row
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_EPI_WARPS = 16;   // 4 per TMEM lane quadrant, each takes every 4th 16-column chunk
+constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
 constexpr int GEMM_MAX_STAGES = 8;
 
 struct GemmParams {
-    int m_tiles_per_batch;   // ceil(a_rows / 128); grid.x = a_batches * m_tiles_per_batch
+    int m_tiles_per_batch;   // ceil(a_rows / 128)
+    int m_tiles_total;       // a_batches * m_tiles_per_batch
+    int n_tiles;             // ceil(n_total / BN)
+    int split_k;             // K slices (>= 1, none empty)
+    int iters_per_split;     // K iterations per slice
+    int total_tiles;         // m_tiles_total * n_tiles * split_k  (persistent loop bound)
     int a_rows;              // valid rows of A per batch (time steps, or weight rows)
     int n_total;             // valid rows of B (output channels, or batch rows)
     int kblocks_per_tap;     // K per tap / 64
@@ -39,16 +45,18 @@ struct GemmParams {
     int transposed;          // 0: element (m,n) -> [(batch*a_rows+m)*ld + n]; 1: -> [n*ld + m]
     const float *bias;       // indexed by feature (n if !transposed else m); NULL = none
     int bias_mask;           // 0 = index by feature, else feature & bias_mask (ConvTranspose phases)
-    const float *scale;      // per-feature multiplier (layer scale / gate is handled elsewhere); NULL = none
+    const float *scale;      // per-feature multiplier (layer scale); NULL = none
     const float *resid;      // fp32 residual added after scale; NULL = none
     float *out_f32;          // fp32 output (may alias resid); NULL = none
     int ldo;
-    size_t split_stride;     // split-K: slice z stores its partial sum at out_f32 + z*split_stride (reduced by the consumer)
+    size_t split_stride;     // split-K: slice z stores its partial sum at out_f32 + z*split_stride (folded by the consumer)
     uint16_t *out_h;         // 16-bit output of act(v); NULL = none
     uint16_t *out_l;         // lo half: 16-bit of act(v) - float(hi); NULL = none
     int ldh;
     int out_bf16;            // encoding of out_h / out_l
     int act;
+    int fast_act;            // 1: hardware exp/tanh approximations (16-bit outputs only)
+    long long *trace;        // optional [16] clock64 stamps written by CTA 0 (kernel timeline debugging)
 };
 
 template <int BN, int SPLIT>
@@ -56,11 +64,41 @@ struct GemmSmem {
     static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     static constexpr int B_BYTES = BN * GEMM_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES * (SPLIT == 1 ? 2 : 1) + B_BYTES * (SPLIT == 2 ? 2 : 1);
-    static constexpr int bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/; }
 };
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread per instruction.
+__device__ __forceinline__ void st_global_v8(void *ptr, const uint32_t (&v)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+                 "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const void *ptr, float (&v)[8]) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(ptr));
+}
+
+struct TileCoord { int batch, m0, n0, it0, it1, z; };
+__device__ __forceinline__ TileCoord gemm_tile(const GemmParams &p, int tile, int BN) {
+    // n fastest: CTAs working at the same time share the A (activation) rows through L2
+    TileCoord t;
+    const int nt = tile % p.n_tiles;
+    int r = tile / p.n_tiles;
+    const int mt = r % p.m_tiles_total;
+    t.z = r / p.m_tiles_total;
+    t.batch = mt / p.m_tiles_per_batch;
+    t.m0 = (mt - t.batch * p.m_tiles_per_batch) * GEMM_BM;
+    t.n0 = nt * BN;
+    t.it0 = t.z * p.iters_per_split;
+    t.it1 = min(p.taps * p.kblocks_per_tap, t.it0 + p.iters_per_split);
+    return t;
+}
+
+// Persistent: each CTA loops over tiles (tile = blockIdx.x + i*gridDim.x). The shared-memory ring
+// keeps streaming across tile boundaries and the accumulator is double-buffered in TMEM, so the
+// epilogue of tile i overlaps the main loop of tile i+1.
 template <int BN, int SPLIT>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
                const GemmParams p) {
@@ -68,20 +106,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + p.stages * SM::STAGE_BYTES);
-    uint64_t *full = bars;                         // [stages]
-    uint64_t *empty = bars + GEMM_MAX_STAGES;      // [stages]
-    uint64_t *tmem_full = bars + 2 * GEMM_MAX_STAGES;
-    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * GEMM_MAX_STAGES + 1);
+    uint64_t *full = bars;                          // [stages]   TMA -> MMA
+    uint64_t *empty = bars + GEMM_MAX_STAGES;       // [stages]   MMA -> TMA
+    uint64_t *tfull = bars + 2 * GEMM_MAX_STAGES;   // [2]        MMA -> epilogue
+    uint64_t *tempty = tfull + 2;                   // [2]        epilogue -> MMA
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int batch = blockIdx.x / p.m_tiles_per_batch;
-    const int m0 = (blockIdx.x % p.m_tiles_per_batch) * GEMM_BM;
-    const int n0 = blockIdx.y * BN;
-    const int total_iters = p.taps * p.kblocks_per_tap;
-    const int per = (total_iters + gridDim.z - 1) / gridDim.z;
-    const int it0 = blockIdx.z * per;
-    const int it1 = min(total_iters, it0 + per);
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
@@ -89,7 +121,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (SPLIT == 1) tma_prefetch_desc(&mapAlo);
         if (SPLIT == 2) tma_prefetch_desc(&mapBlo);
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], GEMM_EPI_WARPS); mbar_init(&tempty[1], GEMM_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -100,151 +133,201 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const bool tr = p.trace != nullptr && blockIdx.x == 0;
+    if (tr && threadIdx.x == 0) p.trace[0] = clock64();
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int it = it0; it < it1; it++) {
-                mbar_wait(&empty[s], ph ^ 1);
-                uint8_t *st = smem + s * SM::STAGE_BYTES;
-                mbar_expect_tx(&full[s], SM::STAGE_BYTES);
-                const int tap = it / p.kblocks_per_tap, kb = it - tap * p.kblocks_per_tap;
-                const int ak = kb * GEMM_BK + tap * p.a_k_step;
-                const int ar = m0 + p.a_row_shift0 + tap * p.a_row_step;
-                const int bk = kb * GEMM_BK + tap * p.b_k_step;
-                tma_load_3d(st, &mapA, &full[s], ak, ar, batch);
-                uint8_t *nx = st + SM::A_BYTES;
-                if (SPLIT == 1) { tma_load_3d(nx, &mapAlo, &full[s], ak, ar, batch); nx += SM::A_BYTES; }
-                tma_load_3d(nx, &mapB, &full[s], bk, n0, 0);
-                if (SPLIT == 2) tma_load_3d(nx + SM::B_BYTES, &mapBlo, &full[s], bk, n0, 0);
-                if (++s == p.stages) { s = 0; ph ^= 1; }
+            if (tr) p.trace[1] = clock64();
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = gemm_tile(p, tile, BN);
+                for (int it = t.it0; it < t.it1; it++) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t *st = smem + s * SM::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], SM::STAGE_BYTES);
+                    const int tap = it / p.kblocks_per_tap, kb = it - tap * p.kblocks_per_tap;
+                    const int ak = kb * GEMM_BK + tap * p.a_k_step;
+                    const int ar = t.m0 + p.a_row_shift0 + tap * p.a_row_step;
+                    const int bk = kb * GEMM_BK + tap * p.b_k_step;
+                    tma_load_3d(st, &mapA, &full[s], ak, ar, t.batch);
+                    uint8_t *nx = st + SM::A_BYTES;
+                    if (SPLIT == 1) { tma_load_3d(nx, &mapAlo, &full[s], ak, ar, t.batch); nx += SM::A_BYTES; }
+                    tma_load_3d(nx, &mapB, &full[s], bk, t.n0, 0);
+                    if (SPLIT == 2) tma_load_3d(nx + SM::B_BYTES, &mapBlo, &full[s], bk, t.n0, 0);
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
             }
+            if (tr) p.trace[2] = clock64();
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (one elected lane)
-        int s = 0; uint32_t ph = 0;
-        for (int it = it0; it < it1; it++) {
-            mbar_wait(&full[s], ph);
+        int s = 0; uint32_t ph = 0; int lt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
+            const TileCoord t = gemm_tile(p, tile, BN);
+            const int acc = lt & 1;
+            mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
-                const uint32_t alo_addr = a_addr + SM::A_BYTES;
-                const uint32_t b_addr = a_addr + SM::A_BYTES * (SPLIT == 1 ? 2 : 1);
-                const uint32_t blo_addr = b_addr + SM::B_BYTES;
-                const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
+            const uint32_t d_tmem = tmem_base + acc * BN;
+            for (int it = t.it0; it < t.it1; it++) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (tr && lane == 0 && it == t.it0 && lt == 0) p.trace[3] = clock64();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(smem + s * SM::STAGE_BYTES);
+                    const uint32_t alo_addr = a_addr + SM::A_BYTES;
+                    const uint32_t b_addr = a_addr + SM::A_BYTES * (SPLIT == 1 ? 2 : 1);
+                    const uint32_t blo_addr = b_addr + SM::B_BYTES;
+                    const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
 #pragma unroll
-                for (int k = 0; k < GEMM_BK / 16; k++) {
-                    // advancing 16 elements (32 B) along K inside the swizzled row: +2 in 16-byte units
-                    umma_f16(tmem_base, ad + 2 * k, bd + 2 * k, p.idesc, (it > it0 || k > 0) ? 1u : 0u);
-                    if (SPLIT == 1) umma_f16(tmem_base, umma_desc_sw128(alo_addr) + 2 * k, bd + 2 * k, p.idesc, 1u);
-                    if (SPLIT == 2) umma_f16(tmem_base, ad + 2 * k, umma_desc_sw128(blo_addr) + 2 * k, p.idesc, 1u);
+                    for (int k = 0; k < GEMM_BK / 16; k++) {
+                        // advancing 16 elements (32 B) along K inside the swizzled row: +2 in 16-byte units
+                        umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (it > t.it0 || k > 0) ? 1u : 0u);
+                        if (SPLIT == 1) umma_f16(d_tmem, umma_desc_sw128(alo_addr) + 2 * k, bd + 2 * k, p.idesc, 1u);
+                        if (SPLIT == 2) umma_f16(d_tmem, ad + 2 * k, umma_desc_sw128(blo_addr) + 2 * k, p.idesc, 1u);
+                    }
+                    umma_commit(&empty[s]);                       // smem slot reusable once these MMAs retire
+                    if (it == t.it1 - 1) umma_commit(&tfull[acc]);  // accumulator complete
+                    if (tr && it == t.it1 - 1) p.trace[4] = clock64();
                 }
-                umma_commit(&empty[s]);                 // smem slot reusable once these MMAs retire
-                if (it == it1 - 1) umma_commit(tmem_full);  // accumulator complete
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
             }
-            __syncwarp();
-            if (++s == p.stages) { s = 0; ph ^= 1; }
         }
-    } else if (it1 > it0) {
-        // ------------------------------------------------ epilogue warps (TMEM lane quadrant = warp % 4)
-        const int quad = warp & 3;
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int m = m0 + quad * 32 + lane;
-        const bool m_ok = m < p.a_rows;
+    } else {
+        // ------------------------------------------------ epilogue warps
+        // TMEM lane quadrant = warp % 4 (hardware rule); the 4 warps of a quadrant interleave the
+        // 16-column chunks. tcgen05.ld of the next chunk is in flight while this one is processed.
+        const int quad = warp & 3, cg = (warp - 2) >> 2;
+        constexpr int NCG = GEMM_EPI_WARPS / 4;
         const bool bf = p.out_bf16 != 0;
-        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
-        if (!p.transposed) {
-            const size_t grow = (size_t)batch * p.a_rows + m;
-            float *of = p.out_f32 ? p.out_f32 + blockIdx.z * p.split_stride + grow * p.ldo : nullptr;
-            const float *rs = p.resid ? p.resid + grow * p.ldo : nullptr;
-            uint16_t *oh = p.out_h ? p.out_h + grow * p.ldh : nullptr;
-            uint16_t *ol = p.out_l ? p.out_l + grow * p.ldh : nullptr;
+        const int act = p.act, ldo = p.ldo, ldh = p.ldh, n_total = p.n_total, bias_mask = p.bias_mask;
+        const bool fast = p.fast_act != 0;
+        const float *bias = p.bias, *scale = p.scale, *resid = p.resid;
+        uint16_t *out_h = p.out_h, *out_l = p.out_l;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
+            const TileCoord t = gemm_tile(p, tile, BN);
+            const int acc = lt & 1;
+            mbar_wait(&tfull[acc], (lt >> 1) & 1);
+            tc_fence_after();
+            if (tr && lt == 0 && warp == 2 && lane == 0) p.trace[5] = clock64();
+            const int m = t.m0 + quad * 32 + lane;
+            const bool m_ok = m < p.a_rows;
+            const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+            float *out_f32 = p.out_f32 ? p.out_f32 + (size_t)t.z * p.split_stride : nullptr;
+            const bool add_bias = bias != nullptr && t.z == 0;
+            uint32_t r[16], rn[16];
+            if (cg * 16 < BN) { tmem_ld16(trow + cg * 16, r); tmem_ld_wait16(r); }
+            if (!p.transposed) {
+                const size_t grow = (size_t)t.batch * p.a_rows + m;
+                float *of = out_f32 ? out_f32 + grow * ldo : nullptr;
+                const float *rs = resid ? resid + grow * ldo : nullptr;
+                uint16_t *oh = out_h ? out_h + grow * ldh : nullptr;
+                uint16_t *ol = out_l ? out_l + grow * ldh : nullptr;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t r[16];
-                __syncwarp();
-                tmem_ld16(trow + c, r);
-                tmem_ld_wait();
-                const int nb = n0 + c;
-                if (m_ok && nb < p.n_total) {
-                    float v[16];
+                for (int c = cg * 16; c < BN; c += 16 * NCG) {
+                    const bool more = c + 16 * NCG < BN;
+                    if (more) tmem_ld16(trow + c + 16 * NCG, rn);   // in flight while this chunk is processed
+                    const int nb = t.n0 + c;
+                    if (m_ok && nb < n_total) {
+                        float v[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int n = nb + j;
-                        float x = __uint_as_float(r[j]);
-                        if (p.bias && blockIdx.z == 0) x += p.bias[p.bias_mask ? (n & p.bias_mask) : n];
-                        if (p.scale) x *= p.scale[n];
-                        v[j] = x;
-                    }
-                    if (rs) {
+                        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
+                        if (add_bias) {
+                            const float4 *bp = (const float4 *)(bias + (bias_mask ? (nb & bias_mask) : nb));
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            const float4 t = *(const float4 *)(rs + nb + j);
-                            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                            for (int j = 0; j < 4; j++) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
                         }
-                    }
-                    if (of) {
+                        if (scale) {
+                            const float4 *sp = (const float4 *)(scale + nb);
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) *(float4 *)(of + nb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
-                    if (oh) {
-                        uint32_t hw[8], lw[8];
+                            for (int j = 0; j < 4; j++) { const float4 ss = sp[j]; v[4 * j] *= ss.x; v[4 * j + 1] *= ss.y; v[4 * j + 2] *= ss.z; v[4 * j + 3] *= ss.w; }
+                        }
+                        if (rs) {
+                            float t0[8], t1[8];
+                            ld_global_v8(rs + nb, t0);
+                            ld_global_v8(rs + nb + 8, t1);
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float a0 = act_apply(p.act, v[j]), a1 = act_apply(p.act, v[j + 1]);
-                            const uint16_t h0 = f2h16(a0, bf), h1 = f2h16(a1, bf);
-                            hw[j / 2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                            if (ol) {
-                                const uint16_t l0 = f2h16(a0 - h162f(h0, bf), bf), l1 = f2h16(a1 - h162f(h1, bf), bf);
-                                lw[j / 2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                            for (int j = 0; j < 8; j++) { v[j] += t0[j]; v[8 + j] += t1[j]; }
+                        }
+                        if (of) {
+                            uint32_t w0[8], w1[8];
+#pragma unroll
+                            for (int j = 0; j < 8; j++) { w0[j] = __float_as_uint(v[j]); w1[j] = __float_as_uint(v[8 + j]); }
+                            st_global_v8(of + nb, w0);
+                            st_global_v8(of + nb + 8, w1);
+                        }
+                        if (oh) {
+                            uint32_t hw[8], lw[8];
+#pragma unroll
+                            for (int j = 0; j < 16; j += 2) {
+                                const float a0 = fast ? act_apply_fast(act, v[j]) : act_apply(act, v[j]);
+                                const float a1 = fast ? act_apply_fast(act, v[j + 1]) : act_apply(act, v[j + 1]);
+                                const uint16_t h0 = f2h16(a0, bf), h1 = f2h16(a1, bf);
+                                hw[j / 2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                                if (ol) {
+                                    const uint16_t l0 = f2h16(a0 - h162f(h0, bf), bf), l1 = f2h16(a1 - h162f(h1, bf), bf);
+                                    lw[j / 2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                                }
                             }
+                            st_global_v8(oh + nb, hw);
+                            if (ol) st_global_v8(ol + nb, lw);
                         }
-                        *(uint4 *)(oh + nb) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                        *(uint4 *)(oh + nb + 8) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
-                        if (ol) {
-                            *(uint4 *)(ol + nb) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                            *(uint4 *)(ol + nb + 8) = make_uint4(lw[4], lw[5], lw[6], lw[7]);
-                        }
+                    }
+                    if (more) {
+                        tmem_ld_wait16(rn);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) r[j] = rn[j];
                     }
                 }
-            }
-        } else {
-            // transposed: this thread owns output FEATURE m; columns are batch rows n. Stores are
-            // coalesced across the warp (32 consecutive features per batch row).
-            float bv = 0.0f, sv = 1.0f;
-            if (m_ok) {
-                if (p.bias && blockIdx.z == 0) bv = p.bias[p.bias_mask ? (m & p.bias_mask) : m];
-                if (p.scale) sv = p.scale[m];
-            }
-            float *of = p.out_f32 ? p.out_f32 + blockIdx.z * p.split_stride : nullptr;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                uint32_t r[16];
-                __syncwarp();
-                tmem_ld16(trow + c, r);
-                tmem_ld_wait();
+            } else {
+                // transposed: this thread owns output FEATURE m; columns are batch rows n. Stores are
+                // coalesced across the warp (32 consecutive features per batch row).
+                float bv = 0.0f, sv = 1.0f;
                 if (m_ok) {
+                    if (add_bias) bv = bias[bias_mask ? (m & bias_mask) : m];
+                    if (scale) sv = scale[m];
+                }
+                const int ncols = min(BN, n_total - t.n0);
+#pragma unroll 1
+                for (int c = cg * 16; c < BN; c += 16 * NCG) {
+                    const bool more = c + 16 * NCG < BN;
+                    if (more) tmem_ld16(trow + c + 16 * NCG, rn);
+                    if (m_ok && c < ncols) {
+                        const size_t o0 = (size_t)(t.n0 + c) * ldo + m, h0i = (size_t)(t.n0 + c) * ldh + m;
+                        float *of = out_f32 ? out_f32 + o0 : nullptr;
+                        const float *rs = resid ? resid + o0 : nullptr;
+                        uint16_t *oh = out_h ? out_h + h0i : nullptr;
+                        uint16_t *ol = out_l ? out_l + h0i : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 16; j++) {
-                        const int n = n0 + c + j;
-                        if (n < p.n_total) {
-                            float x = (__uint_as_float(r[j]) + bv) * sv;
-                            const size_t o = (size_t)n * p.ldo + m;
-                            if (p.resid) x += p.resid[o];
-                            if (of) of[o] = x;
-                            if (p.out_h) {
-                                const float a = act_apply(p.act, x);
-                                const uint16_t h = f2h16(a, bf);
-                                const size_t oh = (size_t)n * p.ldh + m;
-                                p.out_h[oh] = h;
-                                if (p.out_l) p.out_l[oh] = f2h16(a - h162f(h, bf), bf);
+                        for (int j = 0; j < 16; j++) {
+                            if (c + j < ncols) {
+                                float x = (__uint_as_float(r[j]) + bv) * sv;
+                                if (rs) x += rs[(size_t)j * ldo];
+                                if (of) of[(size_t)j * ldo] = x;
+                                if (oh) {
+                                    const float a = act_apply(act, x);
+                                    const uint16_t h = f2h16(a, bf);
+                                    oh[(size_t)j * ldh] = h;
+                                    if (ol) ol[(size_t)j * ldh] = f2h16(a - h162f(h, bf), bf);
+                                }
                             }
                         }
                     }
+                    if (more) {
+                        tmem_ld_wait16(rn);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) r[j] = rn[j];
+                    }
                 }
             }
+            if (cg * 16 >= BN) { /* this warp had no chunk of a narrow tile */ }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);   // all epilogue warps -> accumulator reusable
+            if (tr && lt == 0 && warp == 2 && lane == 0) p.trace[6] = clock64();
         }
     }
     tc_fence_before();
@@ -253,6 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+    if (tr && threadIdx.x == 0) p.trace[7] = clock64();
 }
 
 // ---------------------------------------------------------------- host side
@@ -275,7 +359,7 @@ struct GemmOp {
     GemmParams p;
     int bn;        // N tile (B-operand box rows)
     int split;     // 0 none, 1 = A has lo, 2 = B has lo
-    dim3 grid;
+    dim3 grid;       // persistent: min(total_tiles, max_ctas)
     int smem_bytes;
 };
 

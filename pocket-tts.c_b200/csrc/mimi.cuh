@@ -117,6 +117,7 @@ static int mimi_gemm(Engine *e, const __half *A, int Bc, int T, int C, const __h
     d.bf16 = false; d.taps = taps; d.k_per_tap = C; d.shift0 = shift0; d.step = step; d.a_k_step = 0; d.b_k_step = C;
     d.bn = bn; d.split_k = 1; d.two_cta = true;
     d.epi = epi;
+    d.epi.fast_act = 1;   // fp16 outputs: hardware exp/tanh approximations are below the rounding error
     GemmOp op;
     if (gemm_build(op, d) != 0) return -1;
     return run_gemm(e, op, KC_GEMM_MIMI);

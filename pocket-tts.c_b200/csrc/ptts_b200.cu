@@ -67,6 +67,7 @@ extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b
     Engine *e = new Engine();
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
+    g_num_sms = prop.multiProcessorCount;
     HostWeights hw{tensors, n_tensors};
     if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
         cudaEventCreate(&e->ev1) != cudaSuccess) {
@@ -491,12 +492,25 @@ extern "C" int ptts_b200_test_gemm(ptts_b200_engine *e, const float *A, const fl
         d.bn = bn; d.split_k = split_k; d.two_cta = true;
         d.epi.transposed = transposed; d.epi.out_f32 = dout; d.epi.ldo = transposed ? rows : N; d.epi.split_stride = no;
         GemmOp op;
-        if (gemm_build(op, d) == 0 && run_gemm(e, op, KC_GEMM_MIMI) == 0 && cudaStreamSynchronize(e->st) == cudaSuccess) {
-            std::vector<float> tmp((size_t)op.grid.z * no);
+        long long *dtrace = nullptr;
+        const bool want_trace = getenv("PTTS_B200_GEMM_TRACE") != nullptr;
+        if (want_trace && e->dalloc(&dtrace, 16) == 0) { cudaMemset(dtrace, 0, 16 * 8); d.epi.trace = dtrace; }
+        if (gemm_build(op, d) == 0 && run_gemm(e, op, KC_GEMM_MIMI) == 0 && run_gemm(e, op, KC_GEMM_MIMI) == 0 &&
+            cudaStreamSynchronize(e->st) == cudaSuccess) {
+            if (dtrace) {
+                long long t[16];
+                cudaMemcpy(t, dtrace, sizeof t, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "gemm trace (cycles from CTA0 start) rows=%d N=%d K=%d bn=%d split=%d tiles=%d grid=%u stages=%d: "
+                        "producer_start=%lld producer_end=%lld first_full=%lld last_commit=%lld epi_start=%lld epi_end=%lld end=%lld\n",
+                        rows, N, K, bn, split, op.p.total_tiles, op.grid.x, op.p.stages, t[1] - t[0], t[2] - t[0], t[3] - t[0],
+                        t[4] - t[0], t[5] - t[0], t[6] - t[0], t[7] - t[0]);
+                e->dfree(dtrace);
+            }
+            std::vector<float> tmp((size_t)op.p.split_k * no);
             cudaMemcpy(tmp.data(), dout, tmp.size() * 4, cudaMemcpyDeviceToHost);
             for (size_t i = 0; i < no; i++) {
                 float a = 0.0f;
-                for (unsigned z = 0; z < op.grid.z; z++) a += tmp[z * no + i];
+                for (int z = 0; z < op.p.split_k; z++) a += tmp[z * no + i];
                 out[i] = a;
             }
             rc = 0;
