@@ -43,7 +43,8 @@ struct Prof {
     int64_t n[KC_COUNT] = {0};
     // algorithmic work issued per class while profiling (host-side accounting from launch shapes)
     double flops[KC_COUNT] = {0}, bytes[KC_COUNT] = {0};
-    int cur_step = 0;   // lock-step index of the step being launched (profile mode runs without graphs)
+    int cur_step = 0;   // decode iteration being launched (profile mode runs without graphs)
+    double mean_own_base = 0.0;   // mean prompt rows per utterance already in the own cache
 };
 
 // ---------------------------------------------------------------- TMA host API
@@ -280,6 +281,12 @@ struct ptts_b200_engine {
     float *pk = nullptr, *pv = nullptr;           // prefix KV [L][H][capCond][64]
     float *ok = nullptr, *ov = nullptr;           // own KV [L][capB][H][capS][64]
     float *d_cond = nullptr;                      // voice rows on device [capCond,1024]
+    // batched prefill workspace (capRows packed rows)
+    int capRows = 0;
+    int *d_row_b = nullptr, *d_row_i = nullptr, *d_row_start = nullptr, *d_own_base = nullptr;
+    float *pf_x = nullptr, *pf_qkv = nullptr;
+    uint16_t *pf_xn_h = nullptr, *pf_xn_l = nullptr, *pf_att_h = nullptr, *pf_att_l = nullptr, *pf_ffh_h = nullptr, *pf_ffh_l = nullptr;
+    int st_rows = 0, st_maxq = 0, st_cond = 0;
     std::vector<float> voice_host;                // copy of the cached voice prefix
     int voice_len = -1;
     // step graphs keyed by (mode, B, lsd_steps, precise); `gen` bumps whenever device pointers change

@@ -134,11 +134,11 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
                      (void **)&e->ffh_h, (void **)&e->ffh_l, (void **)&e->normed_h, (void **)&e->normed_l, (void **)&e->partA,
                      (void **)&e->partB, (void **)&e->fx, (void **)&e->ada, (void **)&e->ft, (void **)&e->flow, (void **)&e->sc,
                      (void **)&e->fg, (void **)&e->sc_h, (void **)&e->sc_l, (void **)&e->fh_h, (void **)&e->fh_l,
-                     (void **)&e->fg_h, (void **)&e->fg_l, (void **)&e->ok, (void **)&e->ov};
+                     (void **)&e->fg_h, (void **)&e->fg_l, (void **)&e->ok, (void **)&e->ov, (void **)&e->d_own_base};
     for (void **p : bufs) { e->dfree(*p); *p = nullptr; }
     const size_t b = (size_t)B;
 #define DA(ptr, count) if (e->dalloc(&e->ptr, (count)) != 0) return -1
-    DA(d_tokens, b * tok); DA(d_tok_len, b); DA(d_max_frames, b); DA(d_eos_after, b);
+    DA(d_own_base, b); DA(d_tokens, b * tok); DA(d_tok_len, b); DA(d_max_frames, b); DA(d_eos_after, b);
     DA(d_noise, b * F * FL_LAT); DA(d_latent, b * FL_LAT); DA(d_out_latents, b * F * FL_LAT);
     DA(d_eos_step, b); DA(d_done, b); DA(d_used, b); DA(d_first_eos, b); DA(d_first_cond, b * FL_D); DA(d_first_flow, b * FL_LAT);
     DA(x, b * FL_D); DA(qkv, b * 3 * FL_D); DA(att, b * FL_D); DA(ffh, b * FL_FF); DA(normed, b * FL_D);
@@ -162,11 +162,11 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
     return 0;
 }
 
-static FlowState make_state(Engine *e, int B, int lsd_steps, const float *ext_in) {
+static FlowState make_state(Engine *e, int B, int lsd_steps) {
     FlowState s = {};
     s.step = &e->ctrl->step;
     s.B = B; s.max_tok = e->capTok; s.max_frames_cap = e->capF; s.cond_len = 0;
-    s.tokens = e->d_tokens; s.tok_len = e->d_tok_len; s.max_frames = e->d_max_frames; s.ext_in = ext_in;
+    s.tokens = e->d_tokens; s.tok_len = e->d_tok_len; s.max_frames = e->d_max_frames;
     s.noise = e->d_noise; s.latent = e->d_latent; s.out_latents = e->d_out_latents;
     s.eos_step = e->d_eos_step; s.done = e->d_done; s.used = e->d_used;
     s.first_eos = e->d_first_eos; s.first_cond = e->d_first_cond; s.first_flow = e->d_first_flow;
@@ -186,31 +186,26 @@ static int gemv(Engine *e, const __nv_bfloat16 *W, int N, const float *x, GemvPa
     return launch_check("k_gemv");
 }
 
-static int attn_decode(Engine *e, int B, int layer, bool voice_mode, bool out16) {
+static int attn_decode(Engine *e, int B, int layer, bool out16) {
     AttnDecodeParams a = {};
     a.qkv = e->qkv;
     a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin;
-    a.ctrl_cond_len = voice_mode ? nullptr : &e->ctrl->cond_len;
+    a.ctrl_cond_len = &e->ctrl->cond_len;
+    a.own_base = e->d_own_base;
     a.pstride = e->capCond;
-    if (voice_mode) {   // the voice prefix is prefilled into the prefix buffers themselves
-        a.pk = nullptr; a.pv = nullptr;
-        a.ok = e->pk + (size_t)layer * FL_D * e->capCond; a.ov = e->pv + (size_t)layer * FL_D * e->capCond;
-        a.max_s = e->capCond;
-    } else {
-        a.pk = e->pk + (size_t)layer * FL_D * e->capCond; a.pv = e->pv + (size_t)layer * FL_D * e->capCond;
-        a.ok = e->ok + (size_t)layer * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)layer * e->capB * FL_D * e->capS;
-        a.max_s = e->capS;
-    }
+    a.pk = e->pk + (size_t)layer * FL_D * e->capCond; a.pv = e->pv + (size_t)layer * FL_D * e->capCond;
+    a.ok = e->ok + (size_t)layer * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)layer * e->capB * FL_D * e->capS;
+    a.max_s = e->capS;
     a.step = &e->ctrl->step;
     if (out16) { a.out_h = e->att_h; a.out_l = e->att_l; } else a.out_f32 = e->att;
-    const int pcap = ((e->capCond + std::max(e->capS, e->capCond) + 63) / 32) * 32;
+    const int pcap = ((e->capCond + e->capS + 63) / 32) * 32;
     const int G = B >= 128 ? 8 : (B >= 64 ? 4 : (B >= 32 ? 2 : 1));
     const size_t smem = attn2_smem_bytes(pcap, G);
     PTTS_CHECK(smem <= 200 * 1024, "attention score buffer of %zu bytes exceeds shared memory (sequence too long)", smem);
     if (e->prof.on) {
-        // algorithmic bytes: shared prefix K/V once, each utterance's own K/V (s+1 positions) once,
-        // the new K/V row written, q/k/v read and the output written
-        const double own = e->prof.cur_step + 1, pre = voice_mode ? 0 : e->voice_len;
+        // algorithmic bytes: shared prefix K/V once, each utterance's own K/V rows once, the new K/V
+        // row written, q/k/v read and the output written (own rows: mean prompt length + frames so far)
+        const double own = e->prof.mean_own_base + e->prof.cur_step + 1, pre = e->voice_len;
         e->prof.bytes[KC_ATTN_DECODE] += 2.0 * FL_D * 4.0 * (pre + (double)B * own) + (double)B * FL_D * 4.0 * (2 + 3 + 1);
         e->prof.flops[KC_ATTN_DECODE] += 4.0 * FL_D * (double)B * (pre + own);
     }
@@ -220,7 +215,7 @@ static int attn_decode(Engine *e, int B, int layer, bool voice_mode, bool out16)
     else if (G == 4) k_attn_decode2<2><<<grid, 256, smem, e->st>>>(a, B, pcap);
     else if (G == 2) k_attn_decode2<4><<<grid, 256, smem, e->st>>>(a, B, pcap);
     else k_attn_decode2<8><<<grid, 256, smem, e->st>>>(a, B, pcap);
-    return launch_check("k_attn_decode");
+    return launch_check("k_attn_decode2");
 }
 
 static int rownorm(Engine *e, int rows, RowNormParams p, int cls = KC_ROWNORM) {
@@ -229,29 +224,8 @@ static int rownorm(Engine *e, int rows, RowNormParams p, int cls = KC_ROWNORM) {
     return launch_check("k_rownorm");
 }
 
-static int flow_step_gemv(Engine *e, const FlowState &st, bool voice_mode, const float *cbias) {
-    {
-        LaunchScope ls(e, KC_FLOW_MISC);
-        k_prepare_x<<<1, 256, 0, e->st>>>(st, e->embed, e->bos_proj, e->in_lin, e->x);
-        if (launch_check("k_prepare_x") != 0) return -1;
-    }
-    for (int l = 0; l < FL_L; l++) {
-        GemvParams g = {};
-        g.ln_w = e->L[l].n1w; g.ln_b = e->L[l].n1b; g.eps = 1e-5f; g.out = e->qkv;
-        if (gemv<FL_D, 8, 1>(e, e->L[l].inproj, 3 * FL_D, e->x, g) != 0) return -1;
-        if (attn_decode(e, 1, l, voice_mode, false) != 0) return -1;
-        g = {}; g.acc_out = e->x;
-        if (gemv<FL_D, 4, 0>(e, e->L[l].outproj, FL_D, e->att, g) != 0) return -1;
-        g = {}; g.ln_w = e->L[l].n2w; g.ln_b = e->L[l].n2b; g.eps = 1e-5f; g.act = ACT_GELU_ERF; g.out = e->ffh;
-        if (gemv<FL_D, 8, 1>(e, e->L[l].l1, FL_FF, e->x, g) != 0) return -1;
-        g = {}; g.acc_out = e->x;
-        if (gemv<FL_FF, 4, 0>(e, e->L[l].l2, FL_D, e->ffh, g) != 0) return -1;
-    }
-    if (voice_mode) {
-        LaunchScope ls(e, KC_FLOW_MISC);
-        k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
-        return launch_check("k_advance_step");
-    }
+// One decode iteration, batch-1 path: head (frame j) then transformer body for frame j+1.
+static int flow_step_gemv(Engine *e, const FlowState &st, const float *cbias) {
     RowNormParams r = {};
     r.x = e->x; r.D = FL_D; r.w = e->onorm_w; r.b = e->onorm_b; r.eps = 1e-5f; r.do_norm = 1; r.out_f32 = e->normed;
     if (rownorm(e, 1, r) != 0) return -1;
@@ -287,6 +261,23 @@ static int flow_step_gemv(Engine *e, const FlowState &st, bool voice_mode, const
             k_flow_update<<<1, 32, 0, e->st>>>(st, e->ctrl, e->d_eos_after, k, e->flow);
             if (launch_check("k_flow_update") != 0) return -1;
         }
+    }
+    {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_prepare_x<<<1, 256, 0, e->st>>>(st, e->in_lin, e->x);
+        if (launch_check("k_prepare_x") != 0) return -1;
+    }
+    for (int l = 0; l < FL_L; l++) {
+        GemvParams g = {};
+        g.ln_w = e->L[l].n1w; g.ln_b = e->L[l].n1b; g.eps = 1e-5f; g.out = e->qkv;
+        if (gemv<FL_D, 8, 1>(e, e->L[l].inproj, 3 * FL_D, e->x, g) != 0) return -1;
+        if (attn_decode(e, 1, l, false) != 0) return -1;
+        g = {}; g.acc_out = e->x;
+        if (gemv<FL_D, 4, 0>(e, e->L[l].outproj, FL_D, e->att, g) != 0) return -1;
+        g = {}; g.ln_w = e->L[l].n2w; g.ln_b = e->L[l].n2b; g.eps = 1e-5f; g.act = ACT_GELU_ERF; g.out = e->ffh;
+        if (gemv<FL_D, 8, 1>(e, e->L[l].l1, FL_FF, e->x, g) != 0) return -1;
+        g = {}; g.acc_out = e->x;
+        if (gemv<FL_FF, 4, 0>(e, e->L[l].l2, FL_D, e->ffh, g) != 0) return -1;
     }
     LaunchScope ls(e, KC_FLOW_MISC);
     k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
@@ -352,31 +343,12 @@ static int flow_gemms_build(Engine *e, FlowGemms &G, int B, int precise, int lsd
     return 0;
 }
 
+// One decode iteration, batched tcgen05 path: head (frame j) then transformer body for frame j+1.
+// The split-K partials of the last FFN2 of iteration j-1 (zeroed before the first iteration) are
+// folded into x by the out_norm row kernel.
 static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int precise) {
     const int B = st.B;
     const size_t ps = (size_t)e->capB * FL_D;
-    {
-        LaunchScope ls(e, KC_FLOW_MISC);
-        k_prepare_x<<<B, 256, 0, e->st>>>(st, e->embed, e->bos_proj, e->in_lin, e->x);
-        if (launch_check("k_prepare_x") != 0) return -1;
-    }
-    for (int l = 0; l < FL_L; l++) {
-        RowNormParams r = {};
-        r.x = e->x; r.D = FL_D; r.w = e->L[l].n1w; r.b = e->L[l].n1b; r.eps = 1e-5f; r.do_norm = 1;
-        r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
-        if (l > 0) { r.part = e->partB; r.nsplit = (int)G.ff2[l - 1].p.split_k; r.split_stride = ps; }
-        if (rownorm(e, B, r) != 0) return -1;
-        if (run_gemm(e, G.qkv[l], KC_GEMM_FLOW) != 0) return -1;
-        if (attn_decode(e, B, l, false, true) != 0) return -1;
-        if (run_gemm(e, G.outp[l], KC_GEMM_FLOW) != 0) return -1;
-        r = {};
-        r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
-        r.part = e->partA; r.nsplit = (int)G.outp[l].p.split_k; r.split_stride = ps;
-        r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
-        if (rownorm(e, B, r) != 0) return -1;
-        if (run_gemm(e, G.ff1[l], KC_GEMM_FLOW) != 0) return -1;
-        if (run_gemm(e, G.ff2[l], KC_GEMM_FLOW) != 0) return -1;
-    }
     {
         RowNormParams r = {};
         r.x = e->x; r.D = FL_D; r.w = e->onorm_w; r.b = e->onorm_b; r.eps = 1e-5f; r.do_norm = 1;
@@ -414,9 +386,123 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
         k_flow_update<<<B, 32, 0, e->st>>>(st, e->ctrl, e->d_eos_after, k, e->flow);
         if (launch_check("k_flow_update") != 0) return -1;
     }
+    {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_prepare_x<<<B, 256, 0, e->st>>>(st, e->in_lin, e->x);
+        if (launch_check("k_prepare_x") != 0) return -1;
+    }
+    for (int l = 0; l < FL_L; l++) {
+        RowNormParams r = {};
+        r.x = e->x; r.D = FL_D; r.w = e->L[l].n1w; r.b = e->L[l].n1b; r.eps = 1e-5f; r.do_norm = 1;
+        r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
+        if (l > 0) { r.part = e->partB; r.nsplit = (int)G.ff2[l - 1].p.split_k; r.split_stride = ps; }
+        if (rownorm(e, B, r) != 0) return -1;
+        if (run_gemm(e, G.qkv[l], KC_GEMM_FLOW) != 0) return -1;
+        if (attn_decode(e, B, l, true) != 0) return -1;
+        if (run_gemm(e, G.outp[l], KC_GEMM_FLOW) != 0) return -1;
+        r = {};
+        r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
+        r.part = e->partA; r.nsplit = (int)G.outp[l].p.split_k; r.split_stride = ps;
+        r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
+        if (rownorm(e, B, r) != 0) return -1;
+        if (run_gemm(e, G.ff1[l], KC_GEMM_FLOW) != 0) return -1;
+        if (run_gemm(e, G.ff2[l], KC_GEMM_FLOW) != 0) return -1;
+    }
     LaunchScope ls(e, KC_FLOW_MISC);
     k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
     return launch_check("k_advance_step");
+}
+
+// ---------------------------------------------------------------- batched prefill
+// Grow the packed-row workspace.
+static int prefill_ensure(Engine *e, int rows, int n) {
+    if (rows <= e->capRows && e->d_row_start) return 0;
+    cudaStreamSynchronize(e->st);
+    rows = std::max(rows, e->capRows);
+    void **bufs[] = {(void **)&e->d_row_b, (void **)&e->d_row_i, (void **)&e->d_row_start, (void **)&e->pf_x, (void **)&e->pf_qkv,
+                     (void **)&e->pf_xn_h, (void **)&e->pf_xn_l, (void **)&e->pf_att_h, (void **)&e->pf_att_l,
+                     (void **)&e->pf_ffh_h, (void **)&e->pf_ffh_l};
+    for (void **p : bufs) { e->dfree(*p); *p = nullptr; }
+    const size_t r = (size_t)rows;
+#define DA(ptr, count) if (e->dalloc(&e->ptr, (count)) != 0) return -1
+    DA(d_row_b, r); DA(d_row_i, r); DA(d_row_start, 1024); DA(pf_x, r * FL_D); DA(pf_qkv, r * 3 * FL_D);
+    DA(pf_xn_h, r * FL_D); DA(pf_xn_l, r * FL_D); DA(pf_att_h, r * FL_D); DA(pf_att_l, r * FL_D);
+    DA(pf_ffh_h, r * FL_FF); DA(pf_ffh_l, r * FL_FF);
+#undef DA
+    (void)n;
+    e->capRows = rows;
+    return 0;
+}
+
+// activations [M, K] (bf16 hi + lo, the A operand) x weights [N, K] (B operand), normal orientation
+static int prefill_gemm(Engine *e, const uint16_t *ah, const uint16_t *al, int M, int K, const __nv_bfloat16 *W, int N,
+                        GemmParams epi) {
+    GemmDesc d;
+    d.A = ah; d.Alo = al; d.a_k = K; d.a_rows = M; d.a_batches = 1; d.a_ld = K;
+    d.B = W; d.b_k = K; d.b_rows = N; d.b_ld = K;
+    d.bf16 = true; d.taps = 1; d.k_per_tap = K;
+    d.bn = M <= 256 ? 64 : (M <= 1024 ? 128 : 256);   // short prompts: more, narrower tiles to spread the weight stream
+    d.epi = epi; d.epi.out_bf16 = 1;
+    GemmOp op;
+    if (gemm_build(op, d) != 0) return -1;
+    return run_gemm(e, op, KC_GEMM_FLOW);
+}
+
+// Run the transformer over M packed rows. voice_mode: rows are the voice frames (d_cond), K/V go to
+// the prefix buffers, no prefix is attended. Otherwise rows are text tokens + BOS of n utterances,
+// K/V go to the own caches and x[b] receives the BOS-position hidden state.
+static int flow_prefill(Engine *e, int n, int M, int max_q, int cond_len, bool voice_mode) {
+    PrefillRows pr = {e->d_row_b, e->d_row_i, e->d_row_start};
+    const size_t smem = pf_attn_smem_bytes(cond_len, max_q);
+    PTTS_CHECK(smem <= 200 * 1024, "prefill attention needs %zu bytes of shared memory (voice prefix %d + prompt %d rows too long)",
+               smem, cond_len, max_q);
+    {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_pf_gather<<<M, 256, 0, e->st>>>(pr, e->d_tokens, e->capTok, e->d_tok_len, e->embed, e->bos_proj,
+                                          voice_mode ? e->d_cond : nullptr, e->pf_x);
+        if (launch_check("k_pf_gather") != 0) return -1;
+    }
+    for (int l = 0; l < FL_L; l++) {
+        RowNormParams r = {};
+        r.x = e->pf_x; r.D = FL_D; r.w = e->L[l].n1w; r.b = e->L[l].n1b; r.eps = 1e-5f; r.do_norm = 1;
+        r.out_h = e->pf_xn_h; r.out_l = e->pf_xn_l; r.out_bf16 = 1;
+        if (rownorm(e, M, r) != 0) return -1;
+        GemmParams g = {};
+        g.out_f32 = e->pf_qkv; g.ldo = 3 * FL_D;
+        if (prefill_gemm(e, e->pf_xn_h, e->pf_xn_l, M, FL_D, e->L[l].inproj, 3 * FL_D, g) != 0) return -1;
+        {
+            PrefillAttnParams a = {};
+            a.qkv = e->pf_qkv; a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin;
+            a.cond_len = cond_len; a.pstride = e->capCond; a.max_q = max_q;
+            if (voice_mode) {
+                a.ok = e->pk + (size_t)l * FL_D * e->capCond; a.ov = e->pv + (size_t)l * FL_D * e->capCond; a.max_s = e->capCond;
+            } else {
+                a.pk = e->pk + (size_t)l * FL_D * e->capCond; a.pv = e->pv + (size_t)l * FL_D * e->capCond;
+                a.ok = e->ok + (size_t)l * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)l * e->capB * FL_D * e->capS;
+                a.max_s = e->capS;
+            }
+            a.out_h = e->pf_att_h; a.out_l = e->pf_att_l;
+            LaunchScope ls(e, KC_ATTN_DECODE);
+            k_pf_attn<<<dim3(FL_H, n), 256, smem, e->st>>>(a, pr);
+            if (launch_check("k_pf_attn") != 0) return -1;
+        }
+        g = {}; g.resid = e->pf_x; g.out_f32 = e->pf_x; g.ldo = FL_D;
+        if (prefill_gemm(e, e->pf_att_h, e->pf_att_l, M, FL_D, e->L[l].outproj, FL_D, g) != 0) return -1;
+        r = {};
+        r.x = e->pf_x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
+        r.out_h = e->pf_xn_h; r.out_l = e->pf_xn_l; r.out_bf16 = 1;
+        if (rownorm(e, M, r) != 0) return -1;
+        g = {}; g.out_h = e->pf_ffh_h; g.out_l = e->pf_ffh_l; g.ldh = FL_FF; g.act = ACT_GELU_ERF;
+        if (prefill_gemm(e, e->pf_xn_h, e->pf_xn_l, M, FL_D, e->L[l].l1, FL_FF, g) != 0) return -1;
+        g = {}; g.resid = e->pf_x; g.out_f32 = e->pf_x; g.ldo = FL_D;
+        if (prefill_gemm(e, e->pf_ffh_h, e->pf_ffh_l, M, FL_FF, e->L[l].l2, FL_D, g) != 0) return -1;
+    }
+    if (!voice_mode) {
+        LaunchScope ls(e, KC_FLOW_MISC);
+        k_pf_last<<<n, 256, 0, e->st>>>(pr, e->pf_x, e->x);
+        if (launch_check("k_pf_last") != 0) return -1;
+    }
+    return 0;
 }
 
 }  // namespace ptts

@@ -213,21 +213,20 @@ __global__ void __launch_bounds__((K / 8 < 128 ? K / 8 : 128)) k_gemv(const Gemv
 }
 
 // =====================================================================================
-// FlowLM lock-step state machine (ptts_flowlm.c:1138-1251 restructured for a batch):
-// every utterance b consumes one input per step s after the shared voice prefix:
-//   s <  tok_len[b]          text embedding row           (prefill)
-//   s == tok_len[b]          input_linear . bos_emb
-//   s >  tok_len[b]          input_linear . latent[b]     (frame i = s - tok_len[b] - 1 fed back)
-// After the transformer step, frame index i = s - tok_len[b] is sampled when
-// 0 <= i < max_frames[b] and the utterance has not stopped.
+// FlowLM generation state machine (ptts_flowlm.c:1138-1251 restructured for a batch).
+// Prefill (voice prefix once per voice; text tokens + BOS of every utterance in ONE batched pass,
+// k_pf_* below) leaves x[b] = hidden state at the BOS position and the own KV rows
+// 0..tok_len[b]. Decode iteration j (device counter `step`) then does, for all utterances in
+// lock-step:   head: out_norm(x) -> EOS rule -> noise -> LSD/flow -> latent_j   (frame j)
+//              body: x = input_linear . latent_j -> transformer step at own position
+//                    tok_len[b] + 1 + j  -> x for frame j+1
 // =====================================================================================
 struct FlowState {
-    int *step;                 // device step counter s
+    int *step;                 // device decode-iteration counter j (= frame index)
     int B, max_tok, max_frames_cap, cond_len;
     const int *tokens;         // [B, max_tok]
     const int *tok_len;        // [B]
     const int *max_frames;     // [B]
-    const float *ext_in;       // optional [n, 1024] inputs used instead (voice prefill)
     const float *noise;        // [B, max_frames_cap, 32]
     float *latent;             // [B, 32] running latent of the current frame
     float *out_latents;        // [B, max_frames_cap, 32]
@@ -243,38 +242,24 @@ struct FlowCtrl {
     float eos_threshold;
 };
 
-// x[b,:] for step s. grid B, block 256.
-__global__ void __launch_bounds__(256) k_prepare_x(const FlowState st, const __nv_bfloat16 *embed, const float *bos_proj,
-                                                   const __nv_bfloat16 *in_lin, float *x) {
-    const int b = blockIdx.x, s = *st.step;
+// x[b,:] = input_linear . latent[b] (ptts_flowlm.c:1240-1241). grid B, block 256.
+__global__ void __launch_bounds__(256) k_prepare_x(const FlowState st, const __nv_bfloat16 *in_lin, float *x) {
+    const int b = blockIdx.x;
     float *xr = x + (size_t)b * FL_D;
-    if (st.ext_in) {
-        for (int i = threadIdx.x; i < FL_D; i += 256) xr[i] = st.ext_in[(size_t)s * FL_D + i];
-        return;
-    }
-    const int tl = st.tok_len[b];
-    if (s < tl) {
-        int id = st.tokens[(size_t)b * st.max_tok + s];
-        if (id < 0 || id > 4000) id = 0;  // ptts_flowlm.c:1170
-        for (int i = threadIdx.x; i < FL_D; i += 256) xr[i] = __bfloat162float(embed[(size_t)id * FL_D + i]);
-    } else if (s == tl) {
-        for (int i = threadIdx.x; i < FL_D; i += 256) xr[i] = bos_proj[i];
-    } else {
-        __shared__ float lat[FL_LAT];
-        if (threadIdx.x < FL_LAT) lat[threadIdx.x] = st.latent[b * FL_LAT + threadIdx.x];
-        __syncthreads();
-        for (int i = threadIdx.x; i < FL_D; i += 256) {
-            const uint4 *wr = (const uint4 *)(in_lin + (size_t)i * FL_LAT);
-            float a = 0.0f;
+    __shared__ float lat[FL_LAT];
+    if (threadIdx.x < FL_LAT) lat[threadIdx.x] = st.latent[b * FL_LAT + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.x; i < FL_D; i += 256) {
+        const uint4 *wr = (const uint4 *)(in_lin + (size_t)i * FL_LAT);
+        float a = 0.0f;
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const uint4 u = wr[c];
-                const float *l = lat + c * 8;
-                a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] +
-                     bf16lo(u.z) * l[4] + bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
-            }
-            xr[i] = a;
+        for (int c = 0; c < 4; c++) {
+            const uint4 u = wr[c];
+            const float *l = lat + c * 8;
+            a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] +
+                 bf16lo(u.z) * l[4] + bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
         }
+        xr[i] = a;
     }
 }
 
@@ -287,8 +272,8 @@ __global__ void __launch_bounds__(256) k_eos_state(const FlowState st, const Flo
     float a = 0.0f;
     for (int i = threadIdx.x; i < FL_D; i += 256) a += eos_w[i] * nr[i];
     const float eos = block_sum(a, red) + eos_b[0];
-    const int i = s - st.tok_len[b];
-    const bool valid = i >= 0 && i < st.max_frames[b] && !st.done[b];
+    const int i = s;
+    const bool valid = i < st.max_frames[b] && !st.done[b];
     if (!valid) return;
     if (i == 0) {
         for (int k = threadIdx.x; k < FL_D; k += 256) st.first_cond[(size_t)b * FL_D + k] = nr[k];
@@ -305,8 +290,7 @@ __global__ void __launch_bounds__(256) k_eos_state(const FlowState st, const Flo
 __global__ void __launch_bounds__(512) k_flow_init(const FlowState st, int k, const __nv_bfloat16 *inp_w /*[512,32]*/,
                                                    const float *inp_b, float *fx) {
     __shared__ float lat[FL_LAT];
-    const int b = blockIdx.x, s = *st.step;
-    int i = s - st.tok_len[b];
+    const int b = blockIdx.x, i = *st.step;
     if (threadIdx.x < FL_LAT) {
         float v;
         if (k == 0) {
@@ -336,9 +320,8 @@ __global__ void __launch_bounds__(512) k_flow_init(const FlowState st, int k, co
 // apply the stop rule (ptts_flowlm.c:1235-1238). grid B, block 32.
 __global__ void __launch_bounds__(32) k_flow_update(const FlowState st, const FlowCtrl *ctrl, const int *eos_after, int k,
                                                     const float *flow /*[B,32]*/) {
-    const int b = blockIdx.x, s = *st.step, d = threadIdx.x;
-    const int i = s - st.tok_len[b];
-    const bool valid = i >= 0 && i < st.max_frames[b] && !st.done[b];
+    const int b = blockIdx.x, i = *st.step, d = threadIdx.x;
+    const bool valid = i < st.max_frames[b] && !st.done[b];
     const float f = flow[b * FL_LAT + d];
     const float v = st.latent[b * FL_LAT + d] + f / (float)st.lsd_steps;
     st.latent[b * FL_LAT + d] = v;
@@ -367,7 +350,8 @@ struct AttnDecodeParams {
     const float *rope_cos, *rope_sin;  // [max_pos][32]
     const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
     float *ok, *ov;            // own cache of this layer
-    const int *ctrl_cond_len;  // device cond_len (NULL = 0: voice prefill writes the prefix buffers as "own")
+    const int *ctrl_cond_len;  // device cond_len
+    const int *own_base;       // [B] own-cache rows already filled by the prefill (tok_len + 1)
     int pstride;               // row capacity of the prefix buffers
     int max_s;
     const int *step;
@@ -375,82 +359,8 @@ struct AttnDecodeParams {
     uint16_t *out_h, *out_l;   // bf16 hi/lo (tensor path)
 };
 
-__global__ void __launch_bounds__(128) k_attn_decode(const AttnDecodeParams p) {
-    extern __shared__ float sc[];  // [cond_len + max_s] scores
-    __shared__ __align__(16) float sq[FL_HD];
-    __shared__ float red[32];
-    __shared__ float so[2][FL_HD];
-    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
-    const int s = *p.step, pos = cond_len + s, P = pos + 1;
-    const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD;
-    float *okb = p.ok + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
-    float *ovb = p.ov + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
-    if (tid < 32) {
-        const float c = p.rope_cos[pos * 32 + tid], sn = p.rope_sin[pos * 32 + tid];
-        const float q0 = row[2 * tid], q1 = row[2 * tid + 1];
-        const float k0 = row[FL_D + 2 * tid], k1 = row[FL_D + 2 * tid + 1];
-        // 1/sqrt(64) = 0.125 is a power of two: scaling q here equals scaling each score
-        sq[2 * tid] = (q0 * c - q1 * sn) * 0.125f;
-        sq[2 * tid + 1] = (q0 * sn + q1 * c) * 0.125f;
-        okb[(size_t)s * FL_HD + 2 * tid] = k0 * c - k1 * sn;
-        okb[(size_t)s * FL_HD + 2 * tid + 1] = k0 * sn + k1 * c;
-    } else if (tid < 96) {
-        ovb[(size_t)s * FL_HD + (tid - 32)] = row[2 * FL_D + (tid - 32)];
-    }
-    __syncthreads();
-    const float *pkh = p.pk ? p.pk + (size_t)h * p.pstride * FL_HD : nullptr;
-    const float *pvh = p.pv ? p.pv + (size_t)h * p.pstride * FL_HD : nullptr;
-    float mx = -INFINITY;
-    for (int t = tid; t < P; t += 128) {
-        const float4 *kp = (const float4 *)(t < cond_len ? pkh + (size_t)t * FL_HD : okb + (size_t)(t - cond_len) * FL_HD);
-        float a = 0.0f;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            const float4 kv = kp[j];
-            const float4 qv = *(const float4 *)(sq + 4 * j);
-            a += kv.x * qv.x + kv.y * qv.y + kv.z * qv.z + kv.w * qv.w;
-        }
-        sc[t] = a;
-        mx = fmaxf(mx, a);
-    }
-    mx = block_max(mx, red);
-    float sum = 0.0f;
-    for (int t = tid; t < P; t += 128) {
-        const float e = expf(sc[t] - mx);
-        sc[t] = e;
-        sum += e;
-    }
-    sum = block_sum(sum, red);  // includes __syncthreads: sc[] complete
-    const int g = tid >> 6, d = tid & 63;
-    float a0 = 0.0f, a1 = 0.0f;
-    int t = g;
-    for (; t + 2 < P; t += 4) {
-        const float *v0 = t < cond_len ? pvh + (size_t)t * FL_HD : ovb + (size_t)(t - cond_len) * FL_HD;
-        const float *v1 = (t + 2) < cond_len ? pvh + (size_t)(t + 2) * FL_HD : ovb + (size_t)(t + 2 - cond_len) * FL_HD;
-        a0 += sc[t] * v0[d];
-        a1 += sc[t + 2] * v1[d];
-    }
-    for (; t < P; t += 2) {
-        const float *v0 = t < cond_len ? pvh + (size_t)t * FL_HD : ovb + (size_t)(t - cond_len) * FL_HD;
-        a0 += sc[t] * v0[d];
-    }
-    so[g][d] = a0 + a1;
-    __syncthreads();
-    if (tid < FL_HD) {
-        const float o = (so[0][tid] + so[1][tid]) / sum;
-        const size_t oi = (size_t)b * FL_D + h * FL_HD + tid;
-        if (p.out_f32) p.out_f32[oi] = o;
-        if (p.out_h) {
-            const uint16_t hh = f2h16(o, true);
-            p.out_h[oi] = hh;
-            if (p.out_l) p.out_l[oi] = f2h16(o - h162f(hh, true), true);
-        }
-    }
-}
-
 // =====================================================================================
-// v2 of the decode attention (same arithmetic as k_attn_decode): one CTA = one head x G
+// Decode attention: one CTA = one head x G
 // utterances, 8 warps, WPU = 8/G warps per utterance.
 //   * the shared voice-prefix K / V tiles are staged ONCE per CTA in shared memory and reused
 //     by all G utterances (the prefix is utterance-independent, ptts_flowlm.c:1159-1166);
@@ -478,7 +388,8 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
     const int b = blockIdx.y * G + g;
     const bool live = b < B;
     const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
-    const int s = *p.step, pos = cond_len + s, P = pos + 1;
+    const int s = *p.step + (live ? p.own_base[b] : 0);   // own-cache row written by this step
+    const int pos = cond_len + s, P = pos + 1;
     float *okb = p.ok + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
     float *ovb = p.ov + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
     float *sc = scores + w * pcap;
@@ -634,6 +545,129 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
                 *(uint32_t *)(p.out_l + oi) = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
         }
+    }
+}
+
+// =====================================================================================
+// Batched prefill: all text tokens + BOS of all utterances (or all voice
+// frames) are packed into M rows and go through each layer as one GEMM pass; this kernel set is
+// the glue around those GEMMs.
+// =====================================================================================
+struct PrefillRows {
+    const int *row_b;      // [M] utterance of each packed row
+    const int *row_i;      // [M] own position of each packed row (0 .. tok_len[b])
+    const int *row_start;  // [n+1] first packed row of each utterance
+};
+
+// X[r,:] = embedding of token i of utterance b, or input_linear.bos_emb for the last row
+// (ptts_flowlm.c:1168-1181); ext (voice frames, ptts_flowlm.c:1159-1161) overrides. grid M, block 256.
+__global__ void __launch_bounds__(256) k_pf_gather(const PrefillRows pr, const int *tokens, int max_tok, const int *tok_len,
+                                                   const __nv_bfloat16 *embed, const float *bos_proj, const float *ext, float *X) {
+    const int r = blockIdx.x;
+    float *xr = X + (size_t)r * FL_D;
+    if (ext) {
+        for (int i = threadIdx.x; i < FL_D; i += 256) xr[i] = ext[(size_t)r * FL_D + i];
+        return;
+    }
+    const int b = pr.row_b[r], i = pr.row_i[r];
+    if (i < tok_len[b]) {
+        int id = tokens[(size_t)b * max_tok + i];
+        if (id < 0 || id > 4000) id = 0;  // ptts_flowlm.c:1170
+        for (int k = threadIdx.x; k < FL_D; k += 256) xr[k] = __bfloat162float(embed[(size_t)id * FL_D + k]);
+    } else {
+        for (int k = threadIdx.x; k < FL_D; k += 256) xr[k] = bos_proj[k];
+    }
+}
+
+// x[b,:] = X[last row of utterance b]. grid n, block 256.
+__global__ void __launch_bounds__(256) k_pf_last(const PrefillRows pr, const float *X, float *x) {
+    const int b = blockIdx.x, r = pr.row_start[b + 1] - 1;
+    for (int k = threadIdx.x; k < FL_D; k += 256) x[(size_t)b * FL_D + k] = X[(size_t)r * FL_D + k];
+}
+
+// Causal attention for the packed prefill rows of one (head, utterance): RoPE at pos = cond_len + i,
+// K/V appended to the own cache rows 0..nq-1, keys = shared voice prefix + own rows <= i
+// (ptts_flowlm.c:465-525 applied to every prefill position at once). grid (16, n), block 256.
+// smem: Kp[cond][65] Vp[cond][64] Ko[nq][65] Vo[nq][64] sc[8][cond+nq] q[8][64].
+struct PrefillAttnParams {
+    const float *qkv;          // [M, 3072]
+    const float *rope_cos, *rope_sin;
+    const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
+    float *ok, *ov;            // own cache of this layer [n][H][max_s][64]
+    int cond_len, pstride, max_s, max_q;
+    uint16_t *out_h, *out_l;   // [M,1024] bf16 hi/lo
+};
+__host__ __device__ inline size_t pf_attn_smem_bytes(int cond_len, int max_q) {
+    const size_t rows = (size_t)cond_len + max_q, kfl = (rows * AD_LD + 3) & ~(size_t)3, scf = (rows + 3) & ~(size_t)3;
+    return (kfl + rows * FL_HD + 8 * scf + 8 * FL_HD) * sizeof(float);
+}
+__global__ void __launch_bounds__(256) k_pf_attn(const PrefillAttnParams p, const PrefillRows pr) {
+    extern __shared__ __align__(16) float pf_smem[];
+    const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int r0 = pr.row_start[b], nq = pr.row_start[b + 1] - r0, cl = p.cond_len, P = cl + nq;
+    const size_t nrows = (size_t)cl + p.max_q, scf = (nrows + 3) & ~(size_t)3;
+    float *K = pf_smem;                                        // [rows][65]  prefix rows then own rows
+    float *V = K + ((nrows * AD_LD + 3) & ~(size_t)3);         // [rows][64], 16-byte aligned
+    float *sc = V + nrows * FL_HD;                             // [8][scf]
+    float *qs = sc + 8 * scf;                                  // [8][64]
+    float *okb = p.ok + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+    float *ovb = p.ov + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+    for (int idx = tid; idx < cl * 16; idx += 256) {
+        const int r = idx >> 4, c4 = (idx & 15) * 4;
+        const float4 kv = *(const float4 *)(p.pk + ((size_t)h * p.pstride + r) * FL_HD + c4);
+        float *d = K + r * AD_LD + c4;
+        d[0] = kv.x; d[1] = kv.y; d[2] = kv.z; d[3] = kv.w;
+        *(float4 *)(V + r * FL_HD + c4) = *(const float4 *)(p.pv + ((size_t)h * p.pstride + r) * FL_HD + c4);
+    }
+    for (int idx = tid; idx < nq * 32; idx += 256) {
+        const int i = idx >> 5, l = idx & 31, pos = cl + i;
+        const float *row = p.qkv + (size_t)(r0 + i) * 3 * FL_D + h * FL_HD;
+        const float c = p.rope_cos[pos * 32 + l], sn = p.rope_sin[pos * 32 + l];
+        const float2 kk = *(const float2 *)(row + FL_D + 2 * l), vv = *(const float2 *)(row + 2 * FL_D + 2 * l);
+        const float2 kr = make_float2(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
+        K[(cl + i) * AD_LD + 2 * l] = kr.x; K[(cl + i) * AD_LD + 2 * l + 1] = kr.y;
+        *(float2 *)(V + (cl + i) * FL_HD + 2 * l) = vv;
+        *(float2 *)(okb + (size_t)i * FL_HD + 2 * l) = kr;
+        *(float2 *)(ovb + (size_t)i * FL_HD + 2 * l) = vv;
+    }
+    __syncthreads();
+    float *scw = sc + w * scf, *qw = qs + w * FL_HD;
+    for (int i = w; i < nq; i += 8) {
+        const int pos = cl + i, nk = pos + 1;
+        const float *row = p.qkv + (size_t)(r0 + i) * 3 * FL_D + h * FL_HD;
+        const float c = p.rope_cos[pos * 32 + lane], sn = p.rope_sin[pos * 32 + lane];
+        const float2 qq = *(const float2 *)(row + 2 * lane);
+        __syncwarp();
+        qw[2 * lane] = (qq.x * c - qq.y * sn) * 0.125f;
+        qw[2 * lane + 1] = (qq.x * sn + qq.y * c) * 0.125f;
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int t = lane; t < nk; t += 32) {
+            const float *kr = K + t * AD_LD;
+            float a = 0.0f;
+#pragma unroll 16
+            for (int d = 0; d < FL_HD; d++) a += qw[d] * kr[d];
+            scw[t] = a;
+            mx = fmaxf(mx, a);
+        }
+        mx = warp_max(mx);
+        float sum = 0.0f;
+        for (int t = lane; t < nk; t += 32) { const float e = expf(scw[t] - mx); scw[t] = e; sum += e; }
+        sum = warp_sum(sum);
+        __syncwarp();
+        float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll 4
+        for (int t = 0; t < nk; t++) {
+            const float pw = scw[t];
+            const float2 v = *(const float2 *)(V + t * FL_HD + 2 * lane);
+            acc.x += pw * v.x; acc.y += pw * v.y;
+        }
+        acc.x /= sum; acc.y /= sum;
+        const size_t oi = (size_t)(r0 + i) * FL_D + h * FL_HD + 2 * lane;
+        const uint16_t h0 = f2h16(acc.x, true), h1 = f2h16(acc.y, true);
+        *(uint32_t *)(p.out_h + oi) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        const uint16_t l0 = f2h16(acc.x - h162f(h0, true), true), l1 = f2h16(acc.y - h162f(h1, true), true);
+        *(uint32_t *)(p.out_l + oi) = (uint32_t)l0 | ((uint32_t)l1 << 16);
     }
 }
 

@@ -75,7 +75,8 @@ extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b
         ptts_b200_destroy(e);
         return -1;
     }
-    if (cudaFuncSetAttribute(k_attn_decode2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_pf_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(k_attn_decode2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
@@ -112,13 +113,12 @@ static uint64_t gkey(int mode, int B, int lsd, int precise) {
     return ((uint64_t)mode << 48) | ((uint64_t)B << 24) | ((uint64_t)lsd << 8) | (uint64_t)precise;
 }
 
-// mode 0: voice prefill (B = 1, GEMV), 1: batch-1 GEMV decode, 2: batched tcgen05 decode
+// mode 1: batch-1 GEMV decode iteration, 2: batched tcgen05 decode iteration
 static int step_launch(Engine *e, int mode, int B, int lsd, int precise) {
     float *cbias = nullptr;
     if (ensure_cbias(e, lsd, &cbias) != 0) return -1;
-    FlowState st = make_state(e, B, lsd, mode == 0 ? e->d_cond : nullptr);
-    if (mode == 0) return flow_step_gemv(e, st, true, cbias);
-    if (mode == 1) return flow_step_gemv(e, st, false, cbias);
+    FlowState st = make_state(e, B, lsd);
+    if (mode == 1) return flow_step_gemv(e, st, cbias);
     const uint64_t key = gkey(mode, B, lsd, precise);
     auto &gm = g_gemms[e];
     auto it = gm.find(key);
@@ -200,15 +200,20 @@ static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nstep
 }
 
 // ---------------------------------------------------------------- voice prefix
+// The voice frames come first and attention is causal, so their K/V are utterance-independent
+// (ptts_flowlm.c:1159-1166): computed once per voice in one batched prefill pass and cached.
 static int set_voice(Engine *e, const float *cond, int cond_len) {
     if (cond_len == e->voice_len && (cond_len == 0 || memcmp(e->voice_host.data(), cond, (size_t)cond_len * FL_D * 4) == 0)) return 0;
     e->voice_len = -1;
     if (cond_len > 0) {
+        if (prefill_ensure(e, cond_len, 1) != 0) return -1;
+        std::vector<int> rb(cond_len, 0), ri(cond_len), rs = {0, cond_len};
+        for (int i = 0; i < cond_len; i++) ri[i] = i;
         PTTS_CUDA_OK(cudaMemcpyAsync(e->d_cond, cond, (size_t)cond_len * FL_D * 4, cudaMemcpyHostToDevice, e->st));
-        FlowCtrl c = {0, 0, 0, 1, 0, 0.0f};
-        PTTS_CUDA_OK(cudaMemcpyAsync(e->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, e->st));
-        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));   // &c is a stack temporary
-        if (run_steps(e, 0, 1, 1, 1, cond_len, false) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_b, rb.data(), cond_len * 4, cudaMemcpyHostToDevice, e->st));
+        PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_i, ri.data(), cond_len * 4, cudaMemcpyHostToDevice, e->st));
+        PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_start, rs.data(), 2 * 4, cudaMemcpyHostToDevice, e->st));
+        if (flow_prefill(e, 1, cond_len, cond_len, 0, true) != 0) return -1;
         PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     }
     e->voice_host.assign(cond, cond + (size_t)cond_len * FL_D);
@@ -223,28 +228,38 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     PTTS_CHECK(cond_len >= 0 && (cond_len == 0 || cond_prefix), "batch_stage: cond_prefix missing");
     PTTS_CHECK(gp->lsd_steps >= 1 && gp->lsd_steps <= 64, "batch_stage: lsd_steps %d out of range", gp->lsd_steps);
     PTTS_CUDA_OK(cudaSetDevice(e->device));
-    int max_tok = 0, cap_f = 0, steps = 0;
+    int max_tok = 0, cap_f = 0, rows = 0;
     for (int i = 0; i < n; i++) {
         const int tl = token_offsets[i + 1] - token_offsets[i];
         PTTS_CHECK(tl > 0, "batch_stage: utterance %d has no tokens", i);
         PTTS_CHECK(max_frames[i] >= 1, "batch_stage: utterance %d has max_frames < 1", i);
         max_tok = std::max(max_tok, tl);
         cap_f = std::max(cap_f, max_frames[i]);
-        steps = std::max(steps, tl + max_frames[i]);
+        rows += tl + 1;
     }
+    const int steps = cap_f;                    // decode iterations (frames); prompts are prefilled in one pass
+    const int own_rows = max_tok + 1 + cap_f;   // own-cache rows per utterance
     const int B = n == 1 ? 1 : (n + 15) / 16 * 16;
     PTTS_CHECK(B <= 256, "batch_stage: at most 256 utterances per call (got %d); shard larger jobs on the host", n);
-    if (flow_ensure_capacity(e, B, steps, max_tok, cap_f, std::max(cond_len, 1)) != 0) return -1;
-    if (ensure_rope(e, cond_len + steps + 1) != 0) return -1;
+    if (flow_ensure_capacity(e, B, own_rows, max_tok, cap_f, std::max(cond_len, 1)) != 0) return -1;
+    if (prefill_ensure(e, std::max(rows, cond_len), n) != 0) return -1;
+    if (ensure_rope(e, cond_len + own_rows + 1) != 0) return -1;
     if (set_voice(e, cond_prefix, cond_len) != 0) return -1;
     // host staging
     const int capTok = e->capTok, capF = e->capF;
     std::vector<int> h_tok((size_t)B * capTok, 0), h_tl(B, 1), h_mf(B, 0), h_ea(B, 0), h_done(B, 1), h_es(B, -1), h_used(B, 0);
     std::vector<float> h_noise((size_t)n * cap_f * FL_LAT);
-    for (int i = 0; i < n; i++) {
+    std::vector<int> h_rb(rows), h_ri(rows), h_rs(n + 1, 0), h_ob(B, 0);
+    double mean_ob = 0.0;
+    for (int i = 0, r = 0; i < n; i++) {
         const int tl = token_offsets[i + 1] - token_offsets[i];
         memcpy(&h_tok[(size_t)i * capTok], tokens_flat + token_offsets[i], sizeof(int) * tl);
         h_tl[i] = tl; h_mf[i] = max_frames[i]; h_done[i] = 0;
+        h_rs[i] = r;
+        for (int k = 0; k <= tl; k++, r++) { h_rb[r] = i; h_ri[r] = k; }
+        h_rs[i + 1] = r;
+        h_ob[i] = tl + 1;
+        mean_ob += (double)(tl + 1) / n;
         int ea = eos_after ? eos_after[i] : gp->eos_after;
         h_ea[i] = ea < 0 ? 0 : ea;
         host_noise(seeds[i], gp->temp, gp->noise_clamp, max_frames[i], &h_noise[(size_t)i * cap_f * FL_LAT]);
@@ -256,6 +271,10 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     cudaStream_t st = e->st;
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_tokens, h_tok.data(), h_tok.size() * 4, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_tok_len, h_tl.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_own_base, h_ob.data(), B * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_b, h_rb.data(), rows * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_i, h_ri.data(), rows * 4, cudaMemcpyHostToDevice, st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_start, h_rs.data(), (n + 1) * 4, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_max_frames, h_mf.data(), B * 4, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_eos_after, h_ea.data(), B * 4, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_done, h_done.data(), B * 4, cudaMemcpyHostToDevice, st));
@@ -270,6 +289,7 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     PTTS_CUDA_OK(cudaMemcpyAsync(e->ctrl, &c, sizeof c, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaStreamSynchronize(st));   // host vectors go out of scope
     e->st_n = n; e->curB = B; e->st_steps = steps; e->st_capF = cap_f; e->st_lsd = gp->lsd_steps;
+    e->st_rows = rows; e->st_maxq = max_tok + 1; e->st_cond = cond_len; e->prof.mean_own_base = mean_ob;
     e->st_precise = gp->precise ? 1 : 0;
     e->st_maxf.assign(max_frames, max_frames + n);
     e->st_eos = gp->eos_enabled;
@@ -299,6 +319,9 @@ static int run_impl(Engine *e, int with_mimi) {
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_used, h_used.data(), B * 4, cudaMemcpyHostToDevice, e->st));
     PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     const int mode = B == 1 ? 1 : 2;
+    // prompts (text tokens + BOS) of all utterances in one batched pass; x[b] = BOS hidden state
+    if (flow_prefill(e, n, e->st_rows, e->st_maxq, e->st_cond, false) != 0) return -1;
+    if (mode == 2) PTTS_CUDA_OK(cudaMemsetAsync(e->partB, 0, (size_t)4 * e->capB * FL_D * 4, e->st));
     if (run_steps(e, mode, B, e->st_lsd, e->st_precise, e->st_steps, e->st_eos != 0) != 0) return -1;
     if (with_mimi) {
         const int F = e->st_capF;
