@@ -56,6 +56,10 @@ struct GemmParams {
     int out_bf16;            // encoding of out_h / out_l
     int act;
     int fast_act;            // 1: hardware exp/tanh approximations (16-bit outputs only)
+    // fused Mimi QKV epilogue (ptts_mimi.c:329-341): columns are [q|k|v] x 8 heads x 64; q,k get RoPE at
+    // position m (row within the batch item), q is pre-scaled by 1/8; fp16 head-major [B][H][T][64] outputs
+    uint16_t *rope_q, *rope_k, *rope_v;
+    const float *rope_cos, *rope_sin;   // [T][32]
     long long *trace;        // optional [16] clock64 stamps written by CTA 0 (kernel timeline debugging)
 };
 
@@ -244,6 +248,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             const float4 *sp = (const float4 *)(scale + nb);
 #pragma unroll
                             for (int j = 0; j < 4; j++) { const float4 ss = sp[j]; v[4 * j] *= ss.x; v[4 * j + 1] *= ss.y; v[4 * j + 2] *= ss.z; v[4 * j + 3] *= ss.w; }
+                        }
+                        if (p.rope_q) {
+                            const int which = nb >> 9, within = nb & 511, head = within >> 6, d0 = within & 63;
+                            uint32_t hw[8];
+                            if (which < 2) {
+                                float cs[8], sn[8];
+                                ld_global_v8(p.rope_cos + (size_t)m * 32 + (d0 >> 1), cs);
+                                ld_global_v8(p.rope_sin + (size_t)m * 32 + (d0 >> 1), sn);
+                                const float sc = which == 0 ? 0.125f : 1.0f;   // 1/sqrt(64) folded into q
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    const float a0 = v[2 * j], a1 = v[2 * j + 1];
+                                    const __half2 h2 = __floats2half2_rn((a0 * cs[j] - a1 * sn[j]) * sc, (a0 * sn[j] + a1 * cs[j]) * sc);
+                                    hw[j] = *(const uint32_t *)&h2;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) { const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]); hw[j] = *(const uint32_t *)&h2; }
+                            }
+                            uint16_t *dst = (which == 0 ? p.rope_q : which == 1 ? p.rope_k : p.rope_v) +
+                                            (((size_t)t.batch * 8 + head) * p.a_rows + m) * 64 + d0;
+                            st_global_v8(dst, hw);
                         }
                         if (rs) {
                             float t0[8], t1[8];

@@ -714,8 +714,8 @@ __global__ void __launch_bounds__(512) k_time_embed(const float *l0w, const floa
 // =====================================================================================
 __global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32], item stride lat_stride*/, size_t lat_stride, int F,
                                                     const float *emb_std, const float *emb_mean,
-                                                    int apply_scale, const float *quant_w /*[512,32]*/, const float *ups /*[512,32]*/,
-                                                    float *x /*[B,16F,512]*/) {
+                                                    int apply_scale, const float *quant_wt /*[32,512] transposed*/,
+                                                    const float *ups_t /*[32,512] transposed*/, float *x /*[B,16F,512]*/) {
     __shared__ float l0[32], l1[32];
     const int t = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
     if (c < 32) {
@@ -734,16 +734,47 @@ __global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32],
     float q0 = 0.0f, q1 = 0.0f;
 #pragma unroll
     for (int i = 0; i < 32; i++) {
-        const float w = quant_w[c * 32 + i];
+        const float w = quant_wt[i * MI_D + c];
         q0 += w * l0[i];
         q1 += w * l1[i];
     }
     float *xo = x + ((size_t)b * F + t) * 16 * MI_D + c;
 #pragma unroll
     for (int r = 0; r < 16; r++) {
-        float v = ups[c * 32 + r] * q0;
-        if (t > 0) v += ups[c * 32 + 16 + r] * q1;
+        float v = ups_t[r * MI_D + c] * q0;
+        if (t > 0) v += ups_t[(16 + r) * MI_D + c] * q1;
         xo[(size_t)r * MI_D] = v;
+    }
+}
+
+// Warp-per-row LayerNorm for 512-wide rows (Mimi transformer norms, ptts_mimi.c:184-206): two-pass in
+// registers, shuffle reductions only, fp16 output. grid ceil(R/8), block 256.
+__global__ void __launch_bounds__(256) k_ln512_f16(const float *x, size_t R, const float *w, const float *b, float eps, __half *out) {
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const int lane = threadIdx.x & 31;
+    const float4 *xr = (const float4 *)(x + row * MI_D);
+    float4 v[4];
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { v[j] = xr[lane + 32 * j]; s += v[j].x + v[j].y + v[j].z + v[j].w; }
+    const float mean = warp_sum(s) / (float)MI_D;
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const float a = v[j].x - mean, c = v[j].y - mean, d = v[j].z - mean, e = v[j].w - mean;
+        q += a * a + c * c + d * d + e * e;
+    }
+    const float inv = 1.0f / sqrtf(warp_sum(q) / (float)MI_D + eps);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = (lane + 32 * j) * 4;
+        const float4 ww = *(const float4 *)(w + i), bb = *(const float4 *)(b + i);
+        const __half2 h0 = __floats2half2_rn((v[j].x - mean) * inv * ww.x + bb.x, (v[j].y - mean) * inv * ww.y + bb.y);
+        const __half2 h1 = __floats2half2_rn((v[j].z - mean) * inv * ww.z + bb.z, (v[j].w - mean) * inv * ww.w + bb.w);
+        uint2 pk;
+        pk.x = *(const uint32_t *)&h0; pk.y = *(const uint32_t *)&h1;
+        *(uint2 *)(out + row * MI_D + i) = pk;
     }
 }
 
@@ -771,121 +802,153 @@ __global__ void __launch_bounds__(256) k_mimi_rope_heads(const float *qkv, int T
 }
 
 // Mimi banded causal attention: key tk visible to query tq iff 0 <= tq - tk < 250
-// (ptts_mimi.c:264-299). One CTA = 32 consecutive queries of one (batch, head); its <= 281 keys
-// and values are staged once in shared memory (fp16, padded rows); each warp owns 4 queries and
-// shares every K / V shared-memory load between them. fp32 math.
-// grid (ceil(T/32), H, B), block 256.
-constexpr int WA_Q = 32, WA_KEYS = WA_Q + MI_CTX - 1, WA_LD = 66;  // 281 keys, row stride 66 halves
-__global__ void __launch_bounds__(256) k_mimi_win_attn(const __half *q, const __half *k, const __half *v, int T,
+// (ptts_mimi.c:264-299; the reference is an O(T^2) masked loop, this is O(T*250)).
+// Flash-style: one CTA = 64 consecutive queries of one (batch, head), 4 warps x 16 query rows;
+// key/value blocks of 64 rows are staged in shared memory, S = Q.K^T and O += P.V run on
+// mma.sync.m16n8k16 (fp16 in, fp32 accumulate) with an online softmax in registers. The attention
+// is 3 % of Mimi's FLOPs (16.4 of 541.5 MFLOP per frame), so the warp-level MMA path is enough to
+// take it off the profile; the GEMM-shaped 97 % run on tcgen05.
+// q is pre-scaled by 1/8 and q, k are RoPE-rotated by k_mimi_rope_heads. grid (ceil(T/64), H, B), block 128.
+constexpr int FA_LD = 72;   // padded row stride in halves: conflict-free 32-bit fragment loads
+__device__ __forceinline__ void mma_f16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *(const uint32_t *)&h;
+}
+__global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __half *k, const __half *v, int T,
                                                        __half *out /*[B*T, 512]*/) {
-    extern __shared__ __align__(16) uint8_t wa_smem[];
-    __half *sk = (__half *)wa_smem;                 // [WA_KEYS][WA_LD]
-    __half *sv = sk + WA_KEYS * WA_LD;              // [WA_KEYS][WA_LD]
-    float *sqf = (float *)(sv + WA_KEYS * WA_LD);   // [32][64] queries fp32
-    float *sp = sqf + WA_Q * 64;                    // [8 warps][4][WA_KEYS + 7] probabilities
-    constexpr int SPLD = WA_KEYS + 7;
-    const int q0 = blockIdx.x * WA_Q, h = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    __shared__ __align__(16) __half sQ[64 * FA_LD], sK[64 * FA_LD], sV[64 * FA_LD];
+    const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const size_t base = ((size_t)b * MI_H + h) * T;
-    const int klo = max(0, q0 - (MI_CTX - 1));
-    const int khi = min(T - 1, q0 + WA_Q - 1);
-    const int nk = khi - klo + 1;
-    for (int idx = tid; idx < nk * 32; idx += 256) {
-        const int r = idx >> 5, c = idx & 31;
-        *(__half2 *)(sk + r * WA_LD + 2 * c) = *(const __half2 *)(k + (base + klo + r) * 64 + 2 * c);
-        *(__half2 *)(sv + r * WA_LD + 2 * c) = *(const __half2 *)(v + (base + klo + r) * 64 + 2 * c);
-    }
-    for (int idx = tid; idx < WA_Q * 64; idx += 256) {
-        const int r = idx >> 6, c = idx & 63;
-        sqf[idx] = (q0 + r < T) ? __half2float(q[(base + q0 + r) * 64 + c]) : 0.0f;
+    for (int idx = tid; idx < 512; idx += 128) {
+        const int r = idx >> 3, c = (idx & 7) * 8;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (q0 + r < T) val = *(const uint4 *)(q + (base + q0 + r) * 64 + c);
+        *(uint4 *)(sQ + r * FA_LD + c) = val;
     }
     __syncthreads();
-    constexpr int NCH = (WA_KEYS + 31) / 32;  // 9 key chunks of 32
-    float s[4][NCH];
-    const float *qw = sqf + (w * 4) * 64;
+    uint32_t qa[4][4];
+    {
+        const __half *r0 = sQ + (warp * 16 + g) * FA_LD, *r1 = r0 + 8 * FA_LD;
 #pragma unroll
-    for (int c = 0; c < NCH; c++) {
-        const int kr = c * 32 + lane;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
-        if (kr < nk) {
-            const __half2 *kp = (const __half2 *)(sk + kr * WA_LD);
-#pragma unroll 8
-            for (int d2 = 0; d2 < 32; d2++) {
-                const float2 kv = __half22float2(kp[d2]);
-                const float2 x0 = *(const float2 *)(qw + 2 * d2);
-                const float2 x1 = *(const float2 *)(qw + 64 + 2 * d2);
-                const float2 x2 = *(const float2 *)(qw + 128 + 2 * d2);
-                const float2 x3 = *(const float2 *)(qw + 192 + 2 * d2);
-                a0 += kv.x * x0.x + kv.y * x0.y;
-                a1 += kv.x * x1.x + kv.y * x1.y;
-                a2 += kv.x * x2.x + kv.y * x2.y;
-                a3 += kv.x * x3.x + kv.y * x3.y;
+        for (int ks = 0; ks < 4; ks++) {
+            qa[ks][0] = *(const uint32_t *)(r0 + ks * 16 + 2 * t);
+            qa[ks][1] = *(const uint32_t *)(r1 + ks * 16 + 2 * t);
+            qa[ks][2] = *(const uint32_t *)(r0 + ks * 16 + 8 + 2 * t);
+            qa[ks][3] = *(const uint32_t *)(r1 + ks * 16 + 8 + 2 * t);
+        }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    const int tq0 = q0 + warp * 16 + g, tq1 = tq0 + 8;
+    const int kb_start = max(0, q0 - (MI_CTX - 1)) & ~63;
+    for (int kb = kb_start; kb <= q0 && kb < T; kb += 64) {
+        __syncthreads();   // all warps are done with the previous K/V block
+        for (int idx = tid; idx < 512; idx += 128) {
+            const int r = idx >> 3, c = (idx & 7) * 8;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+            if (kb + r < T) {
+                kv = *(const uint4 *)(k + (base + kb + r) * 64 + c);
+                vv = *(const uint4 *)(v + (base + kb + r) * 64 + c);
+            }
+            *(uint4 *)(sK + r * FA_LD + c) = kv;
+            *(uint4 *)(sV + r * FA_LD + c) = vv;
+        }
+        __syncthreads();
+        float sc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.0f;
+            const __half *kr = sK + (nt * 8 + g) * FA_LD + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++)
+                mma_f16_16816(sc[nt], qa[ks], *(const uint32_t *)(kr + ks * 16), *(const uint32_t *)(kr + ks * 16 + 8));
+        }
+        float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int key = kb + nt * 8 + 2 * t + (e & 1);
+                const int tq = e < 2 ? tq0 : tq1;
+                const bool ok = key <= tq && tq - key < MI_CTX;
+                if (!ok) sc[nt][e] = -INFINITY;
+            }
+            bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+            bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+        // a row whose keys so far are all masked keeps m = -inf: scale 1, p = 0 (no NaN from inf - inf)
+        const float f0 = mn0 == -INFINITY ? 1.0f : __expf(m0 - mn0), f1 = mn1 == -INFINITY ? 1.0f : __expf(m1 - mn1);
+        const float sub0 = mn0 == -INFINITY ? 0.0f : mn0, sub1 = mn1 == -INFINITY ? 0.0f : mn1;
+        float rs0 = 0.0f, rs1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            sc[nt][0] = __expf(sc[nt][0] - sub0); sc[nt][1] = __expf(sc[nt][1] - sub0);
+            sc[nt][2] = __expf(sc[nt][2] - sub1); sc[nt][3] = __expf(sc[nt][3] - sub1);
+            rs0 += sc[nt][0] + sc[nt][1];
+            rs1 += sc[nt][2] + sc[nt][3];
+            o[nt][0] *= f0; o[nt][1] *= f0; o[nt][2] *= f1; o[nt][3] *= f1;
+        }
+        l0 = l0 * f0 + rs0; l1 = l1 * f1 + rs1;
+        m0 = mn0; m1 = mn1;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            uint32_t pa[4];
+            pa[0] = pack_h2(sc[2 * ks][0], sc[2 * ks][1]);
+            pa[1] = pack_h2(sc[2 * ks][2], sc[2 * ks][3]);
+            pa[2] = pack_h2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
+            pa[3] = pack_h2(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
+            const __half *v0 = sV + (ks * 16 + 2 * t) * FA_LD + g, *v1 = v0 + 8 * FA_LD;
+#pragma unroll
+            for (int nd = 0; nd < 8; nd++) {
+                const uint32_t b0 = (uint32_t)__half_as_ushort(v0[nd * 8]) | ((uint32_t)__half_as_ushort(v0[FA_LD + nd * 8]) << 16);
+                const uint32_t b1 = (uint32_t)__half_as_ushort(v1[nd * 8]) | ((uint32_t)__half_as_ushort(v1[FA_LD + nd * 8]) << 16);
+                mma_f16_16816(o[nd], pa, b0, b1);
             }
         }
-        const int tk = klo + kr;
-        const int tq = q0 + w * 4;
-        s[0][c] = (kr < nk && tk <= tq && tq - tk < MI_CTX) ? a0 : -INFINITY;
-        s[1][c] = (kr < nk && tk <= tq + 1 && tq + 1 - tk < MI_CTX) ? a1 : -INFINITY;
-        s[2][c] = (kr < nk && tk <= tq + 2 && tq + 2 - tk < MI_CTX) ? a2 : -INFINITY;
-        s[3][c] = (kr < nk && tk <= tq + 3 && tq + 3 - tk < MI_CTX) ? a3 : -INFINITY;
     }
-    float inv[4];
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = l0 > 0.0f ? 1.0f / l0 : 0.0f, i1 = l1 > 0.0f ? 1.0f / l1 : 0.0f;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) mx = fmaxf(mx, s[j][c]);
-        mx = warp_max(mx);
-        float sum = 0.0f;
-        float *pj = sp + (w * 4 + j) * SPLD;
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const float e = (s[j][c] == -INFINITY) ? 0.0f : expf(s[j][c] - mx);
-            sum += e;
-            if (c * 32 + lane < SPLD) pj[c * 32 + lane] = e;
-        }
-        sum = warp_sum(sum);
-        inv[j] = sum > 0.0f ? 1.0f / sum : 0.0f;
-    }
-    __syncwarp();
-    float o[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-    const float *p0 = sp + (w * 4) * SPLD;
-    for (int kr = 0; kr < nk; kr++) {
-        const float2 vv = __half22float2(*(const __half2 *)(sv + kr * WA_LD + 2 * lane));
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float pw = p0[j * SPLD + kr];
-            o[j][0] += pw * vv.x;
-            o[j][1] += pw * vv.y;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const int tq = q0 + w * 4 + j;
-        if (tq < T) {
-            __half *dst = out + ((size_t)b * T + tq) * MI_D + h * 64 + 2 * lane;
-            *(__half2 *)dst = __floats2half2_rn(o[j][0] * inv[j], o[j][1] * inv[j]);
-        }
+    for (int nd = 0; nd < 8; nd++) {
+        if (tq0 < T) *(__half2 *)(out + ((size_t)b * T + tq0) * MI_D + h * 64 + nd * 8 + 2 * t) = __floats2half2_rn(o[nd][0] * i0, o[nd][1] * i0);
+        if (tq1 < T) *(__half2 *)(out + ((size_t)b * T + tq1) * MI_D + h * 64 + nd * 8 + 2 * t) = __floats2half2_rn(o[nd][2] * i1, o[nd][3] * i1);
     }
 }
-constexpr int WA_SMEM = 2 * WA_KEYS * WA_LD * 2 + WA_Q * 64 * 4 + 32 * (WA_KEYS + 7) * 4;
 
 // Final Conv1d 64 -> 1, k = 3 on ELU'd fp16 activations [B, T, 64] -> pcm [B, T] fp32
-// (ptts_mimi.c:723-726 with ptts_kernels.c:128-153). Thread per sample.
+// (ptts_mimi.c:723-726 with ptts_kernels.c:128-153). 256 samples per block; the 258 input rows are
+// staged once in shared memory (coalesced), then one thread per sample.
 __global__ void __launch_bounds__(256) k_dec_out(const __half *e, int T, const float *w /*[64*3] as [c][kk]*/, const float *bias,
                                                  float *pcm) {
     __shared__ float sw[3][64];
+    __shared__ __align__(16) __half se[258 * FA_LD];
     if (threadIdx.x < 192) sw[threadIdx.x % 3][threadIdx.x / 3] = w[threadIdx.x];
+    const int b = blockIdx.y, t0 = blockIdx.x * 256;
+    for (int idx = threadIdx.x; idx < 258 * 8; idx += 256) {
+        const int r = idx >> 3, c = (idx & 7) * 8, tt = t0 - 2 + r;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (tt >= 0 && tt < T) val = *(const uint4 *)(e + ((size_t)b * T + tt) * 64 + c);
+        *(uint4 *)(se + r * FA_LD + c) = val;
+    }
     __syncthreads();
-    const int b = blockIdx.y;
-    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int t = t0 + threadIdx.x;
     if (t >= T) return;
     float a = bias[0];
 #pragma unroll
     for (int kk = 0; kk < 3; kk++) {
-        const int tt = t - 2 + kk;
-        if (tt < 0) continue;
-        const uint4 *row = (const uint4 *)(e + ((size_t)b * T + tt) * 64);
+        const uint4 *row = (const uint4 *)(se + (threadIdx.x + kk) * FA_LD);
 #pragma unroll
         for (int c8 = 0; c8 < 8; c8++) {
             const uint4 u = row[c8];

@@ -54,11 +54,16 @@ static int mimi_load_convtr(Engine *e, const HostWeights &hw, const char *name, 
 static int mimi_load_weights(Engine *e, const HostWeights &hw) {
     std::vector<float> v;
     char nm[256];
-    if (hw.get("quantizer.output_proj.weight", MIMI_PFX, MI_D * 32, v) != 0 || e->up_f32(&e->quant_w, v) != 0) return -1;
+    auto transpose_512x32 = [](const std::vector<float> &in) {   // [512,32] -> [32,512]: coalesced per-channel reads
+        std::vector<float> o(in.size());
+        for (int c = 0; c < MI_D; c++) for (int i = 0; i < 32; i++) o[(size_t)i * MI_D + c] = in[(size_t)c * 32 + i];
+        return o;
+    };
+    if (hw.get("quantizer.output_proj.weight", MIMI_PFX, MI_D * 32, v) != 0 || e->up_f32(&e->quant_w, transpose_512x32(v)) != 0) return -1;
     int r = hw.get("upsample.convtr.weight", MIMI_PFX, MI_D * 32, v, true);   // ptts_mimi.c:385-388
     if (r < 0) return -1;
     if (r == 1 && hw.get("upsample.convtr.convtr.weight", MIMI_PFX, MI_D * 32, v) != 0) return -1;
-    if (e->up_f32(&e->ups_w, v) != 0) return -1;
+    if (e->up_f32(&e->ups_w, transpose_512x32(v)) != 0) return -1;
     for (int l = 0; l < MI_L; l++) {
 #define MW(field, suffix, ne, up) snprintf(nm, sizeof nm, "decoder_transformer.transformer.layers.%d." suffix, l); \
         if (hw.get(nm, MIMI_PFX, ne, v) != 0 || e->up(&e->ML[l].field, v) != 0) return -1
@@ -85,13 +90,12 @@ static int mimi_load_weights(Engine *e, const HostWeights &hw) {
     if (mimi_load_conv(e, hw, "decoder.model.9.block.3.conv", e->res2[2], 32, 64, 1, 64, 64) != 0) return -1;
     if (hw.get("decoder.model.11.conv.weight", MIMI_PFX, 64 * 3, v) != 0 || e->up_f32(&e->dec_out_w, v) != 0) return -1;
     if (hw.get("decoder.model.11.conv.bias", MIMI_PFX, 1, v) != 0 || e->up_f32(&e->dec_out_b, v) != 0) return -1;
-    PTTS_CUDA_OK(cudaFuncSetAttribute(k_mimi_win_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, WA_SMEM));
     return 0;
 }
 
 // Workspace bytes per latent frame (16 tokens, 96 / 480 / 1920 rows in the three SEANet stages).
 static size_t mimi_ws_per_frame() {
-    const size_t tok = 16 * (size_t)(MI_D * 4 + MI_D * 2 + 3 * MI_D * 4 + 3 * MI_D * 2 + MI_D * 2 + MI_FF * 2 + MI_D * 2);
+    const size_t tok = 16 * (size_t)(MI_D * 4 + MI_D * 2 + 3 * MI_D * 2 + MI_D * 2 + MI_FF * 2 + MI_D * 2);
     const size_t s0 = 96 * (size_t)(256 * 4 + 256 * 2 + 128 * 2 + 256 * 2);
     const size_t s1 = 480 * (size_t)(128 * 4 + 128 * 2 + 64 * 2 + 128 * 2);
     const size_t s2 = 1920 * (size_t)(64 * 4 + 64 * 2 + 64 * 2 + 64 * 2);
@@ -148,7 +152,6 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
     Bump ws{(uint8_t *)e->mimi_ws};
     float *x = ws.take<float>(R * MI_D);
     __half *xn = ws.take<__half>(R * MI_D);
-    float *qkv = ws.take<float>(R * 3 * MI_D);
     __half *q = ws.take<__half>(R * MI_D), *k = ws.take<__half>(R * MI_D), *v = ws.take<__half>(R * MI_D);
     __half *att = ws.take<__half>(R * MI_D);
     __half *hb = ws.take<__half>(R * MI_FF);
@@ -159,17 +162,15 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         if (launch_check("k_mimi_front") != 0) return -1;
     }
     for (int l = 0; l < MI_L; l++) {
-        RowNormParams r = {};
-        r.x = x; r.D = MI_D; r.w = e->ML[l].n1w; r.b = e->ML[l].n1b; r.eps = 1e-5f; r.do_norm = 1; r.out_h = (uint16_t *)xn;
-        if (rownorm(e, (int)R, r, KC_MIMI_MISC) != 0) return -1;
-        GemmParams g = {};
-        g.out_f32 = qkv; g.ldo = 3 * MI_D;
-        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
         {
             LaunchScope ls(e, KC_MIMI_MISC);
-            k_mimi_rope_heads<<<(unsigned)R, 256, 0, e->st>>>(qkv, T, e->rope_cos, e->rope_sin, q, k, v);
-            if (launch_check("k_mimi_rope_heads") != 0) return -1;
+            k_ln512_f16<<<(unsigned)((R + 7) / 8), 256, 0, e->st>>>(x, R, e->ML[l].n1w, e->ML[l].n1b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
         }
+        GemmParams g = {};
+        g.rope_q = (uint16_t *)q; g.rope_k = (uint16_t *)k; g.rope_v = (uint16_t *)v;   // RoPE + head split fused in the epilogue
+        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin;
+        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
         {
             if (e->prof.on) {   // banded attention: <= 250 keys per query, QK^T and PV
                 double pairs = 0.0;
@@ -178,14 +179,16 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
                 e->prof.bytes[KC_MIMI_ATTN] += (double)R * MI_D * 2.0 * 4.0;
             }
             LaunchScope ls(e, KC_MIMI_ATTN);
-            k_mimi_win_attn<<<dim3((T + WA_Q - 1) / WA_Q, MI_H, Bc), 256, WA_SMEM, e->st>>>(q, k, v, T, att);
+            k_mimi_win_attn<<<dim3((T + 63) / 64, MI_H, Bc), 128, 0, e->st>>>(q, k, v, T, att);
             if (launch_check("k_mimi_win_attn") != 0) return -1;
         }
         g = {}; g.scale = e->ML[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls1 * out_proj(att)
         if (mimi_gemm(e, att, Bc, T, MI_D, e->ML[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
-        r = {};
-        r.x = x; r.D = MI_D; r.w = e->ML[l].n2w; r.b = e->ML[l].n2b; r.eps = 1e-5f; r.do_norm = 1; r.out_h = (uint16_t *)xn;
-        if (rownorm(e, (int)R, r, KC_MIMI_MISC) != 0) return -1;
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            k_ln512_f16<<<(unsigned)((R + 7) / 8), 256, 0, e->st>>>(x, R, e->ML[l].n2w, e->ML[l].n2b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
+        }
         g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
         if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].l1, MI_FF, 1, 0, 0, 256, g) != 0) return -1;
         g = {}; g.scale = e->ML[l].ls2; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls2 * linear2(h)
