@@ -44,6 +44,15 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every kernel of the engine is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (engine.cuh launch_k): the next kernel's CTAs may become resident while this one is still
+// running. pdl_wait() blocks until the preceding grid has completed and its writes are visible;
+// it must precede the first access to any buffer another kernel writes. pdl_trigger() lets the
+// following grid start being scheduled. Both are no-ops for a plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 enum Act : int { ACT_NONE = 0, ACT_GELU_ERF = 1, ACT_GELU_TANH = 2, ACT_SILU = 3, ACT_ELU = 4 };
 
 __device__ __forceinline__ float act_apply(int act, float x) {

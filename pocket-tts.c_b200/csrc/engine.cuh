@@ -1,9 +1,11 @@
 // engine.cuh - engine object: device weights, workspaces, launch bookkeeping, GEMM op builder.
 #pragma once
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <string>
 #include <unordered_map>
+#include <utility>
 #include <vector>
 
 #include "../../include/ptts_b200.h"
@@ -78,6 +80,28 @@ int make_tmap(CUtensorMap *out, const void *base, bool bf16, int k, int rows, in
     return 0;
 }
 
+// ---------------------------------------------------------------- kernel launch (programmatic dependent launch)
+// All kernels go out with the programmatic-stream-serialization attribute, so a kernel's launch
+// latency, prologue (barrier init, TMEM allocation, tensor-map prefetch) and - for the GEMMs - the
+// first weight tiles overlap the tail of its predecessor; each kernel orders itself with pdl_wait()
+// (common.cuh). Stream capture turns these into programmatic edges of the step graph.
+// PTTS_B200_NO_PDL=1 falls back to plain serialized launches (A/B measurements).
+static bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("PTTS_B200_NO_PDL") == nullptr ? 1 : 0;
+    return v != 0;
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors are picked up by launch_check / cudaGetLastError
+}
+
 // ---------------------------------------------------------------- GEMM dispatch
 template <int BN, int SPLIT>
 static int gemm_launch_t(const GemmOp &op, cudaStream_t st) {
@@ -86,7 +110,7 @@ static int gemm_launch_t(const GemmOp &op, cudaStream_t st) {
         PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    gemm_tc_kernel<BN, SPLIT><<<op.grid, GEMM_THREADS, op.smem_bytes, st>>>(op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.p);
+    launch_k(gemm_tc_kernel<BN, SPLIT>, op.grid, GEMM_THREADS, op.smem_bytes, st, op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.p);
     PTTS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -126,6 +150,7 @@ struct GemmDesc {
     int taps = 1, k_per_tap = 0, shift0 = 0, step = 0, a_k_step = 0, b_k_step = 0;
     int bn = 128, split_k = 1;
     bool two_cta = true;
+    bool b_static = true;                      // B is a weight matrix (never written by a kernel)
     GemmParams epi = {};                       // epilogue fields only
 };
 
@@ -161,6 +186,7 @@ static int gemm_build(GemmOp &op, const GemmDesc &d) {
     const long long tiles = (long long)p.m_tiles_total * p.n_tiles * split_k;
     PTTS_CHECK(tiles < (1ll << 31), "gemm_build: too many tiles");
     p.total_tiles = (int)tiles;
+    p.b_static = d.b_static ? 1 : 0;
     p.stages = gemm_pick_stages(d.bn, op.split, per, d.two_cta);
     p.idesc = umma_idesc_f16(GEMM_BM, d.bn, d.bf16, d.bf16);
     op.p = p;
@@ -302,6 +328,7 @@ struct ptts_b200_engine {
     // staged batch
     int st_n = 0, st_steps = 0, st_capF = 0, st_lsd = 1, st_precise = 1, st_eos = 0;
     std::vector<int> st_maxf;
+    unsigned long long *mega_ctl = nullptr;   // persistent step kernel: [0] grid barrier, [1] done count, [8..] phase timers
     // pinned staging
     void *pin = nullptr;
     size_t pin_bytes = 0;

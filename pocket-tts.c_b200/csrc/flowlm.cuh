@@ -90,7 +90,7 @@ static int ensure_rope(Engine *e, int len) {
     while (n < len) n *= 2;
     e->dfree(e->rope_cos); e->dfree(e->rope_sin);
     if (e->dalloc(&e->rope_cos, (size_t)n * 32) != 0 || e->dalloc(&e->rope_sin, (size_t)n * 32) != 0) return -1;
-    k_rope_table<<<(n * 32 + 255) / 256, 256, 0, e->st>>>(e->rope_cos, e->rope_sin, n);
+    launch_k(k_rope_table, (n * 32 + 255) / 256, 256, 0, e->st, e->rope_cos, e->rope_sin, n);
     if (launch_check("k_rope_table") != 0) return -1;
     e->rope_len = n;
     e->invalidate_graphs();
@@ -107,9 +107,9 @@ static int ensure_cbias(Engine *e, int steps, float **out) {
     for (int k = 0; k < steps; k++) {
         PTTS_CUDA_OK(cudaMemcpyAsync(buf + (size_t)k * FN_D, e->cond_b, FN_D * sizeof(float), cudaMemcpyDeviceToDevice, e->st));
         const float s = (float)k / (float)steps, t = (float)(k + 1) / (float)steps;
-        k_time_embed<<<1, 512, 0, e->st>>>(e->te[0].l0w, e->te[0].l0b, e->te[0].l2w, e->te[0].l2b, e->te[0].alpha, e->te[0].freqs, s,
+        launch_k(k_time_embed, 1, 512, 0, e->st, e->te[0].l0w, e->te[0].l0b, e->te[0].l2w, e->te[0].l2b, e->te[0].alpha, e->te[0].freqs, s,
                                           buf + (size_t)k * FN_D);
-        k_time_embed<<<1, 512, 0, e->st>>>(e->te[1].l0w, e->te[1].l0b, e->te[1].l2w, e->te[1].l2b, e->te[1].alpha, e->te[1].freqs, t,
+        launch_k(k_time_embed, 1, 512, 0, e->st, e->te[1].l0w, e->te[1].l0b, e->te[1].l2w, e->te[1].l2b, e->te[1].alpha, e->te[1].freqs, t,
                                           buf + (size_t)k * FN_D);
         if (launch_check("k_time_embed") != 0) return -1;
     }
@@ -141,10 +141,10 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
     DA(d_own_base, b); DA(d_tokens, b * tok); DA(d_tok_len, b); DA(d_max_frames, b); DA(d_eos_after, b);
     DA(d_noise, b * F * FL_LAT); DA(d_latent, b * FL_LAT); DA(d_out_latents, b * F * FL_LAT);
     DA(d_eos_step, b); DA(d_done, b); DA(d_used, b); DA(d_first_eos, b); DA(d_first_cond, b * FL_D); DA(d_first_flow, b * FL_LAT);
-    DA(x, b * FL_D); DA(qkv, b * 3 * FL_D); DA(att, b * FL_D); DA(ffh, b * FL_FF); DA(normed, b * FL_D);
+    DA(x, b * FL_D); DA(qkv, 8 * b * 3 * FL_D); DA(att, b * FL_D); DA(ffh, b * FL_FF); DA(normed, b * FL_D);
     DA(xn_h, b * FL_D); DA(xn_l, b * FL_D); DA(att_h, b * FL_D); DA(att_l, b * FL_D); DA(ffh_h, b * FL_FF); DA(ffh_l, b * FL_FF);
-    DA(normed_h, b * FL_D); DA(normed_l, b * FL_D); DA(partA, 4 * b * FL_D); DA(partB, 4 * b * FL_D);
-    DA(fx, b * FN_D); DA(ada, b * FN_ADA); DA(ft, 4 * b * FN_D); DA(flow, b * FL_LAT); DA(sc, b * FN_D); DA(fg, b * FN_D);
+    DA(normed_h, b * FL_D); DA(normed_l, b * FL_D); DA(partA, 8 * b * FL_D); DA(partB, 8 * b * FL_D);
+    DA(fx, b * FN_D); DA(ada, b * FN_ADA); DA(ft, 8 * b * FN_D); DA(flow, b * FL_LAT); DA(sc, b * FN_D); DA(fg, b * FN_D);
     DA(sc_h, b * FN_D); DA(sc_l, b * FN_D); DA(fh_h, b * FN_D); DA(fh_l, b * FN_D); DA(fg_h, b * FN_D); DA(fg_l, b * FN_D);
     DA(ok, (size_t)FL_L * b * FL_D * S); DA(ov, (size_t)FL_L * b * FL_D * S);
     if (regrow_prefix || !e->pk) {
@@ -182,13 +182,13 @@ static int gemv(Engine *e, const __nv_bfloat16 *W, int N, const float *x, GemvPa
     constexpr int THREADS = K / 8 < 128 ? K / 8 : 128;
     if (e->prof.on) { e->prof.bytes[KC_GEMV] += 2.0 * N * K + 4.0 * (K + N); e->prof.flops[KC_GEMV] += 2.0 * N * K; }
     LaunchScope ls(e, KC_GEMV);
-    k_gemv<K, RPC, PRO><<<(N + RPC - 1) / RPC, THREADS, 0, e->st>>>(p);
+    launch_k(k_gemv<K, RPC, PRO>, (N + RPC - 1) / RPC, THREADS, 0, e->st, p);
     return launch_check("k_gemv");
 }
 
-static int attn_decode(Engine *e, int B, int layer, bool out16) {
+static int attn_decode(Engine *e, int B, int layer, bool out16, int qkv_nsplit = 1) {
     AttnDecodeParams a = {};
-    a.qkv = e->qkv;
+    a.qkv = e->qkv; a.qkv_nsplit = qkv_nsplit; a.qkv_stride = (size_t)e->capB * 3 * FL_D;
     a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin;
     a.ctrl_cond_len = &e->ctrl->cond_len;
     a.own_base = e->d_own_base;
@@ -211,16 +211,16 @@ static int attn_decode(Engine *e, int B, int layer, bool out16) {
     }
     LaunchScope ls(e, KC_ATTN_DECODE);
     const dim3 grid(FL_H, (B + G - 1) / G);
-    if (G == 8) k_attn_decode2<1><<<grid, 256, smem, e->st>>>(a, B, pcap);
-    else if (G == 4) k_attn_decode2<2><<<grid, 256, smem, e->st>>>(a, B, pcap);
-    else if (G == 2) k_attn_decode2<4><<<grid, 256, smem, e->st>>>(a, B, pcap);
-    else k_attn_decode2<8><<<grid, 256, smem, e->st>>>(a, B, pcap);
+    if (G == 8) launch_k(k_attn_decode2<1>, grid, 256, smem, e->st, a, B, pcap);
+    else if (G == 4) launch_k(k_attn_decode2<2>, grid, 256, smem, e->st, a, B, pcap);
+    else if (G == 2) launch_k(k_attn_decode2<4>, grid, 256, smem, e->st, a, B, pcap);
+    else launch_k(k_attn_decode2<8>, grid, 256, smem, e->st, a, B, pcap);
     return launch_check("k_attn_decode2");
 }
 
 static int rownorm(Engine *e, int rows, RowNormParams p, int cls = KC_ROWNORM) {
     LaunchScope ls(e, cls);
-    k_rownorm<<<rows, 256, 0, e->st>>>(p);
+    launch_k(k_rownorm, rows, 256, 0, e->st, p);
     return launch_check("k_rownorm");
 }
 
@@ -231,13 +231,13 @@ static int flow_step_gemv(Engine *e, const FlowState &st, const float *cbias) {
     if (rownorm(e, 1, r) != 0) return -1;
     {
         LaunchScope ls(e, KC_FLOW_MISC);
-        k_eos_state<<<1, 256, 0, e->st>>>(st, e->ctrl, e->d_eos_after, e->normed, e->eos_w, e->eos_b);
+        launch_k(k_eos_state, 1, 256, 0, e->st, st, e->ctrl, e->d_eos_after, e->normed, e->eos_w, e->eos_b);
         if (launch_check("k_eos_state") != 0) return -1;
     }
     for (int k = 0; k < st.lsd_steps; k++) {
         {
             LaunchScope ls(e, KC_FLOW_MISC);
-            k_flow_init<<<1, 512, 0, e->st>>>(st, k, e->inp_w, e->inp_b, e->fx);
+            launch_k(k_flow_init, 1, 512, 0, e->st, st, k, e->inp_w, e->inp_b, e->fx);
             if (launch_check("k_flow_init") != 0) return -1;
         }
         GemvParams g = {};
@@ -258,13 +258,13 @@ static int flow_step_gemv(Engine *e, const FlowState &st, const float *cbias) {
         if (gemv<FN_D, 4, 2>(e, e->fin_w, FL_LAT, e->fx, g) != 0) return -1;
         {
             LaunchScope ls(e, KC_FLOW_MISC);
-            k_flow_update<<<1, 32, 0, e->st>>>(st, e->ctrl, e->d_eos_after, k, e->flow);
+            launch_k(k_flow_update, 1, 32, 0, e->st, st, e->ctrl, e->d_eos_after, k, e->flow);
             if (launch_check("k_flow_update") != 0) return -1;
         }
     }
     {
         LaunchScope ls(e, KC_FLOW_MISC);
-        k_prepare_x<<<1, 256, 0, e->st>>>(st, e->in_lin, e->x);
+        launch_k(k_prepare_x, 1, 256, 0, e->st, st, e->in_lin, e->x);
         if (launch_check("k_prepare_x") != 0) return -1;
     }
     for (int l = 0; l < FL_L; l++) {
@@ -280,7 +280,7 @@ static int flow_step_gemv(Engine *e, const FlowState &st, const float *cbias) {
         if (gemv<FL_FF, 4, 0>(e, e->L[l].l2, FL_D, e->ffh, g) != 0) return -1;
     }
     LaunchScope ls(e, KC_FLOW_MISC);
-    k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
+    launch_k(k_advance_step, 1, 1, 0, e->st, &e->ctrl->step);
     return launch_check("k_advance_step");
 }
 
@@ -293,20 +293,22 @@ struct FlowGemms {
     uint64_t gen = 0;
 };
 
-static int pick_bn(int B) { return B <= 32 ? 32 : (B <= 64 ? 64 : (B <= 128 ? 128 : 256)); }
+constexpr int FLOW_MAX_SPLIT = 8;   // split-K slices a consumer kernel folds (partA / partB / ft / qkv are sized for it)
 
-// weights [N_w, K] bf16 as the A operand; activations [B, K] (hi, lo) as the B operand; output
-// out[b*ld + feature] (transposed store).
+// Decode-step GEMM: activations [B, K] (bf16 hi + lo, the A operand, M = utterances) x weights
+// [n_w, K] (the B operand), output rows = utterances. The weights are streamed once per M tile; K is
+// split across CTAs until the grid covers the SMs, and the consumer kernel folds the partial sums.
 static int flow_gemm_build(GemmOp &op, const __nv_bfloat16 *W, int n_w, int K, const uint16_t *xh, const uint16_t *xl, int B,
-                           int split_k, const float *bias, float *out_f32, int ldo, size_t split_stride, uint16_t *oh,
+                           int bn, int max_split, const float *bias, float *out_f32, int ldo, size_t split_stride, uint16_t *oh,
                            uint16_t *ol, int ldh, int act) {
     GemmDesc d;
-    d.A = W; d.a_k = K; d.a_rows = n_w; d.a_batches = 1; d.a_ld = K;
-    d.B = xh; d.Blo = xl; d.b_k = K; d.b_rows = B; d.b_ld = K;
+    d.A = xh; d.Alo = xl; d.a_k = K; d.a_rows = B; d.a_batches = 1; d.a_ld = K;
+    d.B = W; d.b_k = K; d.b_rows = n_w; d.b_ld = K;
     d.bf16 = true; d.taps = 1; d.k_per_tap = K;
-    d.bn = std::min(pick_bn(B), 64);   // N tiles of <= 64 utterances: more CTAs pulling weights
-    d.split_k = split_k; d.two_cta = true;
-    d.epi.transposed = 1; d.epi.bias = bias; d.epi.out_f32 = out_f32; d.epi.ldo = ldo; d.epi.split_stride = split_stride;
+    d.bn = std::min(bn, std::max(32, n_w));
+    const int tiles = ((B + GEMM_BM - 1) / GEMM_BM) * ((n_w + d.bn - 1) / d.bn);
+    d.split_k = std::max(1, std::min(std::min(max_split, g_num_sms / tiles), K / (2 * GEMM_BK)));
+    d.epi.transposed = 0; d.epi.bias = bias; d.epi.out_f32 = out_f32; d.epi.ldo = ldo; d.epi.split_stride = split_stride;
     d.epi.out_h = oh; d.epi.out_l = ol; d.epi.ldh = ldh; d.epi.out_bf16 = 1; d.epi.act = act;
     return gemm_build(op, d);
 }
@@ -315,29 +317,29 @@ static int flow_gemms_build(Engine *e, FlowGemms &G, int B, int precise, int lsd
     const size_t ps = (size_t)e->capB * FL_D;
     const uint16_t *xl = precise ? e->xn_l : nullptr, *al = precise ? e->att_l : nullptr, *fl = precise ? e->ffh_l : nullptr;
     for (int l = 0; l < FL_L; l++) {
-        if (flow_gemm_build(G.qkv[l], e->L[l].inproj, 3 * FL_D, FL_D, e->xn_h, xl, B, 1, nullptr, e->qkv, 3 * FL_D, 0, nullptr,
-                            nullptr, 0, ACT_NONE) != 0) return -1;
-        if (flow_gemm_build(G.outp[l], e->L[l].outproj, FL_D, FL_D, e->att_h, al, B, 4, nullptr, e->partA, FL_D, ps, nullptr,
-                            nullptr, 0, ACT_NONE) != 0) return -1;
-        if (flow_gemm_build(G.ff1[l], e->L[l].l1, FL_FF, FL_D, e->xn_h, xl, B, 1, nullptr, nullptr, 0, 0, e->ffh_h,
+        if (flow_gemm_build(G.qkv[l], e->L[l].inproj, 3 * FL_D, FL_D, e->xn_h, xl, B, 128, FLOW_MAX_SPLIT, nullptr, e->qkv, 3 * FL_D,
+                            (size_t)e->capB * 3 * FL_D, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
+        if (flow_gemm_build(G.outp[l], e->L[l].outproj, FL_D, FL_D, e->att_h, al, B, 128, FLOW_MAX_SPLIT, nullptr, e->partA, FL_D, ps,
+                            nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
+        if (flow_gemm_build(G.ff1[l], e->L[l].l1, FL_FF, FL_D, e->xn_h, xl, B, 64, 1, nullptr, nullptr, 0, 0, e->ffh_h,
                             precise ? e->ffh_l : nullptr, FL_FF, ACT_GELU_ERF) != 0) return -1;
-        if (flow_gemm_build(G.ff2[l], e->L[l].l2, FL_D, FL_FF, e->ffh_h, fl, B, 4, nullptr, e->partB, FL_D, ps, nullptr, nullptr,
-                            0, ACT_NONE) != 0) return -1;
+        if (flow_gemm_build(G.ff2[l], e->L[l].l2, FL_D, FL_FF, e->ffh_h, fl, B, 128, FLOW_MAX_SPLIT, nullptr, e->partB, FL_D, ps, nullptr,
+                            nullptr, 0, ACT_NONE) != 0) return -1;
     }
     G.cond.resize(lsd);
     for (int k = 0; k < lsd; k++)
-        if (flow_gemm_build(G.cond[k], e->cond_w, FN_D, FL_D, e->normed_h, precise ? e->normed_l : nullptr, B, 1,
+        if (flow_gemm_build(G.cond[k], e->cond_w, FN_D, FL_D, e->normed_h, precise ? e->normed_l : nullptr, B, 32, 1,
                             cbias + (size_t)k * FN_D, nullptr, 0, 0, e->sc_h, precise ? e->sc_l : nullptr, FN_D, ACT_SILU) != 0)
             return -1;
-    if (flow_gemm_build(G.ada, e->ada_w, FN_ADA, FN_D, e->sc_h, precise ? e->sc_l : nullptr, B, 1, e->ada_b, e->ada, FN_ADA, 0,
+    if (flow_gemm_build(G.ada, e->ada_w, FN_ADA, FN_D, e->sc_h, precise ? e->sc_l : nullptr, B, 128, 1, e->ada_b, e->ada, FN_ADA, 0,
                         nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
     for (int b = 0; b < FN_DEPTH; b++) {
-        if (flow_gemm_build(G.m0[b], e->FB[b].m0w, FN_D, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 1, e->FB[b].m0b, nullptr, 0,
+        if (flow_gemm_build(G.m0[b], e->FB[b].m0w, FN_D, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 32, 1, e->FB[b].m0b, nullptr, 0,
                             0, e->fg_h, precise ? e->fg_l : nullptr, FN_D, ACT_SILU) != 0) return -1;
-        if (flow_gemm_build(G.m2[b], e->FB[b].m2w, FN_D, FN_D, e->fg_h, precise ? e->fg_l : nullptr, B, 4, e->FB[b].m2b, e->ft,
-                            FN_D, (size_t)e->capB * FN_D, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
+        if (flow_gemm_build(G.m2[b], e->FB[b].m2w, FN_D, FN_D, e->fg_h, precise ? e->fg_l : nullptr, B, 64, FLOW_MAX_SPLIT, e->FB[b].m2b,
+                            e->ft, FN_D, (size_t)e->capB * FN_D, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
     }
-    if (flow_gemm_build(G.fin, e->fin_w, FL_LAT, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 1, e->fin_b, e->flow, FL_LAT, 0,
+    if (flow_gemm_build(G.fin, e->fin_w, FL_LAT, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 32, 1, e->fin_b, e->flow, FL_LAT, 0,
                         nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
     G.B = B; G.precise = precise; G.lsd = lsd; G.gen = e->gen;
     return 0;
@@ -356,13 +358,13 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
         r.out_f32 = e->normed; r.out_h = e->normed_h; r.out_l = precise ? e->normed_l : nullptr; r.out_bf16 = 1;
         if (rownorm(e, B, r) != 0) return -1;
         LaunchScope ls(e, KC_FLOW_MISC);
-        k_eos_state<<<B, 256, 0, e->st>>>(st, e->ctrl, e->d_eos_after, e->normed, e->eos_w, e->eos_b);
+        launch_k(k_eos_state, B, 256, 0, e->st, st, e->ctrl, e->d_eos_after, e->normed, e->eos_w, e->eos_b);
         if (launch_check("k_eos_state") != 0) return -1;
     }
     for (int k = 0; k < st.lsd_steps; k++) {
         {
             LaunchScope ls(e, KC_FLOW_MISC);
-            k_flow_init<<<B, 512, 0, e->st>>>(st, k, e->inp_w, e->inp_b, e->fx);
+            launch_k(k_flow_init, B, 512, 0, e->st, st, k, e->inp_w, e->inp_b, e->fx);
             if (launch_check("k_flow_init") != 0) return -1;
         }
         if (run_gemm(e, G.cond[k], KC_GEMM_FLOW) != 0) return -1;
@@ -383,12 +385,12 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
         }
         if (run_gemm(e, G.fin, KC_GEMM_FLOW) != 0) return -1;
         LaunchScope ls(e, KC_FLOW_MISC);
-        k_flow_update<<<B, 32, 0, e->st>>>(st, e->ctrl, e->d_eos_after, k, e->flow);
+        launch_k(k_flow_update, B, 32, 0, e->st, st, e->ctrl, e->d_eos_after, k, e->flow);
         if (launch_check("k_flow_update") != 0) return -1;
     }
     {
         LaunchScope ls(e, KC_FLOW_MISC);
-        k_prepare_x<<<B, 256, 0, e->st>>>(st, e->in_lin, e->x);
+        launch_k(k_prepare_x, B, 256, 0, e->st, st, e->in_lin, e->x);
         if (launch_check("k_prepare_x") != 0) return -1;
     }
     for (int l = 0; l < FL_L; l++) {
@@ -398,7 +400,7 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
         if (l > 0) { r.part = e->partB; r.nsplit = (int)G.ff2[l - 1].p.split_k; r.split_stride = ps; }
         if (rownorm(e, B, r) != 0) return -1;
         if (run_gemm(e, G.qkv[l], KC_GEMM_FLOW) != 0) return -1;
-        if (attn_decode(e, B, l, true) != 0) return -1;
+        if (attn_decode(e, B, l, true, G.qkv[l].p.split_k) != 0) return -1;
         if (run_gemm(e, G.outp[l], KC_GEMM_FLOW) != 0) return -1;
         r = {};
         r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
@@ -409,7 +411,7 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
         if (run_gemm(e, G.ff2[l], KC_GEMM_FLOW) != 0) return -1;
     }
     LaunchScope ls(e, KC_FLOW_MISC);
-    k_advance_step<<<1, 1, 0, e->st>>>(&e->ctrl->step);
+    launch_k(k_advance_step, 1, 1, 0, e->st, &e->ctrl->step);
     return launch_check("k_advance_step");
 }
 
@@ -458,7 +460,7 @@ static int flow_prefill(Engine *e, int n, int M, int max_q, int cond_len, bool v
                smem, cond_len, max_q);
     {
         LaunchScope ls(e, KC_FLOW_MISC);
-        k_pf_gather<<<M, 256, 0, e->st>>>(pr, e->d_tokens, e->capTok, e->d_tok_len, e->embed, e->bos_proj,
+        launch_k(k_pf_gather, M, 256, 0, e->st, pr, e->d_tokens, e->capTok, e->d_tok_len, e->embed, e->bos_proj,
                                           voice_mode ? e->d_cond : nullptr, e->pf_x);
         if (launch_check("k_pf_gather") != 0) return -1;
     }
@@ -483,7 +485,7 @@ static int flow_prefill(Engine *e, int n, int M, int max_q, int cond_len, bool v
             }
             a.out_h = e->pf_att_h; a.out_l = e->pf_att_l;
             LaunchScope ls(e, KC_ATTN_DECODE);
-            k_pf_attn<<<dim3(FL_H, n), 256, smem, e->st>>>(a, pr);
+            launch_k(k_pf_attn, dim3(FL_H, n), 256, smem, e->st, a, pr);
             if (launch_check("k_pf_attn") != 0) return -1;
         }
         g = {}; g.resid = e->pf_x; g.out_f32 = e->pf_x; g.ldo = FL_D;
@@ -499,7 +501,7 @@ static int flow_prefill(Engine *e, int n, int M, int max_q, int cond_len, bool v
     }
     if (!voice_mode) {
         LaunchScope ls(e, KC_FLOW_MISC);
-        k_pf_last<<<n, 256, 0, e->st>>>(pr, e->pf_x, e->x);
+        launch_k(k_pf_last, n, 256, 0, e->st, pr, e->pf_x, e->x);
         if (launch_check("k_pf_last") != 0) return -1;
     }
     return 0;

@@ -40,6 +40,8 @@ struct GemmParams {
     int a_k_step;            // K offset per tap inside A (0 when taps shift rows)
     int b_k_step;            // K offset per tap inside B
     int stages;
+    int b_static;            // 1: the B operand (weights) is never written by a kernel -> its first tiles are
+                             // fetched before the programmatic-dependency wait (overlaps the previous kernel's tail)
     uint32_t idesc;
     // ---- epilogue
     int transposed;          // 0: element (m,n) -> [(batch*a_rows+m)*ld + n]; 1: -> [n*ld + m]
@@ -137,29 +139,52 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_trigger();   // the next kernel may start its own prologue now
     const bool tr = p.trace != nullptr && blockIdx.x == 0;
     if (tr && threadIdx.x == 0) p.trace[0] = clock64();
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
             if (tr) p.trace[1] = clock64();
+            // Pass 0 (before the dependency wait): arm the first `stages` slots and fetch their weight
+            // tiles. Pass 1: everything else, in ring order.
+            int pre = 0;
+            if (p.b_static) {
+                int s = 0;
+                for (int tile = blockIdx.x; tile < p.total_tiles && pre < p.stages; tile += gridDim.x) {
+                    const TileCoord t = gemm_tile(p, tile, BN);
+                    for (int it = t.it0; it < t.it1 && pre < p.stages; it++, pre++, s++) {
+                        uint8_t *nx = smem + s * SM::STAGE_BYTES + SM::A_BYTES * (SPLIT == 1 ? 2 : 1);
+                        mbar_expect_tx(&full[s], SM::STAGE_BYTES);
+                        const int tap = it / p.kblocks_per_tap, kb = it - tap * p.kblocks_per_tap;
+                        const int bk = kb * GEMM_BK + tap * p.b_k_step;
+                        tma_load_3d(nx, &mapB, &full[s], bk, t.n0, 0);
+                        if (SPLIT == 2) tma_load_3d(nx + SM::B_BYTES, &mapBlo, &full[s], bk, t.n0, 0);
+                    }
+                }
+            }
+            pdl_wait();
+            int s = 0, n = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const TileCoord t = gemm_tile(p, tile, BN);
-                for (int it = t.it0; it < t.it1; it++) {
-                    mbar_wait(&empty[s], ph ^ 1);
+                for (int it = t.it0; it < t.it1; it++, n++) {
                     uint8_t *st = smem + s * SM::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], SM::STAGE_BYTES);
                     const int tap = it / p.kblocks_per_tap, kb = it - tap * p.kblocks_per_tap;
                     const int ak = kb * GEMM_BK + tap * p.a_k_step;
                     const int ar = t.m0 + p.a_row_shift0 + tap * p.a_row_step;
-                    const int bk = kb * GEMM_BK + tap * p.b_k_step;
+                    if (n >= pre) {
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], SM::STAGE_BYTES);
+                    }
                     tma_load_3d(st, &mapA, &full[s], ak, ar, t.batch);
                     uint8_t *nx = st + SM::A_BYTES;
                     if (SPLIT == 1) { tma_load_3d(nx, &mapAlo, &full[s], ak, ar, t.batch); nx += SM::A_BYTES; }
-                    tma_load_3d(nx, &mapB, &full[s], bk, t.n0, 0);
-                    if (SPLIT == 2) tma_load_3d(nx + SM::B_BYTES, &mapBlo, &full[s], bk, t.n0, 0);
+                    if (n >= pre) {
+                        const int bk = kb * GEMM_BK + tap * p.b_k_step;
+                        tma_load_3d(nx, &mapB, &full[s], bk, t.n0, 0);
+                        if (SPLIT == 2) tma_load_3d(nx + SM::B_BYTES, &mapBlo, &full[s], bk, t.n0, 0);
+                    }
                     if (++s == p.stages) { s = 0; ph ^= 1; }
                 }
             }
@@ -205,6 +230,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // 16-column chunks. tcgen05.ld of the next chunk is in flight while this one is processed.
         const int quad = warp & 3, cg = (warp - 2) >> 2;
         constexpr int NCG = GEMM_EPI_WARPS / 4;
+        pdl_wait();   // residual / outputs belong to earlier kernels
         const bool bf = p.out_bf16 != 0;
         const int act = p.act, ldo = p.ldo, ldh = p.ldh, n_total = p.n_total, bias_mask = p.bias_mask;
         const bool fast = p.fast_act != 0;

@@ -55,6 +55,7 @@ struct RowNormParams {
 };
 
 __global__ void __launch_bounds__(256) k_rownorm(const RowNormParams p) {
+    pdl_wait(); pdl_trigger();
     __shared__ float red[32];
     const size_t row = blockIdx.x;
     float v[4];
@@ -148,6 +149,8 @@ __global__ void __launch_bounds__((K / 8 < 128 ? K / 8 : 128)) k_gemv(const Gemv
             const int row = min(r0 + r, p.N - 1);
             wv[r][c] = __ldcs((const uint4 *)(p.W + (size_t)row * K) + tid + c * THREADS);
         }
+    pdl_wait();      // the weights above are constants; everything below depends on the previous kernel
+    pdl_trigger();
 
     float xv[NCH][8];
 #pragma unroll
@@ -244,6 +247,7 @@ struct FlowCtrl {
 
 // x[b,:] = input_linear . latent[b] (ptts_flowlm.c:1240-1241). grid B, block 256.
 __global__ void __launch_bounds__(256) k_prepare_x(const FlowState st, const __nv_bfloat16 *in_lin, float *x) {
+    pdl_wait(); pdl_trigger();
     const int b = blockIdx.x;
     float *xr = x + (size_t)b * FL_D;
     __shared__ float lat[FL_LAT];
@@ -266,6 +270,7 @@ __global__ void __launch_bounds__(256) k_prepare_x(const FlowState st, const __n
 // EOS logit + stop rule (ptts_flowlm.c:1202-1209). grid B, block 256. normed [B,1024].
 __global__ void __launch_bounds__(256) k_eos_state(const FlowState st, const FlowCtrl *ctrl, const int *eos_after, const float *normed,
                                                    const float *eos_w, const float *eos_b) {
+    pdl_wait(); pdl_trigger();
     __shared__ float red[32];
     const int b = blockIdx.x, s = *st.step;
     const float *nr = normed + (size_t)b * FL_D;
@@ -289,6 +294,7 @@ __global__ void __launch_bounds__(256) k_eos_state(const FlowState st, const Flo
 // (ptts_flowlm.c:710). grid B, block 512.
 __global__ void __launch_bounds__(512) k_flow_init(const FlowState st, int k, const __nv_bfloat16 *inp_w /*[512,32]*/,
                                                    const float *inp_b, float *fx) {
+    pdl_wait(); pdl_trigger();
     __shared__ float lat[FL_LAT];
     const int b = blockIdx.x, i = *st.step;
     if (threadIdx.x < FL_LAT) {
@@ -320,6 +326,7 @@ __global__ void __launch_bounds__(512) k_flow_init(const FlowState st, int k, co
 // apply the stop rule (ptts_flowlm.c:1235-1238). grid B, block 32.
 __global__ void __launch_bounds__(32) k_flow_update(const FlowState st, const FlowCtrl *ctrl, const int *eos_after, int k,
                                                     const float *flow /*[B,32]*/) {
+    pdl_wait(); pdl_trigger();
     const int b = blockIdx.x, i = *st.step, d = threadIdx.x;
     const bool valid = i < st.max_frames[b] && !st.done[b];
     const float f = flow[b * FL_LAT + d];
@@ -338,7 +345,8 @@ __global__ void __launch_bounds__(32) k_flow_update(const FlowState st, const Fl
         }
     }
 }
-__global__ void k_advance_step(int *step) { *step += 1; }
+__global__ void k_advance_step(int *step) {
+    pdl_wait(); pdl_trigger(); *step += 1; }
 
 // =====================================================================================
 // RoPE + KV append + single-query attention over [shared voice prefix | own positions]
@@ -346,7 +354,9 @@ __global__ void k_advance_step(int *step) { *step += 1; }
 // cache layout: prefix [H][pstride][64], own [B][H][max_s][64], fp32.
 // =====================================================================================
 struct AttnDecodeParams {
-    const float *qkv;          // [B, 3072]
+    const float *qkv;          // [B, 3072], or split-K partial sums [qkv_nsplit][..] qkv_stride floats apart
+    int qkv_nsplit;            // <= 1: plain
+    size_t qkv_stride;
     const float *rope_cos, *rope_sin;  // [max_pos][32]
     const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
     float *ok, *ov;            // own cache of this layer
@@ -375,20 +385,34 @@ __host__ __device__ inline size_t attn2_smem_bytes(int pcap, int G) {
     return (size_t)(AD_TILE * AD_LD + 8 * pcap + G * FL_HD + 8 * 66) * sizeof(float);
 }
 
-template <int WPU>
-__global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, int B, int pcap) {
+// Sum of up to 8 split-K partial values; the loads are independent (all in flight together).
+__device__ __forceinline__ float2 ld_fold2(const float *ptr, int nsplit, size_t stride) {
+    float2 a[8];
+    a[0] = *(const float2 *)ptr;
+#pragma unroll
+    for (int z = 1; z < 8; z++) a[z] = z < nsplit ? *(const float2 *)(ptr + z * stride) : make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int z = 1; z < 8; z++) { a[0].x += a[z].x; a[0].y += a[z].y; }
+    return a[0];
+}
+
+// One work item = (head h, utterance group gi) processed by 256 threads (tid 0..255); `sync` is the
+// barrier of exactly those threads (the whole CTA in k_attn_decode2, a named barrier in the
+// persistent step kernel); `step` is the decode iteration.
+template <int WPU, typename Sync>
+__device__ __forceinline__ void attn_decode_item(const AttnDecodeParams &p, int B, int pcap, int h, int gi, int tid, float *ad_smem,
+                                                 int step, Sync sync) {
     constexpr int G = 8 / WPU;
-    extern __shared__ __align__(16) float ad_smem[];
     float *tile = ad_smem;                       // [128][65]
     float *scores = tile + AD_TILE * AD_LD;      // [8][pcap]
     float *sq = scores + 8 * pcap;               // [G][64]
     float *comb = sq + G * FL_HD;                // [8][66]
-    const int h = blockIdx.x, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int w = tid >> 5, lane = tid & 31;
     const int g = w / WPU, wu = w % WPU;
-    const int b = blockIdx.y * G + g;
+    const int b = gi * G + g;
     const bool live = b < B;
     const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
-    const int s = *p.step + (live ? p.own_base[b] : 0);   // own-cache row written by this step
+    const int s = step + (live ? p.own_base[b] : 0);   // own-cache row written by this step
     const int pos = cond_len + s, P = pos + 1;
     float *okb = p.ok + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
     float *ovb = p.ov + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
@@ -397,17 +421,17 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
     if (live) {
         const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD;
         const float c = p.rope_cos[pos * 32 + lane], sn = p.rope_sin[pos * 32 + lane];
-        const float2 qq = *(const float2 *)(row + 2 * lane);
+        const float2 qq = ld_fold2(row + 2 * lane, p.qkv_nsplit, p.qkv_stride);
         // 1/sqrt(64) = 0.125 is a power of two: scaling q equals scaling every score
         q = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
         if (wu == 0) {
-            const float2 kk = *(const float2 *)(row + FL_D + 2 * lane);
+            const float2 kk = ld_fold2(row + FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
             *(float2 *)(okb + (size_t)s * FL_HD + 2 * lane) = make_float2(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
-            *(float2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = *(const float2 *)(row + 2 * FL_D + 2 * lane);
+            *(float2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = ld_fold2(row + 2 * FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
             *(float2 *)(sq + g * FL_HD + 2 * lane) = q;
         }
     }
-    __syncthreads();   // appended row + sq visible to every warp of the CTA
+    sync();   // appended row + sq visible to every warp of the CTA
     const float *pkh = p.pk ? p.pk + (size_t)h * p.pstride * FL_HD : nullptr;
     const float *pvh = p.pv ? p.pv + (size_t)h * p.pstride * FL_HD : nullptr;
     const float *qs = sq + g * FL_HD;
@@ -421,7 +445,7 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
             float *d = tile + r * AD_LD + c4;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
-        __syncthreads();
+        sync();
         if (live) {
             for (int rr = 0; rr < AD_TILE / 32; rr++) {
                 const int blk = t0 / 32 + rr;
@@ -436,7 +460,7 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
                 }
             }
         }
-        __syncthreads();
+        sync();
     }
     // ---- scores, own part: lane = dimension pair, coalesced 256 B rows from HBM, 8 in flight
     float mx = -INFINITY;
@@ -481,7 +505,7 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
             const int r = idx >> 4, c4 = (idx & 15) * 4;
             *(float4 *)(tile + r * FL_HD + c4) = *(const float4 *)(pvh + (size_t)(t0 + r) * FL_HD + c4);
         }
-        __syncthreads();
+        sync();
         if (live) {
             for (int rr = 0; rr < AD_TILE / 32; rr++) {
                 const int blk = t0 / 32 + rr;
@@ -495,7 +519,7 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
                 }
             }
         }
-        __syncthreads();
+        sync();
     }
     // ---- P.V, own part from HBM
     if (live) {
@@ -519,7 +543,7 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
     float *cw = comb + w * 66;
     if (lane == 0) { cw[64] = mx; cw[65] = sum; }
     *(float2 *)(cw + 2 * lane) = acc;
-    __syncthreads();
+    sync();
     if (live && wu == 0) {
         float M = -INFINITY;
 #pragma unroll
@@ -548,6 +572,13 @@ __global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, 
     }
 }
 
+template <int WPU>
+__global__ void __launch_bounds__(256) k_attn_decode2(const AttnDecodeParams p, int B, int pcap) {
+    pdl_wait(); pdl_trigger();
+    extern __shared__ __align__(16) float ad_smem_dyn[];
+    attn_decode_item<WPU>(p, B, pcap, blockIdx.x, blockIdx.y, threadIdx.x, ad_smem_dyn, *p.step, [] { __syncthreads(); });
+}
+
 // =====================================================================================
 // Batched prefill: all text tokens + BOS of all utterances (or all voice
 // frames) are packed into M rows and go through each layer as one GEMM pass; this kernel set is
@@ -563,6 +594,7 @@ struct PrefillRows {
 // (ptts_flowlm.c:1168-1181); ext (voice frames, ptts_flowlm.c:1159-1161) overrides. grid M, block 256.
 __global__ void __launch_bounds__(256) k_pf_gather(const PrefillRows pr, const int *tokens, int max_tok, const int *tok_len,
                                                    const __nv_bfloat16 *embed, const float *bos_proj, const float *ext, float *X) {
+    pdl_wait(); pdl_trigger();
     const int r = blockIdx.x;
     float *xr = X + (size_t)r * FL_D;
     if (ext) {
@@ -581,6 +613,7 @@ __global__ void __launch_bounds__(256) k_pf_gather(const PrefillRows pr, const i
 
 // x[b,:] = X[last row of utterance b]. grid n, block 256.
 __global__ void __launch_bounds__(256) k_pf_last(const PrefillRows pr, const float *X, float *x) {
+    pdl_wait(); pdl_trigger();
     const int b = blockIdx.x, r = pr.row_start[b + 1] - 1;
     for (int k = threadIdx.x; k < FL_D; k += 256) x[(size_t)b * FL_D + k] = X[(size_t)r * FL_D + k];
 }
@@ -602,6 +635,7 @@ __host__ __device__ inline size_t pf_attn_smem_bytes(int cond_len, int max_q) {
     return (kfl + rows * FL_HD + 8 * scf + 8 * FL_HD) * sizeof(float);
 }
 __global__ void __launch_bounds__(256) k_pf_attn(const PrefillAttnParams p, const PrefillRows pr) {
+    pdl_wait(); pdl_trigger();
     extern __shared__ __align__(16) float pf_smem[];
     const int h = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int r0 = pr.row_start[b], nq = pr.row_start[b + 1] - r0, cl = p.cond_len, P = cl + nq;
@@ -673,6 +707,7 @@ __global__ void __launch_bounds__(256) k_pf_attn(const PrefillAttnParams p, cons
 
 // cos/sin table: freq_i = exp(-ln(10000) * 2i/64) (ptts_flowlm.c:361-364), angle = freq_i * pos.
 __global__ void k_rope_table(float *cs, float *sn, int max_pos) {
+    pdl_wait(); pdl_trigger();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= max_pos * 32) return;
     const int pos = idx >> 5, i = idx & 31;
@@ -686,6 +721,7 @@ __global__ void k_rope_table(float *cs, float *sn, int max_pos) {
 // Accumulates 0.5 * embed into out (call for s and for t), out pre-initialised with cond_embed.bias.
 __global__ void __launch_bounds__(512) k_time_embed(const float *l0w, const float *l0b, const float *l2w, const float *l2b,
                                                     const float *alpha, const float *freqs, float tval, float *out) {
+    pdl_wait(); pdl_trigger();
     __shared__ float e[256], h[FN_D], red[32];
     const int n = threadIdx.x;
     if (n < 128) {
@@ -716,6 +752,7 @@ __global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32],
                                                     const float *emb_std, const float *emb_mean,
                                                     int apply_scale, const float *quant_wt /*[32,512] transposed*/,
                                                     const float *ups_t /*[32,512] transposed*/, float *x /*[B,16F,512]*/) {
+    pdl_wait(); pdl_trigger();
     __shared__ float l0[32], l1[32];
     const int t = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
     if (c < 32) {
@@ -750,6 +787,7 @@ __global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32],
 // Warp-per-row LayerNorm for 512-wide rows (Mimi transformer norms, ptts_mimi.c:184-206): two-pass in
 // registers, shuffle reductions only, fp16 output. grid ceil(R/8), block 256.
 __global__ void __launch_bounds__(256) k_ln512_f16(const float *x, size_t R, const float *w, const float *b, float eps, __half *out) {
+    pdl_wait(); pdl_trigger();
     const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (row >= R) return;
     const int lane = threadIdx.x & 31;
@@ -782,6 +820,7 @@ __global__ void __launch_bounds__(256) k_ln512_f16(const float *x, size_t R, con
 // pos = t) and v, stored fp16 [B][H][T][64] (ptts_mimi.c:329-341). grid R, block 256.
 __global__ void __launch_bounds__(256) k_mimi_rope_heads(const float *qkv, int T, const float *rope_cos, const float *rope_sin,
                                                          __half *q, __half *k, __half *v) {
+    pdl_wait(); pdl_trigger();
     const size_t row = blockIdx.x;
     const int b = (int)(row / T), t = (int)(row % T);
     const float *r = qkv + row * 3 * MI_D;
@@ -821,6 +860,7 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 }
 __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __half *k, const __half *v, int T,
                                                        __half *out /*[B*T, 512]*/) {
+    pdl_wait(); pdl_trigger();
     __shared__ __align__(16) __half sQ[64 * FA_LD], sK[64 * FA_LD], sV[64 * FA_LD];
     const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -932,6 +972,7 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
 // staged once in shared memory (coalesced), then one thread per sample.
 __global__ void __launch_bounds__(256) k_dec_out(const __half *e, int T, const float *w /*[64*3] as [c][kk]*/, const float *bias,
                                                  float *pcm) {
+    pdl_wait(); pdl_trigger();
     __shared__ float sw[3][64];
     __shared__ __align__(16) __half se[258 * FA_LD];
     if (threadIdx.x < 192) sw[threadIdx.x % 3][threadIdx.x / 3] = w[threadIdx.x];
@@ -964,6 +1005,7 @@ __global__ void __launch_bounds__(256) k_dec_out(const __half *e, int T, const f
 }
 
 __global__ void k_f32_to_h16(const float *in, uint16_t *out, size_t n, int bf) {
+    pdl_wait(); pdl_trigger();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = f2h16(in[i], bf != 0);
 }

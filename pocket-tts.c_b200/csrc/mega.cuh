@@ -1,0 +1,917 @@
+// mega.cuh - the persistent FlowLM step kernel: the whole lock-step decode loop
+// (ptts_flowlm.c:1187-1251, every frame of every utterance of a batch) in ONE cooperative launch.
+//
+// One CTA per SM walks a small phase program once per frame; phases are separated by a grid-wide
+// barrier (a monotonic counter in global memory). A phase is one of
+//   HEAD : per utterance - fold the last FFN2 partial sums, out_norm, EOS rule, noise -> latent,
+//          flow input projection                               (ptts_flowlm.c:1197-1231, 710)
+//   GEMM : one dense contraction on tcgen05 (TMA -> smem ring -> tcgen05.mma -> TMEM -> epilogue);
+//          the ring, the mbarrier phases and the TMEM accumulators persist across phases, and the
+//          producer fetches the NEXT contraction's weight tiles before it reaches the barrier
+//   ROW  : per utterance - split-K fold (+ gate) + residual + LayerNorm / adaLN + bf16 hi/lo split
+//   MID  : per utterance - Euler update k, flow input projection for k + 1    (lsd_steps > 1)
+//   TAIL : per utterance - Euler update, record the frame, stop rule, x = input_linear . latent,
+//          LayerNorm 1 of layer 0                              (ptts_flowlm.c:775-777, 1235-1241)
+//   ATTN : RoPE + KV append + decode attention, one warp per (utterance, head) unit, no block barriers
+// Nothing is launched per layer or per frame: kernel-boundary drains, TMEM allocation, barrier
+// initialisation and cold prologues are paid once per generate call.
+#pragma once
+#include "flowlm.cuh"
+
+namespace ptts {
+
+constexpr int MG_EPI_WARPS = 12;                  // 3 per TMEM lane quadrant
+constexpr int MG_THREADS = 512;                   // warp 0 TMA, warp 1 MMA, warps 2..13 epilogue; 16 warps -> 128 registers per thread
+constexpr int MG_STAGES = 4;
+constexpr int MG_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB: A hi at +0, A lo at +16 KB, B at +32 KB
+constexpr int MG_SLOT_BYTES = 3 * MG_A_BYTES;      // B tile <= 128 rows
+constexpr int MG_RING_BYTES = MG_STAGES * MG_SLOT_BYTES;
+constexpr int MG_MAX_BN = 128;
+constexpr int MG_SMEM_BYTES = MG_RING_BYTES + 1024 /*alignment*/ + 1024 /*barriers + scratch*/;
+
+enum MegaPhaseType : int { MP_HEAD = 0, MP_GEMM, MP_ROW, MP_MID, MP_TAIL, MP_ATTN, MP_COUNT };
+
+struct MegaPhase {
+    int type;
+    int idx;         // GEMM / ROW / ATTN: index into the respective array; MID: LSD step k just finished
+    int next_gemm;   // GEMM whose first weight tiles the producer fetches after this phase's own loads (-1: none)
+};
+
+struct MegaProgram {
+    const MegaPhase *phases;
+    int n_phases;
+    const GemmOp *gemms;
+    const RowNormParams *rows;
+    const AttnDecodeParams *attn;
+    int B, pcap, attn_g;            // padded batch, score-buffer length, utterances per attention item
+    FlowState st;
+    FlowCtrl *ctrl;
+    const int *eos_after;
+    // HEAD
+    RowNormParams onorm;
+    const float *eos_w, *eos_b;
+    const __nv_bfloat16 *inp_w;     // [512, 32]
+    const float *inp_b;
+    float *fx;                      // [B, 512]
+    // flow output of the final-layer GEMM: split-K partial sums [flow_nsplit][.] flow_stride floats apart
+    const float *flow;
+    int flow_nsplit;
+    size_t flow_stride;
+    // TAIL
+    const __nv_bfloat16 *in_lin;    // [1024, 32]
+    RowNormParams ln0;              // LayerNorm 1 of layer 0 (x -> xn hi/lo); ln0.x is the residual stream
+    // control
+    unsigned int *bar;              // grid barrier counter, zeroed by the host before the launch
+    int *done_count;                // utterances that reached their stop point, zeroed by the host
+    int n_live, nsteps, first_gemm;
+    int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
+                                    // (only when the loop cannot stop early, i.e. EOS detection is off)
+    unsigned long long *prof;       // optional [MP_COUNT][2]: ns and phase count per type (written by CTA 0)
+    unsigned long long *trace;      // optional [n_phases][2]: ns of CTA 0's own work / ns including the barrier, summed over frames
+};
+
+// ---------------------------------------------------------------- sync primitives
+__device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Sum over a 256-thread group (8 warps); `red` holds 8 floats owned by the group.
+__device__ __forceinline__ float group_sum(float v, float *red, int tid, int bar_id) {
+    const int lane = tid & 31, w = tid >> 5;
+    v = warp_sum(v);
+    group_bar(bar_id);
+    if (lane == 0) red[w] = v;
+    group_bar(bar_id);
+    return warp_sum(lane < 8 ? red[lane] : 0.0f);
+}
+
+// Grid-wide barrier: every CTA arrives once on a monotonic counter; `epoch` is the value the counter
+// reaches when all CTAs have arrived. Global writes made before the barrier by any thread of any CTA
+// are visible after it to generic loads and to TMA (async proxy) loads.
+__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncthreads();
+    epoch += gridDim.x;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        if (ld_acquire_u32(bar) < epoch) {
+            const long long t0 = clock64();
+            uint32_t spins = 0;
+            while (ld_acquire_u32(bar) < epoch) {
+                if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) {
+                    printf("ptts_b200: grid barrier timed out (block %d, epoch %u, counter %u)\n", blockIdx.x, epoch, ld_acquire_u32(bar));
+                    __trap();
+                }
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------- row helpers (256 threads per row)
+// Thread tid owns the 4 consecutive elements tid*4 .. tid*4+3 of a row (D <= 1024): every access is a
+// 16-byte vector, and the split-K partial sums are fetched with independent loads (all in flight at
+// once) before they are added.
+constexpr int ROW_MAX_SPLIT = 8;
+__device__ __forceinline__ void row_load_fold(const RowNormParams &p, size_t row, int tid, float (&v)[4]) {
+    const int i = tid * 4;
+    v[0] = v[1] = v[2] = v[3] = 0.0f;
+    if (i >= p.D) return;
+    float *xr = p.x + row * p.D + i;
+    float4 t = *(const float4 *)xr;
+    if (p.nsplit > 0) {
+        float4 a[ROW_MAX_SPLIT];
+        const float *pp = p.part + row * p.D + i;
+#pragma unroll
+        for (int z = 0; z < ROW_MAX_SPLIT; z++) a[z] = z < p.nsplit ? *(const float4 *)(pp + z * p.split_stride) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 g = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        if (p.gate) g = *(const float4 *)(p.gate + row * p.ldmod + i);
+        float4 sum = a[0];
+#pragma unroll
+        for (int z = 1; z < ROW_MAX_SPLIT; z++) { sum.x += a[z].x; sum.y += a[z].y; sum.z += a[z].z; sum.w += a[z].w; }
+        t.x += sum.x * g.x; t.y += sum.y * g.y; t.z += sum.z * g.z; t.w += sum.w * g.w;
+        *(float4 *)xr = t;
+    }
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ uint2 pack4_bf16(const float (&o)[4]) {
+    uint2 r;
+    r.x = (uint32_t)f2h16(o[0], true) | ((uint32_t)f2h16(o[1], true) << 16);
+    r.y = (uint32_t)f2h16(o[2], true) | ((uint32_t)f2h16(o[3], true) << 16);
+    return r;
+}
+// LayerNorm (+ adaLN) of the row held in v (ptts_flowlm.c:159-181, 735-737); y returns the outputs.
+__device__ __forceinline__ void row_ln_store(const RowNormParams &p, size_t row, int tid, const float (&v)[4], float *red, int bar_id,
+                                             float (&y)[4]) {
+    const int i = tid * 4;
+    const bool on = i < p.D;
+    // affine / modulation vectors do not depend on the statistics: fetch them before the reductions
+    float4 w4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f), b4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), sc4 = b4, sh4 = b4;
+    if (on) {
+        if (p.w) w4 = *(const float4 *)(p.w + i);
+        if (p.b) b4 = *(const float4 *)(p.b + i);
+        if (p.scale) { sc4 = *(const float4 *)(p.scale + row * p.ldmod + i); sh4 = *(const float4 *)(p.shift + row * p.ldmod + i); }
+    }
+    const float mean = group_sum(on ? v[0] + v[1] + v[2] + v[3] : 0.0f, red, tid, bar_id) / (float)p.D;
+    float q = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) { const float d = v[j] - mean; q += d * d; }
+    const float var = group_sum(on ? q : 0.0f, red, tid, bar_id) / (float)p.D;
+    const float inv = 1.0f / sqrtf(var + p.eps);
+    y[0] = y[1] = y[2] = y[3] = 0.0f;
+    if (!on) return;
+    const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {sc4.x, sc4.y, sc4.z, sc4.w},
+                hh[4] = {sh4.x, sh4.y, sh4.z, sh4.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        float o = (v[j] - mean) * inv;
+        if (p.w) o *= ww[j];
+        if (p.b) o += bb[j];
+        if (p.scale) o = o * (1.0f + ss[j]) + hh[j];
+        y[j] = o;
+    }
+    if (p.out_f32) *(float4 *)(p.out_f32 + row * p.D + i) = make_float4(y[0], y[1], y[2], y[3]);
+    if (p.out_h) {
+        const uint2 hi = pack4_bf16(y);
+        *(uint2 *)(p.out_h + row * p.D + i) = hi;
+        if (p.out_l) {
+            const float lo[4] = {y[0] - bf16lo(hi.x), y[1] - bf16hi(hi.x), y[2] - bf16lo(hi.y), y[3] - bf16hi(hi.y)};
+            *(uint2 *)(p.out_l + row * p.D + i) = pack4_bf16(lo);
+        }
+    }
+}
+
+// fx[b, n] = input_proj . lat + bias for n = tid, tid + 256 (ptts_flowlm.c:710); lat in shared memory
+__device__ __forceinline__ void flow_input_proj(const MegaProgram &P, int b, int tid, const float *lat) {
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int n = tid + r * 256;
+        const uint4 *wr = (const uint4 *)(P.inp_w + (size_t)n * FL_LAT);
+        float a = P.inp_b[n];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 u = wr[c];
+            const float *l = lat + c * 8;
+            a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] + bf16lo(u.z) * l[4] +
+                 bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
+        }
+        P.fx[(size_t)b * FN_D + n] = a;
+    }
+}
+
+// HEAD for utterance b at decode iteration `step` (k_rownorm + k_eos_state + k_flow_init(k = 0) fused).
+__device__ __forceinline__ void mega_head(const MegaProgram &P, int b, int tid, int step, float *red, float *lat, int bar_id) {
+    const FlowState &st = P.st;
+    float v[4], y[4];
+    row_load_fold(P.onorm, b, tid, v);
+    row_ln_store(P.onorm, b, tid, v, red, bar_id, y);
+    const float4 ew = *(const float4 *)(P.eos_w + tid * 4);
+    const float eos = group_sum(ew.x * y[0] + ew.y * y[1] + ew.z * y[2] + ew.w * y[3], red, tid, bar_id) + P.eos_b[0];
+    const bool valid = step < st.max_frames[b] && !st.done[b];
+    if (valid) {
+        if (step == 0) *(float4 *)(st.first_cond + (size_t)b * FL_D + tid * 4) = make_float4(y[0], y[1], y[2], y[3]);
+        if (tid == 0) {
+            if (step == 0) st.first_eos[b] = eos;
+            if (st.eos_log) st.eos_log[(size_t)b * st.max_frames_cap + step] = eos;
+            if (P.ctrl->eos_enabled && step + 1 >= P.ctrl->eos_min_frames && eos >= P.ctrl->eos_threshold && st.eos_step[b] < 0)
+                st.eos_step[b] = step;
+        }
+    }
+    if (tid < FL_LAT) {
+        const int fi = min(max(step, 0), st.max_frames_cap - 1);
+        const float z = st.noise[((size_t)b * st.max_frames_cap + fi) * FL_LAT + tid];
+        st.latent[b * FL_LAT + tid] = z;
+        lat[tid] = z;
+    }
+    group_bar(bar_id);
+    flow_input_proj(P, b, tid, lat);
+}
+
+// Euler update of LSD step k for utterance b (k_flow_update): returns the new latent in lat[] (threads < 32).
+__device__ __forceinline__ void mega_flow_update(const MegaProgram &P, int b, int tid, int step, int k, float *lat) {
+    const FlowState &st = P.st;
+    if (tid < FL_LAT) {
+        const bool valid = step < st.max_frames[b] && !st.done[b];
+        float f = 0.0f;
+        for (int z = 0; z < P.flow_nsplit; z++) f += P.flow[z * P.flow_stride + (size_t)b * FL_LAT + tid];
+        const float v = st.latent[b * FL_LAT + tid] + f / (float)st.lsd_steps;
+        st.latent[b * FL_LAT + tid] = v;
+        lat[tid] = v;
+        if (valid) {
+            if (step == 0 && k == 0) st.first_flow[b * FL_LAT + tid] = f;
+            if (k == st.lsd_steps - 1) st.out_latents[((size_t)b * st.max_frames_cap + step) * FL_LAT + tid] = v;
+        }
+        __syncwarp();
+        if (k == st.lsd_steps - 1 && tid == 0 && valid) {
+            st.used[b] = step + 1;
+            const int es = st.eos_step[b];
+            if ((es >= 0 && step >= es + P.eos_after[b]) || step + 1 >= st.max_frames[b]) {
+                st.done[b] = 1;
+                atomicAdd(P.done_count, 1);
+            }
+        }
+    }
+}
+
+// TAIL for utterance b (k_flow_update(last k) + k_prepare_x + LayerNorm 1 of layer 0 fused).
+__device__ __forceinline__ void mega_tail(const MegaProgram &P, int b, int tid, int step, float *red, float *lat, int bar_id) {
+    mega_flow_update(P, b, tid, step, P.st.lsd_steps - 1, lat);
+    group_bar(bar_id);
+    float v[4], y[4];
+    float *xr = P.ln0.x + (size_t)b * FL_D;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int i = tid * 4 + j;
+        const uint4 *wr = (const uint4 *)(P.in_lin + (size_t)i * FL_LAT);
+        float a = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 u = wr[c];
+            const float *l = lat + c * 8;
+            a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] + bf16lo(u.z) * l[4] +
+                 bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
+        }
+        v[j] = a;
+    }
+    *(float4 *)(xr + tid * 4) = make_float4(v[0], v[1], v[2], v[3]);
+    row_ln_store(P.ln0, b, tid, v, red, bar_id, y);
+}
+
+
+// ---------------------------------------------------------------- decode attention, persistent-kernel version
+// Work unit = one (utterance, head) pair, owned by ONE warp from start to end - no block-level barrier
+// sits between a unit's loads and its math, so the 16 warps of a CTA keep 16 independent streams of
+// 256-bit loads in flight (the per-utterance K / V rows are read exactly once, straight from HBM, and a
+// unit's rows are one contiguous region). Warps draw units from a per-CTA counter, so long and short
+// utterances balance out. The first 128 keys of the shared voice prefix sit in shared memory (one copy per CTA
+// and head); longer prefixes are read from L2 like the own rows.
+// Lane layout everywhere: 8 lanes per key row (32 bytes each), 4 rows per warp instruction.
+// Numerics follow ptts_flowlm.c:465-525: fp32 throughout, max-subtracted softmax, 1/sqrt(64) folded into q.
+constexpr int A4_TILE = 128, A4_WARPS = MG_THREADS / 32;
+__host__ __device__ inline size_t attn4_smem_bytes(int pcap) {
+    return (size_t)(2 * A4_TILE * FL_HD + A4_WARPS * (pcap + FL_HD) + 8) * sizeof(float);
+}
+__device__ __forceinline__ void ld_global_v8_pred(const float *ptr, bool ok, float (&v)[8]) {
+    if (ok) ld_global_v8(ptr, v);
+    else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = 0.0f;
+    }
+}
+__device__ __forceinline__ float dot8_reduce(const float (&q)[8], const float (&k)[8]) {
+    float a = q[0] * k[0] + q[1] * k[1] + q[2] * k[2] + q[3] * k[3] + q[4] * k[4] + q[5] * k[5] + q[6] * k[6] + q[7] * k[7];
+    a += __shfl_xor_sync(0xffffffffu, a, 1);
+    a += __shfl_xor_sync(0xffffffffu, a, 2);
+    a += __shfl_xor_sync(0xffffffffu, a, 4);
+    return a;
+}
+// scores of rows [0, n) of a global K region (row stride 64 floats) -> sc[0..n); `first` holds rows 0..31 already loaded
+__device__ __forceinline__ void qk_rows_global(const float *kb, int n, const float (&q8)[8], float *sc, int k4, int l8, float (&first)[8][8]) {
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int key = it * 4 + k4;
+        const float a = dot8_reduce(q8, first[it]);
+        if (l8 == 0 && key < n) sc[key] = a;
+    }
+    for (int r0 = 32; r0 < n; r0 += 32) {
+        float kr[8][8];
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int key = r0 + it * 4 + k4;
+            ld_global_v8_pred(kb + (size_t)key * FL_HD + l8 * 8, key < n, kr[it]);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int key = r0 + it * 4 + k4;
+            const float a = dot8_reduce(q8, kr[it]);
+            if (l8 == 0 && key < n) sc[key] = a;
+        }
+    }
+}
+__device__ __forceinline__ void load_rows32(const float *base, int n, int k4, int l8, float (&out)[8][8]) {
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int key = it * 4 + k4;
+        ld_global_v8_pred(base + (size_t)key * FL_HD + l8 * 8, key < n, out[it]);
+    }
+}
+// acc += sum_r sc[r] * V[r] over rows [0, n) of a global V region; `first` holds rows 0..31 already loaded
+__device__ __forceinline__ void pv_rows_global(const float *vb, int n, const float *sc, int k4, int l8, float (&first)[8][8], float (&acc)[8]) {
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+        const int key = it * 4 + k4;
+        const float pw = key < n ? sc[key] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] += pw * first[it][i];
+    }
+    for (int r0 = 32; r0 < n; r0 += 32) {
+        float vr[8][8];
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int key = r0 + it * 4 + k4;
+            ld_global_v8_pred(vb + (size_t)key * FL_HD + l8 * 8, key < n, vr[it]);
+        }
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int key = r0 + it * 4 + k4;
+            const float pw = key < n ? sc[key] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] += pw * vr[it][i];
+        }
+    }
+}
+
+__device__ __forceinline__ void attn4_unit(const AttnDecodeParams &p, int b, int h, int step, int cond_len, const float *kt, const float *vt,
+                                           float *sc, float *sqw, int lane) {
+    const int k4 = lane >> 3, l8 = lane & 7;
+    const int s = step + p.own_base[b], pos = cond_len + s, n_own = s + 1, P = cond_len + n_own;
+    const int n_tile = min(cond_len, A4_TILE), n_far = cond_len - n_tile;   // prefix keys in shared memory / beyond the tile
+    float *okb = p.ok + ((size_t)b * FL_H + h) * p.max_s * FL_HD, *ovb = p.ov + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+    const float *pkh = p.pk ? p.pk + (size_t)h * p.pstride * FL_HD : nullptr;
+    const float *pvh = p.pv ? p.pv + (size_t)h * p.pstride * FL_HD : nullptr;
+    // ---- new position: RoPE(q), RoPE(k) and v appended to the own cache (lane = dimension pair)
+    {
+        const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD;
+        const float c = p.rope_cos[pos * 32 + lane], sn = p.rope_sin[pos * 32 + lane];
+        const float2 qq = ld_fold2(row + 2 * lane, p.qkv_nsplit, p.qkv_stride);
+        const float2 kk = ld_fold2(row + FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
+        const float2 vv = ld_fold2(row + 2 * FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
+        *(float2 *)(okb + (size_t)s * FL_HD + 2 * lane) = make_float2(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
+        *(float2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = vv;
+        *(float2 *)(sqw + 2 * lane) = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
+    }
+    __syncwarp();
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q8[i] = sqw[l8 * 8 + i];
+    // ---- scores: the first 32 own rows are requested before the shared-memory prefix work
+    float rows[8][8];
+    load_rows32(okb, n_own, k4, l8, rows);
+    for (int r0 = 0; r0 < n_tile; r0 += 4) {
+        const int key = r0 + k4;
+        float kk[8];
+        const bool ok = key < n_tile;
+        const float4 k0 = ok ? *(const float4 *)(kt + key * FL_HD + l8 * 8) : make_float4(0, 0, 0, 0);
+        const float4 k1 = ok ? *(const float4 *)(kt + key * FL_HD + l8 * 8 + 4) : make_float4(0, 0, 0, 0);
+        kk[0] = k0.x; kk[1] = k0.y; kk[2] = k0.z; kk[3] = k0.w; kk[4] = k1.x; kk[5] = k1.y; kk[6] = k1.z; kk[7] = k1.w;
+        const float a = dot8_reduce(q8, kk);
+        if (l8 == 0 && ok) sc[key] = a;
+    }
+    qk_rows_global(okb, n_own, q8, sc + cond_len, k4, l8, rows);
+    if (n_far > 0) {
+        load_rows32(pkh + (size_t)n_tile * FL_HD, n_far, k4, l8, rows);
+        qk_rows_global(pkh + (size_t)n_tile * FL_HD, n_far, q8, sc + n_tile, k4, l8, rows);
+    }
+    __syncwarp();
+    // ---- softmax; the first 32 own V rows are requested before it
+    load_rows32(ovb, n_own, k4, l8, rows);
+    float mx = -INFINITY;
+    for (int t = lane; t < P; t += 32) mx = fmaxf(mx, sc[t]);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int t = lane; t < P; t += 32) { const float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
+    sum = warp_sum(sum);
+    __syncwarp();
+    // ---- P.V
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
+    for (int r0 = 0; r0 < n_tile; r0 += 4) {
+        const int key = r0 + k4;
+        if (key < n_tile) {
+            const float pw = sc[key];
+            const float4 v0 = *(const float4 *)(vt + key * FL_HD + l8 * 8), v1 = *(const float4 *)(vt + key * FL_HD + l8 * 8 + 4);
+            acc[0] += pw * v0.x; acc[1] += pw * v0.y; acc[2] += pw * v0.z; acc[3] += pw * v0.w;
+            acc[4] += pw * v1.x; acc[5] += pw * v1.y; acc[6] += pw * v1.z; acc[7] += pw * v1.w;
+        }
+    }
+    pv_rows_global(ovb, n_own, sc + cond_len, k4, l8, rows, acc);
+    if (n_far > 0) {
+        load_rows32(pvh + (size_t)n_tile * FL_HD, n_far, k4, l8, rows);
+        pv_rows_global(pvh + (size_t)n_tile * FL_HD, n_far, sc + n_tile, k4, l8, rows, acc);
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+        acc[i] *= inv;
+    }
+    if (k4 == 0) {   // lanes 0..7 hold the 64 outputs, 8 consecutive dimensions each
+        const size_t oi = (size_t)b * FL_D + h * FL_HD + l8 * 8;
+        if (p.out_f32) {
+            *(float4 *)(p.out_f32 + oi) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *(float4 *)(p.out_f32 + oi + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        if (p.out_h) {
+            uint4 hv, lv;
+            uint32_t *hp = (uint32_t *)&hv, *lp = (uint32_t *)&lv;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint16_t h0 = f2h16(acc[2 * i], true), h1 = f2h16(acc[2 * i + 1], true);
+                hp[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                const uint16_t l0 = f2h16(acc[2 * i] - h162f(h0, true), true), l1 = f2h16(acc[2 * i + 1] - h162f(h1, true), true);
+                lp[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+            }
+            *(uint4 *)(p.out_h + oi) = hv;
+            if (p.out_l) *(uint4 *)(p.out_l + oi) = lv;
+        }
+    }
+    __syncwarp();   // sc / sqw reusable by this warp's next unit
+}
+
+// One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
+__device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, int pcap, int step, float *sm, int tid) {
+    float *kt = sm, *vt = kt + A4_TILE * FL_HD, *scw = vt + A4_TILE * FL_HD;
+    int *ctr = (int *)(scw + A4_WARPS * (pcap + FL_HD));
+    const int w = tid >> 5, lane = tid & 31;
+    float *sc = scw + w * (pcap + FL_HD), *sqw = sc + pcap;
+    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
+    // units in head-major order (unit = h * B + b). With at least one CTA per head, every CTA stays inside
+    // one head (one prefix tile, no mid-phase reload): gridDim / 16 CTAs share a head's utterances.
+    int u0, u1;
+    const int cph = (int)gridDim.x / FL_H;
+    if (cph >= 1) {
+        const int h = (int)blockIdx.x / cph, j = (int)blockIdx.x % cph;
+        if (h < FL_H) { u0 = h * B + (int)(((long long)j * B) / cph); u1 = h * B + (int)(((long long)(j + 1) * B) / cph); }
+        else { u0 = u1 = 0; }
+    } else {
+        const int units = FL_H * B;
+        u0 = (int)(((long long)blockIdx.x * units) / gridDim.x); u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
+    }
+    for (int ua = u0; ua < u1;) {
+        const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
+        __syncthreads();                                    // previous head's tile no longer in use
+        if (cond_len > 0) {
+            const int nt = min(A4_TILE, cond_len);
+            const float *pkh = p.pk + (size_t)h * p.pstride * FL_HD, *pvh = p.pv + (size_t)h * p.pstride * FL_HD;
+            for (int idx = tid; idx < nt * 16; idx += MG_THREADS) {
+                *(float4 *)(kt + idx * 4) = *(const float4 *)(pkh + idx * 4);
+                *(float4 *)(vt + idx * 4) = *(const float4 *)(pvh + idx * 4);
+            }
+        }
+        if (tid == 0) *ctr = ua;
+        __syncthreads();
+        while (true) {
+            int u = 0;
+            if (lane == 0) u = atomicAdd(ctr, 1);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= ub) break;
+            attn4_unit(p, u - h * B, h, step, cond_len, kt, vt, sc, sqw, lane);
+        }
+        ua = ub;
+    }
+}
+
+// ---------------------------------------------------------------- GEMM phase
+struct MegaPipe {
+    int s;          // ring slot (producer and MMA threads keep their own copy)
+    uint32_t ph;    // ring phase parity
+    int lt;         // accumulator tiles processed by this CTA (MMA and epilogue threads)
+    int pre;        // producer: leading items of the coming GEMM whose B tile is already in flight
+};
+
+__device__ __forceinline__ uint32_t mg_stage_bytes(const GemmOp &g) {
+    return (uint32_t)(MG_A_BYTES * (g.split == 1 ? 2 : 1) + g.bn * GEMM_BK * 2);
+}
+
+__device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, MegaPipe &pipe, uint8_t *ring, uint64_t *full,
+                                          uint64_t *empty, uint64_t *tfull, uint64_t *tempty, uint32_t tmem_base) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const GemmParams &p = g.p;
+    const int BN = g.bn;
+    const bool lo = g.split == 1;
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            const uint32_t sb = mg_stage_bytes(g);
+            int n = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = gemm_tile(p, tile, BN);
+                for (int it = t.it0; it < t.it1; it++, n++) {
+                    uint8_t *st = ring + pipe.s * MG_SLOT_BYTES;
+                    if (n >= pipe.pre) {
+                        mbar_wait(&empty[pipe.s], pipe.ph ^ 1);
+                        mbar_expect_tx(&full[pipe.s], sb);
+                    }
+                    tma_load_3d(st, &g.mapA, &full[pipe.s], it * GEMM_BK, t.m0, 0);
+                    if (lo) tma_load_3d(st + MG_A_BYTES, &g.mapAlo, &full[pipe.s], it * GEMM_BK, t.m0, 0);
+                    if (n >= pipe.pre) tma_load_3d(st + 2 * MG_A_BYTES, &g.mapB, &full[pipe.s], it * GEMM_BK, t.n0, 0);
+                    if (++pipe.s == MG_STAGES) { pipe.s = 0; pipe.ph ^= 1; }
+                }
+            }
+            // weights of the next contraction do not depend on anything computed in between
+            pipe.pre = 0;
+            if (next) {
+                const uint32_t sbn = mg_stage_bytes(*next);
+                int s2 = pipe.s; uint32_t ph2 = pipe.ph;
+                for (int tile = blockIdx.x; tile < next->p.total_tiles && pipe.pre < MG_STAGES; tile += gridDim.x) {
+                    const TileCoord t = gemm_tile(next->p, tile, next->bn);
+                    for (int it = t.it0; it < t.it1 && pipe.pre < MG_STAGES; it++, pipe.pre++) {
+                        mbar_wait(&empty[s2], ph2 ^ 1);
+                        mbar_expect_tx(&full[s2], sbn);
+                        tma_load_3d(ring + s2 * MG_SLOT_BYTES + 2 * MG_A_BYTES, &next->mapB, &full[s2], it * GEMM_BK, t.n0, 0);
+                        if (++s2 == MG_STAGES) { s2 = 0; ph2 ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer (one elected lane)
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, pipe.lt++) {
+            const TileCoord t = gemm_tile(p, tile, BN);
+            const int acc = pipe.lt & 1;
+            mbar_wait(&tempty[acc], ((pipe.lt >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * MG_MAX_BN;
+            for (int it = t.it0; it < t.it1; it++) {
+                mbar_wait(&full[pipe.s], pipe.ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(ring + pipe.s * MG_SLOT_BYTES);
+                    const uint64_t ad = umma_desc_sw128(a_addr), ald = umma_desc_sw128(a_addr + MG_A_BYTES),
+                                   bd = umma_desc_sw128(a_addr + 2 * MG_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; k++) {
+                        umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (it > t.it0 || k > 0) ? 1u : 0u);
+                        if (lo) umma_f16(d_tmem, ald + 2 * k, bd + 2 * k, p.idesc, 1u);
+                    }
+                    umma_commit(&empty[pipe.s]);
+                    if (it == t.it1 - 1) umma_commit(&tfull[acc]);
+                }
+                __syncwarp();
+                if (++pipe.s == MG_STAGES) { pipe.s = 0; pipe.ph ^= 1; }
+            }
+        }
+    } else if (warp < 2 + MG_EPI_WARPS) {
+        // ------------------------------------------------ epilogue warps (row-major outputs only)
+        const int quad = warp & 3, cg = (warp - 2) >> 2;
+        constexpr int NCG = MG_EPI_WARPS / 4;
+        const int act = p.act, ldo = p.ldo, ldh = p.ldh, n_total = p.n_total;
+        const float *bias = p.bias;
+        uint16_t *out_h = p.out_h, *out_l = p.out_l;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, pipe.lt++) {
+            const TileCoord t = gemm_tile(p, tile, BN);
+            const int acc = pipe.lt & 1;
+            mbar_wait(&tfull[acc], (pipe.lt >> 1) & 1);
+            tc_fence_after();
+            const int m = t.m0 + quad * 32 + lane;
+            const bool m_ok = m < p.a_rows;
+            const uint32_t trow = tmem_base + acc * MG_MAX_BN + ((uint32_t)(quad * 32) << 16);
+            float *of = p.out_f32 ? p.out_f32 + (size_t)t.z * p.split_stride + (size_t)m * ldo : nullptr;
+            uint16_t *oh = out_h ? out_h + (size_t)m * ldh : nullptr;
+            uint16_t *ol = out_l ? out_l + (size_t)m * ldh : nullptr;
+            const bool add_bias = bias != nullptr && t.z == 0;
+            uint32_t r[16];
+#pragma unroll 1
+            for (int c = cg * 16; c < BN; c += 16 * NCG) {
+                tmem_ld16(trow + c, r);
+                tmem_ld_wait16(r);
+                const int nb = t.n0 + c;
+                if (m_ok && nb < n_total) {
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
+                    if (add_bias) {
+                        const float4 *bp = (const float4 *)(bias + nb);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+                    }
+                    if (of) {
+                        uint32_t w0[8], w1[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { w0[j] = __float_as_uint(v[j]); w1[j] = __float_as_uint(v[8 + j]); }
+                        st_global_v8(of + nb, w0);
+                        st_global_v8(of + nb + 8, w1);
+                    }
+                    if (oh) {
+                        uint32_t hw[8], lw[8];
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2) {
+                            const float a0 = act_apply(act, v[j]), a1 = act_apply(act, v[j + 1]);
+                            const uint16_t h0 = f2h16(a0, true), h1 = f2h16(a1, true);
+                            hw[j / 2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                            const uint16_t l0 = f2h16(a0 - h162f(h0, true), true), l1 = f2h16(a1 - h162f(h1, true), true);
+                            lw[j / 2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                        }
+                        st_global_v8(oh + nb, hw);
+                        if (ol) st_global_v8(ol + nb, lw);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the kernel
+__global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_constant__ MegaProgram P) {
+    extern __shared__ uint8_t mg_smem_raw[];
+    uint8_t *ring = (uint8_t *)(((uintptr_t)mg_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(ring + MG_RING_BYTES);
+    uint64_t *full = bars, *empty = bars + MG_STAGES, *tfull = bars + 2 * MG_STAGES, *tempty = tfull + 2;
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    float *scratch = (float *)(ring + MG_RING_BYTES + 256);   // per row group: red[8] + lat[32]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+    constexpr uint32_t TMEM_COLS = 2 * MG_MAX_BN;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < MG_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], MG_EPI_WARPS); mbar_init(&tempty[1], MG_EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    MegaPipe pipe = {0, 0u, 0, 0};
+    unsigned int epoch = 0;
+    const int step0 = P.ctrl->step;
+    const int grp = tid >> 8;                       // row group 0, 1
+    const int gt = tid & 255;
+    float *red = scratch + grp * 64, *lat = red + 16;
+    const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
+    int steps_done = 0;
+
+    // the first contraction's weight tiles can be requested right away
+    if (warp == 0 && lane == 0 && P.first_gemm >= 0) {
+        const GemmOp &g0 = P.gemms[P.first_gemm];
+        const uint32_t sb0 = mg_stage_bytes(g0);
+        for (int tile = blockIdx.x; tile < g0.p.total_tiles && pipe.pre < MG_STAGES; tile += gridDim.x) {
+            const TileCoord t = gemm_tile(g0.p, tile, g0.bn);
+            for (int it = t.it0; it < t.it1 && pipe.pre < MG_STAGES; it++, pipe.pre++) {
+                mbar_expect_tx(&full[pipe.pre], sb0);
+                tma_load_3d(ring + pipe.pre * MG_SLOT_BYTES + 2 * MG_A_BYTES, &g0.mapB, &full[pipe.pre], it * GEMM_BK, t.n0, 0);
+            }
+        }
+    }
+
+    for (int si = 0; si < P.nsteps; si++) {
+        const int step = step0 + si;
+        for (int pi = 0; pi < P.n_phases; pi++) {
+            const MegaPhase ph = P.phases[pi];
+            unsigned long long t0 = 0;
+            if (prof) t0 = globaltimer_ns();
+            switch (ph.type) {
+                case MP_GEMM: {
+                    // a fetch that wraps into the next frame must be consumed: never past the end of the launch
+                    const bool wraps = ph.next_gemm >= 0 && ph.next_gemm <= ph.idx;
+                    const GemmOp *nx = ph.next_gemm >= 0 && !(wraps && (!P.wrap_prefetch || si + 1 == P.nsteps)) ? &P.gemms[ph.next_gemm] : nullptr;
+                    mega_gemm(P.gemms[ph.idx], nx, pipe, ring, full, empty, tfull, tempty, tmem_base);
+                    break;
+                }
+                case MP_ROW:
+                    if (tid < 512) {
+                        const RowNormParams &rp = P.rows[ph.idx];
+                        for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
+                            float v[4], y[4];
+                            row_load_fold(rp, b, gt, v);
+                            if (rp.do_norm) row_ln_store(rp, b, gt, v, red, 1 + grp, y);
+                        }
+                    }
+                    break;
+                case MP_HEAD:
+                    if (tid < 512)
+                        for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
+                            mega_head(P, b, gt, step, red, lat, 1 + grp);
+                            group_bar(1 + grp);   // lat[] reusable
+                        }
+                    break;
+                case MP_MID:
+                    if (tid < 512)
+                        for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
+                            mega_flow_update(P, b, gt, step, ph.idx, lat);
+                            group_bar(1 + grp);
+                            flow_input_proj(P, b, gt, lat);
+                            group_bar(1 + grp);
+                        }
+                    break;
+                case MP_TAIL:
+                    if (tid < 512)
+                        for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
+                            mega_tail(P, b, gt, step, red, lat, 1 + grp);
+                            group_bar(1 + grp);
+                        }
+                    break;
+                case MP_ATTN:
+                    attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid);
+                    break;
+                default: break;
+            }
+            unsigned long long t1 = 0;
+            if (prof && P.trace) t1 = globaltimer_ns();
+            grid_sync(P.bar, epoch);
+            if (prof) {
+                const unsigned long long t2 = globaltimer_ns();
+                P.prof[2 * ph.type] += t2 - t0;
+                P.prof[2 * ph.type + 1] += 1;
+                if (P.trace) { P.trace[2 * pi] += t1 - t0; P.trace[2 * pi + 1] += t2 - t0; }
+            }
+        }
+        steps_done = si + 1;
+        // every utterance has reached its stop point: done_count only changes in TAIL phases, several
+        // barriers before this read, so all CTAs take the same branch
+        if (*(volatile int *)P.done_count >= P.n_live) break;
+    }
+    if (blockIdx.x == 0 && tid == 0) P.ctrl->step = step0 + steps_done;
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------- host side: program construction and launch
+struct MegaHost {
+    uint64_t gen = ~0ull;
+    int B = 0, lsd = 0, precise = -1;
+    MegaPhase *d_phases = nullptr;
+    GemmOp *d_gemms = nullptr;
+    RowNormParams *d_rows = nullptr;
+    AttnDecodeParams *d_attn = nullptr;
+    MegaProgram prog = {};
+    std::vector<MegaPhase> phases;
+    std::vector<GemmOp> gemms;
+    // algorithmic work of one frame step, per phase type (profile accounting)
+    double flops[MP_COUNT] = {0}, bytes[MP_COUNT] = {0};
+};
+
+static AttnDecodeParams make_attn_params(Engine *e, int layer, bool out16, int qkv_nsplit) {
+    AttnDecodeParams a = {};
+    a.qkv = e->qkv; a.qkv_nsplit = qkv_nsplit; a.qkv_stride = (size_t)e->capB * 3 * FL_D;
+    a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin;
+    a.ctrl_cond_len = &e->ctrl->cond_len;
+    a.own_base = e->d_own_base;
+    a.pstride = e->capCond;
+    a.pk = e->pk + (size_t)layer * FL_D * e->capCond; a.pv = e->pv + (size_t)layer * FL_D * e->capCond;
+    a.ok = e->ok + (size_t)layer * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)layer * e->capB * FL_D * e->capS;
+    a.max_s = e->capS;
+    a.step = &e->ctrl->step;
+    if (out16) { a.out_h = e->att_h; a.out_l = e->att_l; } else a.out_f32 = e->att;
+    return a;
+}
+
+static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd, int precise) {
+    void *old[] = {M.d_phases, M.d_gemms, M.d_rows, M.d_attn};
+    for (void *q : old) e->dfree(q);
+    M = MegaHost();
+    std::vector<RowNormParams> rows;
+    std::vector<AttnDecodeParams> attn;
+    auto &ph = M.phases;
+    auto &gm = M.gemms;
+    const size_t ps = (size_t)e->capB * FL_D;
+    auto add_gemm = [&](const GemmOp &op) -> int {
+        if (op.bn > MG_MAX_BN || op.split == 2 || op.p.taps != 1 || op.p.transposed) {
+            set_error("mega_build: contraction shape not supported by the persistent step kernel");
+            return -1;
+        }
+        gm.push_back(op);
+        ph.push_back({MP_GEMM, (int)gm.size() - 1, -1});
+        const double rows_ = op.p.a_rows, n = op.p.n_total, k = (double)op.p.kblocks_per_tap * GEMM_BK;
+        M.flops[MP_GEMM] += 2.0 * rows_ * n * k;
+        M.bytes[MP_GEMM] += 2.0 * n * k;   // weights once; activations stay in L2
+        return 0;
+    };
+    auto add_row = [&](const RowNormParams &r) { rows.push_back(r); ph.push_back({MP_ROW, (int)rows.size() - 1, -1}); };
+    ph.push_back({MP_HEAD, 0, -1});
+    for (int k = 0; k < lsd; k++) {
+        if (add_gemm(G.cond[k]) != 0 || add_gemm(G.ada) != 0) return -1;
+        for (int b = 0; b <= FN_DEPTH; b++) {
+            RowNormParams r = {};
+            r.x = e->fx; r.D = FN_D; r.eps = 1e-6f; r.do_norm = 1; r.ldmod = FN_ADA;
+            if (b > 0) { r.part = e->ft; r.nsplit = G.m2[b - 1].p.split_k; r.split_stride = (size_t)e->capB * FN_D; r.gate = e->ada + (size_t)(b - 1) * 3 * FN_D + 2 * FN_D; }
+            if (b < FN_DEPTH) { r.w = e->FB[b].lnw; r.b = e->FB[b].lnb; }
+            r.shift = e->ada + (size_t)b * 3 * FN_D; r.scale = r.shift + FN_D;
+            r.out_h = e->fh_h; r.out_l = precise ? e->fh_l : nullptr; r.out_bf16 = 1;
+            add_row(r);
+            if (b < FN_DEPTH && (add_gemm(G.m0[b]) != 0 || add_gemm(G.m2[b]) != 0)) return -1;
+        }
+        if (add_gemm(G.fin) != 0) return -1;
+        if (k + 1 < lsd) ph.push_back({MP_MID, k, -1});
+    }
+    ph.push_back({MP_TAIL, 0, -1});
+    for (int l = 0; l < FL_L; l++) {
+        RowNormParams r = {};
+        if (l > 0) {
+            r.x = e->x; r.D = FL_D; r.w = e->L[l].n1w; r.b = e->L[l].n1b; r.eps = 1e-5f; r.do_norm = 1;
+            r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
+            r.part = e->partB; r.nsplit = (int)G.ff2[l - 1].p.split_k; r.split_stride = ps;
+            add_row(r);
+        }
+        if (add_gemm(G.qkv[l]) != 0) return -1;
+        attn.push_back(make_attn_params(e, l, true, G.qkv[l].p.split_k));
+        ph.push_back({MP_ATTN, (int)attn.size() - 1, -1});
+        if (add_gemm(G.outp[l]) != 0) return -1;
+        r = {};
+        r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
+        r.part = e->partA; r.nsplit = (int)G.outp[l].p.split_k; r.split_stride = ps;
+        r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
+        add_row(r);
+        if (add_gemm(G.ff1[l]) != 0 || add_gemm(G.ff2[l]) != 0) return -1;
+    }
+    // next contraction reachable without an attention phase in between (attention aliases the ring)
+    const int np = (int)ph.size();
+    int first_gemm = -1;
+    for (int i = 0; i < np; i++) {
+        if (ph[i].type != MP_GEMM) continue;
+        if (first_gemm < 0) first_gemm = ph[i].idx;
+        for (int d = 1; d < np; d++) {
+            const MegaPhase &q = ph[(i + d) % np];
+            if (q.type == MP_ATTN) break;
+            if (q.type == MP_GEMM) { ph[i].next_gemm = q.idx; break; }
+        }
+    }
+    const int Gu = 1;
+    const int pcap = ((e->capCond + e->capS + 63) / 32) * 32;
+    PTTS_CHECK(attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES,
+               "attention score buffers of %zu bytes exceed the persistent kernel's shared memory (sequence too long)",
+               attn4_smem_bytes(pcap));
+    if (e->dalloc(&M.d_phases, ph.size()) != 0 || e->dalloc(&M.d_gemms, gm.size()) != 0 || e->dalloc(&M.d_rows, rows.size()) != 0 ||
+        e->dalloc(&M.d_attn, attn.size()) != 0) return -1;
+    PTTS_CUDA_OK(cudaMemcpy(M.d_phases, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+    PTTS_CUDA_OK(cudaMemcpy(M.d_gemms, gm.data(), gm.size() * sizeof(GemmOp), cudaMemcpyHostToDevice));
+    PTTS_CUDA_OK(cudaMemcpy(M.d_rows, rows.data(), rows.size() * sizeof(RowNormParams), cudaMemcpyHostToDevice));
+    PTTS_CUDA_OK(cudaMemcpy(M.d_attn, attn.data(), attn.size() * sizeof(AttnDecodeParams), cudaMemcpyHostToDevice));
+    MegaProgram &P = M.prog;
+    P.phases = M.d_phases; P.n_phases = np; P.gemms = M.d_gemms; P.rows = M.d_rows; P.attn = M.d_attn;
+    P.B = B; P.pcap = pcap; P.attn_g = Gu;
+    P.st = make_state(e, B, lsd);
+    P.ctrl = e->ctrl; P.eos_after = e->d_eos_after;
+    RowNormParams r = {};
+    r.x = e->x; r.D = FL_D; r.w = e->onorm_w; r.b = e->onorm_b; r.eps = 1e-5f; r.do_norm = 1;
+    r.part = e->partB; r.nsplit = (int)G.ff2[FL_L - 1].p.split_k; r.split_stride = ps;
+    r.out_f32 = e->normed; r.out_h = e->normed_h; r.out_l = precise ? e->normed_l : nullptr; r.out_bf16 = 1;
+    P.onorm = r;
+    P.eos_w = e->eos_w; P.eos_b = e->eos_b; P.inp_w = e->inp_w; P.inp_b = e->inp_b; P.fx = e->fx;
+    P.flow = e->flow; P.flow_nsplit = G.fin.p.split_k; P.flow_stride = (size_t)e->capB * FL_LAT;
+    P.in_lin = e->in_lin;
+    r = {};
+    r.x = e->x; r.D = FL_D; r.w = e->L[0].n1w; r.b = e->L[0].n1b; r.eps = 1e-5f; r.do_norm = 1;
+    r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
+    P.ln0 = r;
+    P.first_gemm = first_gemm;
+    M.gen = e->gen; M.B = B; M.lsd = lsd; M.precise = precise;
+    return 0;
+}
+
+}  // namespace ptts

@@ -158,13 +158,13 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
     __half *d0 = ws.take<__half>(R * MI_D);
     {
         LaunchScope ls(e, KC_MIMI_MISC);
-        k_mimi_front<<<dim3(F, Bc), 512, 0, e->st>>>(d_lat, lat_stride, F, e->emb_std, e->emb_mean, apply_scale, e->quant_w, e->ups_w, x);
+        launch_k(k_mimi_front, dim3(F, Bc), 512, 0, e->st, d_lat, lat_stride, F, e->emb_std, e->emb_mean, apply_scale, e->quant_w, e->ups_w, x);
         if (launch_check("k_mimi_front") != 0) return -1;
     }
     for (int l = 0; l < MI_L; l++) {
         {
             LaunchScope ls(e, KC_MIMI_MISC);
-            k_ln512_f16<<<(unsigned)((R + 7) / 8), 256, 0, e->st>>>(x, R, e->ML[l].n1w, e->ML[l].n1b, 1e-5f, xn);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n1w, e->ML[l].n1b, 1e-5f, xn);
             if (launch_check("k_ln512_f16") != 0) return -1;
         }
         GemmParams g = {};
@@ -179,14 +179,14 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
                 e->prof.bytes[KC_MIMI_ATTN] += (double)R * MI_D * 2.0 * 4.0;
             }
             LaunchScope ls(e, KC_MIMI_ATTN);
-            k_mimi_win_attn<<<dim3((T + 63) / 64, MI_H, Bc), 128, 0, e->st>>>(q, k, v, T, att);
+            launch_k(k_mimi_win_attn, dim3((T + 63) / 64, MI_H, Bc), 128, 0, e->st, q, k, v, T, att);
             if (launch_check("k_mimi_win_attn") != 0) return -1;
         }
         g = {}; g.scale = e->ML[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls1 * out_proj(att)
         if (mimi_gemm(e, att, Bc, T, MI_D, e->ML[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
         {
             LaunchScope ls(e, KC_MIMI_MISC);
-            k_ln512_f16<<<(unsigned)((R + 7) / 8), 256, 0, e->st>>>(x, R, e->ML[l].n2w, e->ML[l].n2b, 1e-5f, xn);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n2w, e->ML[l].n2b, 1e-5f, xn);
             if (launch_check("k_ln512_f16") != 0) return -1;
         }
         g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
@@ -218,7 +218,7 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
     }
     {
         LaunchScope ls(e, KC_MIMI_MISC);
-        k_dec_out<<<dim3((Tc + 255) / 256, Bc), 256, 0, e->st>>>(last, Tc, e->dec_out_w, e->dec_out_b, d_pcm);
+        launch_k(k_dec_out, dim3((Tc + 255) / 256, Bc), 256, 0, e->st, last, Tc, e->dec_out_w, e->dec_out_b, d_pcm);
         if (launch_check("k_dec_out") != 0) return -1;
     }
     return 0;

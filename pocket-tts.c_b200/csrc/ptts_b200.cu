@@ -5,7 +5,7 @@
 
 #include <algorithm>
 
-#include "flowlm.cuh"
+#include "mega.cuh"
 #include "mimi.cuh"
 
 using namespace ptts;
@@ -43,6 +43,7 @@ static void host_noise(int64_t seed, float temp, float clampv, int frames, float
 
 // ---------------------------------------------------------------- lifetime
 static std::unordered_map<Engine *, std::unordered_map<uint64_t, FlowGemms>> g_gemms;
+static std::unordered_map<Engine *, std::unordered_map<uint64_t, MegaHost>> g_mega;
 extern "C" const char *ptts_b200_last_error(void) { return g_last_error; }
 
 static int gemm_set_attrs() {
@@ -99,6 +100,7 @@ extern "C" void ptts_b200_destroy(ptts_b200_engine *e) {
     if (e->st) cudaStreamSynchronize(e->st);
     for (auto &g : e->graphs) cudaGraphExecDestroy(g.second);
     g_gemms.erase(e);
+    g_mega.erase(e);
     for (void *p : e->allocs) cudaFree(p);
     if (e->pin) cudaFreeHost(e->pin);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -131,8 +133,96 @@ static int step_launch(Engine *e, int mode, int B, int lsd, int precise) {
     return flow_step_tc(e, st, it->second, precise);
 }
 
+// The batched decode loop as ONE cooperative launch of the persistent step kernel (mega.cuh).
+static bool mega_enabled() {
+    static int v = -1;
+    if (v < 0) v = getenv("PTTS_B200_NO_MEGA") == nullptr ? 1 : 0;
+    return v != 0;
+}
+static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
+    float *cb = nullptr;
+    if (ensure_cbias(e, lsd, &cb) != 0) return -1;
+    const uint64_t key = ((uint64_t)2 << 48) | ((uint64_t)B << 24) | ((uint64_t)lsd << 8) | (uint64_t)precise;
+    auto &gm = g_gemms[e];
+    auto gi = gm.find(key);
+    if (gi == gm.end() || gi->second.gen != e->gen) {
+        FlowGemms G;
+        if (flow_gemms_build(e, G, B, precise, lsd, cb) != 0) return -1;
+        gm[key] = G;
+        gi = gm.find(key);
+    }
+    MegaHost &M = g_mega[e][key];
+    if (M.gen != e->gen || M.B != B || M.lsd != lsd || M.precise != precise) {
+        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+        if (mega_build(e, M, gi->second, B, lsd, precise) != 0) return -1;
+    }
+    if (!e->mega_ctl) {
+        if (e->dalloc(&e->mega_ctl, 64) != 0) return -1;
+        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
+    }
+    PTTS_CUDA_OK(cudaMemsetAsync(e->mega_ctl, 0, 64 * sizeof(unsigned long long), e->st));
+    MegaProgram P = M.prog;
+    P.bar = (unsigned int *)e->mega_ctl;
+    P.done_count = (int *)(e->mega_ctl + 1);
+    P.prof = e->prof.on ? e->mega_ctl + 8 : nullptr;
+    P.nsteps = nsteps; P.n_live = e->st_n; P.wrap_prefetch = e->st_eos ? 0 : 1;
+    const bool want_trace = e->prof.on && getenv("PTTS_B200_MEGA_TRACE") != nullptr;
+    unsigned long long *d_trace = nullptr;
+    if (want_trace) {
+        if (e->dalloc(&d_trace, (size_t)2 * P.n_phases) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemsetAsync(d_trace, 0, (size_t)2 * P.n_phases * 8, e->st));
+        P.trace = d_trace;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)e->num_sms); cfg.blockDim = dim3(MG_THREADS); cfg.dynamicSmemBytes = MG_SMEM_BYTES; cfg.stream = e->st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident or the launch fails: the grid barrier relies on it
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e->launches++;
+    PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega, P));
+    if (e->prof.on) {
+        unsigned long long h[2 * MP_COUNT];
+        PTTS_CUDA_OK(cudaMemcpyAsync(h, e->mega_ctl + 8, sizeof h, cudaMemcpyDeviceToHost, e->st));
+        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+        if (d_trace) {   // per-phase timeline of CTA 0 (PTTS_B200_MEGA_TRACE=1), microseconds per frame
+            std::vector<unsigned long long> tr((size_t)2 * P.n_phases);
+            PTTS_CUDA_OK(cudaMemcpy(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+            static const char *const tn[MP_COUNT] = {"HEAD", "GEMM", "ROW", "MID", "TAIL", "ATTN"};
+            const double st_ = (double)h[2 * MP_HEAD + 1];
+            fprintf(stderr, "mega trace: B=%d steps=%.0f phases=%d (us per frame: own work of CTA 0 / including barrier)\n", B, st_, P.n_phases);
+            for (int i = 0; i < P.n_phases; i++) {
+                const MegaPhase &q = M.phases[i];
+                char extra[96] = "";
+                if (q.type == MP_GEMM) {
+                    const GemmOp &g = M.gemms[q.idx];
+                    snprintf(extra, sizeof extra, "N=%d K=%d bn=%d tiles=%d splitk=%d next=%d", g.p.n_total, g.p.kblocks_per_tap * GEMM_BK, g.bn,
+                             g.p.total_tiles, g.p.split_k, q.next_gemm);
+                }
+                fprintf(stderr, "  %3d %-4s %7.2f %7.2f  %s\n", i, tn[q.type], tr[2 * i] * 1e-3 / st_, tr[2 * i + 1] * 1e-3 / st_, extra);
+            }
+            e->dfree(d_trace);
+        }
+        static const int cls_of[MP_COUNT] = {KC_FLOW_MISC, KC_GEMM_FLOW, KC_ROWNORM, KC_FLOW_MISC, KC_FLOW_MISC, KC_ATTN_DECODE};
+        const double steps = (double)h[2 * MP_HEAD + 1];
+        for (int t = 0; t < MP_COUNT; t++) {
+            e->prof.ms[cls_of[t]] += (float)((double)h[2 * t] * 1e-6);
+            e->prof.n[cls_of[t]] += (int64_t)h[2 * t + 1];
+            e->prof.flops[cls_of[t]] += M.flops[t] * steps;
+            e->prof.bytes[cls_of[t]] += M.bytes[t] * steps;
+        }
+        for (int sidx = 0; sidx < (int)steps; sidx++) {   // KV traffic grows with the frame index (same accounting as attn_decode())
+            const double own = e->prof.mean_own_base + sidx + 1, pre = e->voice_len, n = e->st_n;
+            e->prof.bytes[KC_ATTN_DECODE] += FL_L * (2.0 * FL_D * 4.0 * (pre + n * own) + n * FL_D * 4.0 * (2 + 3 + 1));
+            e->prof.flops[KC_ATTN_DECODE] += FL_L * 4.0 * FL_D * n * (pre + own);
+        }
+    }
+    return 0;
+}
+
 static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nsteps, bool poll_done) {
     if (nsteps <= 0) return 0;
+    if (mode == 2 && mega_enabled()) return run_mega(e, B, lsd, precise, nsteps);
     const bool use_graph = !e->prof.on && getenv("PTTS_B200_NO_GRAPH") == nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t gk = 0;
@@ -321,7 +411,7 @@ static int run_impl(Engine *e, int with_mimi) {
     const int mode = B == 1 ? 1 : 2;
     // prompts (text tokens + BOS) of all utterances in one batched pass; x[b] = BOS hidden state
     if (flow_prefill(e, n, e->st_rows, e->st_maxq, e->st_cond, false) != 0) return -1;
-    if (mode == 2) PTTS_CUDA_OK(cudaMemsetAsync(e->partB, 0, (size_t)4 * e->capB * FL_D * 4, e->st));
+    if (mode == 2) PTTS_CUDA_OK(cudaMemsetAsync(e->partB, 0, (size_t)8 * e->capB * FL_D * 4, e->st));
     if (run_steps(e, mode, B, e->st_lsd, e->st_precise, e->st_steps, e->st_eos != 0) != 0) return -1;
     if (with_mimi) {
         const int F = e->st_capF;

@@ -92,3 +92,25 @@ def test_batched_eos_stops_each_utterance_independently(eng, pkg, oracle, voice,
         o = oracle.flowlm_generate(t, voice, 12, lsd_steps=1, temp=0.0, eos_enabled=1, eos_threshold=-1.2, eos_after=2)
         assert int(out["frames"][i]) == o["frames"], f"utterance {i}"
         assert max_rel(out["latents"][i, :o["frames"]], o["latents"]) < TOL
+
+
+def test_batched_multi_step_lsd_and_wider_batch(eng, pkg, oracle, voice, golden):
+    """40 utterances (attention groups of 2, one partial row tile) with 4 Euler steps per frame: covers
+    the MID phase of the persistent step kernel and the split-K folds at a second batch size."""
+    base = [golden["p0_ids"], golden["p1_ids"], golden["p2_ids"], golden["p1_ids"][:9], golden["p2_ids"][2:17]]
+    toks = [base[i % 5] for i in range(40)]
+    frames = [3 + (i % 3) for i in range(40)]
+    seeds = [100 + i for i in range(40)]
+    out = eng.generate_batch(toks, voice, frames, seeds=seeds, params=pkg.default_params(lsd_steps=4, temp=0.7), want_audio=False)
+    assert list(out["frames"]) == frames
+    for i in (0, 1, 2, 3, 4, 17, 39):
+        o = oracle.flowlm_generate(toks[i], voice, frames[i], lsd_steps=4, temp=0.7, seed=seeds[i])
+        assert max_rel(out["latents"][i, :frames[i]], o["latents"]) < TOL, f"utterance {i}"
+
+
+def test_batched_run_is_repeatable(eng, pkg, voice, golden):
+    """The persistent kernel keeps no state between launches: two runs of one staged batch agree bit for bit."""
+    toks = [golden["p0_ids"], golden["p1_ids"], golden["p2_ids"]] * 6
+    a = eng.generate_batch(toks, voice, 5, seeds=3, params=pkg.default_params(temp=0.7), want_audio=False)
+    b = eng.generate_batch(toks, voice, 5, seeds=3, params=pkg.default_params(temp=0.7), want_audio=False)
+    assert np.array_equal(a["latents"], b["latents"])
