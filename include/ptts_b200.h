@@ -102,6 +102,17 @@ int ptts_b200_batch_stage(ptts_b200_engine *e, int n, const int *tokens_flat, co
 int ptts_b200_batch_run(ptts_b200_engine *e, int with_mimi);
 int ptts_b200_batch_fetch(ptts_b200_engine *e, float *out_latents, int *out_frames_used, float *out_audio);
 
+/* ---- additive streaming entry (roadmap item of the reference, README.md:162-167):
+ * single utterance, audio handed out as it is generated, so first-audio latency is observable
+ * through the API. begin = stage + prompt prefill; next = up to want_frames more FlowLM frames, then
+ * the Mimi decoder over those frames plus a left context that covers its whole receptive field
+ * (2 x 250-token attention windows + the causal conv tails = 33 latent frames, RoPE at absolute
+ * positions), so the PCM equals the one-shot decode of the full utterance. out_pcm receives
+ * *out_frames * 1920 samples; *out_done != 0 after the last frame (EOS rule or max_frames). */
+int ptts_b200_stream_begin(ptts_b200_engine *e, const int *tokens, int token_len, const float *cond_prefix, int cond_len,
+                           int max_frames, int64_t seed, const ptts_b200_gen_params *params);
+int ptts_b200_stream_next(ptts_b200_engine *e, int want_frames, float *out_pcm, int *out_frames, int *out_done);
+
 /* ---- measurement hooks (CUDA events on the engine's own stream). */
 int ptts_b200_sync(ptts_b200_engine *e);
 int ptts_b200_timer_start(ptts_b200_engine *e);

@@ -43,6 +43,7 @@ EXPORTS = [
     "ptts_b200_generate_batch", "ptts_b200_batch_stage", "ptts_b200_batch_run", "ptts_b200_batch_fetch",
     "ptts_b200_sync", "ptts_b200_timer_start", "ptts_b200_timer_stop", "ptts_b200_profile_enable",
     "ptts_b200_profile_read", "ptts_b200_profile_work", "ptts_b200_profile_class_name", "ptts_b200_launch_count", "ptts_b200_test_gemm",
+    "ptts_b200_stream_begin", "ptts_b200_stream_next",
 ]
 
 
@@ -78,6 +79,8 @@ def load_library():
     L.ptts_b200_launch_count.argtypes = [vp]
     L.ptts_b200_launch_count.restype = C.c_int64
     L.ptts_b200_test_gemm.argtypes = [vp, _fp, _fp, _fp] + [C.c_int] * 12
+    L.ptts_b200_stream_begin.argtypes = [vp, _ip, C.c_int, _fp, C.c_int, C.c_int, C.c_int64, C.POINTER(GenParams)]
+    L.ptts_b200_stream_next.argtypes = [vp, C.c_int, _fp, _ip, _ip]
     return L
 
 
@@ -210,6 +213,33 @@ class Engine:
         self.stage(token_lists, cond, max_frames, seeds, eos_after, params)
         self.run(with_mimi=want_audio)
         return self.fetch(True, want_audio, audio_out)
+
+    # ---- additive streaming entry (single utterance)
+    def stream_begin(self, tokens, cond, max_frames, seed=123, params: GenParams | None = None):
+        params = params or default_params()
+        tokens = np.ascontiguousarray(tokens, np.int32)
+        cond = np.ascontiguousarray(cond, dtype=np.float32).reshape(-1, 1024)
+        self._ck(self.lib.ptts_b200_stream_begin(self.h, _i(tokens), len(tokens), _f(cond) if cond.shape[0] else None, cond.shape[0],
+                                                 int(max_frames), int(seed), C.byref(params)), "stream_begin")
+
+    def stream_next(self, want_frames=1):
+        """-> (pcm [frames*1920], done)"""
+        out = np.zeros(want_frames * FRAME_SAMPLES, np.float32)
+        nf, done = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.ptts_b200_stream_next(self.h, int(want_frames), _f(out), C.byref(nf), C.byref(done)), "stream_next")
+        return out[: nf.value * FRAME_SAMPLES], bool(done.value)
+
+    def stream(self, tokens, cond, max_frames, seed=123, params: GenParams | None = None, chunk=4):
+        """Generator of PCM chunks (first chunk = 1 frame, for first-audio latency)."""
+        self.stream_begin(tokens, cond, max_frames, seed, params)
+        want = 1
+        while True:
+            pcm, done = self.stream_next(want)
+            if len(pcm):
+                yield pcm
+            if done:
+                return
+            want = chunk
 
     # ---- measurement hooks
     def sync(self):

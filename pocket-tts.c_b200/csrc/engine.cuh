@@ -329,6 +329,7 @@ struct ptts_b200_engine {
     int st_n = 0, st_steps = 0, st_capF = 0, st_lsd = 1, st_precise = 1, st_eos = 0;
     std::vector<int> st_maxf;
     unsigned long long *mega_ctl = nullptr;   // persistent step kernel: [0] grid barrier, [1] done count, [8..] phase timers
+    int stream_pos = -1;                      // streaming entry: frames already handed out (-1: no stream open)
     // pinned staging
     void *pin = nullptr;
     size_t pin_bytes = 0;

@@ -62,6 +62,7 @@ struct GemmParams {
     // position m (row within the batch item), q is pre-scaled by 1/8; fp16 head-major [B][H][T][64] outputs
     uint16_t *rope_q, *rope_k, *rope_v;
     const float *rope_cos, *rope_sin;   // [T][32]
+    int rope_pos0;           // position of row 0 (streaming decode of a window that starts mid-utterance)
     long long *trace;        // optional [16] clock64 stamps written by CTA 0 (kernel timeline debugging)
 };
 
@@ -280,8 +281,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                             uint32_t hw[8];
                             if (which < 2) {
                                 float cs[8], sn[8];
-                                ld_global_v8(p.rope_cos + (size_t)m * 32 + (d0 >> 1), cs);
-                                ld_global_v8(p.rope_sin + (size_t)m * 32 + (d0 >> 1), sn);
+                                ld_global_v8(p.rope_cos + (size_t)(m + p.rope_pos0) * 32 + (d0 >> 1), cs);
+                                ld_global_v8(p.rope_sin + (size_t)(m + p.rope_pos0) * 32 + (d0 >> 1), sn);
                                 const float sc = which == 0 ? 0.125f : 1.0f;   // 1/sqrt(64) folded into q
 #pragma unroll
                                 for (int j = 0; j < 8; j++) {

@@ -64,6 +64,7 @@ struct MegaProgram {
     unsigned int *bar;              // grid barrier counter, zeroed by the host before the launch
     int *done_count;                // utterances that reached their stop point, zeroed by the host
     int n_live, nsteps, first_gemm;
+    int flags;                      // bit 0: L2 prefetch of attention units, bit 1: light grid barrier (experiments)
     int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
                                     // (only when the loop cannot stop early, i.e. EOS detection is off)
     unsigned long long *prof;       // optional [MP_COUNT][2]: ns and phase count per type (written by CTA 0)
@@ -95,13 +96,18 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid, int bar
 // Grid-wide barrier: every CTA arrives once on a monotonic counter; `epoch` is the value the counter
 // reaches when all CTAs have arrived. Global writes made before the barrier by any thread of any CTA
 // are visible after it to generic loads and to TMA (async proxy) loads.
-__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch) {
-    asm volatile("fence.proxy.async.global;" ::: "memory");
+__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch, bool light = false) {
+    if (!light) asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
     epoch += gridDim.x;
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
+        if (light) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+        } else {
+            __threadfence();
+            atomicAdd(bar, 1u);
+        }
         if (ld_acquire_u32(bar) < epoch) {
             const long long t0 = clock64();
             uint32_t spins = 0;
@@ -469,8 +475,17 @@ __device__ __forceinline__ void attn4_unit(const AttnDecodeParams &p, int b, int
     __syncwarp();   // sc / sqw reusable by this warp's next unit
 }
 
+// Pull a unit's own K / V rows into L2 ahead of its turn (lanes 0, 1 issue one bulk prefetch each).
+__device__ __forceinline__ void attn4_prefetch(const AttnDecodeParams &p, int b, int h, int step, int lane) {
+    if (lane < 2) {
+        const float *ptr = (lane ? p.ov : p.ok) + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+        const uint32_t bytes = (uint32_t)(step + p.own_base[b]) * FL_HD * 4u;
+        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+    }
+}
+
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
-__device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, int pcap, int step, float *sm, int tid) {
+__device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, int pcap, int step, float *sm, int tid, bool P_PREFETCH) {
     float *kt = sm, *vt = kt + A4_TILE * FL_HD, *scw = vt + A4_TILE * FL_HD;
     int *ctr = (int *)(scw + A4_WARPS * (pcap + FL_HD));
     const int w = tid >> 5, lane = tid & 31;
@@ -490,6 +505,7 @@ __device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, in
     }
     for (int ua = u0; ua < u1;) {
         const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
+        if (P_PREFETCH && ua + w < ub) attn4_prefetch(p, ua + w - h * B, h, step, lane);   // first round: HBM -> L2 starts now
         __syncthreads();                                    // previous head's tile no longer in use
         if (cond_len > 0) {
             const int nt = min(A4_TILE, cond_len);
@@ -506,6 +522,7 @@ __device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, in
             if (lane == 0) u = atomicAdd(ctr, 1);
             u = __shfl_sync(0xffffffffu, u, 0);
             if (u >= ub) break;
+            if (P_PREFETCH && u + A4_WARPS < ub) attn4_prefetch(p, u + A4_WARPS - h * B, h, step, lane);   // one round ahead
             attn4_unit(p, u - h * B, h, step, cond_len, kt, vt, sc, sqw, lane);
         }
         ua = ub;
@@ -752,13 +769,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid);
+                    attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid, (P.flags & 1) != 0);
                     break;
                 default: break;
             }
             unsigned long long t1 = 0;
             if (prof && P.trace) t1 = globaltimer_ns();
-            grid_sync(P.bar, epoch);
+            grid_sync(P.bar, epoch, (P.flags & 2) != 0);
             if (prof) {
                 const unsigned long long t2 = globaltimer_ns();
                 P.prof[2 * ph.type] += t2 - t0;

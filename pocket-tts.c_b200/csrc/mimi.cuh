@@ -137,10 +137,11 @@ static int conv_gemm(Engine *e, const ConvW &c, const __half *A, int Bc, int T, 
 }
 
 // Decode Bc equal-length items. d_lat [Bc,F,32] fp32 on the device; d_pcm [Bc, F*1920].
-static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm) {
+// pos0 = token position of the first row (RoPE is absolute: ptts_mimi.c:341).
+static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm, int pos0 = 0) {
     const int T = 16 * F;
     const size_t R = (size_t)Bc * T;
-    if (ensure_rope(e, T) != 0) return -1;
+    if (ensure_rope(e, T + pos0) != 0) return -1;
     const size_t need = mimi_ws_per_frame() * (size_t)Bc * F + (1 << 20);
     if (need > e->mimi_ws_bytes) {
         cudaStreamSynchronize(e->st);
@@ -169,7 +170,7 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         }
         GemmParams g = {};
         g.rope_q = (uint16_t *)q; g.rope_k = (uint16_t *)k; g.rope_v = (uint16_t *)v;   // RoPE + head split fused in the epilogue
-        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin;
+        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_pos0 = pos0;
         if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
         {
             if (e->prof.on) {   // banded attention: <= 250 keys per query, QK^T and PV

@@ -166,6 +166,7 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     P.done_count = (int *)(e->mega_ctl + 1);
     P.prof = e->prof.on ? e->mega_ctl + 8 : nullptr;
     P.nsteps = nsteps; P.n_live = e->st_n; P.wrap_prefetch = e->st_eos ? 0 : 1;
+    { const char *fl = getenv("PTTS_B200_MEGA_FLAGS"); P.flags = fl ? atoi(fl) : 0; }
     const bool want_trace = e->prof.on && getenv("PTTS_B200_MEGA_TRACE") != nullptr;
     unsigned long long *d_trace = nullptr;
     if (want_trace) {
@@ -395,10 +396,11 @@ static int ensure_pcm(Engine *e, size_t samples) {
     return 0;
 }
 
-static int run_impl(Engine *e, int with_mimi) {
+// Rewind the device state of the staged batch and run the prompt prefill (text tokens + BOS of all
+// utterances in one batched pass; x[b] = BOS hidden state).
+static int run_begin(Engine *e) {
     PTTS_CHECK(e && e->st_n > 0, "batch_run: nothing staged");
     PTTS_CUDA_OK(cudaSetDevice(e->device));
-    // rewind the device state so that run may be repeated on the same staged batch
     const int B = e->curB, n = e->st_n;
     std::vector<int> h_done(B, 1), h_es(B, -1), h_used(B, 0);
     for (int i = 0; i < n; i++) h_done[i] = 0;
@@ -408,10 +410,15 @@ static int run_impl(Engine *e, int with_mimi) {
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_eos_step, h_es.data(), B * 4, cudaMemcpyHostToDevice, e->st));
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_used, h_used.data(), B * 4, cudaMemcpyHostToDevice, e->st));
     PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
-    const int mode = B == 1 ? 1 : 2;
-    // prompts (text tokens + BOS) of all utterances in one batched pass; x[b] = BOS hidden state
     if (flow_prefill(e, n, e->st_rows, e->st_maxq, e->st_cond, false) != 0) return -1;
-    if (mode == 2) PTTS_CUDA_OK(cudaMemsetAsync(e->partB, 0, (size_t)8 * e->capB * FL_D * 4, e->st));
+    if (B > 1) PTTS_CUDA_OK(cudaMemsetAsync(e->partB, 0, (size_t)8 * e->capB * FL_D * 4, e->st));
+    return 0;
+}
+
+static int run_impl(Engine *e, int with_mimi) {
+    if (run_begin(e) != 0) return -1;
+    const int B = e->curB, n = e->st_n;
+    const int mode = B == 1 ? 1 : 2;
     if (run_steps(e, mode, B, e->st_lsd, e->st_precise, e->st_steps, e->st_eos != 0) != 0) return -1;
     if (with_mimi) {
         const int F = e->st_capF;
@@ -519,6 +526,50 @@ extern "C" int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, 
     PTTS_CHECK(e && latents && out_audio && out_len && frames >= 1, "mimi_decode: bad arguments");   // ptts_mimi.c:572
     if (ptts_b200_mimi_decode_batch(e, latents, 1, frames, out_audio) != 0) return -1;
     *out_len = frames * 1920;
+    return 0;
+}
+
+// ---------------------------------------------------------------- streaming (single utterance)
+// Mimi's receptive field in latent frames: two stacked 250-token attention windows (500 tokens = 31.25
+// frames, ptts_mimi.c:264-299), the 7-tap input conv (6 tokens) and the k=32/s=16 upsampler (1 frame).
+static const int STREAM_CTX_FRAMES = 34;
+
+extern "C" int ptts_b200_stream_begin(ptts_b200_engine *e, const int *tokens, int token_len, const float *cond_prefix, int cond_len,
+                                      int max_frames, int64_t seed, const ptts_b200_gen_params *params) {
+    PTTS_CHECK(e && tokens && token_len > 0 && params && max_frames >= 1, "stream_begin: bad arguments");
+    e->stream_pos = -1;
+    const int offs[2] = {0, token_len};
+    if (stage_impl(e, 1, tokens, offs, cond_prefix, cond_len, &max_frames, &seed, nullptr, params) != 0) return -1;
+    if (run_begin(e) != 0) return -1;
+    e->stream_pos = 0;
+    return 0;
+}
+
+extern "C" int ptts_b200_stream_next(ptts_b200_engine *e, int want_frames, float *out_pcm, int *out_frames, int *out_done) {
+    PTTS_CHECK(e && out_pcm && out_frames && out_done && want_frames >= 1, "stream_next: bad arguments");
+    PTTS_CHECK(e->stream_pos >= 0 && e->st_n == 1 && e->curB == 1, "stream_next: no stream is open (call stream_begin first)");
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    *out_frames = 0;
+    const int left = e->st_steps - e->stream_pos;
+    if (left <= 0) { *out_done = 1; return 0; }
+    const int k = std::min(want_frames, left);
+    if (run_steps(e, 1, 1, e->st_lsd, e->st_precise, k, false) != 0) return -1;
+    int h[2] = {0, 0};
+    PTTS_CUDA_OK(cudaMemcpyAsync(&h[0], e->d_used, 4, cudaMemcpyDeviceToHost, e->st));
+    PTTS_CUDA_OK(cudaMemcpyAsync(&h[1], e->d_done, 4, cudaMemcpyDeviceToHost, e->st));
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    const int newf = h[0] - e->stream_pos;   // frames past the stop point are not part of the utterance
+    if (newf > 0) {
+        const int f0 = std::max(0, e->stream_pos - STREAM_CTX_FRAMES), nwin = e->stream_pos + newf - f0;
+        if (ensure_pcm(e, (size_t)nwin * 1920) != 0) return -1;
+        if (mimi_run_chunk(e, 1, nwin, e->d_out_latents + (size_t)f0 * FL_LAT, (size_t)e->capF * FL_LAT, 1, e->d_pcm, 16 * f0) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemcpyAsync(out_pcm, e->d_pcm + (size_t)(e->stream_pos - f0) * 1920, (size_t)newf * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
+        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    }
+    e->stream_pos += newf;
+    *out_frames = newf;
+    *out_done = (h[1] != 0 || newf < k || e->stream_pos >= e->st_steps) ? 1 : 0;
+    if (*out_done) e->stream_pos = e->st_steps;
     return 0;
 }
 

@@ -70,3 +70,27 @@ def test_end_to_end_generate_batch_audio(eng, pkg, oracle, voice, golden):
     ref = oracle.mimi_decode(oracle.scale_latents(o["latents"]))
     assert snr_db(out["audio"][1, : 4 * 1920], ref) > 40.0
     assert not out["audio"][0, 3 * 1920:].any()        # padding beyond frames_used is silence
+
+
+def test_streaming_matches_one_shot_decode(pkg, weights, voice, golden):
+    """Additive streaming entry: chunks of 1, 3, 3, ... frames, each decoded by Mimi over
+    the new frames plus a 34-frame left context, must reproduce the one-shot PCM of the whole
+    utterance (more than 34 frames, so the window really slides and RoPE uses absolute positions)."""
+    e = pkg.Engine(weights, 0)
+    try:
+        ids, F = golden["p2_ids"], 45
+        p = pkg.default_params(temp=0.7)
+        ref = e.generate_batch([ids], voice, F, seeds=[5], params=p)
+        chunks = list(e.stream(ids, voice, F, seed=5, params=p, chunk=3))
+        pcm = np.concatenate(chunks)
+        assert len(chunks[0]) == 1920 and len(pcm) == F * 1920
+        assert snr_db(pcm, ref["audio"][0]) > 50.0
+        # EOS rule: the stream stops where the one-shot call stops
+        pe = pkg.default_params(temp=0.0, eos_enabled=1, eos_threshold=-1.2, eos_after=2)
+        ref = e.generate_batch([golden["p0_ids"]], voice, 12, seeds=[1], params=pe)
+        pcm = np.concatenate(list(e.stream(golden["p0_ids"], voice, 12, seed=1, params=pe, chunk=4)))
+        used = int(ref["frames"][0])
+        assert len(pcm) == used * 1920
+        assert snr_db(pcm, ref["audio"][0, : used * 1920]) > 50.0
+    finally:
+        e.close()
