@@ -195,6 +195,66 @@ __device__ __forceinline__ float act_apply_fast(int act, float x) {
     }
 }
 
+// Compile-time activation (the epilogues dispatch on `act` once per 16-column chunk, not per element;
+// everything inside is straight-line code: selects instead of branches).
+template <int ACT, bool FAST>
+__device__ __forceinline__ float act_t(float x) {
+    if constexpr (ACT == ACT_GELU_ERF) return 0.5f * x * (1.0f + erff(x * 0.7071067811865475f));
+    else if constexpr (ACT == ACT_GELU_TANH)
+        return 0.5f * x * (1.0f + (FAST ? tanh_fast(0.7978845608f * (x + 0.044715f * x * x * x)) : tanhf(0.7978845608f * (x + 0.044715f * x * x * x))));
+    else if constexpr (ACT == ACT_SILU) return FAST ? __fdividef(x, 1.0f + __expf(-x)) : x / (1.0f + expf(-x));
+    else if constexpr (ACT == ACT_ELU) {
+        const float e = (FAST ? __expf(fminf(x, 0.0f)) : expf(fminf(x, 0.0f))) - 1.0f;
+        return x >= 0.0f ? x : e;
+    } else return x;
+}
+// 16 fp32 values -> activation -> 8 packed 16-bit pairs (hi) and optionally the rounding residues (lo)
+template <int ACT, bool FAST, bool BF, bool LO>
+__device__ __forceinline__ void act_pack16(const float (&v)[16], uint32_t (&hw)[8], uint32_t (&lw)[8]) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float a0 = act_t<ACT, FAST>(v[2 * j]), a1 = act_t<ACT, FAST>(v[2 * j + 1]);
+        if constexpr (BF) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a0, a1);
+            hw[j] = *(const uint32_t *)&h;
+            if constexpr (LO) {
+                const __nv_bfloat162 l = __floats2bfloat162_rn(a0 - __low2float(h), a1 - __high2float(h));
+                lw[j] = *(const uint32_t *)&l;
+            }
+        } else {
+            const __half2 h = __floats2half2_rn(a0, a1);
+            hw[j] = *(const uint32_t *)&h;
+            if constexpr (LO) {
+                const __half2 l = __floats2half2_rn(a0 - __low2float(h), a1 - __high2float(h));
+                lw[j] = *(const uint32_t *)&l;
+            }
+        }
+    }
+}
+// Run-time dispatch to the compile-time variants actually used by the engine (one uniform branch per chunk).
+__device__ __forceinline__ void act_pack16_dispatch(int act, bool fast, bool bf, bool lo, const float (&v)[16], uint32_t (&hw)[8],
+                                                    uint32_t (&lw)[8]) {
+    if (bf) {   // FlowLM: bf16, precise math
+        if (lo) {
+            if (act == ACT_GELU_ERF) act_pack16<ACT_GELU_ERF, false, true, true>(v, hw, lw);
+            else if (act == ACT_SILU) act_pack16<ACT_SILU, false, true, true>(v, hw, lw);
+            else act_pack16<ACT_NONE, false, true, true>(v, hw, lw);
+        } else {
+            if (act == ACT_GELU_ERF) act_pack16<ACT_GELU_ERF, false, true, false>(v, hw, lw);
+            else if (act == ACT_SILU) act_pack16<ACT_SILU, false, true, false>(v, hw, lw);
+            else act_pack16<ACT_NONE, false, true, false>(v, hw, lw);
+        }
+    } else if (fast) {   // Mimi: fp16, hardware exp / tanh
+        if (act == ACT_ELU) act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
+        else if (act == ACT_GELU_TANH) act_pack16<ACT_GELU_TANH, true, false, false>(v, hw, lw);
+        else act_pack16<ACT_NONE, true, false, false>(v, hw, lw);
+    } else {
+        if (act == ACT_ELU) act_pack16<ACT_ELU, false, false, false>(v, hw, lw);
+        else if (act == ACT_GELU_TANH) act_pack16<ACT_GELU_TANH, false, false, false>(v, hw, lw);
+        else act_pack16<ACT_NONE, false, false, false>(v, hw, lw);
+    }
+}
+
 // Shared-memory matrix descriptor for a K-major tile whose rows are exactly 128 bytes
 // (64 16-bit elements) laid out by TMA with CU_TENSOR_MAP_SWIZZLE_128B: 8-row core groups
 // are 1024 bytes apart (SBO), LBO is unused for swizzled K-major, descriptor version 1 (sm_100),

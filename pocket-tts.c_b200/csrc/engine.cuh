@@ -39,7 +39,7 @@ static const char *const KCLASS_NAMES[KC_COUNT] = {"gemv_bf16", "gemm_tc_flowlm"
 
 struct Prof {
     bool on = false;
-    struct Rec { int cls; cudaEvent_t a, b; };
+    struct Rec { int cls; cudaEvent_t a, b; int rows, n, k, bn; double flops, bytes; };
     std::vector<Rec> recs;
     float ms[KC_COUNT] = {0};
     int64_t n[KC_COUNT] = {0};
@@ -398,7 +398,7 @@ struct LaunchScope {
     ~LaunchScope() {
         if (e->prof.on) {
             cudaEventRecord(b, e->st);
-            e->prof.recs.push_back({cls, a, b});
+            e->prof.recs.push_back({cls, a, b, 0, 0, 0, 0, 0.0, 0.0});
         }
     }
 };
@@ -423,8 +423,18 @@ static int run_gemm(Engine *e, const GemmOp &op, int cls) {
                               rows * n * ((op.p.out_f32 ? 4.0 : 0.0) + (op.p.resid ? 4.0 : 0.0) + (op.p.out_h ? 2.0 : 0.0) +
                                           (op.p.out_l ? 2.0 : 0.0));
     }
-    LaunchScope ls(e, cls);
-    return gemm_launch(op, e->st);
+    int rc;
+    {
+        LaunchScope ls(e, cls);
+        rc = gemm_launch(op, e->st);
+    }
+    if (e->prof.on && !e->prof.recs.empty()) {   // shape tag for the per-launch log (PTTS_B200_GEMM_LOG=1)
+        Prof::Rec &r = e->prof.recs.back();
+        r.rows = (op.p.m_tiles_total / op.p.m_tiles_per_batch) * op.p.a_rows; r.n = op.p.n_total;
+        r.k = op.p.taps * op.p.kblocks_per_tap * GEMM_BK; r.bn = op.bn;
+        r.flops = 2.0 * r.rows * (double)r.n * r.k;
+    }
+    return rc;
 }
 
 }  // namespace ptts

@@ -115,12 +115,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint64_t *bars = (uint64_t *)(smem + p.stages * SM::STAGE_BYTES);
     uint64_t *full = bars;                          // [stages]   TMA -> MMA
     uint64_t *empty = bars + GEMM_MAX_STAGES;       // [stages]   MMA -> TMA
-    uint64_t *tfull = bars + 2 * GEMM_MAX_STAGES;   // [2]        MMA -> epilogue
-    uint64_t *tempty = tfull + 2;                   // [2]        epilogue -> MMA
-    uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
+    // NACC accumulator buffers in TMEM, one per epilogue team: with narrow tiles (short K, the SEANet
+    // convolutions) a tile's epilogue is a latency chain (tcgen05.ld -> residual load -> store), so four
+    // tiles are drained concurrently by four teams of 4 warps; BN = 256 keeps two teams of 8 warps.
+    constexpr int NACC = BN <= 128 ? 4 : 2;
+    constexpr int ACC_COLS = BN <= 128 ? 128 : 256;
+    constexpr int WPT = GEMM_EPI_WARPS / NACC;      // warps per team
+    uint64_t *tfull = bars + 2 * GEMM_MAX_STAGES;   // [NACC]     MMA -> epilogue
+    uint64_t *tempty = tfull + 4;                   // [NACC]     epilogue -> MMA
+    uint32_t *tmem_slot = (uint32_t *)(tempty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    constexpr uint32_t TMEM_COLS = 512;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA);
@@ -128,8 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (SPLIT == 1) tma_prefetch_desc(&mapAlo);
         if (SPLIT == 2) tma_prefetch_desc(&mapBlo);
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], GEMM_EPI_WARPS); mbar_init(&tempty[1], GEMM_EPI_WARPS);
+        for (int a = 0; a < NACC; a++) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], WPT); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -196,10 +201,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int s = 0; uint32_t ph = 0; int lt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
             const TileCoord t = gemm_tile(p, tile, BN);
-            const int acc = lt & 1;
-            mbar_wait(&tempty[acc], ((lt >> 1) & 1) ^ 1);   // epilogue has drained this accumulator
+            const int acc = lt % NACC;
+            mbar_wait(&tempty[acc], ((lt / NACC) & 1) ^ 1);   // its team has drained this accumulator
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + acc * BN;
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
             for (int it = t.it0; it < t.it1; it++) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
@@ -229,24 +234,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // ------------------------------------------------ epilogue warps
         // TMEM lane quadrant = warp % 4 (hardware rule); the 4 warps of a quadrant interleave the
         // 16-column chunks. tcgen05.ld of the next chunk is in flight while this one is processed.
-        const int quad = warp & 3, cg = (warp - 2) >> 2;
-        constexpr int NCG = GEMM_EPI_WARPS / 4;
+        const int team = (warp - 2) / WPT, quad = warp & 3, cg = ((warp - 2) % WPT) >> 2;
+        constexpr int NCG = WPT / 4;
         pdl_wait();   // residual / outputs belong to earlier kernels
         const bool bf = p.out_bf16 != 0;
         const int act = p.act, ldo = p.ldo, ldh = p.ldh, n_total = p.n_total, bias_mask = p.bias_mask;
         const bool fast = p.fast_act != 0;
         const float *bias = p.bias, *scale = p.scale, *resid = p.resid;
         uint16_t *out_h = p.out_h, *out_l = p.out_l;
-        int lt = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, lt++) {
+        // team `team` owns accumulator `team` and the CTA's tiles team, team + NACC, ...
+        for (int lt = team, tile = blockIdx.x + team * gridDim.x; tile < p.total_tiles; tile += NACC * gridDim.x, lt += NACC) {
             const TileCoord t = gemm_tile(p, tile, BN);
-            const int acc = lt & 1;
-            mbar_wait(&tfull[acc], (lt >> 1) & 1);
+            const int acc = team;
+            mbar_wait(&tfull[acc], (lt / NACC) & 1);
             tc_fence_after();
             if (tr && lt == 0 && warp == 2 && lane == 0) p.trace[5] = clock64();
             const int m = t.m0 + quad * 32 + lane;
             const bool m_ok = m < p.a_rows;
-            const uint32_t trow = tmem_base + acc * BN + ((uint32_t)(quad * 32) << 16);
+            const uint32_t trow = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
             float *out_f32 = p.out_f32 ? p.out_f32 + (size_t)t.z * p.split_stride : nullptr;
             const bool add_bias = bias != nullptr && t.z == 0;
             uint32_t r[16], rn[16];
@@ -314,17 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         }
                         if (oh) {
                             uint32_t hw[8], lw[8];
-#pragma unroll
-                            for (int j = 0; j < 16; j += 2) {
-                                const float a0 = fast ? act_apply_fast(act, v[j]) : act_apply(act, v[j]);
-                                const float a1 = fast ? act_apply_fast(act, v[j + 1]) : act_apply(act, v[j + 1]);
-                                const uint16_t h0 = f2h16(a0, bf), h1 = f2h16(a1, bf);
-                                hw[j / 2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                                if (ol) {
-                                    const uint16_t l0 = f2h16(a0 - h162f(h0, bf), bf), l1 = f2h16(a1 - h162f(h1, bf), bf);
-                                    lw[j / 2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                                }
-                            }
+                            act_pack16_dispatch(act, fast, bf, ol != nullptr, v, hw, lw);
                             st_global_v8(oh + nb, hw);
                             if (ol) st_global_v8(ol + nb, lw);
                         }

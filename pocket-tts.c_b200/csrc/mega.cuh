@@ -653,14 +653,7 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
                     }
                     if (oh) {
                         uint32_t hw[8], lw[8];
-#pragma unroll
-                        for (int j = 0; j < 16; j += 2) {
-                            const float a0 = act_apply(act, v[j]), a1 = act_apply(act, v[j + 1]);
-                            const uint16_t h0 = f2h16(a0, true), h1 = f2h16(a1, true);
-                            hw[j / 2] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                            const uint16_t l0 = f2h16(a0 - h162f(h0, true), true), l1 = f2h16(a1 - h162f(h1, true), true);
-                            lw[j / 2] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                        }
+                        act_pack16_dispatch(act, false, true, ol != nullptr, v, hw, lw);
                         st_global_v8(oh + nb, hw);
                         if (ol) st_global_v8(ol + nb, lw);
                     }

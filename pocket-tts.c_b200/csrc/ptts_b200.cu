@@ -609,6 +609,8 @@ extern "C" int ptts_b200_profile_read(ptts_b200_engine *e, int max_classes, floa
     for (auto &r : e->prof.recs) {
         float t = 0.0f;
         if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { e->prof.ms[r.cls] += t; e->prof.n[r.cls]++; }
+        if (r.rows > 0 && r.cls == KC_GEMM_MIMI && getenv("PTTS_B200_GEMM_LOG"))
+            fprintf(stderr, "gemm rows=%d N=%d K=%d bn=%d  %.3f ms  %.1f TFLOP/s\n", r.rows, r.n, r.k, r.bn, t, r.flops / (t * 1e9));
         cudaEventDestroy(r.a); cudaEventDestroy(r.b);
     }
     e->prof.recs.clear();
