@@ -210,9 +210,20 @@ class Engine:
 
     def generate_batch(self, token_lists, cond, max_frames, seeds=123, eos_after=None, params: GenParams | None = None,
                        want_audio=True, audio_out=None):
-        self.stage(token_lists, cond, max_frames, seeds, eos_after, params)
-        self.run(with_mimi=want_audio)
-        return self.fetch(True, want_audio, audio_out)
+        """ptts_b200_generate_batch: host buffers in, host buffers out (H2D, kernels and the chunk-pipelined D2H
+        of the PCM all inside the one C call)."""
+        params = params or default_params()
+        cond = np.ascontiguousarray(cond, dtype=np.float32).reshape(-1, 1024)
+        n, flat, offs, mf, sd, ea = self._pack(token_lists, max_frames, seeds, eos_after)
+        F = int(mf.max())
+        self._staged = (n, F)
+        lat = np.zeros((n, F, 32), np.float32)
+        used = np.zeros(n, np.int32)
+        pcm = audio_out if audio_out is not None else (np.zeros((n, F * FRAME_SAMPLES), np.float32) if want_audio else None)
+        self._ck(self.lib.ptts_b200_generate_batch(self.h, n, _i(flat), _i(offs), _f(cond) if cond.shape[0] else None, cond.shape[0],
+                                                   _i(mf), sd.ctypes.data_as(_lp), _i(ea), C.byref(params), _f(lat), _i(used), _f(pcm)),
+                 "generate_batch")
+        return dict(latents=lat, frames=used, audio=pcm)
 
     # ---- additive streaming entry (single utterance)
     def stream_begin(self, tokens, cond, max_frames, seed=123, params: GenParams | None = None):

@@ -264,8 +264,9 @@ struct ConvW { __half *w; float *b; int cin, cout, k, stride, n_rows /*GEMM N*/,
 
 struct ptts_b200_engine {
     int device = 0;
-    cudaStream_t st = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; device->host copies of finished PCM chunks
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk = nullptr, ev_copy = nullptr;
+    const float *pcm_on_host = nullptr;             // host buffer the last run already delivered its PCM to
     std::vector<void *> allocs;
     int64_t launches = 0;
     ptts::Prof prof;
@@ -420,7 +421,7 @@ static int run_gemm(Engine *e, const GemmOp &op, int cls) {
         const double a_el = op.p.a_k_step == 0 && op.p.taps > 1 ? rows * op.p.kblocks_per_tap * GEMM_BK : rows * k;
         e->prof.flops[cls] += 2.0 * rows * n * k;
         e->prof.bytes[cls] += 2.0 * (a_el * (op.split == 1 ? 2 : 1) + n * k * (op.split == 2 ? 2 : 1)) +
-                              rows * n * ((op.p.out_f32 ? 4.0 : 0.0) + (op.p.resid ? 4.0 : 0.0) + (op.p.out_h ? 2.0 : 0.0) +
+                              rows * n * ((op.p.out_f32 ? 4.0 : 0.0) + (op.p.resid ? 4.0 : 0.0) + (op.p.out_h ? 2.0 : 0.0) + (op.p.resid_h ? 2.0 : 0.0) + (op.p.out_raw ? 2.0 : 0.0) +
                                           (op.p.out_l ? 2.0 : 0.0));
     }
     int rc;

@@ -49,6 +49,8 @@ struct GemmParams {
     int bias_mask;           // 0 = index by feature, else feature & bias_mask (ConvTranspose phases)
     const float *scale;      // per-feature multiplier (layer scale); NULL = none
     const float *resid;      // fp32 residual added after scale; NULL = none
+    const uint16_t *resid_h; // 16-bit residual (same encoding as out_h), row stride ldh; NULL = none
+    uint16_t *out_raw;       // 16-bit output of v BEFORE the activation (the residual stream of a resblock), stride ldh
     float *out_f32;          // fp32 output (may alias resid); NULL = none
     int ldo;
     size_t split_stride;     // split-K: slice z stores its partial sum at out_f32 + z*split_stride (folded by the consumer)
@@ -78,6 +80,11 @@ __device__ __forceinline__ void st_global_v8(void *ptr, const uint32_t (&v)[8]) 
     asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
                  "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
                  : "memory");
+}
+__device__ __forceinline__ void ld_global_v8u(const void *ptr, uint32_t (&v)[8]) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(ptr));
 }
 __device__ __forceinline__ void ld_global_v8(const void *ptr, float (&v)[8]) {
     asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -310,12 +317,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
                             for (int j = 0; j < 8; j++) { v[j] += t0[j]; v[8 + j] += t1[j]; }
                         }
+                        if (p.resid_h) {
+                            uint32_t hr[8];
+                            ld_global_v8u(p.resid_h + grow * ldh + nb, hr);
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float2 f = bf ? __bfloat1622float2(*(const __nv_bfloat162 *)&hr[j]) : __half22float2(*(const __half2 *)&hr[j]);
+                                v[2 * j] += f.x; v[2 * j + 1] += f.y;
+                            }
+                        }
                         if (of) {
                             uint32_t w0[8], w1[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) { w0[j] = __float_as_uint(v[j]); w1[j] = __float_as_uint(v[8 + j]); }
                             st_global_v8(of + nb, w0);
                             st_global_v8(of + nb + 8, w1);
+                        }
+                        if (p.out_raw) {
+                            uint32_t hw[8], lw[8];
+                            act_pack16_dispatch(ACT_NONE, fast, bf, false, v, hw, lw);
+                            st_global_v8(p.out_raw + grow * ldh + nb, hw);
                         }
                         if (oh) {
                             uint32_t hw[8], lw[8];

@@ -96,9 +96,9 @@ static int mimi_load_weights(Engine *e, const HostWeights &hw) {
 // Workspace bytes per latent frame (16 tokens, 96 / 480 / 1920 rows in the three SEANet stages).
 static size_t mimi_ws_per_frame() {
     const size_t tok = 16 * (size_t)(MI_D * 4 + MI_D * 2 + 3 * MI_D * 2 + MI_D * 2 + MI_FF * 2 + MI_D * 2);
-    const size_t s0 = 96 * (size_t)(256 * 4 + 256 * 2 + 128 * 2 + 256 * 2);
-    const size_t s1 = 480 * (size_t)(128 * 4 + 128 * 2 + 64 * 2 + 128 * 2);
-    const size_t s2 = 1920 * (size_t)(64 * 4 + 64 * 2 + 64 * 2 + 64 * 2);
+    const size_t s0 = 96 * (size_t)(256 * 2 + 256 * 2 + 128 * 2 + 256 * 2);
+    const size_t s1 = 480 * (size_t)(128 * 2 + 128 * 2 + 64 * 2 + 128 * 2);
+    const size_t s2 = 1920 * (size_t)(64 * 2 + 64 * 2 + 64 * 2 + 64 * 2);
     return tok + s0 + s1 + s2 + 4096;
 }
 
@@ -207,13 +207,15 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         const ConvW &U = e->up[s];
         const int T2 = Tc * U.stride, C2 = U.cout, Ch = e->res1[s].cout;
         const size_t R2 = (size_t)Bc * T2;
-        float *u = ws.take<float>(R2 * C2);
+        // the resblock's residual stream u is kept in fp16 like every other SEANet activation (2 B instead of 4 B
+        // per element on the two widest tensors of the decoder; the GEMM operands are fp16 anyway)
+        __half *u = ws.take<__half>(R2 * C2);
         __half *eu = ws.take<__half>(R2 * C2), *rm = ws.take<__half>(R2 * Ch), *vv = ws.take<__half>(R2 * C2);
-        g = {}; g.out_f32 = u; g.ldo = U.n_rows; g.out_h = (uint16_t *)eu; g.ldh = U.n_rows; g.act = ACT_ELU;
+        g = {}; g.out_raw = (uint16_t *)u; g.out_h = (uint16_t *)eu; g.ldh = U.n_rows; g.act = ACT_ELU;
         if (conv_gemm(e, U, cur, Bc, Tc, U.n_rows >= 256 ? 256 : 128, g) != 0) return -1;  // u = convT(ELU(prev)), eu = ELU(u)
         g = {}; g.out_h = (uint16_t *)rm; g.ldh = Ch; g.act = ACT_ELU;                      // ELU(conv_k3(ELU(u)))
         if (conv_gemm(e, e->res1[s], eu, Bc, T2, Ch >= 128 ? 128 : 64, g) != 0) return -1;
-        g = {}; g.resid = u; g.ldo = C2; g.out_h = (uint16_t *)vv; g.ldh = C2; g.act = ACT_ELU;  // ELU(u + conv_k1(.))
+        g = {}; g.resid_h = (const uint16_t *)u; g.out_h = (uint16_t *)vv; g.ldh = C2; g.act = ACT_ELU;  // ELU(u + conv_k1(.))
         if (conv_gemm(e, e->res2[s], rm, Bc, T2, C2 >= 256 ? 256 : C2, g) != 0) return -1;
         cur = vv; Tc = T2; last = vv;
     }
@@ -226,8 +228,10 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
 }
 
 // latents on the device [n,F,32] (item stride lat_stride floats) -> pcm on the device [n, F*1920], chunked over items so that the
-// workspace stays within the budget (PTTS_B200_MIMI_WS_GB, default 24 GB).
-static int mimi_run(Engine *e, int n, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm) {
+// workspace stays within the budget (PTTS_B200_MIMI_WS_GB, default 24 GB). When host_out is given, the PCM of
+// chunk i travels to the host on the copy stream while chunk i+1 is being decoded (at least 4 chunks, so that
+// only the last quarter of the device->host transfer is exposed); the caller waits on e->ev_copy.
+static int mimi_run(Engine *e, int n, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm, float *host_out = nullptr) {
     static size_t budget = 0;
     if (!budget) {
         const char *s = getenv("PTTS_B200_MIMI_WS_GB");
@@ -236,9 +240,20 @@ static int mimi_run(Engine *e, int n, int F, const float *d_lat, size_t lat_stri
     int per = (int)(budget / (mimi_ws_per_frame() * (size_t)F));
     if (per < 1) per = 1;
     if (per > n) per = n;
+    if (host_out && n >= 8) per = std::min(per, (n + 3) / 4);
     for (int i = 0; i < n; i += per) {
         const int bc = std::min(per, n - i);
-        if (mimi_run_chunk(e, bc, F, d_lat + (size_t)i * lat_stride, lat_stride, apply_scale, d_pcm + (size_t)i * F * 1920) != 0) return -1;
+        float *dst = d_pcm + (size_t)i * F * 1920;
+        if (mimi_run_chunk(e, bc, F, d_lat + (size_t)i * lat_stride, lat_stride, apply_scale, dst) != 0) return -1;
+        if (host_out) {
+            PTTS_CUDA_OK(cudaEventRecord(e->ev_chunk, e->st));
+            PTTS_CUDA_OK(cudaStreamWaitEvent(e->st_copy, e->ev_chunk, 0));
+            PTTS_CUDA_OK(cudaMemcpyAsync(host_out + (size_t)i * F * 1920, dst, (size_t)bc * F * 1920 * 4, cudaMemcpyDeviceToHost, e->st_copy));
+        }
+    }
+    if (host_out) {
+        PTTS_CUDA_OK(cudaEventRecord(e->ev_copy, e->st_copy));
+        e->pcm_on_host = host_out;
     }
     return 0;
 }

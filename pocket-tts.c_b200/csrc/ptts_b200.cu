@@ -4,6 +4,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <thread>
 
 #include "mega.cuh"
 #include "mimi.cuh"
@@ -70,8 +71,10 @@ extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b
     e->num_sms = prop.multiProcessorCount;
     g_num_sms = prop.multiProcessorCount;
     HostWeights hw{tensors, n_tensors};
-    if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
-        cudaEventCreate(&e->ev1) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
+        cudaEventCreate(&e->ev1) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_chunk, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) != cudaSuccess) {
         set_error("stream/event creation failed");
         ptts_b200_destroy(e);
         return -1;
@@ -105,6 +108,9 @@ extern "C" void ptts_b200_destroy(ptts_b200_engine *e) {
     if (e->pin) cudaFreeHost(e->pin);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->ev_chunk) cudaEventDestroy(e->ev_chunk);
+    if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+    if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -342,6 +348,22 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     std::vector<float> h_noise((size_t)n * cap_f * FL_LAT);
     std::vector<int> h_rb(rows), h_ri(rows), h_rs(n + 1, 0), h_ob(B, 0);
     double mean_ob = 0.0;
+    {   // the noise of different utterances is independent (one generator per seed): spread it over host threads
+        auto fill = [&](int i0, int i1) {
+            for (int i = i0; i < i1; i++) {
+                host_noise(seeds[i], gp->temp, gp->noise_clamp, max_frames[i], &h_noise[(size_t)i * cap_f * FL_LAT]);
+                for (size_t j = (size_t)max_frames[i] * FL_LAT; j < (size_t)cap_f * FL_LAT; j++) h_noise[(size_t)i * cap_f * FL_LAT + j] = 0.0f;
+            }
+        };
+        const int nt = gp->temp > 0.0f ? (int)std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u),
+                                                                (size_t)n * cap_f / 2048 + 1) : 1;
+        if (nt <= 1) fill(0, n);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back(fill, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
+            for (auto &t : th) t.join();
+        }
+    }
     for (int i = 0, r = 0; i < n; i++) {
         const int tl = token_offsets[i + 1] - token_offsets[i];
         memcpy(&h_tok[(size_t)i * capTok], tokens_flat + token_offsets[i], sizeof(int) * tl);
@@ -353,8 +375,6 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
         mean_ob += (double)(tl + 1) / n;
         int ea = eos_after ? eos_after[i] : gp->eos_after;
         h_ea[i] = ea < 0 ? 0 : ea;
-        host_noise(seeds[i], gp->temp, gp->noise_clamp, max_frames[i], &h_noise[(size_t)i * cap_f * FL_LAT]);
-        for (size_t j = (size_t)max_frames[i] * FL_LAT; j < (size_t)cap_f * FL_LAT; j++) h_noise[(size_t)i * cap_f * FL_LAT + j] = 0.0f;
     }
     FlowCtrl c;
     c.step = 0; c.cond_len = cond_len; c.eos_enabled = gp->eos_enabled; c.eos_min_frames = std::max(gp->eos_min_frames, 1);
@@ -415,7 +435,8 @@ static int run_begin(Engine *e) {
     return 0;
 }
 
-static int run_impl(Engine *e, int with_mimi) {
+static int run_impl(Engine *e, int with_mimi, float *host_audio = nullptr) {
+    e->pcm_on_host = nullptr;
     if (run_begin(e) != 0) return -1;
     const int B = e->curB, n = e->st_n;
     const int mode = B == 1 ? 1 : 2;
@@ -423,7 +444,7 @@ static int run_impl(Engine *e, int with_mimi) {
     if (with_mimi) {
         const int F = e->st_capF;
         if (ensure_pcm(e, (size_t)n * F * 1920) != 0) return -1;
-        if (mimi_run(e, n, F, e->d_out_latents, (size_t)e->capF * FL_LAT, 1, e->d_pcm) != 0) return -1;
+        if (mimi_run(e, n, F, e->d_out_latents, (size_t)e->capF * FL_LAT, 1, e->d_pcm, host_audio) != 0) return -1;
     }
     return 0;
 }
@@ -438,7 +459,8 @@ static int fetch_impl(Engine *e, float *out_latents, int *out_frames_used, float
                                        (size_t)F * FL_LAT * 4, n, cudaMemcpyDeviceToHost, e->st));
     if (out_audio) {
         PTTS_CHECK(e->d_pcm && e->pcm_cap >= (size_t)n * F * 1920, "batch_fetch: no PCM was produced (run with_mimi = 1)");
-        PTTS_CUDA_OK(cudaMemcpyAsync(out_audio, e->d_pcm, (size_t)n * F * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
+        if (e->pcm_on_host == out_audio) PTTS_CUDA_OK(cudaEventSynchronize(e->ev_copy));   // delivered chunk by chunk during the run
+        else PTTS_CUDA_OK(cudaMemcpyAsync(out_audio, e->d_pcm, (size_t)n * F * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
     }
     PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     if (out_frames_used) memcpy(out_frames_used, used.data(), n * sizeof(int));
@@ -463,7 +485,7 @@ extern "C" int ptts_b200_generate_batch(ptts_b200_engine *e, int n, const int *t
                                         const int *eos_after, const ptts_b200_gen_params *params, float *out_latents,
                                         int *out_frames_used, float *out_audio) {
     if (stage_impl(e, n, tokens_flat, token_offsets, cond_prefix, cond_len, max_frames, seeds, eos_after, params) != 0) return -1;
-    if (run_impl(e, out_audio != nullptr) != 0) return -1;
+    if (run_impl(e, out_audio != nullptr, out_audio) != 0) return -1;
     return fetch_impl(e, out_latents, out_frames_used, out_audio);
 }
 
