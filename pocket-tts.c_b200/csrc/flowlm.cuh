@@ -195,7 +195,7 @@ static int attn_decode(Engine *e, int B, int layer, bool out16, int qkv_nsplit =
     a.pstride = e->capCond;
     a.pk = e->pk + (size_t)layer * FL_D * e->capCond; a.pv = e->pv + (size_t)layer * FL_D * e->capCond;
     a.ok = e->ok + (size_t)layer * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)layer * e->capB * FL_D * e->capS;
-    a.max_s = e->capS;
+    a.max_s = e->capS; a.cap_b = e->capB;
     a.step = &e->ctrl->step;
     if (out16) { a.out_h = e->att_h; a.out_l = e->att_l; } else a.out_f32 = e->att;
     const int pcap = ((e->capCond + e->capS + 63) / 32) * 32;
@@ -477,11 +477,11 @@ static int flow_prefill(Engine *e, int n, int M, int max_q, int cond_len, bool v
             a.qkv = e->pf_qkv; a.rope_cos = e->rope_cos; a.rope_sin = e->rope_sin;
             a.cond_len = cond_len; a.pstride = e->capCond; a.max_q = max_q;
             if (voice_mode) {
-                a.ok = e->pk + (size_t)l * FL_D * e->capCond; a.ov = e->pv + (size_t)l * FL_D * e->capCond; a.max_s = e->capCond;
+                a.ok = e->pk + (size_t)l * FL_D * e->capCond; a.ov = e->pv + (size_t)l * FL_D * e->capCond; a.max_s = e->capCond; a.cap_b = 1;
             } else {
                 a.pk = e->pk + (size_t)l * FL_D * e->capCond; a.pv = e->pv + (size_t)l * FL_D * e->capCond;
                 a.ok = e->ok + (size_t)l * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)l * e->capB * FL_D * e->capS;
-                a.max_s = e->capS;
+                a.max_s = e->capS; a.cap_b = e->capB;
             }
             a.out_h = e->pf_att_h; a.out_l = e->pf_att_l;
             LaunchScope ls(e, KC_ATTN_DECODE);

@@ -351,7 +351,7 @@ __global__ void k_advance_step(int *step) {
 // =====================================================================================
 // RoPE + KV append + single-query attention over [shared voice prefix | own positions]
 // (ptts_flowlm.c:465-525).  grid (16 heads, B), block 128.
-// cache layout: prefix [H][pstride][64], own [B][H][max_s][64], fp32.
+// cache layout: prefix [H][pstride][64], own [H][B][max_s][64], fp32.
 // =====================================================================================
 struct AttnDecodeParams {
     const float *qkv;          // [B, 3072], or split-K partial sums [qkv_nsplit][..] qkv_stride floats apart
@@ -359,7 +359,9 @@ struct AttnDecodeParams {
     size_t qkv_stride;
     const float *rope_cos, *rope_sin;  // [max_pos][32]
     const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
-    float *ok, *ov;            // own cache of this layer
+    float *ok, *ov;            // own cache of this layer, head-major [H][cap_b][max_s][64]: the utterances one CTA works on
+                               // (one head, consecutive b) are one contiguous span of memory
+    int cap_b;                 // utterance capacity of the own cache
     const int *ctrl_cond_len;  // device cond_len
     const int *own_base;       // [B] own-cache rows already filled by the prefill (tok_len + 1)
     int pstride;               // row capacity of the prefix buffers
@@ -414,8 +416,8 @@ __device__ __forceinline__ void attn_decode_item(const AttnDecodeParams &p, int 
     const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
     const int s = step + (live ? p.own_base[b] : 0);   // own-cache row written by this step
     const int pos = cond_len + s, P = pos + 1;
-    float *okb = p.ok + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
-    float *ovb = p.ov + ((size_t)(live ? b : 0) * FL_H + h) * p.max_s * FL_HD;
+    float *okb = p.ok + ((size_t)h * p.cap_b + (live ? b : 0)) * p.max_s * FL_HD;
+    float *ovb = p.ov + ((size_t)h * p.cap_b + (live ? b : 0)) * p.max_s * FL_HD;
     float *sc = scores + w * pcap;
     float2 q = make_float2(0.0f, 0.0f);
     if (live) {
@@ -626,7 +628,8 @@ struct PrefillAttnParams {
     const float *qkv;          // [M, 3072]
     const float *rope_cos, *rope_sin;
     const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
-    float *ok, *ov;            // own cache of this layer [n][H][max_s][64]
+    float *ok, *ov;            // own cache of this layer [H][cap_b][max_s][64]
+    int cap_b;
     int cond_len, pstride, max_s, max_q;
     uint16_t *out_h, *out_l;   // [M,1024] bf16 hi/lo
 };
@@ -644,8 +647,8 @@ __global__ void __launch_bounds__(256) k_pf_attn(const PrefillAttnParams p, cons
     float *V = K + ((nrows * AD_LD + 3) & ~(size_t)3);         // [rows][64], 16-byte aligned
     float *sc = V + nrows * FL_HD;                             // [8][scf]
     float *qs = sc + 8 * scf;                                  // [8][64]
-    float *okb = p.ok + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
-    float *ovb = p.ov + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+    float *okb = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
+    float *ovb = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
     for (int idx = tid; idx < cl * 16; idx += 256) {
         const int r = idx >> 4, c4 = (idx & 15) * 4;
         const float4 kv = *(const float4 *)(p.pk + ((size_t)h * p.pstride + r) * FL_HD + c4);

@@ -27,7 +27,8 @@ constexpr int MG_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB: A hi at +0, A lo at
 constexpr int MG_SLOT_BYTES = 3 * MG_A_BYTES;      // B tile <= 128 rows
 constexpr int MG_RING_BYTES = MG_STAGES * MG_SLOT_BYTES;
 constexpr int MG_MAX_BN = 128;
-constexpr int MG_SMEM_BYTES = MG_RING_BYTES + 1024 /*alignment*/ + 1024 /*barriers + scratch*/;
+constexpr int MG_ATTN_EXTRA = 0;                  // shared memory beyond the ring would shrink L1 (it holds the rope tables, q/k/v partials and spills)
+constexpr int MG_SMEM_BYTES = 1024 /*alignment*/ + 1024 /*barriers + scratch*/ + MG_RING_BYTES + MG_ATTN_EXTRA;
 
 enum MegaPhaseType : int { MP_HEAD = 0, MP_GEMM, MP_ROW, MP_MID, MP_TAIL, MP_ATTN, MP_COUNT };
 
@@ -43,7 +44,7 @@ struct MegaProgram {
     const GemmOp *gemms;
     const RowNormParams *rows;
     const AttnDecodeParams *attn;
-    int B, pcap, attn_g;            // padded batch, score-buffer length, utterances per attention item
+    int B, pcap, attn_g;            // padded batch, score-buffer length, (unused)
     FlowState st;
     FlowCtrl *ctrl;
     const int *eos_after;
@@ -376,12 +377,41 @@ __device__ __forceinline__ void pv_rows_global(const float *vb, int n, const flo
     }
 }
 
+// shared-memory prefix tile: scores of keys [k0, k1) (multiples of 4 apart) -> sc
+__device__ __forceinline__ void qk_tile(const float *kt, int k0, int k1, int n_tile, const float (&q8)[8], float *sc, int k4, int l8) {
+    for (int r0 = k0; r0 < k1; r0 += 4) {
+        const int key = r0 + k4;
+        const bool ok = key < n_tile;
+        float kk[8];
+        const float4 a = ok ? *(const float4 *)(kt + key * FL_HD + l8 * 8) : make_float4(0, 0, 0, 0);
+        const float4 b = ok ? *(const float4 *)(kt + key * FL_HD + l8 * 8 + 4) : make_float4(0, 0, 0, 0);
+        kk[0] = a.x; kk[1] = a.y; kk[2] = a.z; kk[3] = a.w; kk[4] = b.x; kk[5] = b.y; kk[6] = b.z; kk[7] = b.w;
+        const float d = dot8_reduce(q8, kk);
+        if (l8 == 0 && ok) sc[key] = d;
+    }
+}
+__device__ __forceinline__ void pv_tile(const float *vt, int k0, int k1, int n_tile, const float *sc, int k4, int l8, float (&acc)[8]) {
+    for (int r0 = k0; r0 < k1; r0 += 4) {
+        const int key = r0 + k4;
+        if (key < n_tile) {
+            const float pw = sc[key];
+            const float4 v0 = *(const float4 *)(vt + key * FL_HD + l8 * 8), v1 = *(const float4 *)(vt + key * FL_HD + l8 * 8 + 4);
+            acc[0] += pw * v0.x; acc[1] += pw * v0.y; acc[2] += pw * v0.z; acc[3] += pw * v0.w;
+            acc[4] += pw * v1.x; acc[5] += pw * v1.y; acc[6] += pw * v1.z; acc[7] += pw * v1.w;
+        }
+    }
+}
+
+// The shared-memory prefix work is cut into one quantum per 32-row batch of own K (V) rows and runs
+// between the issue of a batch's loads and their use, so the HBM round trips hide behind it.
 __device__ __forceinline__ void attn4_unit(const AttnDecodeParams &p, int b, int h, int step, int cond_len, const float *kt, const float *vt,
-                                           float *sc, float *sqw, int lane) {
+                                           float *sc, float *sqw, int lane, bool l2pf, unsigned long long *tm = nullptr) {
     const int k4 = lane >> 3, l8 = lane & 7;
+    long long c0 = tm ? clock64() : 0;
+#define A4_STAMP(i) if (tm) { const long long c1 = clock64(); if (lane == 0) tm[i] += (unsigned long long)(c1 - c0); c0 = c1; }
     const int s = step + p.own_base[b], pos = cond_len + s, n_own = s + 1, P = cond_len + n_own;
     const int n_tile = min(cond_len, A4_TILE), n_far = cond_len - n_tile;   // prefix keys in shared memory / beyond the tile
-    float *okb = p.ok + ((size_t)b * FL_H + h) * p.max_s * FL_HD, *ovb = p.ov + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+    float *okb = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD, *ovb = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
     const float *pkh = p.pk ? p.pk + (size_t)h * p.pstride * FL_HD : nullptr;
     const float *pvh = p.pv ? p.pv + (size_t)h * p.pstride * FL_HD : nullptr;
     // ---- new position: RoPE(q), RoPE(k) and v appended to the own cache (lane = dimension pair)
@@ -396,28 +426,39 @@ __device__ __forceinline__ void attn4_unit(const AttnDecodeParams &p, int b, int
         *(float2 *)(sqw + 2 * lane) = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
     }
     __syncwarp();
+    A4_STAMP(0)
     float q8[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) q8[i] = sqw[l8 * 8 + i];
-    // ---- scores: the first 32 own rows are requested before the shared-memory prefix work
+    const int nbatch = (n_own + 31) / 32;
+    const int quantum = (((n_tile + nbatch - 1) / nbatch) + 3) & ~3;
     float rows[8][8];
-    load_rows32(okb, n_own, k4, l8, rows);
-    for (int r0 = 0; r0 < n_tile; r0 += 4) {
-        const int key = r0 + k4;
-        float kk[8];
-        const bool ok = key < n_tile;
-        const float4 k0 = ok ? *(const float4 *)(kt + key * FL_HD + l8 * 8) : make_float4(0, 0, 0, 0);
-        const float4 k1 = ok ? *(const float4 *)(kt + key * FL_HD + l8 * 8 + 4) : make_float4(0, 0, 0, 0);
-        kk[0] = k0.x; kk[1] = k0.y; kk[2] = k0.z; kk[3] = k0.w; kk[4] = k1.x; kk[5] = k1.y; kk[6] = k1.z; kk[7] = k1.w;
-        const float a = dot8_reduce(q8, kk);
-        if (l8 == 0 && ok) sc[key] = a;
+    if (l2pf) {
+        // rows beyond the first K batch (and all V rows) start moving HBM -> L2 now, without holding registers:
+        // one 128-byte line per prefetch, 2 lines per row
+        for (int i = 64 + lane; i < 2 * n_own; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(okb + (size_t)i * 32));
+        for (int i = lane; i < 2 * n_own; i += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(ovb + (size_t)i * 32));
     }
-    qk_rows_global(okb, n_own, q8, sc + cond_len, k4, l8, rows);
+    // ---- scores
+    int pre = 0;
+    for (int r0 = 0; r0 < n_own; r0 += 32) {
+        load_rows32(okb + (size_t)r0 * FL_HD, n_own - r0, k4, l8, rows);
+        qk_tile(kt, pre, min(pre + quantum, n_tile), n_tile, q8, sc, k4, l8);
+        pre = min(pre + quantum, n_tile);
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int key = r0 + it * 4 + k4;
+            const float a = dot8_reduce(q8, rows[it]);
+            if (l8 == 0 && key < n_own) sc[cond_len + key] = a;
+        }
+    }
+    qk_tile(kt, pre, n_tile, n_tile, q8, sc, k4, l8);
     if (n_far > 0) {
         load_rows32(pkh + (size_t)n_tile * FL_HD, n_far, k4, l8, rows);
         qk_rows_global(pkh + (size_t)n_tile * FL_HD, n_far, q8, sc + n_tile, k4, l8, rows);
     }
     __syncwarp();
+    A4_STAMP(1)
     // ---- softmax; the first 32 own V rows are requested before it
     load_rows32(ovb, n_own, k4, l8, rows);
     float mx = -INFINITY;
@@ -427,24 +468,30 @@ __device__ __forceinline__ void attn4_unit(const AttnDecodeParams &p, int b, int
     for (int t = lane; t < P; t += 32) { const float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
     sum = warp_sum(sum);
     __syncwarp();
+    A4_STAMP(2)
     // ---- P.V
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) acc[i] = 0.0f;
-    for (int r0 = 0; r0 < n_tile; r0 += 4) {
-        const int key = r0 + k4;
-        if (key < n_tile) {
-            const float pw = sc[key];
-            const float4 v0 = *(const float4 *)(vt + key * FL_HD + l8 * 8), v1 = *(const float4 *)(vt + key * FL_HD + l8 * 8 + 4);
-            acc[0] += pw * v0.x; acc[1] += pw * v0.y; acc[2] += pw * v0.z; acc[3] += pw * v0.w;
-            acc[4] += pw * v1.x; acc[5] += pw * v1.y; acc[6] += pw * v1.z; acc[7] += pw * v1.w;
+    pre = 0;
+    for (int r0 = 0; r0 < n_own; r0 += 32) {
+        if (r0 > 0) load_rows32(ovb + (size_t)r0 * FL_HD, n_own - r0, k4, l8, rows);
+        pv_tile(vt, pre, min(pre + quantum, n_tile), n_tile, sc, k4, l8, acc);
+        pre = min(pre + quantum, n_tile);
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int key = r0 + it * 4 + k4;
+            const float pw = key < n_own ? sc[cond_len + key] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] += pw * rows[it][i];
         }
     }
-    pv_rows_global(ovb, n_own, sc + cond_len, k4, l8, rows, acc);
+    pv_tile(vt, pre, n_tile, n_tile, sc, k4, l8, acc);
     if (n_far > 0) {
         load_rows32(pvh + (size_t)n_tile * FL_HD, n_far, k4, l8, rows);
         pv_rows_global(pvh + (size_t)n_tile * FL_HD, n_far, sc + n_tile, k4, l8, rows, acc);
     }
+    A4_STAMP(3)
     const float inv = 1.0f / sum;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
@@ -473,19 +520,22 @@ __device__ __forceinline__ void attn4_unit(const AttnDecodeParams &p, int b, int
         }
     }
     __syncwarp();   // sc / sqw reusable by this warp's next unit
+    A4_STAMP(4)
+    if (tm && lane == 0) tm[5] += 1;
+#undef A4_STAMP
 }
 
 // Pull a unit's own K / V rows into L2 ahead of its turn (lanes 0, 1 issue one bulk prefetch each).
 __device__ __forceinline__ void attn4_prefetch(const AttnDecodeParams &p, int b, int h, int step, int lane) {
     if (lane < 2) {
-        const float *ptr = (lane ? p.ov : p.ok) + ((size_t)b * FL_H + h) * p.max_s * FL_HD;
+        const float *ptr = (lane ? p.ov : p.ok) + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
         const uint32_t bytes = (uint32_t)(step + p.own_base[b]) * FL_HD * 4u;
         if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
     }
 }
 
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
-__device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, int pcap, int step, float *sm, int tid, bool P_PREFETCH) {
+__device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, int pcap, int step, float *sm, int tid, bool P_PREFETCH, bool l2pf, unsigned long long *tmw = nullptr) {
     float *kt = sm, *vt = kt + A4_TILE * FL_HD, *scw = vt + A4_TILE * FL_HD;
     int *ctr = (int *)(scw + A4_WARPS * (pcap + FL_HD));
     const int w = tid >> 5, lane = tid & 31;
@@ -523,7 +573,7 @@ __device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, in
             u = __shfl_sync(0xffffffffu, u, 0);
             if (u >= ub) break;
             if (P_PREFETCH && u + A4_WARPS < ub) attn4_prefetch(p, u + A4_WARPS - h * B, h, step, lane);   // one round ahead
-            attn4_unit(p, u - h * B, h, step, cond_len, kt, vt, sc, sqw, lane);
+            attn4_unit(p, u - h * B, h, step, cond_len, kt, vt, sc, sqw, lane, l2pf, (tmw && w == 0) ? tmw : nullptr);
         }
         ua = ub;
     }
@@ -669,11 +719,12 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_constant__ MegaProgram P) {
     extern __shared__ uint8_t mg_smem_raw[];
-    uint8_t *ring = (uint8_t *)(((uintptr_t)mg_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = (uint64_t *)(ring + MG_RING_BYTES);
+    uint8_t *sbase = (uint8_t *)(((uintptr_t)mg_smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)sbase;
     uint64_t *full = bars, *empty = bars + MG_STAGES, *tfull = bars + 2 * MG_STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
-    float *scratch = (float *)(ring + MG_RING_BYTES + 256);   // per row group: red[8] + lat[32]
+    float *scratch = (float *)(sbase + 256);                  // per row group: red[8] + lat[32]
+    uint8_t *ring = sbase + 1024;                             // 1024-byte aligned; the attention phases also use MG_ATTN_EXTRA beyond it
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     constexpr uint32_t TMEM_COLS = 2 * MG_MAX_BN;
 
@@ -762,7 +813,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid, (P.flags & 1) != 0);
+                    attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid, (P.flags & 1) != 0, (P.flags & 4) != 0,
+                                (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     break;
                 default: break;
             }
@@ -815,7 +867,7 @@ static AttnDecodeParams make_attn_params(Engine *e, int layer, bool out16, int q
     a.pstride = e->capCond;
     a.pk = e->pk + (size_t)layer * FL_D * e->capCond; a.pv = e->pv + (size_t)layer * FL_D * e->capCond;
     a.ok = e->ok + (size_t)layer * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)layer * e->capB * FL_D * e->capS;
-    a.max_s = e->capS;
+    a.max_s = e->capS; a.cap_b = e->capB;
     a.step = &e->ctrl->step;
     if (out16) { a.out_h = e->att_h; a.out_l = e->att_l; } else a.out_f32 = e->att;
     return a;
@@ -893,7 +945,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
     }
     const int Gu = 1;
     const int pcap = ((e->capCond + e->capS + 63) / 32) * 32;
-    PTTS_CHECK(attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES,
+    PTTS_CHECK(attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA,
                "attention score buffers of %zu bytes exceed the persistent kernel's shared memory (sequence too long)",
                attn4_smem_bytes(pcap));
     if (e->dalloc(&M.d_phases, ph.size()) != 0 || e->dalloc(&M.d_gemms, gm.size()) != 0 || e->dalloc(&M.d_rows, rows.size()) != 0 ||

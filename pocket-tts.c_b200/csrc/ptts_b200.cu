@@ -176,8 +176,8 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     const bool want_trace = e->prof.on && getenv("PTTS_B200_MEGA_TRACE") != nullptr;
     unsigned long long *d_trace = nullptr;
     if (want_trace) {
-        if (e->dalloc(&d_trace, (size_t)2 * P.n_phases) != 0) return -1;
-        PTTS_CUDA_OK(cudaMemsetAsync(d_trace, 0, (size_t)2 * P.n_phases * 8, e->st));
+        if (e->dalloc(&d_trace, (size_t)2 * P.n_phases + 8) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemsetAsync(d_trace, 0, ((size_t)2 * P.n_phases + 8) * 8, e->st));
         P.trace = d_trace;
     }
     cudaLaunchConfig_t cfg = {};
@@ -193,7 +193,7 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
         PTTS_CUDA_OK(cudaMemcpyAsync(h, e->mega_ctl + 8, sizeof h, cudaMemcpyDeviceToHost, e->st));
         PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
         if (d_trace) {   // per-phase timeline of CTA 0 (PTTS_B200_MEGA_TRACE=1), microseconds per frame
-            std::vector<unsigned long long> tr((size_t)2 * P.n_phases);
+            std::vector<unsigned long long> tr((size_t)2 * P.n_phases + 8);
             PTTS_CUDA_OK(cudaMemcpy(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
             static const char *const tn[MP_COUNT] = {"HEAD", "GEMM", "ROW", "MID", "TAIL", "ATTN"};
             const double st_ = (double)h[2 * MP_HEAD + 1];
@@ -208,6 +208,9 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
                 }
                 fprintf(stderr, "  %3d %-4s %7.2f %7.2f  %s\n", i, tn[q.type], tr[2 * i] * 1e-3 / st_, tr[2 * i + 1] * 1e-3 / st_, extra);
             }
+            { const unsigned long long *a = &tr[(size_t)2 * P.n_phases]; const double nu = (double)std::max<unsigned long long>(a[5], 1);
+              fprintf(stderr, "  attention unit (CTA 0 warp 0, cycles per unit over %.0f units): new-row %.0f  scores %.0f  softmax %.0f  PV %.0f  write %.0f\n",
+                      nu, a[0] / nu, a[1] / nu, a[2] / nu, a[3] / nu, a[4] / nu); }
             e->dfree(d_trace);
         }
         static const int cls_of[MP_COUNT] = {KC_FLOW_MISC, KC_GEMM_FLOW, KC_ROWNORM, KC_FLOW_MISC, KC_FLOW_MISC, KC_ATTN_DECODE};
