@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast", type=int, default=0, help="1: activations as single bf16 (precise=0); default hi+lo pairs")
+    ap.add_argument("--skip-mimi-only", action="store_true", help="skip the configs[3] Mimi decode-only measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -243,7 +244,9 @@ def main():
     }
 
     if rank == 0:
-        # ---------------- per-kernel-class profile of one step (events around every launch, no graphs)
+        # ---------------- per-class profile of one step. The FlowLM decode loop is ONE launch (k_flow_mega, the
+        # persistent step kernel): its classes are timed inside the kernel (%globaltimer stamps of CTA 0 around every
+        # phase, grid barrier included); prefill and Mimi kernels are bracketed by CUDA events on the engine stream.
         pk = peaks()
         eng.profile(True)
         eng.run(True)
@@ -251,23 +254,58 @@ def main():
         eng.profile(False)
         tot = sum(v["ms"] for v in prof.values()) or 1.0
         shares = {k: round(v["ms"] / tot, 4) for k, v in prof.items() if v["launches"]}
-        dom = max((k for k in prof if prof[k]["launches"]), key=lambda k: prof[k]["ms"])
-        d = prof[dom]
-        t_s = d["ms"] / 1000.0
-        mem_frac = d["bytes"] / t_s / 1e9 / pk["hbm"]
-        flop_frac = d["flops"] / t_s / 1e12 / pk["tf_sust"]
-        if flop_frac >= mem_frac:
-            roof = {"bound": "tensor", "achieved": d["flops"] / t_s / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": flop_frac}
-        else:
-            roof = {"bound": "hbm", "achieved": d["bytes"] / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": mem_frac}
-        roof.update({"kernel": dom, "launches_per_step": d["launches"], "avg_launch_us": 1000.0 * d["ms"] / d["launches"],
-                     "peak_source": pk["src"], "traffic": None, "share_of_step": shares.get(dom),
-                     "timing": "CUDA events around each launch on the engine stream, one un-graphed step"})
-        line["roofline"] = roof
         line["kernel_shares"] = shares
         line["kernel_classes"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                       "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
                                       "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in prof.items() if v["launches"]}
+        # dominant kernel = the persistent FlowLM step kernel (one launch per step): time it alone, device events
+        eng.stage(toks, voice, F, seeds, None, params)
+        eng.run(False); eng.sync()
+        eng.timer_start()
+        for _ in range(3):
+            eng.run(False)            # prompt prefill (24 small GEMMs + 6 attention launches) + k_flow_mega
+        ms_flow = eng.timer_stop() / 3
+        flow_cls = ("gemm_tc_flowlm", "attn_decode", "rownorm", "flow_misc")
+        flow_bytes = sum(prof[k]["bytes"] for k in flow_cls if k in prof)      # weights once per frame step + K/V rows once per step
+        flow_flops = sum(prof[k]["flops"] for k in flow_cls if k in prof)
+        mem_frac = flow_bytes / (ms_flow / 1e3) / 1e9 / pk["hbm"]
+        flop_frac = flow_flops / (ms_flow / 1e3) / 1e12 / pk["tf_sust"]
+        traffic = None
+        tr = ROOT / "profiles" / "r01_flow_mega_traffic.json"     # dram__bytes_read+write of one k_flow_mega launch (ncu --set full)
+        if tr.exists():
+            try:
+                traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm" if mem_frac >= flop_frac else "tensor",
+                "achieved": flow_bytes / (ms_flow / 1e3) / 1e9 if mem_frac >= flop_frac else flow_flops / (ms_flow / 1e3) / 1e12,
+                "peak": pk["hbm"] if mem_frac >= flop_frac else pk["tf_sust"], "unit": "GB/s" if mem_frac >= flop_frac else "TFLOP/s",
+                "frac": max(mem_frac, flop_frac), "kernel": "k_flow_mega (persistent FlowLM step kernel, incl. the prompt prefill launches before it)",
+                "launches_per_step": 1, "avg_launch_us": 1000.0 * ms_flow, "peak_source": pk["src"], "traffic": traffic,
+                "share_of_step": round(ms_flow / ms_per_step, 4), "tensor_frac": flop_frac, "hbm_frac": mem_frac,
+                "algorithmic_bytes_per_launch": flow_bytes, "algorithmic_flops_per_launch": flow_flops,
+                "timing": "CUDA events on the engine stream around 3 FlowLM-only runs of the staged batch (inputs resident in HBM)"}
+        line["roofline"] = roof
+        # second kernel of the step: the Mimi tcgen05 implicit-GEMM kernel (all its launches of one step)
+        if "gemm_tc_mimi" in prof and prof["gemm_tc_mimi"]["launches"]:
+            m = prof["gemm_tc_mimi"]
+            line["roofline_mimi_gemm"] = {"bound": "tensor", "achieved": m["flops"] / (m["ms"] / 1e3) / 1e12, "peak": pk["tf_sust"],
+                                          "unit": "TFLOP/s", "frac": m["flops"] / (m["ms"] / 1e3) / 1e12 / pk["tf_sust"],
+                                          "hbm_frac": m["bytes"] / (m["ms"] / 1e3) / 1e9 / pk["hbm"], "launches_per_step": m["launches"],
+                                          "avg_launch_us": 1000.0 * m["ms"] / m["launches"], "share_of_step": shares.get("gemm_tc_mimi")}
+
+        # ---------------- configs[3]: Mimi decode-only, 64 x 4096 latent frames -> 24 kHz PCM (device-resident timing is not
+        # exposed for this entry: host latents in, host PCM out, copies inside the timed call)
+        if not args.skip_mimi_only:
+            lat = np.random.default_rng(0).standard_normal((64, 4096, 32)).astype(np.float32)
+            pcm = torch.empty((64, 4096 * 1920), dtype=torch.float32).pin_memory().numpy()
+            eng.mimi_decode_batch(lat[:2], pcm[:2])
+            t0 = time.perf_counter()
+            eng.mimi_decode_batch(lat, pcm)
+            dt = time.perf_counter() - t0
+            line["mimi_decode_only"] = {"workload": "64 x 4096 latent frames (configs[3])", "seconds": dt, "audio_s_per_s": 64 * 4096 * FRAME_SEC / dt,
+                                        "note": "host latents -> host PCM through ptts_b200_mimi_decode_batch (H2D + 2 GB D2H inside)"}
+            del lat, pcm
 
         # ---------------- batch-1 streaming decode (configs[1]) and first-audio latency
         one = [toks[0]]
@@ -277,6 +315,13 @@ def main():
             t0 = time.perf_counter()
             eng.generate_batch(one, voice, 1, [123], None, params, True)
             lat.append(1000 * (time.perf_counter() - t0))
+        lat_stream = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            eng.stream_begin(one[0], voice, 200, 123, params)
+            pcm1, _done = eng.stream_next(1)
+            lat_stream.append(1000 * (time.perf_counter() - t0))
+            assert len(pcm1) == 1920
         eng.stage(one, voice, 200, [123], None, params)
         eng.run(False)
         eng.sync()
@@ -284,7 +329,7 @@ def main():
         eng.run(False)
         ms1 = eng.timer_stop()
         steps1 = 200   # decode iterations; the prompt is prefilled in one batched pass
-        line["batch1"] = {"first_audio_ms": statistics.median(lat), "first_audio_note": "tokens on host -> first 1920 PCM samples on host, voice prefix KV cached",
+        line["batch1"] = {"first_audio_ms": statistics.median(lat), "first_audio_stream_api_ms": statistics.median(lat_stream), "first_audio_note": "tokens on host -> first 1920 PCM samples on host, voice prefix KV cached",
                           "decode_200_frames_ms": ms1, "us_per_step": 1000 * ms1 / steps1,
                           "audio_s_per_s": 200 * FRAME_SEC / (ms1 / 1000), "hbm_frac": 170.6e6 / (ms1 / steps1 / 1000) / 1e9 / pk["hbm"]}
 

@@ -541,8 +541,9 @@ extern "C" int ptts_b200_mimi_decode_batch(ptts_b200_engine *e, const float *lat
     }
     if (ensure_pcm(e, (size_t)n * frames * 1920) != 0) return -1;
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_mimi_lat, latents, nl * 4, cudaMemcpyHostToDevice, e->st));
-    if (mimi_run(e, n, frames, e->d_mimi_lat, (size_t)frames * FL_LAT, 0, e->d_pcm) != 0) return -1;
-    PTTS_CUDA_OK(cudaMemcpyAsync(out_audio, e->d_pcm, (size_t)n * frames * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
+    // the PCM of each chunk of utterances goes to the host while the next chunk is decoded
+    if (mimi_run(e, n, frames, e->d_mimi_lat, (size_t)frames * FL_LAT, 0, e->d_pcm, out_audio) != 0) return -1;
+    PTTS_CUDA_OK(cudaEventSynchronize(e->ev_copy));
     PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     return 0;
 }
