@@ -151,6 +151,10 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly ONE JSON line: everything libraries print there (e.g. NCCL's version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from __graft_entry__ import load_package
@@ -351,7 +355,7 @@ def main():
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"unavailable: {ex}"}
-        print(json.dumps(line))
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()

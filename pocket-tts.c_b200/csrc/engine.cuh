@@ -306,7 +306,7 @@ struct ptts_b200_engine {
     float *fx = nullptr, *ada = nullptr, *ft = nullptr, *flow = nullptr, *sc = nullptr, *fg = nullptr;
     uint16_t *sc_h = nullptr, *sc_l = nullptr, *fh_h = nullptr, *fh_l = nullptr, *fg_h = nullptr, *fg_l = nullptr;
     float *pk = nullptr, *pv = nullptr;           // prefix KV [L][H][capCond][64]
-    float *ok = nullptr, *ov = nullptr;           // own KV [L][capB][H][capS][64]
+    __half *ok = nullptr, *ov = nullptr;          // own KV, fp16 [L][H][capB][capS][64]
     float *d_cond = nullptr;                      // voice rows on device [capCond,1024]
     // batched prefill workspace (capRows packed rows)
     int capRows = 0;

@@ -206,7 +206,7 @@ static int attn_decode(Engine *e, int B, int layer, bool out16, int qkv_nsplit =
         // algorithmic bytes: shared prefix K/V once, each utterance's own K/V rows once, the new K/V
         // row written, q/k/v read and the output written (own rows: mean prompt length + frames so far)
         const double own = e->prof.mean_own_base + e->prof.cur_step + 1, pre = e->voice_len;
-        e->prof.bytes[KC_ATTN_DECODE] += 2.0 * FL_D * 4.0 * (pre + (double)B * own) + (double)B * FL_D * 4.0 * (2 + 3 + 1);
+        e->prof.bytes[KC_ATTN_DECODE] += 2.0 * FL_D * (4.0 * pre + 2.0 * (double)B * own) + (double)B * FL_D * (2.0 * 2 + 4.0 * (3 + 1));
         e->prof.flops[KC_ATTN_DECODE] += 4.0 * FL_D * (double)B * (pre + own);
     }
     LaunchScope ls(e, KC_ATTN_DECODE);
@@ -478,10 +478,11 @@ static int flow_prefill(Engine *e, int n, int M, int max_q, int cond_len, bool v
             a.cond_len = cond_len; a.pstride = e->capCond; a.max_q = max_q;
             if (voice_mode) {
                 a.ok = e->pk + (size_t)l * FL_D * e->capCond; a.ov = e->pv + (size_t)l * FL_D * e->capCond; a.max_s = e->capCond; a.cap_b = 1;
+                a.own_f16 = 0;
             } else {
                 a.pk = e->pk + (size_t)l * FL_D * e->capCond; a.pv = e->pv + (size_t)l * FL_D * e->capCond;
                 a.ok = e->ok + (size_t)l * e->capB * FL_D * e->capS; a.ov = e->ov + (size_t)l * e->capB * FL_D * e->capS;
-                a.max_s = e->capS; a.cap_b = e->capB;
+                a.max_s = e->capS; a.cap_b = e->capB; a.own_f16 = 1;
             }
             a.out_h = e->pf_att_h; a.out_l = e->pf_att_l;
             LaunchScope ls(e, KC_ATTN_DECODE);

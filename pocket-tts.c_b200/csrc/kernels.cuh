@@ -351,7 +351,8 @@ __global__ void k_advance_step(int *step) {
 // =====================================================================================
 // RoPE + KV append + single-query attention over [shared voice prefix | own positions]
 // (ptts_flowlm.c:465-525).  grid (16 heads, B), block 128.
-// cache layout: prefix [H][pstride][64], own [H][B][max_s][64], fp32.
+// cache layout: prefix [H][pstride][64] fp32, own [H][B][max_s][64] fp16 (measured effect on the latents: 2.7e-5
+// max-relative after 48 frames against a 1e-3 bar, tools/parity_long.py).
 // =====================================================================================
 struct AttnDecodeParams {
     const float *qkv;          // [B, 3072], or split-K partial sums [qkv_nsplit][..] qkv_stride floats apart
@@ -359,7 +360,7 @@ struct AttnDecodeParams {
     size_t qkv_stride;
     const float *rope_cos, *rope_sin;  // [max_pos][32]
     const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
-    float *ok, *ov;            // own cache of this layer, head-major [H][cap_b][max_s][64]: the utterances one CTA works on
+    __half *ok, *ov;           // own cache of this layer (fp16), head-major [H][cap_b][max_s][64]: the utterances one CTA works on
                                // (one head, consecutive b) are one contiguous span of memory
     int cap_b;                 // utterance capacity of the own cache
     const int *ctrl_cond_len;  // device cond_len
@@ -416,8 +417,8 @@ __device__ __forceinline__ void attn_decode_item(const AttnDecodeParams &p, int 
     const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
     const int s = step + (live ? p.own_base[b] : 0);   // own-cache row written by this step
     const int pos = cond_len + s, P = pos + 1;
-    float *okb = p.ok + ((size_t)h * p.cap_b + (live ? b : 0)) * p.max_s * FL_HD;
-    float *ovb = p.ov + ((size_t)h * p.cap_b + (live ? b : 0)) * p.max_s * FL_HD;
+    __half *okb = p.ok + ((size_t)h * p.cap_b + (live ? b : 0)) * p.max_s * FL_HD;
+    __half *ovb = p.ov + ((size_t)h * p.cap_b + (live ? b : 0)) * p.max_s * FL_HD;
     float *sc = scores + w * pcap;
     float2 q = make_float2(0.0f, 0.0f);
     if (live) {
@@ -428,8 +429,9 @@ __device__ __forceinline__ void attn_decode_item(const AttnDecodeParams &p, int 
         q = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
         if (wu == 0) {
             const float2 kk = ld_fold2(row + FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
-            *(float2 *)(okb + (size_t)s * FL_HD + 2 * lane) = make_float2(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
-            *(float2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = ld_fold2(row + 2 * FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
+            *(__half2 *)(okb + (size_t)s * FL_HD + 2 * lane) = __floats2half2_rn(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
+            const float2 vnew = ld_fold2(row + 2 * FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
+            *(__half2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = __floats2half2_rn(vnew.x, vnew.y);
             *(float2 *)(sq + g * FL_HD + 2 * lane) = q;
         }
     }
@@ -474,7 +476,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnDecodeParams &p, int 
                 float2 kv[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++)
-                    kv[j] = (t + j < tb) ? *(const float2 *)(okb + (size_t)(t + j - cond_len) * FL_HD + 2 * lane) : make_float2(0.0f, 0.0f);
+                    kv[j] = (t + j < tb) ? __half22float2(*(const __half2 *)(okb + (size_t)(t + j - cond_len) * FL_HD + 2 * lane)) : make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const float a = warp_sum(q.x * kv[j].x + q.y * kv[j].y);
@@ -532,7 +534,7 @@ __device__ __forceinline__ void attn_decode_item(const AttnDecodeParams &p, int 
                 float2 vv[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++)
-                    vv[j] = (t + j < tb) ? *(const float2 *)(ovb + (size_t)(t + j - cond_len) * FL_HD + 2 * lane) : make_float2(0.0f, 0.0f);
+                    vv[j] = (t + j < tb) ? __half22float2(*(const __half2 *)(ovb + (size_t)(t + j - cond_len) * FL_HD + 2 * lane)) : make_float2(0.0f, 0.0f);
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const float pw = (t + j < tb) ? sc[t + j] : 0.0f;
@@ -628,7 +630,8 @@ struct PrefillAttnParams {
     const float *qkv;          // [M, 3072]
     const float *rope_cos, *rope_sin;
     const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
-    float *ok, *ov;            // own cache of this layer [H][cap_b][max_s][64]
+    void *ok, *ov;             // destination rows [H][cap_b][max_s][64]: the fp16 own cache, or (voice pass) the fp32 prefix cache
+    int own_f16;               // 1: ok / ov are __half, 0: float
     int cap_b;
     int cond_len, pstride, max_s, max_q;
     uint16_t *out_h, *out_l;   // [M,1024] bf16 hi/lo
@@ -647,8 +650,7 @@ __global__ void __launch_bounds__(256) k_pf_attn(const PrefillAttnParams p, cons
     float *V = K + ((nrows * AD_LD + 3) & ~(size_t)3);         // [rows][64], 16-byte aligned
     float *sc = V + nrows * FL_HD;                             // [8][scf]
     float *qs = sc + 8 * scf;                                  // [8][64]
-    float *okb = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-    float *ovb = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
+    const size_t obase = ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
     for (int idx = tid; idx < cl * 16; idx += 256) {
         const int r = idx >> 4, c4 = (idx & 15) * 4;
         const float4 kv = *(const float4 *)(p.pk + ((size_t)h * p.pstride + r) * FL_HD + c4);
@@ -664,8 +666,14 @@ __global__ void __launch_bounds__(256) k_pf_attn(const PrefillAttnParams p, cons
         const float2 kr = make_float2(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
         K[(cl + i) * AD_LD + 2 * l] = kr.x; K[(cl + i) * AD_LD + 2 * l + 1] = kr.y;
         *(float2 *)(V + (cl + i) * FL_HD + 2 * l) = vv;
-        *(float2 *)(okb + (size_t)i * FL_HD + 2 * l) = kr;
-        *(float2 *)(ovb + (size_t)i * FL_HD + 2 * l) = vv;
+        const size_t o = obase + (size_t)i * FL_HD + 2 * l;
+        if (p.own_f16) {
+            *(__half2 *)((__half *)p.ok + o) = __floats2half2_rn(kr.x, kr.y);
+            *(__half2 *)((__half *)p.ov + o) = __floats2half2_rn(vv.x, vv.y);
+        } else {
+            *(float2 *)((float *)p.ok + o) = kr;
+            *(float2 *)((float *)p.ov + o) = vv;
+        }
     }
     __syncthreads();
     float *scw = sc + w * scf, *qw = qs + w * FL_HD;

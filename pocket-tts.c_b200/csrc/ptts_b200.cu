@@ -210,7 +210,8 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
             }
             { const unsigned long long *a = &tr[(size_t)2 * P.n_phases]; const double nu = (double)std::max<unsigned long long>(a[5], 1);
               fprintf(stderr, "  attention unit (CTA 0 warp 0, cycles per unit over %.0f units): new-row %.0f  scores %.0f  softmax %.0f  PV %.0f  write %.0f\n",
-                      nu, a[0] / nu, a[1] / nu, a[2] / nu, a[3] / nu, a[4] / nu); }
+                      nu, a[0] / nu, a[1] / nu, a[2] / nu, a[3] / nu, a[4] / nu);
+              fprintf(stderr, "    inside scores: prefix quanta %.0f  wait for the first own K row of a batch %.0f\n", a[6] / nu, a[7] / nu); }
             e->dfree(d_trace);
         }
         static const int cls_of[MP_COUNT] = {KC_FLOW_MISC, KC_GEMM_FLOW, KC_ROWNORM, KC_FLOW_MISC, KC_FLOW_MISC, KC_ATTN_DECODE};
@@ -223,7 +224,7 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
         }
         for (int sidx = 0; sidx < (int)steps; sidx++) {   // KV traffic grows with the frame index (same accounting as attn_decode())
             const double own = e->prof.mean_own_base + sidx + 1, pre = e->voice_len, n = e->st_n;
-            e->prof.bytes[KC_ATTN_DECODE] += FL_L * (2.0 * FL_D * 4.0 * (pre + n * own) + n * FL_D * 4.0 * (2 + 3 + 1));
+            e->prof.bytes[KC_ATTN_DECODE] += FL_L * (2.0 * FL_D * (4.0 * pre + 2.0 * n * own) + n * FL_D * (2.0 * 2 + 4.0 * (3 + 1)));
             e->prof.flops[KC_ATTN_DECODE] += FL_L * 4.0 * FL_D * n * (pre + own);
         }
     }
