@@ -401,18 +401,19 @@ __device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
 __device__ __forceinline__ void qk_tile2(const float *kt, int k0, int k1, int n_tile, const float (&qx)[2][8], float *sc0, float *sc1,
                                          int k4, int l8) {
     const int o1 = l8 * 8 + ((l8 & 4) ? 4 : 0), o2 = l8 * 8 + ((l8 & 4) ? 0 : 4);
+    // branch-free body (rows past the tile are clamped for the loads and only the store is predicated), so the
+    // shuffles sit in uniform control flow and two iterations overlap
 #pragma unroll 2
     for (int r0 = k0; r0 < k1; r0 += 4) {
-        const int key = r0 + k4;
-        const bool ok = key < n_tile;
-        const float4 a = ok ? *(const float4 *)(kt + key * FL_HD + o1) : make_float4(0, 0, 0, 0);
-        const float4 b = ok ? *(const float4 *)(kt + key * FL_HD + o2) : make_float4(0, 0, 0, 0);
+        const int key = r0 + k4, kc = min(key, n_tile - 1);
+        const float4 a = *(const float4 *)(kt + kc * FL_HD + o1);
+        const float4 b = *(const float4 *)(kt + kc * FL_HD + o2);
         float d0 = qx[0][0] * a.x + qx[0][1] * a.y + qx[0][2] * a.z + qx[0][3] * a.w + qx[0][4] * b.x + qx[0][5] * b.y + qx[0][6] * b.z + qx[0][7] * b.w;
         float d1 = qx[1][0] * a.x + qx[1][1] * a.y + qx[1][2] * a.z + qx[1][3] * a.w + qx[1][4] * b.x + qx[1][5] * b.y + qx[1][6] * b.z + qx[1][7] * b.w;
         d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
         d0 += __shfl_xor_sync(0xffffffffu, d0, 2); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
         d0 += __shfl_xor_sync(0xffffffffu, d0, 4); d1 += __shfl_xor_sync(0xffffffffu, d1, 4);
-        if (l8 == 0 && ok) { sc0[key] = d0; sc1[key] = d1; }
+        if (l8 == 0 && key < n_tile) { sc0[key] = d0; sc1[key] = d1; }
     }
 }
 __device__ __forceinline__ void pv_tile2(const float *vt, int k0, int k1, int n_tile, const float *sc0, const float *sc1, int k4, int l8,
@@ -420,15 +421,13 @@ __device__ __forceinline__ void pv_tile2(const float *vt, int k0, int k1, int n_
     const int o1 = l8 * 8 + ((l8 & 4) ? 4 : 0), o2 = l8 * 8 + ((l8 & 4) ? 0 : 4);
 #pragma unroll 2
     for (int r0 = k0; r0 < k1; r0 += 4) {
-        const int key = r0 + k4;
-        if (key < n_tile) {
-            const float p0 = sc0[key], p1 = sc1[key];
-            const float4 a = *(const float4 *)(vt + key * FL_HD + o1), b = *(const float4 *)(vt + key * FL_HD + o2);
-            acc[0][0] += p0 * a.x; acc[0][1] += p0 * a.y; acc[0][2] += p0 * a.z; acc[0][3] += p0 * a.w;
-            acc[0][4] += p0 * b.x; acc[0][5] += p0 * b.y; acc[0][6] += p0 * b.z; acc[0][7] += p0 * b.w;
-            acc[1][0] += p1 * a.x; acc[1][1] += p1 * a.y; acc[1][2] += p1 * a.z; acc[1][3] += p1 * a.w;
-            acc[1][4] += p1 * b.x; acc[1][5] += p1 * b.y; acc[1][6] += p1 * b.z; acc[1][7] += p1 * b.w;
-        }
+        const int key = r0 + k4, kc = min(key, n_tile - 1);
+        const float p0 = key < n_tile ? sc0[kc] : 0.0f, p1 = key < n_tile ? sc1[kc] : 0.0f;
+        const float4 a = *(const float4 *)(vt + kc * FL_HD + o1), b = *(const float4 *)(vt + kc * FL_HD + o2);
+        acc[0][0] += p0 * a.x; acc[0][1] += p0 * a.y; acc[0][2] += p0 * a.z; acc[0][3] += p0 * a.w;
+        acc[0][4] += p0 * b.x; acc[0][5] += p0 * b.y; acc[0][6] += p0 * b.z; acc[0][7] += p0 * b.w;
+        acc[1][0] += p1 * a.x; acc[1][1] += p1 * a.y; acc[1][2] += p1 * a.z; acc[1][3] += p1 * a.w;
+        acc[1][4] += p1 * b.x; acc[1][5] += p1 * b.y; acc[1][6] += p1 * b.z; acc[1][7] += p1 * b.w;
     }
 }
 
@@ -445,7 +444,7 @@ __device__ __noinline__ void a4_new_row(const AttnDecodeParams &p, int b, int h,
     *(float2 *)(sqd + 2 * lane) = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
 }
 // exp(score - max) in place, returns 1 / sum
-__device__ __noinline__ float a4_softmax(float *sc, int P, int lane) {
+__device__ __forceinline__ float a4_softmax(float *sc, int P, int lane) {
     float mx = -INFINITY;
     for (int t = lane; t < P; t += 32) mx = fmaxf(mx, sc[t]);
     mx = warp_max(mx);
@@ -806,7 +805,9 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
 // ---------------------------------------------------------------- the kernel
 __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_constant__ MegaProgram P) {
     extern __shared__ uint8_t mg_smem_raw[];
-    uint8_t *sbase = (uint8_t *)(((uintptr_t)mg_smem_raw + 1023) & ~(uintptr_t)1023);
+    // aligned by pointer + offset (not through an integer round trip): the compiler keeps the shared address space,
+    // so tile / score / scratch accesses below compile to LDS / STS instead of generic loads and stores
+    uint8_t *sbase = mg_smem_raw + ((1024u - (smem_u32(mg_smem_raw) & 1023u)) & 1023u);
     uint64_t *bars = (uint64_t *)sbase;
     uint64_t *full = bars, *empty = bars + MG_STAGES, *tfull = bars + 2 * MG_STAGES, *tempty = tfull + 2;
     uint32_t *tmem_slot = (uint32_t *)(tempty + 2);
