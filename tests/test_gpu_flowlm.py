@@ -114,3 +114,27 @@ def test_batched_run_is_repeatable(eng, pkg, voice, golden):
     a = eng.generate_batch(toks, voice, 5, seeds=3, params=pkg.default_params(temp=0.7), want_audio=False)
     b = eng.generate_batch(toks, voice, 5, seeds=3, params=pkg.default_params(temp=0.7), want_audio=False)
     assert np.array_equal(a["latents"], b["latents"])
+
+
+def test_batched_long_voice_prefix_beyond_the_shared_memory_tile(eng, pkg, oracle, voice, golden):
+    """Voice prefix of 185 frames: the first 128 prefix keys are served from the shared-memory tile of the
+    persistent kernel's attention phase, the remaining 57 straight from the prefix cache in L2."""
+    cond = np.concatenate([voice, voice[:60] * 0.7], axis=0).astype(np.float32)
+    toks = [golden["p0_ids"], golden["p1_ids"], golden["p2_ids"], golden["p2_ids"][2:15]]
+    out = eng.generate_batch(toks, cond, 5, seeds=[21, 22, 23, 24], params=pkg.default_params(temp=0.7), want_audio=False)
+    for i, t in enumerate(toks):
+        o = oracle.flowlm_generate(t, cond, 5, lsd_steps=1, temp=0.7, seed=21 + i)
+        assert max_rel(out["latents"][i, :5], o["latents"]) < TOL, f"utterance {i}"
+    g = eng.flowlm_generate_latents(golden["p0_ids"], cond, 5, lsd_steps=1, temp=0.7, seed=21)   # batch-1 path, same prefix
+    assert max_rel(g["latents"], out["latents"][0, :5]) < TOL
+
+
+def test_full_batch_of_256_spot_check(eng, pkg, oracle, voice, golden):
+    """The bench-size batch (two row tiles of 128, 9 CTAs per head): a few utterances against the oracle."""
+    base = [golden["p0_ids"], golden["p1_ids"], golden["p2_ids"], golden["p1_ids"][:9], golden["p2_ids"][2:17]]
+    toks = [base[i % 5] for i in range(256)]
+    seeds = [1000 + i for i in range(256)]
+    out = eng.generate_batch(toks, voice, 4, seeds=seeds, params=pkg.default_params(temp=0.7), want_audio=False)
+    for i in (0, 127, 128, 201, 255):
+        o = oracle.flowlm_generate(toks[i], voice, 4, lsd_steps=1, temp=0.7, seed=seeds[i])
+        assert max_rel(out["latents"][i, :4], o["latents"]) < TOL, f"utterance {i}"
