@@ -97,11 +97,11 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid, int bar
 // Grid-wide barrier: every CTA arrives once on a monotonic counter; `epoch` is the value the counter
 // reaches when all CTAs have arrived. Global writes made before the barrier by any thread of any CTA
 // are visible after it to generic loads and to TMA (async proxy) loads.
-__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch, bool light = false) {
+__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch, bool light = false, int bar_tid = 0) {
     if (!light) asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
     epoch += gridDim.x;
-    if (threadIdx.x == 0) {
+    if ((int)threadIdx.x == bar_tid) {   // this thread's fence waits for ITS outstanding loads too: pick one that has none in flight
         if (light) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
             asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");

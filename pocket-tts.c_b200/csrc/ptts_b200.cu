@@ -6,7 +6,7 @@
 #include <algorithm>
 #include <thread>
 
-#include "mega.cuh"
+#include "mega1.cuh"
 #include "mimi.cuh"
 
 using namespace ptts;
@@ -45,6 +45,7 @@ static void host_noise(int64_t seed, float temp, float clampv, int frames, float
 // ---------------------------------------------------------------- lifetime
 static std::unordered_map<Engine *, std::unordered_map<uint64_t, FlowGemms>> g_gemms;
 static std::unordered_map<Engine *, std::unordered_map<uint64_t, MegaHost>> g_mega;
+static std::unordered_map<Engine *, std::unordered_map<int, Mega1Host>> g_mega1;
 extern "C" const char *ptts_b200_last_error(void) { return g_last_error; }
 
 static int gemm_set_attrs() {
@@ -104,6 +105,7 @@ extern "C" void ptts_b200_destroy(ptts_b200_engine *e) {
     for (auto &g : e->graphs) cudaGraphExecDestroy(g.second);
     g_gemms.erase(e);
     g_mega.erase(e);
+    g_mega1.erase(e);
     for (void *p : e->allocs) cudaFree(p);
     if (e->pin) cudaFreeHost(e->pin);
     if (e->ev0) cudaEventDestroy(e->ev0);
@@ -231,9 +233,64 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     return 0;
 }
 
+// Batch-1 streaming decode as one cooperative launch of k_flow_mega1 (mega1.cuh).
+static int run_mega1(Engine *e, int lsd, int nsteps) {
+    float *cb = nullptr;
+    if (ensure_cbias(e, lsd, &cb) != 0) return -1;
+    Mega1Host &M = g_mega1[e][lsd];
+    if (M.gen != e->gen || M.lsd != lsd) {
+        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+        if (mega1_build(e, M, lsd, cb) != 0) return -1;
+    }
+    if (!e->mega_ctl) {
+        if (e->dalloc(&e->mega_ctl, 64) != 0) return -1;
+        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
+    }
+    static bool attr1 = false;
+    if (!attr1) { PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega1, cudaFuncAttributeMaxDynamicSharedMemorySize, M1_DYN_SMEM)); attr1 = true; }
+    PTTS_CUDA_OK(cudaMemsetAsync(e->mega_ctl, 0, 64 * sizeof(unsigned long long), e->st));
+    Mega1Program Q = M.prog;
+    MegaProgram &P = Q.base;
+    P.bar = (unsigned int *)e->mega_ctl;
+    P.done_count = (int *)(e->mega_ctl + 1);
+    P.prof = e->prof.on ? e->mega_ctl + 8 : nullptr;
+    P.nsteps = nsteps; P.n_live = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)e->num_sms); cfg.blockDim = dim3(M1_THREADS); cfg.dynamicSmemBytes = M1_DYN_SMEM; cfg.stream = e->st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    e->launches++;
+    PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega1, Q));
+    if (e->prof.on) {
+        unsigned long long h[24];
+        PTTS_CUDA_OK(cudaMemcpyAsync(h, e->mega_ctl + 8, sizeof h, cudaMemcpyDeviceToHost, e->st));
+        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+        if (getenv("PTTS_B200_MEGA_TRACE"))
+            fprintf(stderr, "batch-1 GEMV phase of CTA 0 (us, cumulative from phase start): prologue %.2f  rows %.2f  look-ahead issued %.2f  phase incl. barrier %.2f\n",
+                    h[16] * 1e-3 / h[2 * M1_GEMV + 1], h[17] * 1e-3 / h[2 * M1_GEMV + 1], h[18] * 1e-3 / h[2 * M1_GEMV + 1],
+                    h[2 * M1_GEMV] * 1e-3 / h[2 * M1_GEMV + 1]);
+        static const int cls_of[M1_COUNT] = {KC_FLOW_MISC, KC_GEMV, KC_ATTN_DECODE, KC_FLOW_MISC, KC_FLOW_MISC};
+        const double steps = (double)h[2 * M1_HEAD + 1];
+        for (int t = 0; t < M1_COUNT; t++) {
+            e->prof.ms[cls_of[t]] += (float)((double)h[2 * t] * 1e-6);
+            e->prof.n[cls_of[t]] += (int64_t)h[2 * t + 1];
+        }
+        e->prof.bytes[KC_GEMV] += M.gemv_bytes * steps;
+        e->prof.flops[KC_GEMV] += M.gemv_bytes * steps;   // 2 FLOP per 2-byte weight
+    }
+    return 0;
+}
+
 static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nsteps, bool poll_done) {
     if (nsteps <= 0) return 0;
     if (mode == 2 && mega_enabled()) return run_mega(e, B, lsd, precise, nsteps);
+    // Batch-1: the persistent kernel (mega1.cuh) is opt-in (PTTS_B200_MEGA1=1). Measured on B200: 6.4 us per GEMV phase
+    // (1.8 grid barrier + 1.8 activation reload / LayerNorm + 2.4 rows + 0.5 look-ahead) x 39 + attention = 335 us per frame,
+    // against 223 us for the 47-node CUDA graph below, whose kernel boundaries cost less than a grid barrier plus a
+    // per-CTA reload of the activation vector. The default stays the graph.
+    if (mode == 1 && mega_enabled() && getenv("PTTS_B200_MEGA1") != nullptr) return run_mega1(e, lsd, nsteps);
     const bool use_graph = !e->prof.on && getenv("PTTS_B200_NO_GRAPH") == nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t gk = 0;

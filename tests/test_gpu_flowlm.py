@@ -138,3 +138,21 @@ def test_full_batch_of_256_spot_check(eng, pkg, oracle, voice, golden):
     for i in (0, 127, 128, 201, 255):
         o = oracle.flowlm_generate(toks[i], voice, 4, lsd_steps=1, temp=0.7, seed=seeds[i])
         assert max_rel(out["latents"][i, :4], o["latents"]) < TOL, f"utterance {i}"
+
+
+def test_batch1_persistent_kernel_opt_in(pkg, weights, voice, golden, monkeypatch):
+    """PTTS_B200_MEGA1=1 runs the single-utterance decode loop as one cooperative launch (mega1.cuh: GEMV phases with
+    cp.async weight look-ahead, flash-decoding attention chunks); same parity bar as the default graph path."""
+    monkeypatch.setenv("PTTS_B200_MEGA1", "1")
+    e = pkg.Engine(weights, 0)
+    try:
+        for steps in (1, 4):
+            g = e.flowlm_generate_latents(golden["p0_ids"], voice, 8, lsd_steps=steps, temp=0.0)
+            assert g["frames"] == 8
+            assert max_rel(g["latents"], golden[f"hello_s{steps}_latents"]) < TOL
+        g = e.flowlm_generate_latents(golden["p0_ids"], voice, 12, lsd_steps=1, temp=0.0, eos_enabled=1, eos_threshold=-1.2,
+                                      eos_min_frames=1, eos_after=2)
+        assert g["frames"] == int(golden["hello_eos_frames"])
+        assert max_rel(g["latents"], golden["hello_eos_latents"]) < TOL
+    finally:
+        e.close()
