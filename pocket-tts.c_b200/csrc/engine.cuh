@@ -110,7 +110,7 @@ static int gemm_launch_t(const GemmOp &op, cudaStream_t st) {
         PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_done = true;
     }
-    launch_k(gemm_tc_kernel<BN, SPLIT>, op.grid, GEMM_THREADS, op.smem_bytes, st, op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.p);
+    launch_k(gemm_tc_kernel<BN, SPLIT>, op.grid, GEMM_THREADS, op.smem_bytes, st, op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.mapOH, op.mapOR, op.p);
     PTTS_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -123,6 +123,21 @@ int gemm_launch(const GemmOp &op, cudaStream_t st) {
 #undef GL
     set_error("gemm_launch: unsupported tile bn=%d split=%d", op.bn, op.split);
     return -1;
+}
+
+// 3D map over a 16-bit OUTPUT tensor [batches][rows][ld] for the TMA-store epilogue: box = 64 columns x 32 rows,
+// 128B swizzle (the staging layout of gemm_tc.cuh); rows past `rows` and columns past `cols` are clipped.
+int make_store_tmap(CUtensorMap *out, const void *base, bool bf16, int cols, int rows, int batches, size_t ld) {
+    if (g_tma.init() != 0) return -1;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)rows * ld * 2};
+    cuuint32_t box[3] = {64, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_tma.encode(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void *>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PTTS_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (store map) failed with %d (cols=%d rows=%d batches=%d ld=%zu)", (int)r, cols, rows, batches, ld);
+    return 0;
 }
 
 static int stage_bytes(int bn, int split) {
@@ -187,11 +202,35 @@ static int gemm_build(GemmOp &op, const GemmDesc &d) {
     PTTS_CHECK(tiles < (1ll << 31), "gemm_build: too many tiles");
     p.total_tiles = (int)tiles;
     p.b_static = d.b_static ? 1 : 0;
-    p.stages = gemm_pick_stages(d.bn, op.split, per, d.two_cta);
+    // 16-bit outputs of row-major GEMMs leave through TMA tensor stores (the per-thread 32-byte stores cap the
+    // store rate at ~11 B/clk per SM: tools/gemm_conv_probe.py)
+    const size_t out_rows = (size_t)d.a_batches * d.a_rows;
+    // measured per GEMM (tools/mimi_log.py): a win for the output-heavy convolutions (ConvTranspose with its two outputs
+    // -17 %, k=3 convs -8 %), a loss where a residual read shares the epilogue (+9 %) and for the long-K linears (the staging
+    // buffers cost ring stages) -> enabled for dual-output and narrow (N tile <= 128) GEMMs without a 16-bit residual
+    p.tma_store = (!p.transposed && (p.out_h || p.out_raw) && !p.out_l && !p.rope_q && !p.resid_h && (p.out_raw || d.bn <= 128) &&
+                   d.bn % 64 == 0 && p.ldh % 8 == 0 && getenv("PTTS_B200_NO_TMA_STORE") == nullptr) ? 1 : 0;
+    if (p.tma_store) {
+        if (p.out_h && (((uintptr_t)p.out_h & 15) != 0)) p.tma_store = 0;
+        if (p.out_raw && (((uintptr_t)p.out_raw & 15) != 0)) p.tma_store = 0;
+    }
+    p.stage_stride = 4096 * ((p.out_h ? 1 : 0) + (p.out_raw ? 1 : 0));   // per warp: [32 rows][128 B] per staged tensor
+    const int staging = p.tma_store ? GEMM_EPI_WARPS * p.stage_stride : 0;
+    int stages = (int)((227 * 1024 - 1024 - 1024 - staging) / stage_bytes(d.bn, op.split));
+    if (stages > GEMM_MAX_STAGES) stages = GEMM_MAX_STAGES;
+    if (stages < 2) { stages = gemm_pick_stages(d.bn, op.split, per, d.two_cta); p.tma_store = 0; }
+    p.stages = stages;
+    p.stage_off = p.stages * stage_bytes(d.bn, op.split) + 1024;   // barriers live in the 1 KB in between; staging stays 1024-aligned
+    memset(&op.mapOH, 0, sizeof op.mapOH); memset(&op.mapOR, 0, sizeof op.mapOR);
+    if (p.tma_store) {
+        if (p.out_h && make_store_tmap(&op.mapOH, p.out_h, p.out_bf16 != 0, d.b_rows, d.a_rows, d.a_batches, (size_t)p.ldh) != 0) return -1;
+        if (p.out_raw && make_store_tmap(&op.mapOR, p.out_raw, p.out_bf16 != 0, d.b_rows, d.a_rows, d.a_batches, (size_t)p.ldh) != 0) return -1;
+    }
+    (void)out_rows;
     p.idesc = umma_idesc_f16(GEMM_BM, d.bn, d.bf16, d.bf16);
     op.p = p;
     op.grid = dim3((unsigned)std::min<long long>(tiles, g_num_sms), 1, 1);
-    op.smem_bytes = p.stages * stage_bytes(d.bn, op.split) + 1024 + 256;
+    op.smem_bytes = p.stages * stage_bytes(d.bn, op.split) + 1024 + 1024 + (p.tma_store ? GEMM_EPI_WARPS * p.stage_stride : 0);
     return 0;
 }
 

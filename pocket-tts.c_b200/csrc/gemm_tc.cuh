@@ -65,6 +65,10 @@ struct GemmParams {
     uint16_t *rope_q, *rope_k, *rope_v;
     const float *rope_cos, *rope_sin;   // [T][32]
     int rope_pos0;           // position of row 0 (streaming decode of a window that starts mid-utterance)
+    int tma_store;           // 1: 16-bit outputs (out_h, out_raw) leave through shared-memory staging + TMA tensor stores
+                             // (whole 128-byte lines) instead of one 32-byte store per thread and chunk
+    int stage_off;           // byte offset (multiple of 1024) of the per-warp staging buffers from the aligned shared-memory base
+    int stage_stride;        // staging bytes per epilogue warp: 4096 per staged output tensor
     long long *trace;        // optional [16] clock64 stamps written by CTA 0 (kernel timeline debugging)
 };
 
@@ -115,6 +119,7 @@ template <int BN, int SPLIT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
+               const __grid_constant__ CUtensorMap mapOH, const __grid_constant__ CUtensorMap mapOR,
                const GemmParams p) {
     using SM = GemmSmem<BN, SPLIT>;
     extern __shared__ uint8_t smem_raw[];
@@ -253,6 +258,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int lt = team, tile = blockIdx.x + team * gridDim.x; tile < p.total_tiles; tile += NACC * gridDim.x, lt += NACC) {
             const TileCoord t = gemm_tile(p, tile, BN);
             const int acc = team;
+            if (p.tma_store) {   // the previous tile's last TMA store has finished reading this warp's staging buffer
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
+            }
             mbar_wait(&tfull[acc], (lt / NACC) & 1);
             tc_fence_after();
             if (tr && lt == 0 && warp == 2 && lane == 0) p.trace[5] = clock64();
@@ -262,19 +271,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             float *out_f32 = p.out_f32 ? p.out_f32 + (size_t)t.z * p.split_stride : nullptr;
             const bool add_bias = bias != nullptr && t.z == 0;
             uint32_t r[16], rn[16];
-            if (cg * 16 < BN) { tmem_ld16(trow + cg * 16, r); tmem_ld_wait16(r); }
             if (!p.transposed) {
+                // each warp owns a contiguous range of BN / NCG columns of its 32 rows
+                constexpr int CW = BN / NCG;
+                const int c_lo = cg * CW;
+                if (CW >= 16) { tmem_ld16(trow + c_lo, r); tmem_ld_wait16(r); }
                 const size_t grow = (size_t)t.batch * p.a_rows + m;
                 float *of = out_f32 ? out_f32 + grow * ldo : nullptr;
                 const float *rs = resid ? resid + grow * ldo : nullptr;
                 uint16_t *oh = out_h ? out_h + grow * ldh : nullptr;
                 uint16_t *ol = out_l ? out_l + grow * ldh : nullptr;
+                const bool ts = p.tma_store != 0;
+                // staging: [32 rows][128 bytes] per output tensor, 128B-swizzled (16-byte piece index ^ (row & 7)): the
+                // 8 rows of a quarter-warp write 8 different pieces -> conflict-free; the TMA store undoes the swizzle
+                uint8_t *stg = smem + p.stage_off + (warp - 2) * p.stage_stride;
 #pragma unroll 1
-                for (int c = cg * 16; c < BN; c += 16 * NCG) {
-                    const bool more = c + 16 * NCG < BN;
-                    if (more) tmem_ld16(trow + c + 16 * NCG, rn);   // in flight while this chunk is processed
+                for (int c = c_lo; c < c_lo + CW; c += 16) {
+                    const bool more = c + 16 < c_lo + CW;
+                    if (more) tmem_ld16(trow + c + 16, rn);   // in flight while this chunk is processed
                     const int nb = t.n0 + c;
-                    if (m_ok && nb < n_total) {
+                    if (ts && (c & 63) == 0 && c > c_lo) {   // previous 64-column group left through TMA: staging reusable?
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+                    }
+                    if ((m_ok || ts) && nb < n_total) {
                         float v[16];
 #pragma unroll
                         for (int j = 0; j < 16; j++) v[j] = __uint_as_float(r[j]);
@@ -310,14 +330,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                             (((size_t)t.batch * 8 + head) * p.a_rows + m) * 64 + d0;
                             st_global_v8(dst, hw);
                         }
-                        if (rs) {
+                        if (rs && m_ok) {
                             float t0[8], t1[8];
                             ld_global_v8(rs + nb, t0);
                             ld_global_v8(rs + nb + 8, t1);
 #pragma unroll
                             for (int j = 0; j < 8; j++) { v[j] += t0[j]; v[8 + j] += t1[j]; }
                         }
-                        if (p.resid_h) {
+                        if (p.resid_h && m_ok) {
                             uint32_t hr[8];
                             ld_global_v8u(p.resid_h + grow * ldh + nb, hr);
 #pragma unroll
@@ -326,23 +346,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 v[2 * j] += f.x; v[2 * j + 1] += f.y;
                             }
                         }
-                        if (of) {
+                        if (of && m_ok) {
                             uint32_t w0[8], w1[8];
 #pragma unroll
                             for (int j = 0; j < 8; j++) { w0[j] = __float_as_uint(v[j]); w1[j] = __float_as_uint(v[8 + j]); }
                             st_global_v8(of + nb, w0);
                             st_global_v8(of + nb + 8, w1);
                         }
+                        const int pc = (c & 63) >> 3;   // first 16-byte piece of this chunk inside the 128-byte staging row
                         if (p.out_raw) {
                             uint32_t hw[8], lw[8];
                             act_pack16_dispatch(ACT_NONE, fast, bf, false, v, hw, lw);
-                            st_global_v8(p.out_raw + grow * ldh + nb, hw);
+                            if (ts) {
+                                uint8_t *row = stg + 4096 + lane * 128;
+                                *(uint4 *)(row + ((pc ^ (lane & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                *(uint4 *)(row + (((pc + 1) ^ (lane & 7)) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                            } else st_global_v8(p.out_raw + grow * ldh + nb, hw);
                         }
                         if (oh) {
                             uint32_t hw[8], lw[8];
                             act_pack16_dispatch(act, fast, bf, ol != nullptr, v, hw, lw);
-                            st_global_v8(oh + nb, hw);
-                            if (ol) st_global_v8(ol + nb, lw);
+                            if (ts) {
+                                uint8_t *row = stg + lane * 128;
+                                *(uint4 *)(row + ((pc ^ (lane & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                *(uint4 *)(row + (((pc + 1) ^ (lane & 7)) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                            } else {
+                                st_global_v8(oh + nb, hw);
+                                if (ol) st_global_v8(ol + nb, lw);
+                            }
+                        }
+                    }
+                    if (ts && ((c & 63) == 48 || !more)) {   // a 64-column group of this warp's 32 rows is staged: hand it to TMA
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0 && t.n0 + (c & ~63) < n_total) {
+                            const int col0 = t.n0 + (c & ~63), row0 = t.m0 + quad * 32;
+                            if (oh) tma_store_3d(&mapOH, stg, col0, row0, t.batch);
+                            if (p.out_raw) tma_store_3d(&mapOR, stg + 4096, col0, row0, t.batch);
+                            bulk_commit();
                         }
                     }
                     if (more) {
@@ -354,6 +395,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             } else {
                 // transposed: this thread owns output FEATURE m; columns are batch rows n. Stores are
                 // coalesced across the warp (32 consecutive features per batch row).
+                if (cg * 16 < BN) { tmem_ld16(trow + cg * 16, r); tmem_ld_wait16(r); }
                 float bv = 0.0f, sv = 1.0f;
                 if (m_ok) {
                     if (add_bias) bv = bias[bias_mask ? (m & bias_mask) : m];
@@ -399,6 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (tr && lt == 0 && warp == 2 && lane == 0) p.trace[6] = clock64();
         }
     }
+    if (p.tma_store && warp >= 2 && lane == 0) bulk_wait0();   // this thread's tensor stores have landed
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -424,7 +467,7 @@ int make_tmap(CUtensorMap *out, const void *base, bool bf16, int k, int rows, in
               int box_rows);
 
 struct GemmOp {
-    CUtensorMap mapA, mapAlo, mapB, mapBlo;
+    CUtensorMap mapA, mapAlo, mapB, mapBlo, mapOH, mapOR;
     GemmParams p;
     int bn;        // N tile (B-operand box rows)
     int split;     // 0 none, 1 = A has lo, 2 = B has lo
