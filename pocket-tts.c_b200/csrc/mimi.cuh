@@ -5,6 +5,7 @@
 // streams. No [C,T] <-> [T,C] transposes exist (ptts_mimi.c:134-150 eliminated by layout choice).
 #pragma once
 #include "engine.cuh"
+#include "resblock.cuh"
 
 namespace ptts {
 
@@ -136,6 +137,60 @@ static int conv_gemm(Engine *e, const ConvW &c, const __half *A, int Bc, int T, 
     return mimi_gemm(e, A, Bc, T, c.cin, c.w, c.n_rows, c.k, -(c.k - 1), 1, bn, epi);
 }
 
+// One fused residual block (resblock.cuh): vv = ELU(u + conv1(ELU(conv3(eu)))) for Bc items of T rows, C2 channels.
+template <int C2>
+static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const __half *eu, const __half *u, __half *vv, int Bc, int T) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        PTTS_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_done = true;
+    }
+    const int chp = c1.cout;   // padded to a multiple of 64 at load time
+    PTTS_CHECK(chp % 64 == 0 && chp <= 128 && c1.cin == C2 && c1.k == 3 && c2.cin == chp && c2.cout == C2 && c2.k == 1,
+               "resblock_launch: unexpected block geometry");
+    CUtensorMap mapA, mapW1, mapW2;
+    if (make_tmap(&mapA, eu, false, C2, T, Bc, (size_t)C2, (size_t)T * C2, GEMM_BM) != 0) return -1;
+    if (make_tmap(&mapW1, c1.w, false, 3 * C2, chp, 1, (size_t)3 * C2, 0, chp) != 0) return -1;
+    if (make_tmap(&mapW2, c2.w, false, chp, C2, 1, (size_t)chp, 0, C2) != 0) return -1;
+    ResParams p = {};
+    p.tiles_per_batch = (T + GEMM_BM - 1) / GEMM_BM;
+    const long long tiles = (long long)Bc * p.tiles_per_batch;
+    PTTS_CHECK(tiles < (1ll << 31), "resblock_launch: too many tiles");
+    p.tiles_total = (int)tiles; p.a_rows = T; p.kb_per_tap = C2 / 64; p.chp = chp;
+    const int stage = GEMM_BM * GEMM_BK * 2 + chp * 128, kb2 = chp / 64;
+    const int fixed = kb2 * C2 * 128 + kb2 * GEMM_BM * GEMM_BK * 2 + 256 + 1024;
+    // C2 <= 128: two CTAs per SM (one's output epilogue overlaps the other's contractions) -> at most ~110 KB each
+    p.stages = std::min(C2 <= 128 ? 3 : GEMM_MAX_STAGES, (227 * 1024 - fixed) / stage);
+    PTTS_CHECK(p.stages >= 2, "resblock_launch: shared memory too small");
+    p.idesc1 = umma_idesc_f16(GEMM_BM, chp, false, false);
+    p.idesc2 = umma_idesc_f16(GEMM_BM, C2, false, false);
+    p.b1 = c1.b; p.b2 = c2.b; p.u = (const uint16_t *)u; p.out = (uint16_t *)vv;
+    const int smem = p.stages * stage + fixed;
+    if (e->prof.on) {
+        const double rows = (double)Bc * T;
+        e->prof.flops[KC_GEMM_MIMI] += 2.0 * rows * (3.0 * C2 * chp + (double)chp * C2);
+        e->prof.bytes[KC_GEMM_MIMI] += rows * C2 * 2.0 * 3.0;   // ELU(u) in, u in, out: the middle tensor stays on chip
+    }
+    {
+        LaunchScope ls(e, KC_GEMM_MIMI);
+        launch_k(resblock_kernel<C2>, dim3((unsigned)std::min<long long>(tiles, (long long)g_num_sms * (C2 <= 128 ? 2 : 1))), dim3(RB_THREADS), (size_t)smem,
+                 e->st, mapA, mapW1, mapW2, p);
+    }
+    if (e->prof.on && !e->prof.recs.empty()) {
+        Prof::Rec &r = e->prof.recs.back();
+        r.rows = Bc * T; r.n = C2; r.k = 3 * C2 + chp; r.bn = -chp;   // bn < 0 marks the fused block in the per-launch log
+        r.flops = 2.0 * (double)Bc * T * (3.0 * C2 * chp + (double)chp * C2);
+    }
+    return launch_check("resblock_kernel");
+}
+static int resblock_launch(Engine *e, const ConvW &c1, const ConvW &c2, const __half *eu, const __half *u, __half *vv, int Bc, int T, int C2) {
+    if (C2 == 64) return resblock_launch_t<64>(e, c1, c2, eu, u, vv, Bc, T);
+    if (C2 == 128) return resblock_launch_t<128>(e, c1, c2, eu, u, vv, Bc, T);
+    if (C2 == 256) return resblock_launch_t<256>(e, c1, c2, eu, u, vv, Bc, T);
+    set_error("resblock_launch: unsupported channel count %d", C2);
+    return -1;
+}
+
 // Decode Bc equal-length items. d_lat [Bc,F,32] fp32 on the device; d_pcm [Bc, F*1920].
 // pos0 = token position of the first row (RoPE is absolute: ptts_mimi.c:341).
 static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm, int pos0 = 0) {
@@ -213,10 +268,15 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         __half *eu = ws.take<__half>(R2 * C2), *rm = ws.take<__half>(R2 * Ch), *vv = ws.take<__half>(R2 * C2);
         g = {}; g.out_raw = (uint16_t *)u; g.out_h = (uint16_t *)eu; g.ldh = U.n_rows; g.act = ACT_ELU;
         if (conv_gemm(e, U, cur, Bc, Tc, U.n_rows >= 256 ? 256 : 128, g) != 0) return -1;  // u = convT(ELU(prev)), eu = ELU(u)
-        g = {}; g.out_h = (uint16_t *)rm; g.ldh = Ch; g.act = ACT_ELU;                      // ELU(conv_k3(ELU(u)))
-        if (conv_gemm(e, e->res1[s], eu, Bc, T2, Ch >= 128 ? 128 : 64, g) != 0) return -1;
-        g = {}; g.resid_h = (const uint16_t *)u; g.out_h = (uint16_t *)vv; g.ldh = C2; g.act = ACT_ELU;  // ELU(u + conv_k1(.))
-        if (conv_gemm(e, e->res2[s], rm, Bc, T2, C2 >= 256 ? 256 : C2, g) != 0) return -1;
+        static const bool fused = getenv("PTTS_B200_NO_RESBLOCK") == nullptr;
+        if (fused) {   // conv_k3 -> ELU -> conv_k1 -> +u -> ELU in one kernel, the middle tensor stays in shared memory
+            if (resblock_launch(e, e->res1[s], e->res2[s], eu, u, vv, Bc, T2, C2) != 0) return -1;
+        } else {
+            g = {}; g.out_h = (uint16_t *)rm; g.ldh = Ch; g.act = ACT_ELU;                      // ELU(conv_k3(ELU(u)))
+            if (conv_gemm(e, e->res1[s], eu, Bc, T2, Ch >= 128 ? 128 : 64, g) != 0) return -1;
+            g = {}; g.resid_h = (const uint16_t *)u; g.out_h = (uint16_t *)vv; g.ldh = C2; g.act = ACT_ELU;  // ELU(u + conv_k1(.))
+            if (conv_gemm(e, e->res2[s], rm, Bc, T2, C2 >= 256 ? 256 : C2, g) != 0) return -1;
+        }
         cur = vv; Tc = T2; last = vv;
     }
     {

@@ -1,0 +1,217 @@
+// resblock.cuh - one SEANet residual block (ptts_mimi.c:160-177) as ONE tcgen05 kernel:
+//     out = ELU( u + W2 . ELU( W1 (*) ELU(u) + b1 ) + b2 )          (*) = causal Conv1d, k = 3
+// The middle tensor (C/2 channels at the stage's sample rate - the single largest SEANet intermediate
+// per output byte) never leaves the SM: the first contraction's accumulator is read from TMEM by the
+// epilogue warps, biased, ELU'd, rounded to fp16 and written straight into shared memory in the
+// K-major 128B-swizzled layout the tensor core reads, where it becomes the A operand of the second
+// contraction (W2 stays resident in shared memory for the whole kernel).
+//
+//   warp 0    : TMA producer - the 3 taps of ELU(u) (shifted row coordinates, OOB rows = causal zero
+//               padding) and the matching W1 slices through a shared-memory ring
+//   warp 1    : MMA issuer   - contraction 1 into TMEM D1, then (once the epilogue has staged the middle
+//               tensor) contraction 2 into TMEM D2
+//   warps 2-5 : epilogue     - D1 -> +b1 -> ELU -> fp16 -> shared memory;  D2 -> +b2 +u -> ELU -> fp16 -> HBM
+// Persistent over 128-row tiles; contraction 1 of tile i+1 overlaps the output epilogue of tile i.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace ptts {
+
+constexpr int RB_EPI_WARPS = 8;              // two per TMEM lane quadrant: each takes half of the columns
+constexpr int RB_THREADS = 64 + 32 * RB_EPI_WARPS;
+
+struct ResParams {
+    int tiles_per_batch, tiles_total, a_rows;
+    int kb_per_tap;          // C2 / 64
+    int chp;                 // middle channels, padded to a multiple of 64
+    int stages;
+    uint32_t idesc1, idesc2;
+    const float *b1, *b2;    // [chp] (zero padded), [C2]
+    const uint16_t *u;       // residual stream, fp16 [rows][C2]
+    uint16_t *out;           // fp16 [rows][C2]
+};
+
+template <int C2>
+__global__ void __launch_bounds__(RB_THREADS, C2 <= 128 ? 2 : 1)
+resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapW1,
+                const __grid_constant__ CUtensorMap mapW2, const ResParams p) {
+    constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;                 // 16 KB
+    constexpr uint32_t D2_COL = C2 == 64 ? 64 : 128;
+    constexpr uint32_t TMEM_COLS = C2 == 64 ? 128 : (C2 == 128 ? 256 : 512);
+    extern __shared__ uint8_t rb_smem_raw[];
+    uint8_t *smem = rb_smem_raw + ((1024u - (smem_u32(rb_smem_raw) & 1023u)) & 1023u);
+    const int chp = p.chp, kb2 = chp / 64;
+    const int w1_bytes = chp * 128, stage_bytes = A_BYTES + w1_bytes;
+    uint8_t *ring = smem;
+    uint8_t *w2s = ring + p.stages * stage_bytes;                 // [kb2][C2 rows][128 B]
+    uint8_t *a2s = w2s + kb2 * C2 * 128;                           // [kb2][128 rows][128 B]
+    uint64_t *bars = (uint64_t *)(a2s + kb2 * A_BYTES);
+    uint64_t *full = bars, *empty = bars + GEMM_MAX_STAGES;
+    uint64_t *w2_full = bars + 2 * GEMM_MAX_STAGES, *d1_full = w2_full + 1, *a2_full = w2_full + 2, *d2_full = w2_full + 3,
+             *d2_empty = w2_full + 4;
+    uint32_t *tmem_slot = (uint32_t *)(w2_full + 5);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
+        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(w2_full, 1); mbar_init(d1_full, 1); mbar_init(a2_full, RB_EPI_WARPS); mbar_init(d2_full, 1); mbar_init(d2_empty, RB_EPI_WARPS);
+        fence_barrier_init();
+    }
+    if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) pdl_trigger();
+    const int iters = 3 * p.kb_per_tap;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // weights are constants: W2 (resident) and the first ring slots' W1 slices go out before the dependency wait
+            mbar_expect_tx(w2_full, (uint32_t)(kb2 * C2 * 128));
+            for (int kb = 0; kb < kb2; kb++) tma_load_3d(w2s + kb * C2 * 128, &mapW2, w2_full, kb * GEMM_BK, 0, 0);
+            pdl_wait();
+            int s = 0; uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+                const int batch = tile / p.tiles_per_batch, m0 = (tile - batch * p.tiles_per_batch) * GEMM_BM;
+                for (int it = 0; it < iters; it++) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+                    const int tap = it / p.kb_per_tap, kb = it - tap * p.kb_per_tap;
+                    uint8_t *st = ring + s * stage_bytes;
+                    tma_load_3d(st, &mapA, &full[s], kb * GEMM_BK, m0 - 2 + tap, batch);          // row t-2+tap: causal, k = 3
+                    tma_load_3d(st + A_BYTES, &mapW1, &full[s], it * GEMM_BK, 0, 0);             // W1 columns tap*C2 + kb*64
+                    if (++s == p.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        int s = 0; uint32_t ph = 0; int lt = 0;
+        mbar_wait(w2_full, 0);
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, lt++) {
+            // contraction 1: D1[128, chp] = sum over taps, channels
+            for (int it = 0; it < iters; it++) {
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_u32(ring + s * stage_bytes);
+                    const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base, ad + 2 * k, bd + 2 * k, p.idesc1, (it > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                    if (it == iters - 1) umma_commit(d1_full);
+                }
+                __syncwarp();
+                if (++s == p.stages) { s = 0; ph ^= 1; }
+            }
+            // contraction 2: D2[128, C2] = mid[128, chp] . W2^T, once the epilogue has staged `mid` and drained the previous D2
+            mbar_wait(a2_full, lt & 1);
+            mbar_wait(d2_empty, (lt & 1) ^ 1);
+            tc_fence_after();
+            if (lane == 0) {
+                for (int kb = 0; kb < kb2; kb++) {
+                    const uint64_t ad = umma_desc_sw128(smem_u32(a2s + kb * A_BYTES)), bd = umma_desc_sw128(smem_u32(w2s + kb * C2 * 128));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base + D2_COL, ad + 2 * k, bd + 2 * k, p.idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(d2_full);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int quad = warp & 3, cg = (warp - 2) >> 2;   // column half
+        const int c1_lo = cg * (chp / 2), c1_hi = c1_lo + chp / 2, c2_lo = cg * (C2 / 2), c2_hi = c2_lo + C2 / 2;
+        pdl_wait();
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, lt++) {
+            const int batch = tile / p.tiles_per_batch, m0 = (tile - batch * p.tiles_per_batch) * GEMM_BM;
+            const int r = quad * 32 + lane, m = m0 + r;
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+            // ---- epilogue 1: D1 -> +b1 -> ELU -> fp16 -> shared memory (A operand of contraction 2)
+            mbar_wait(d1_full, lt & 1);
+            tc_fence_after();
+            {
+                uint32_t rr[16], rn[16];
+                tmem_ld16(trow + c1_lo, rr); tmem_ld_wait16(rr);
+#pragma unroll 1
+                for (int c = c1_lo; c < c1_hi; c += 16) {
+                    const bool more = c + 16 < c1_hi;
+                    if (more) tmem_ld16(trow + c + 16, rn);
+                    float v[16];
+                    const float4 *bp = (const float4 *)(p.b1 + c);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const float4 bb = bp[j];
+                        v[4 * j] = __uint_as_float(rr[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + bb.y;
+                        v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + bb.w;
+                    }
+                    uint32_t hw[8], lw[8];
+                    act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
+                    uint8_t *row = a2s + (c >> 6) * A_BYTES + r * 128;
+                    const int pc = (c & 63) >> 3;
+                    *(uint4 *)(row + ((pc ^ (r & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                    *(uint4 *)(row + (((pc + 1) ^ (r & 7)) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+                    if (more) {
+                        tmem_ld_wait16(rn);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) rr[j] = rn[j];
+                    }
+                }
+            }
+            fence_proxy_async();          // generic-proxy writes of `mid` -> visible to the tensor core's async-proxy reads
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a2_full);
+            // ---- epilogue 2: D2 -> +b2 + u -> ELU -> fp16 -> HBM
+            mbar_wait(d2_full, lt & 1);
+            tc_fence_after();
+            {
+                const bool m_ok = m < p.a_rows;
+                const size_t grow = (size_t)batch * p.a_rows + m;
+                const uint16_t *up = p.u + grow * C2;
+                uint16_t *op = p.out + grow * C2;
+                uint32_t rr[16], rn[16];
+                tmem_ld16(trow + D2_COL + c2_lo, rr); tmem_ld_wait16(rr);
+#pragma unroll 1
+                for (int c = c2_lo; c < c2_hi; c += 16) {
+                    const bool more = c + 16 < c2_hi;
+                    if (more) tmem_ld16(trow + D2_COL + c + 16, rn);
+                    if (m_ok) {
+                        uint32_t hr[8];
+                        ld_global_v8u(up + c, hr);
+                        float v[16];
+                        const float4 *bp = (const float4 *)(p.b2 + c);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float4 bb = bp[j];
+                            v[4 * j] = __uint_as_float(rr[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + bb.y;
+                            v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + bb.w;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const float2 f = __half22float2(*(const __half2 *)&hr[j]);
+                            v[2 * j] += f.x; v[2 * j + 1] += f.y;
+                        }
+                        uint32_t hw[8], lw[8];
+                        act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
+                        st_global_v8(op + c, hw);
+                    }
+                    if (more) {
+                        tmem_ld_wait16(rn);
+#pragma unroll
+                        for (int j = 0; j < 16; j++) rr[j] = rn[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d2_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+}  // namespace ptts
