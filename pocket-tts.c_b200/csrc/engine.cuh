@@ -327,6 +327,7 @@ struct ptts_b200_engine {
 
     // ---- Mimi weights
     float *quant_w = nullptr, *ups_w = nullptr, *dec_out_w = nullptr, *dec_out_b = nullptr;
+    float h_dec_out_b = 0.0f;
     ptts::MimiLayerW ML[ptts::MI_L];
     ptts::ConvW dec_in, up[3], res1[3], res2[3];
 

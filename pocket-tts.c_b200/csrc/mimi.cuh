@@ -91,6 +91,7 @@ static int mimi_load_weights(Engine *e, const HostWeights &hw) {
     if (mimi_load_conv(e, hw, "decoder.model.9.block.3.conv", e->res2[2], 32, 64, 1, 64, 64) != 0) return -1;
     if (hw.get("decoder.model.11.conv.weight", MIMI_PFX, 64 * 3, v) != 0 || e->up_f32(&e->dec_out_w, v) != 0) return -1;
     if (hw.get("decoder.model.11.conv.bias", MIMI_PFX, 1, v) != 0 || e->up_f32(&e->dec_out_b, v) != 0) return -1;
+    e->h_dec_out_b = v[0];
     return 0;
 }
 
@@ -139,7 +140,8 @@ static int conv_gemm(Engine *e, const ConvW &c, const __half *A, int Bc, int T, 
 
 // One fused residual block (resblock.cuh): vv = ELU(u + conv1(ELU(conv3(eu)))) for Bc items of T rows, C2 channels.
 template <int C2>
-static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const __half *eu, const __half *u, __half *vv, int Bc, int T) {
+static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const __half *eu, const __half *u, __half *vv, int Bc, int T,
+                             float *pcm = nullptr, float *edge = nullptr) {
     static bool attr_done = false;
     if (!attr_done) {
         PTTS_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -158,13 +160,18 @@ static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const 
     PTTS_CHECK(tiles < (1ll << 31), "resblock_launch: too many tiles");
     p.tiles_total = (int)tiles; p.a_rows = T; p.kb_per_tap = C2 / 64; p.chp = chp;
     const int stage = GEMM_BM * GEMM_BK * 2 + chp * 128, kb2 = chp / 64;
-    const int fixed = kb2 * C2 * 128 + kb2 * GEMM_BM * GEMM_BK * 2 + 256 + 1024;
+    const int fixed = kb2 * C2 * 128 + kb2 * GEMM_BM * GEMM_BK * 2 + 256 + (192 + 2 * 768) * 4 + 1024;
     // C2 <= 128: two CTAs per SM (one's output epilogue overlaps the other's contractions) -> at most ~110 KB each
     p.stages = std::min(C2 <= 128 ? 3 : GEMM_MAX_STAGES, (227 * 1024 - fixed) / stage);
     PTTS_CHECK(p.stages >= 2, "resblock_launch: shared memory too small");
     p.idesc1 = umma_idesc_f16(GEMM_BM, chp, false, false);
     p.idesc2 = umma_idesc_f16(GEMM_BM, C2, false, false);
     p.b1 = c1.b; p.b2 = c2.b; p.u = (const uint16_t *)u; p.out = (uint16_t *)vv;
+    if (pcm) {   // last block: the final 64 -> 1 conv is applied in the epilogue, the block's output tensor is never written
+        PTTS_CHECK(C2 == 64 && edge, "resblock_launch: the final conv can only be fused into the 64-channel block");
+        p.dbias = e->h_dec_out_b;
+        p.dw = e->dec_out_w; p.pcm = pcm; p.edge = edge; p.out = nullptr;
+    }
     const int smem = p.stages * stage + fixed;
     if (e->prof.on) {
         const double rows = (double)Bc * T;
@@ -181,10 +188,17 @@ static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const 
         r.rows = Bc * T; r.n = C2; r.k = 3 * C2 + chp; r.bn = -chp;   // bn < 0 marks the fused block in the per-launch log
         r.flops = 2.0 * (double)Bc * T * (3.0 * C2 * chp + (double)chp * C2);
     }
-    return launch_check("resblock_kernel");
+    if (launch_check("resblock_kernel") != 0) return -1;
+    if (pcm) {
+        LaunchScope ls(e, KC_MIMI_MISC);
+        launch_k(k_dec_edge_fix, dim3((unsigned)((tiles + 255) / 256)), dim3(256), 0, e->st, (const float *)edge, pcm, p.tiles_per_batch, p.tiles_total, T);
+        return launch_check("k_dec_edge_fix");
+    }
+    return 0;
 }
-static int resblock_launch(Engine *e, const ConvW &c1, const ConvW &c2, const __half *eu, const __half *u, __half *vv, int Bc, int T, int C2) {
-    if (C2 == 64) return resblock_launch_t<64>(e, c1, c2, eu, u, vv, Bc, T);
+static int resblock_launch(Engine *e, const ConvW &c1, const ConvW &c2, const __half *eu, const __half *u, __half *vv, int Bc, int T, int C2,
+                           float *pcm = nullptr, float *edge = nullptr) {
+    if (C2 == 64) return resblock_launch_t<64>(e, c1, c2, eu, u, vv, Bc, T, pcm, edge);
     if (C2 == 128) return resblock_launch_t<128>(e, c1, c2, eu, u, vv, Bc, T);
     if (C2 == 256) return resblock_launch_t<256>(e, c1, c2, eu, u, vv, Bc, T);
     set_error("resblock_launch: unsupported channel count %d", C2);
@@ -258,6 +272,7 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
     const __half *cur = d0;
     int Tc = T;
     __half *last = nullptr;
+    bool pcm_done = false;
     for (int s = 0; s < 3; s++) {
         const ConvW &U = e->up[s];
         const int T2 = Tc * U.stride, C2 = U.cout, Ch = e->res1[s].cout;
@@ -269,7 +284,12 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         g = {}; g.out_raw = (uint16_t *)u; g.out_h = (uint16_t *)eu; g.ldh = U.n_rows; g.act = ACT_ELU;
         if (conv_gemm(e, U, cur, Bc, Tc, U.n_rows >= 256 ? 256 : 128, g) != 0) return -1;  // u = convT(ELU(prev)), eu = ELU(u)
         static const bool fused = getenv("PTTS_B200_NO_RESBLOCK") == nullptr;
-        if (fused) {   // conv_k3 -> ELU -> conv_k1 -> +u -> ELU in one kernel, the middle tensor stays in shared memory
+        static const bool fuse_out = getenv("PTTS_B200_NO_FUSED_OUT") == nullptr;
+        if (fused && s == 2 && fuse_out) {   // last block: + the final 64 -> 1 conv, straight to PCM
+            float *edge = ws.take<float>((size_t)Bc * ((T2 + GEMM_BM - 1) / GEMM_BM) * 4);
+            if (resblock_launch(e, e->res1[s], e->res2[s], eu, u, vv, Bc, T2, C2, d_pcm, edge) != 0) return -1;
+            pcm_done = true;
+        } else if (fused) {   // conv_k3 -> ELU -> conv_k1 -> +u -> ELU in one kernel, the middle tensor stays in shared memory
             if (resblock_launch(e, e->res1[s], e->res2[s], eu, u, vv, Bc, T2, C2) != 0) return -1;
         } else {
             g = {}; g.out_h = (uint16_t *)rm; g.ldh = Ch; g.act = ACT_ELU;                      // ELU(conv_k3(ELU(u)))
@@ -279,7 +299,7 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         }
         cur = vv; Tc = T2; last = vv;
     }
-    {
+    if (!pcm_done) {
         LaunchScope ls(e, KC_MIMI_MISC);
         launch_k(k_dec_out, dim3((Tc + 255) / 256, Bc), 256, 0, e->st, last, Tc, e->dec_out_w, e->dec_out_b, d_pcm);
         if (launch_check("k_dec_out") != 0) return -1;

@@ -28,7 +28,14 @@ struct ResParams {
     uint32_t idesc1, idesc2;
     const float *b1, *b2;    // [chp] (zero padded), [C2]
     const uint16_t *u;       // residual stream, fp16 [rows][C2]
-    uint16_t *out;           // fp16 [rows][C2]
+    uint16_t *out;           // fp16 [rows][C2] (NULL when the final conv is fused)
+    // last block only (C2 = 64): the decoder's final Conv1d 64 -> 1, k = 3 (ptts_mimi.c:723-726) is applied to the block's
+    // output rows while they are still in registers: pcm[t] = bias + w2.e[t] + w1.e[t-1] + w0.e[t-2]. The two rows before a
+    // tile belong to another tile: their contributions are left in `edge` and added by k_dec_edge_fix.
+    const float *dw;         // [64][3] (NULL = not fused)
+    float dbias;
+    float *pcm;              // [batches][a_rows]
+    float *edge;             // [tiles][4]: w1.e[127], w0.e[127], w0.e[126] of each tile
 };
 
 template <int C2>
@@ -50,7 +57,10 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint64_t *w2_full = bars + 2 * GEMM_MAX_STAGES, *d1_full = w2_full + 1, *a2_full = w2_full + 2, *d2_full = w2_full + 3,
              *d2_empty = w2_full + 4;
     uint32_t *tmem_slot = (uint32_t *)(w2_full + 5);
+    float *dws = (float *)(bars + 32);            // [3][64] final-conv weights
+    float *dpart = dws + 192;                     // [2 buffers][2 column halves][128 rows][3]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (C2 == 64 && p.dw && threadIdx.x < 192) dws[(threadIdx.x % 3) * 64 + threadIdx.x / 3] = p.dw[threadIdx.x];
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
@@ -170,7 +180,8 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const bool m_ok = m < p.a_rows;
                 const size_t grow = (size_t)batch * p.a_rows + m;
                 const uint16_t *up = p.u + grow * C2;
-                uint16_t *op = p.out + grow * C2;
+                uint16_t *op = p.out ? p.out + grow * C2 : nullptr;
+                float dsum[3] = {0.0f, 0.0f, 0.0f};
                 uint32_t rr[16], rn[16];
                 tmem_ld16(trow + D2_COL + c2_lo, rr); tmem_ld_wait16(rr);
 #pragma unroll 1
@@ -195,12 +206,34 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         }
                         uint32_t hw[8], lw[8];
                         act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
-                        st_global_v8(op + c, hw);
+                        if (op) st_global_v8(op + c, hw);
+                        if (C2 == 64 && p.dw) {   // final conv on the fp16-rounded block output (what the unfused path reads back)
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float2 f = __half22float2(*(const __half2 *)&hw[j]);
+#pragma unroll
+                                for (int k = 0; k < 3; k++) dsum[k] += f.x * dws[k * 64 + c + 2 * j] + f.y * dws[k * 64 + c + 2 * j + 1];
+                            }
+                        }
                     }
                     if (more) {
                         tmem_ld_wait16(rn);
 #pragma unroll
                         for (int j = 0; j < 16; j++) rr[j] = rn[j];
+                    }
+                }
+                if (C2 == 64 && p.dw) {
+                    float *pb = dpart + (lt & 1) * 768;               // double-buffered: one barrier per tile is enough
+                    float *mine = pb + (cg * 128 + r) * 3;
+                    mine[0] = dsum[0]; mine[1] = dsum[1]; mine[2] = dsum[2];
+                    asm volatile("bar.sync 1, 256;" ::: "memory");    // the 8 epilogue warps
+                    if (cg == 0) {
+                        auto D = [&](int row, int k) { return pb[row * 3 + k] + pb[(128 + row) * 3 + k]; };
+                        float y = p.dbias + D(r, 2);
+                        if (r >= 1) y += D(r - 1, 1);
+                        if (r >= 2) y += D(r - 2, 0);
+                        if (m_ok) p.pcm[grow] = y;
+                        if (r == 127) { float *e = p.edge + (size_t)tile * 4; e[0] = D(127, 1); e[1] = D(127, 0); e[2] = D(126, 0); }
                     }
                 }
             }
@@ -212,6 +245,19 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// Contributions of the two rows before each tile to its first two samples (see ResParams::dw). One thread per tile.
+__global__ void k_dec_edge_fix(const float *edge, float *pcm, int tiles_per_batch, int tiles_total, int a_rows) {
+    pdl_wait(); pdl_trigger();
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= tiles_total) return;
+    const int batch = tile / tiles_per_batch, j = tile - batch * tiles_per_batch;
+    if (j == 0) return;                          // causal zero padding before the first row of an utterance
+    const float *e = edge + (size_t)(tile - 1) * 4;
+    const size_t o = (size_t)batch * a_rows + (size_t)j * GEMM_BM;
+    pcm[o] += e[0] + e[2];                       // w1.e[t-1] + w0.e[t-2]
+    if (j * GEMM_BM + 1 < a_rows) pcm[o + 1] += e[1];   // w0.e[t-1]
 }
 
 }  // namespace ptts
