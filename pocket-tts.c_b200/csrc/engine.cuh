@@ -346,6 +346,7 @@ struct ptts_b200_engine {
     float *fx = nullptr, *ada = nullptr, *ft = nullptr, *flow = nullptr, *sc = nullptr, *fg = nullptr;
     uint16_t *sc_h = nullptr, *sc_l = nullptr, *fh_h = nullptr, *fh_l = nullptr, *fg_h = nullptr, *fg_l = nullptr;
     float *pk = nullptr, *pv = nullptr;           // prefix KV [L][H][capCond][64]
+    __half *pk16 = nullptr, *pv16 = nullptr;      // fp16 copy (made once per voice)
     __half *ok = nullptr, *ov = nullptr;          // own KV, fp16 [L][H][capB][capS][64]
     float *d_cond = nullptr;                      // voice rows on device [capCond,1024]
     // batched prefill workspace (capRows packed rows)

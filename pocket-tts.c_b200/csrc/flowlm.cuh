@@ -148,8 +148,9 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
     DA(sc_h, b * FN_D); DA(sc_l, b * FN_D); DA(fh_h, b * FN_D); DA(fh_l, b * FN_D); DA(fg_h, b * FN_D); DA(fg_l, b * FN_D);
     DA(ok, (size_t)FL_L * b * FL_D * S); DA(ov, (size_t)FL_L * b * FL_D * S);
     if (regrow_prefix || !e->pk) {
-        e->dfree(e->pk); e->dfree(e->pv); e->dfree(e->d_cond);
+        e->dfree(e->pk); e->dfree(e->pv); e->dfree(e->d_cond); e->dfree(e->pk16); e->dfree(e->pv16);
         DA(pk, (size_t)FL_L * FL_D * cond + 16); DA(pv, (size_t)FL_L * FL_D * cond + 16); DA(d_cond, (size_t)cond * FL_D + 16);
+        DA(pk16, (size_t)FL_L * FL_D * cond + 16); DA(pv16, (size_t)FL_L * FL_D * cond + 16);
         e->voice_len = -1;
     }
     if (!e->ctrl) DA(ctrl, 1);

@@ -360,6 +360,13 @@ struct AttnDecodeParams {
     size_t qkv_stride;
     const float *rope_cos, *rope_sin;  // [max_pos][32]
     const float *pk, *pv;      // prefix cache of this layer (NULL when cond_len == 0)
+    const __half *pk16, *pv16; // fp16 copy of the prefix cache (tensor-core attention of the persistent kernel)
+    const __half *nk, *nv;     // own caches of the layer whose attention phase comes next (L2 prefetch), n_extra rows beyond `step`
+    int n_extra;
+    // persistent kernel only: values fixed for the whole launch, filled in by the kernel itself
+    int cond_len_val;          // *ctrl_cond_len
+    const int *ob_cache;       // own_base[ob_first .. ob_first + ob_count) in shared memory (NULL: read own_base)
+    int ob_first, ob_count;
     __half *ok, *ov;           // own cache of this layer (fp16), head-major [H][cap_b][max_s][64]: the utterances one CTA works on
                                // (one head, consecutive b) are one contiguous span of memory
     int cap_b;                 // utterance capacity of the own cache

@@ -166,7 +166,8 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     }
     if (!e->mega_ctl) {
         if (e->dalloc(&e->mega_ctl, 64) != 0) return -1;
-        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
+        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
+        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
     }
     PTTS_CUDA_OK(cudaMemsetAsync(e->mega_ctl, 0, 64 * sizeof(unsigned long long), e->st));
     MegaProgram P = M.prog;
@@ -189,7 +190,8 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     e->launches++;
-    PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega, P));
+    if (P.attn_tc) PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega<true>, P));
+    else PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega<false>, P));
     if (e->prof.on) {
         unsigned long long h[2 * MP_COUNT];
         PTTS_CUDA_OK(cudaMemcpyAsync(h, e->mega_ctl + 8, sizeof h, cudaMemcpyDeviceToHost, e->st));
@@ -199,7 +201,8 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
             PTTS_CUDA_OK(cudaMemcpy(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
             static const char *const tn[MP_COUNT] = {"HEAD", "GEMM", "ROW", "MID", "TAIL", "ATTN"};
             const double st_ = (double)h[2 * MP_HEAD + 1];
-            fprintf(stderr, "mega trace: B=%d steps=%.0f phases=%d (us per frame: own work of CTA 0 / including barrier)\n", B, st_, P.n_phases);
+            fprintf(stderr, "mega trace: B=%d steps=%.0f phases=%d attention=%s (us per frame: own work of CTA 0 / including barrier)\n", B, st_, P.n_phases,
+                    P.attn_tc ? "mma.sync" : "scalar");
             for (int i = 0; i < P.n_phases; i++) {
                 const MegaPhase &q = M.phases[i];
                 char extra[96] = "";
@@ -213,7 +216,7 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
             { const unsigned long long *a = &tr[(size_t)2 * P.n_phases]; const double nu = (double)std::max<unsigned long long>(a[5], 1);
               fprintf(stderr, "  attention unit (CTA 0 warp 0, cycles per unit over %.0f units): new-row %.0f  scores %.0f  softmax %.0f  PV %.0f  write %.0f\n",
                       nu, a[0] / nu, a[1] / nu, a[2] / nu, a[3] / nu, a[4] / nu);
-              fprintf(stderr, "    inside scores: prefix quanta %.0f  wait for the first own K row of a batch %.0f\n", a[6] / nu, a[7] / nu); }
+              fprintf(stderr, "    inside new-row (cumulative): loads and ring blocks issued %.0f  new rows stored %.0f\n", a[6] / nu, a[7] / nu); }
             e->dfree(d_trace);
         }
         static const int cls_of[MP_COUNT] = {KC_FLOW_MISC, KC_GEMM_FLOW, KC_ROWNORM, KC_FLOW_MISC, KC_FLOW_MISC, KC_ATTN_DECODE};
@@ -244,7 +247,8 @@ static int run_mega1(Engine *e, int lsd, int nsteps) {
     }
     if (!e->mega_ctl) {
         if (e->dalloc(&e->mega_ctl, 64) != 0) return -1;
-        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
+        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
+        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
     }
     static bool attr1 = false;
     if (!attr1) { PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega1, cudaFuncAttributeMaxDynamicSharedMemorySize, M1_DYN_SMEM)); attr1 = true; }
@@ -372,6 +376,13 @@ static int set_voice(Engine *e, const float *cond, int cond_len) {
         PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_i, ri.data(), cond_len * 4, cudaMemcpyHostToDevice, e->st));
         PTTS_CUDA_OK(cudaMemcpyAsync(e->d_row_start, rs.data(), 2 * 4, cudaMemcpyHostToDevice, e->st));
         if (flow_prefill(e, 1, cond_len, cond_len, 0, true) != 0) return -1;
+        {   // fp16 copy of the prefix K / V for the tensor-core attention of the persistent step kernel
+            LaunchScope ls(e, KC_FLOW_MISC);
+            const size_t n8 = (size_t)FL_L * FL_D * e->capCond / 8;
+            launch_k(k_f32_to_f16, 296, 256, 0, e->st, (const float *)e->pk, e->pk16, n8);
+            launch_k(k_f32_to_f16, 296, 256, 0, e->st, (const float *)e->pv, e->pv16, n8);
+            if (launch_check("k_f32_to_f16") != 0) return -1;
+        }
         PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     }
     e->voice_host.assign(cond, cond + (size_t)cond_len * FL_D);
