@@ -25,6 +25,7 @@ struct ResParams {
     int kb_per_tap;          // C2 / 64
     int chp;                 // middle channels, padded to a multiple of 64
     int stages;
+    int prefetch_u;          // 1: L2 prefetch of each tile's residual rows by the producer (A/B switch)
     uint32_t idesc1, idesc2;
     const float *b1, *b2;    // [chp] (zero padded), [C2]
     const uint16_t *u;       // residual stream, fp16 [rows][C2]
@@ -85,6 +86,10 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             int s = 0; uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
                 const int batch = tile / p.tiles_per_batch, m0 = (tile - batch * p.tiles_per_batch) * GEMM_BM;
+                if (p.prefetch_u) {   // the tile's residual rows (read by the output epilogue with plain loads): towards L2 now
+                    const int nr = min(GEMM_BM, p.a_rows - m0);
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.u + ((size_t)batch * p.a_rows + m0) * C2), "r"((uint32_t)nr * C2 * 2u) : "memory");
+                }
                 for (int it = 0; it < iters; it++) {
                     mbar_wait(&empty[s], ph ^ 1);
                     mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
