@@ -487,7 +487,12 @@ static int flow_prefill(Engine *e, int n, int M, int max_q, int cond_len, bool v
             }
             a.out_h = e->pf_att_h; a.out_l = e->pf_att_l;
             LaunchScope ls(e, KC_ATTN_DECODE);
-            launch_k(k_pf_attn, dim3(FL_H, n), 256, smem, e->st, a, pr);
+            // prompts: tensor-core kernel over [fp16 prefix copy | own rows]; the voice pass (once per voice, fp32 prefix cache
+            // as its product) keeps the fp32 scalar kernel. PTTS_B200_PF_ATTN_SCALAR=1 selects the scalar kernel for A/B runs.
+            static const bool pf_scalar = getenv("PTTS_B200_PF_ATTN_SCALAR") != nullptr;
+            if (voice_mode || pf_scalar) launch_k(k_pf_attn, dim3(FL_H, n), 256, smem, e->st, a, pr);
+            else launch_k(k_pf_attn_tc, dim3((max_q + 63) / 64, FL_H, n), 128, 0, e->st, a, pr,
+                          (const __half *)(e->pk16 + (size_t)l * FL_D * e->capCond), (const __half *)(e->pv16 + (size_t)l * FL_D * e->capCond));
             if (launch_check("k_pf_attn") != 0) return -1;
         }
         g = {}; g.resid = e->pf_x; g.out_f32 = e->pf_x; g.ldo = FL_D;

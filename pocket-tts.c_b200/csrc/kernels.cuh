@@ -985,6 +985,179 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
     }
 }
 
+// =====================================================================================
+// Prompt prefill attention on warp-level tensor cores (same contract as k_pf_attn, ptts_flowlm.c:465-525 applied to
+// every prompt position at once): one CTA = up to 64 prompt rows of one (head, utterance), 4 warps x 16 query rows,
+// flash-style over key blocks of 64 = [voice prefix (fp16 copy) | the utterance's own rows]. The own K / V rows are
+// produced on the fly from the QKV projection (RoPE at pos = cond_len + i), rounded to fp16 - exactly what lands in the
+// own cache and what every later decode step reads - and appended to the cache by the CTA whose query tile holds the row.
+// Queries and probabilities enter the MMAs as fp16 hi + lo pairs (two MMAs each), accumulation and softmax in fp32.
+// grid (ceil(max_q / 64), 16, n), block 128.
+// =====================================================================================
+__device__ __forceinline__ void split_h2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *(const uint32_t *)&h; lo = *(const uint32_t *)&l;
+}
+__global__ void __launch_bounds__(128) k_pf_attn_tc(const PrefillAttnParams p, const PrefillRows pr, const __half *pk16, const __half *pv16) {
+    pdl_wait(); pdl_trigger();
+    __shared__ __align__(16) __half sQh[64 * FA_LD], sQl[64 * FA_LD], sK[64 * FA_LD], sV[64 * FA_LD];
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int r0 = pr.row_start[b], nq = pr.row_start[b + 1] - r0, cl = p.cond_len, i0 = qt * 64;
+    if (i0 >= nq) return;
+    const size_t obase = ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
+    for (int idx = tid; idx < 64 * 32; idx += 128) {
+        const int r = idx >> 5, l = idx & 31, i = i0 + r;
+        float2 q = make_float2(0.0f, 0.0f);
+        if (i < nq) {
+            const float *row = p.qkv + (size_t)(r0 + i) * 3 * FL_D + h * FL_HD;
+            const float c = p.rope_cos[(cl + i) * 32 + l], sn = p.rope_sin[(cl + i) * 32 + l];
+            const float2 qq = *(const float2 *)(row + 2 * l);
+            q = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
+        }
+        uint32_t hi, lo;
+        split_h2(q.x, q.y, hi, lo);
+        *(uint32_t *)(sQh + r * FA_LD + 2 * l) = hi;
+        *(uint32_t *)(sQl + r * FA_LD + 2 * l) = lo;
+    }
+    __syncthreads();
+    uint32_t qh[4][4], ql[4][4];
+    {
+        const int ro = (warp * 16 + g) * FA_LD;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            qh[ks][0] = *(const uint32_t *)(sQh + ro + ks * 16 + 2 * t);
+            qh[ks][1] = *(const uint32_t *)(sQh + ro + 8 * FA_LD + ks * 16 + 2 * t);
+            qh[ks][2] = *(const uint32_t *)(sQh + ro + ks * 16 + 8 + 2 * t);
+            qh[ks][3] = *(const uint32_t *)(sQh + ro + 8 * FA_LD + ks * 16 + 8 + 2 * t);
+            ql[ks][0] = *(const uint32_t *)(sQl + ro + ks * 16 + 2 * t);
+            ql[ks][1] = *(const uint32_t *)(sQl + ro + 8 * FA_LD + ks * 16 + 2 * t);
+            ql[ks][2] = *(const uint32_t *)(sQl + ro + ks * 16 + 8 + 2 * t);
+            ql[ks][3] = *(const uint32_t *)(sQl + ro + 8 * FA_LD + ks * 16 + 8 + 2 * t);
+        }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    const int tq0 = i0 + warp * 16 + g, tq1 = tq0 + 8;          // prompt rows of this lane's two accumulator rows
+    const bool warp_live = i0 + warp * 16 < nq;
+    const int kend = cl + min(nq, i0 + 64);                     // keys [0, kend) can be visible to this tile
+    for (int kb = 0; kb < kend; kb += 64) {
+        __syncthreads();   // all warps are done with the previous K/V block
+        for (int idx = tid; idx < 512; idx += 128) {
+            const int r = idx >> 3, c = (idx & 7) * 8, kk = kb + r;
+            uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
+            if (kk < cl) {
+                kv = *(const uint4 *)(pk16 + ((size_t)h * p.pstride + kk) * FL_HD + c);
+                vv = *(const uint4 *)(pv16 + ((size_t)h * p.pstride + kk) * FL_HD + c);
+            } else if (kk - cl < nq) {
+                const int i = kk - cl;
+                const float *row = p.qkv + (size_t)(r0 + i) * 3 * FL_D + h * FL_HD + c;
+                const float4 k0 = *(const float4 *)(row + FL_D), k1 = *(const float4 *)(row + FL_D + 4);
+                const float4 v0 = *(const float4 *)(row + 2 * FL_D), v1 = *(const float4 *)(row + 2 * FL_D + 4);
+                const float4 cs = *(const float4 *)(p.rope_cos + (cl + i) * 32 + (c >> 1)), sn = *(const float4 *)(p.rope_sin + (cl + i) * 32 + (c >> 1));
+                const float kr[8] = {k0.x * cs.x - k0.y * sn.x, k0.x * sn.x + k0.y * cs.x, k0.z * cs.y - k0.w * sn.y, k0.z * sn.y + k0.w * cs.y,
+                                     k1.x * cs.z - k1.y * sn.z, k1.x * sn.z + k1.y * cs.z, k1.z * cs.w - k1.w * sn.w, k1.z * sn.w + k1.w * cs.w};
+                kv = make_uint4(pack_h2(kr[0], kr[1]), pack_h2(kr[2], kr[3]), pack_h2(kr[4], kr[5]), pack_h2(kr[6], kr[7]));
+                vv = make_uint4(pack_h2(v0.x, v0.y), pack_h2(v0.z, v0.w), pack_h2(v1.x, v1.y), pack_h2(v1.z, v1.w));
+                if ((i >> 6) == qt) {   // this tile owns the row: append it to the cache
+                    const size_t o_ = obase + (size_t)i * FL_HD + c;
+                    if (p.own_f16) {
+                        *(uint4 *)((__half *)p.ok + o_) = kv;
+                        *(uint4 *)((__half *)p.ov + o_) = vv;
+                    } else {
+                        *(float4 *)((float *)p.ok + o_) = make_float4(kr[0], kr[1], kr[2], kr[3]);
+                        *(float4 *)((float *)p.ok + o_ + 4) = make_float4(kr[4], kr[5], kr[6], kr[7]);
+                        *(float4 *)((float *)p.ov + o_) = v0;
+                        *(float4 *)((float *)p.ov + o_ + 4) = v1;
+                    }
+                }
+            }
+            *(uint4 *)(sK + r * FA_LD + c) = kv;
+            *(uint4 *)(sV + r * FA_LD + c) = vv;
+        }
+        __syncthreads();
+        if (!warp_live) continue;   // padding rows only: nothing to compute (the barriers above are still reached)
+        float sc[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.0f;
+            const __half *kr = sK + (nt * 8 + g) * FA_LD + 2 * t;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+                const uint32_t b0 = *(const uint32_t *)(kr + ks * 16), b1 = *(const uint32_t *)(kr + ks * 16 + 8);
+                mma_f16_16816(sc[nt], qh[ks], b0, b1);
+                mma_f16_16816(sc[nt], ql[ks], b0, b1);
+            }
+        }
+        float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int key = kb + nt * 8 + 2 * t + (e & 1);
+                if (key > cl + (e < 2 ? tq0 : tq1)) sc[nt][e] = -INFINITY;   // causal: prefix + own rows <= i
+            }
+            bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
+            bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
+        }
+        bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+        bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+        const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+        const float f0 = mn0 == -INFINITY ? 1.0f : expf(m0 - mn0), f1 = mn1 == -INFINITY ? 1.0f : expf(m1 - mn1);
+        const float sub0 = mn0 == -INFINITY ? 0.0f : mn0, sub1 = mn1 == -INFINITY ? 0.0f : mn1;
+        float rs0 = 0.0f, rs1 = 0.0f;
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            sc[nt][0] = expf(sc[nt][0] - sub0); sc[nt][1] = expf(sc[nt][1] - sub0);
+            sc[nt][2] = expf(sc[nt][2] - sub1); sc[nt][3] = expf(sc[nt][3] - sub1);
+            rs0 += sc[nt][0] + sc[nt][1];
+            rs1 += sc[nt][2] + sc[nt][3];
+            o[nt][0] *= f0; o[nt][1] *= f0; o[nt][2] *= f1; o[nt][3] *= f1;
+        }
+        l0 = l0 * f0 + rs0; l1 = l1 * f1 + rs1;
+        m0 = mn0; m1 = mn1;
+#pragma unroll
+        for (int ks = 0; ks < 4; ks++) {
+            uint32_t ph[4], pl[4];
+            split_h2(sc[2 * ks][0], sc[2 * ks][1], ph[0], pl[0]);
+            split_h2(sc[2 * ks][2], sc[2 * ks][3], ph[1], pl[1]);
+            split_h2(sc[2 * ks + 1][0], sc[2 * ks + 1][1], ph[2], pl[2]);
+            split_h2(sc[2 * ks + 1][2], sc[2 * ks + 1][3], ph[3], pl[3]);
+            const __half *v0 = sV + (ks * 16 + 2 * t) * FA_LD + g, *v1 = v0 + 8 * FA_LD;
+#pragma unroll
+            for (int nd = 0; nd < 8; nd++) {
+                const uint32_t b0 = (uint32_t)__half_as_ushort(v0[nd * 8]) | ((uint32_t)__half_as_ushort(v0[FA_LD + nd * 8]) << 16);
+                const uint32_t b1 = (uint32_t)__half_as_ushort(v1[nd * 8]) | ((uint32_t)__half_as_ushort(v1[FA_LD + nd * 8]) << 16);
+                mma_f16_16816(o[nd], ph, b0, b1);
+                mma_f16_16816(o[nd], pl, b0, b1);
+            }
+        }
+    }
+    if (!warp_live) return;
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0_ = 1.0f / l0, i1_ = 1.0f / l1;
+#pragma unroll
+    for (int nd = 0; nd < 8; nd++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int tq = e ? tq1 : tq0;
+            if (tq < nq) {
+                const float a = o[nd][2 * e] * (e ? i1_ : i0_), c = o[nd][2 * e + 1] * (e ? i1_ : i0_);
+                const size_t oi = (size_t)(r0 + tq) * FL_D + h * FL_HD + nd * 8 + 2 * t;
+                const uint16_t h0 = f2h16(a, true), h1 = f2h16(c, true);
+                *(uint32_t *)(p.out_h + oi) = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                const uint16_t l0_ = f2h16(a - h162f(h0, true), true), l1_ = f2h16(c - h162f(h1, true), true);
+                *(uint32_t *)(p.out_l + oi) = (uint32_t)l0_ | ((uint32_t)l1_ << 16);
+            }
+        }
+    }
+}
+
 // Final Conv1d 64 -> 1, k = 3 on ELU'd fp16 activations [B, T, 64] -> pcm [B, T] fp32
 // (ptts_mimi.c:723-726 with ptts_kernels.c:128-153). 256 samples per block; the 258 input rows are
 // staged once in shared memory (coalesced), then one thread per sample.
