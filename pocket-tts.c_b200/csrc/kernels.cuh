@@ -879,10 +879,25 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __half *k, const __half *v, int T,
                                                        __half *out /*[B*T, 512]*/) {
     pdl_wait(); pdl_trigger();
-    __shared__ __align__(16) __half sQ[64 * FA_LD], sK[64 * FA_LD], sV[64 * FA_LD];
+    __shared__ __align__(16) __half sQ[64 * FA_LD], sKb[2][64 * FA_LD], sVb[2][64 * FA_LD];   // K / V blocks double-buffered (cp.async)
     const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     const size_t base = ((size_t)b * MI_H + h) * T;
+    const int kb_start = max(0, q0 - (MI_CTX - 1)) & ~63;
+    // K / V block kb -> buffer `buf` with cp.async (rows past T are zero-filled); one commit group per block
+    auto stage = [&](int kb, int buf) {
+        const uint32_t ka = smem_u32(sKb[buf]), va = smem_u32(sVb[buf]);
+        for (int idx = tid; idx < 512; idx += 128) {
+            const int r = idx >> 3, c = (idx & 7) * 8;
+            const bool ok = kb + r < T;
+            const size_t so = ok ? (base + kb + r) * 64 + c : base * 64;
+            const uint32_t off = (uint32_t)((r * FA_LD + c) * 2), sz = ok ? 16u : 0u;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ka + off), "l"(k + so), "r"(sz) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(va + off), "l"(v + so), "r"(sz) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    stage(kb_start, 0);
     for (int idx = tid; idx < 512; idx += 128) {
         const int r = idx >> 3, c = (idx & 7) * 8;
         uint4 val = make_uint4(0, 0, 0, 0);
@@ -906,20 +921,13 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
     for (int i = 0; i < 8; i++) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f; }
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     const int tq0 = q0 + warp * 16 + g, tq1 = tq0 + 8;
-    const int kb_start = max(0, q0 - (MI_CTX - 1)) & ~63;
-    for (int kb = kb_start; kb <= q0 && kb < T; kb += 64) {
-        __syncthreads();   // all warps are done with the previous K/V block
-        for (int idx = tid; idx < 512; idx += 128) {
-            const int r = idx >> 3, c = (idx & 7) * 8;
-            uint4 kv = make_uint4(0, 0, 0, 0), vv = kv;
-            if (kb + r < T) {
-                kv = *(const uint4 *)(k + (base + kb + r) * 64 + c);
-                vv = *(const uint4 *)(v + (base + kb + r) * 64 + c);
-            }
-            *(uint4 *)(sK + r * FA_LD + c) = kv;
-            *(uint4 *)(sV + r * FA_LD + c) = vv;
-        }
+    int buf = 0;
+    for (int kb = kb_start; kb <= q0 && kb < T; kb += 64, buf ^= 1) {
+        const bool more = kb + 64 <= q0 && kb + 64 < T;
+        if (more) stage(kb + 64, buf ^ 1);          // the next block lands while this one is multiplied
+        if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
+        const __half *sK = sKb[buf], *sV = sVb[buf];
         float sc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
@@ -974,6 +982,7 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
                 mma_f16_16816(o[nd], pa, b0, b1);
             }
         }
+        __syncthreads();   // all warps are done with this buffer before the stage of the next iteration overwrites it
     }
     l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
