@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast", type=int, default=0, help="1: activations as single bf16 (precise=0); default hi+lo pairs")
     ap.add_argument("--skip-mimi-only", action="store_true", help="skip the configs[3] Mimi decode-only measurement")
+    ap.add_argument("--total-prompts", type=int, default=0,
+                    help="configs[4]: also push this many prompts (sharded over the ranks, batches of --batch) through the host-buffer API")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -246,6 +248,27 @@ def main():
         "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "realtime_factor_per_gpu": value / world,
     }
+
+    if args.total_prompts > 0:
+        # ---------------- configs[4]: a long prompt list sharded over the ranks, every batch through the host-buffer call
+        # (tokens and noise up, PCM down), different prompts in every batch; tokenisation is outside the timed region.
+        per_rank = args.total_prompts // world
+        nb = max(1, per_rank // B)
+        allp = pkg.synth.make_prompts(nb * B * world, seed=777)[rank * nb * B:(rank + 1) * nb * B]
+        alltok = tokenize_prompts(pkg, md, allp)
+        eng.generate_batch(alltok[:B], voice, F, seeds, None, params, True, audio)   # shapes of this prompt set
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for j in range(nb):
+            eng.generate_batch(alltok[j * B:(j + 1) * B], voice, F, seeds + j * B, None, params, True, audio)
+        eng.sync()
+        sweep_s = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        line["sweep"] = {"workload": f"throughput sweep: {nb * B * world} synthetic prompts x {F} frames sharded across {world} B200 (configs[4])",
+                         "prompts": nb * B * world, "batches_per_gpu": nb, "seconds": sweep_s,
+                         "audio_s_per_s": nb * B * world * F * FRAME_SEC / sweep_s,
+                         "note": "host token lists -> host PCM through ptts_b200 generate_batch, H2D / D2H inside"}
 
     if rank == 0:
         # ---------------- per-class profile of one step. The FlowLM decode loop is ONE launch (k_flow_mega, the
