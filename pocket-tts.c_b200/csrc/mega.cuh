@@ -67,6 +67,7 @@ struct MegaProgram {
     unsigned int *bar;              // grid barrier counter, zeroed by the host before the launch
     int *done_count;                // utterances that reached their stop point, zeroed by the host
     int n_live, nsteps, first_gemm;
+    int n_gemms;                    // contractions per frame (parity of the ring-state slots below)
     int flags;                      // bit 0: L2 prefetch of attention units, bit 1: light grid barrier (experiments)
     int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
                                     // (only when the loop cannot stop early, i.e. EOS detection is off)
@@ -840,7 +841,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    MegaPipe pipe = {0, 0u, 0, 0};
+    // Ring / accumulator state of the GEMM roles lives in shared memory between the contractions (two slots, alternating per
+    // contraction: a role writes the slot the NEXT contraction reads, so a late reader of this one never sees it), not in
+    // registers that would stay allocated - or be spilled - across every other phase: [slot][0..2] producer s, ph, pre;
+    // [4..6] MMA warp s, ph, lt; [8] epilogue lt
+    int *pst = (int *)(sbase + 128);
+    if (tid < 32) pst[tid] = 0;
+    __syncthreads();
     unsigned int epoch = 0;
     const int step0 = P.ctrl->step;
     const int grp = tid >> 8;                       // row group 0, 1
@@ -870,13 +877,15 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
     if (warp == 0 && lane == 0 && P.first_gemm >= 0) {
         const GemmOp &g0 = P.gemms[P.first_gemm];
         const uint32_t sb0 = mg_stage_bytes(g0);
-        for (int tile = blockIdx.x; tile < g0.p.total_tiles && pipe.pre < MG_STAGES; tile += gridDim.x) {
+        int pre = 0;
+        for (int tile = blockIdx.x; tile < g0.p.total_tiles && pre < MG_STAGES; tile += gridDim.x) {
             const TileCoord t = gemm_tile(g0.p, tile, g0.bn);
-            for (int it = t.it0; it < t.it1 && pipe.pre < MG_STAGES; it++, pipe.pre++) {
-                mbar_expect_tx(&full[pipe.pre], sb0);
-                tma_load_3d(ring + pipe.pre * MG_SLOT_BYTES + 2 * MG_A_BYTES, &g0.mapB, &full[pipe.pre], it * GEMM_BK, t.n0, 0);
+            for (int it = t.it0; it < t.it1 && pre < MG_STAGES; it++, pre++) {
+                mbar_expect_tx(&full[pre], sb0);
+                tma_load_3d(ring + pre * MG_SLOT_BYTES + 2 * MG_A_BYTES, &g0.mapB, &full[pre], it * GEMM_BK, t.n0, 0);
             }
         }
+        pst[(P.first_gemm & 1) * 16 + 2] = pre;   // read by the first contraction (parity of 0 * n_gemms + first_gemm)
     }
 
     for (int si = 0; si < P.nsteps; si++) {
@@ -890,7 +899,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                     // a fetch that wraps into the next frame must be consumed: never past the end of the launch
                     const bool wraps = ph.next_gemm >= 0 && ph.next_gemm <= ph.idx;
                     const GemmOp *nx = ph.next_gemm >= 0 && !(wraps && (!P.wrap_prefetch || si + 1 == P.nsteps)) ? &P.gemms[ph.next_gemm] : nullptr;
+                    const int par = (si * P.n_gemms + ph.idx) & 1;
+                    const int *rd = pst + par * 16;
+                    int *wr = pst + (par ^ 1) * 16;
+                    MegaPipe pipe = {0, 0u, 0, 0};
+                    if (warp == 0) { pipe.s = rd[0]; pipe.ph = (uint32_t)rd[1]; pipe.pre = rd[2]; }
+                    else if (warp == 1) { pipe.s = rd[4]; pipe.ph = (uint32_t)rd[5]; pipe.lt = rd[6]; }
+                    else pipe.lt = rd[8];
                     mega_gemm(P.gemms[ph.idx], nx, pipe, ring, full, empty, tfull, tempty, tmem_base);
+                    if (lane == 0) {
+                        if (warp == 0) { wr[0] = pipe.s; wr[1] = (int)pipe.ph; wr[2] = pipe.pre; }
+                        else if (warp == 1) { wr[4] = pipe.s; wr[5] = (int)pipe.ph; wr[6] = pipe.lt; }
+                        else if (warp == 2) wr[8] = pipe.lt;
+                    }
                     break;
                 }
                 case MP_ROW:
@@ -1099,7 +1120,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
     r.x = e->x; r.D = FL_D; r.w = e->L[0].n1w; r.b = e->L[0].n1b; r.eps = 1e-5f; r.do_norm = 1;
     r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
     P.ln0 = r;
-    P.first_gemm = first_gemm;
+    P.first_gemm = first_gemm; P.n_gemms = (int)gm.size();
     M.gen = e->gen; M.B = B; M.lsd = lsd; M.precise = precise;
     return 0;
 }
