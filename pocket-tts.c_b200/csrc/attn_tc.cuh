@@ -99,7 +99,7 @@ struct A5Pair {
 
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b); warp w takes the pairs
 // w, w + 16, ... of the CTA's range (one pair per warp for B <= 288 on 148 SMs).
-__device__ __noinline__ void attn5_phase(const AttnDecodeParams &p, int B, int pcap, int step, uint8_t *sm, int tid, unsigned long long *tmw, int flags) {
+__device__ __forceinline__ void attn5_phase(const AttnDecodeParams &p, int B, int pcap, int step, uint8_t *sm, int tid, unsigned long long *tmw, int flags) {
     uint8_t *kt = sm, *vt = kt + A4_TILE * 128, *scb = vt + A4_TILE * 128;
     const size_t wbytes = attn5_warp_bytes(pcap);
     const int w = tid >> 5, lane = tid & 31;

@@ -1,8 +1,8 @@
-# same-box A/B: bench with the tensor-core attention vs the scalar one, interleaved twice
+# same-box A/B: bench with the tensor-core attention (PTTS_B200_ATTN_TC=1) vs the scalar one, interleaved twice
 mkdir -p gpurun_out
 for i in 1 2; do
-  timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --skip-mimi-only > gpurun_out/bench_tc$i.json 2> gpurun_out/bench.err || tail -3 gpurun_out/bench.err
-  PTTS_B200_ATTN_SCALAR=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --skip-mimi-only > gpurun_out/bench_sc$i.json 2> gpurun_out/bench.err || tail -3 gpurun_out/bench.err
+  PTTS_B200_ATTN_TC=1 timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --skip-mimi-only > gpurun_out/bench_tc$i.json 2> gpurun_out/bench.err || tail -3 gpurun_out/bench.err
+  timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --skip-mimi-only > gpurun_out/bench_sc$i.json 2> gpurun_out/bench.err || tail -3 gpurun_out/bench.err
 done
 python - <<'PY'
 import json
