@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast", type=int, default=0, help="1: activations as single bf16 (precise=0); default hi+lo pairs")
     ap.add_argument("--skip-mimi-only", action="store_true", help="skip the configs[3] Mimi decode-only measurement")
+    ap.add_argument("--ragged", action="store_true",
+                    help="also time a batch whose frame counts are drawn from U[60, 140] (SURVEY.md 8d ragged variant)")
     ap.add_argument("--total-prompts", type=int, default=0,
                     help="configs[4]: also push this many prompts (sharded over the ranks, batches of --batch) through the host-buffer API")
     args = ap.parse_args()
@@ -248,6 +250,25 @@ def main():
         "e2e": {"value": e2e_val, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "realtime_factor_per_gpu": value / world,
     }
+
+    if args.ragged:
+        # ---------------- ragged variant: per-utterance frame counts U[60, 140]; the lock-step loop runs until the longest
+        # utterance is done (finished utterances keep their batch slot), audio seconds count the frames actually produced
+        rf = np.random.default_rng(99 + rank).integers(60, 141, size=B).astype(np.int32)
+        raudio = torch.empty((B, int(rf.max()) * 1920), dtype=torch.float32).pin_memory().numpy()
+        eng.stage(toks, voice, rf, seeds, None, params)
+        eng.run(True); eng.sync()
+        barrier()
+        eng.timer_start()
+        for _ in range(args.steps):
+            eng.run(True)
+        rms = max_over_ranks(eng.timer_stop()) / args.steps
+        out = eng.fetch(True, True, raudio)
+        assert (out["frames"] == rf).all()
+        line["ragged"] = {"workload": f"{B} prompts per GPU, frames ~ U[60, 140] (mean {float(rf.mean()):.1f}, max {int(rf.max())})",
+                          "ms_per_step": rms, "audio_s_per_s": world * float(rf.sum()) * FRAME_SEC / (rms / 1000.0),
+                          "note": "inputs resident in HBM; value counts produced frames only"}
+        eng.stage(toks, voice, F, seeds, None, params)   # restore the uniform batch for the profile section below
 
     if args.total_prompts > 0:
         # ---------------- configs[4]: a long prompt list sharded over the ranks, every batch through the host-buffer call
