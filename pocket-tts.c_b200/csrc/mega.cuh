@@ -484,17 +484,50 @@ __device__ __forceinline__ void attn4_pair(const AttnDecodeParams &p, int b0, in
     float *sq = scw + 2 * pcap;
     int n_own[2];
     __half *okb[2], *ovb[2];
-    // ---- new positions: RoPE(q), RoPE(k) and v appended to the own caches (lane = dimension pair)
+    // ---- new positions: RoPE(q), RoPE(k) and v appended to the own caches (lane = dimension pair). The partial sums and
+    // RoPE rows of BOTH units are requested before either is used (one global round trip per pair instead of two).
+    {
+        float2 rq[2][3][4];
+        float cs[2], sn[2];
+        int s_[2];
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-        const bool live = u < nlive;
-        const int b = live ? b0 + u : b0;
-        const int s = step + p.own_base[b], pos = cond_len + s;
-        n_own[u] = live ? s + 1 : 0;
-        okb[u] = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-        ovb[u] = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-        if (live) a4_new_row(p, b, h, s, pos, okb[u], ovb[u], sq + u * FL_HD, lane);
-        else *(float2 *)(sq + u * FL_HD + 2 * lane) = make_float2(0.0f, 0.0f);
+        for (int u = 0; u < 2; u++) {
+            const bool live = u < nlive;
+            const int b = live ? b0 + u : b0;
+            const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD + 2 * lane;
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+#pragma unroll
+                for (int z = 0; z < 4; z++)
+                    rq[u][c][z] = (z == 0 || z < p.qkv_nsplit) ? *(const float2 *)(row + c * FL_D + z * p.qkv_stride) : make_float2(0.0f, 0.0f);
+            s_[u] = step + p.own_base[b];
+            n_own[u] = live ? s_[u] + 1 : 0;
+            okb[u] = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
+            ovb[u] = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int pos = cond_len + s_[u];
+            cs[u] = p.rope_cos[pos * 32 + lane]; sn[u] = p.rope_sin[pos * 32 + lane];
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (u < nlive) {
+                float2 f[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    f[c] = make_float2((rq[u][c][0].x + rq[u][c][1].x) + (rq[u][c][2].x + rq[u][c][3].x),
+                                       (rq[u][c][0].y + rq[u][c][1].y) + (rq[u][c][2].y + rq[u][c][3].y));
+                    for (int z = 4; z < p.qkv_nsplit; z++) {   // more than four partial sums (not produced by the step kernel's QKV split)
+                        const float2 e = *(const float2 *)(p.qkv + (size_t)(b0 + u) * 3 * FL_D + h * FL_HD + 2 * lane + c * FL_D + z * p.qkv_stride);
+                        f[c].x += e.x; f[c].y += e.y;
+                    }
+                }
+                *(__half2 *)(okb[u] + (size_t)s_[u] * FL_HD + 2 * lane) = __floats2half2_rn(f[1].x * cs[u] - f[1].y * sn[u], f[1].x * sn[u] + f[1].y * cs[u]);
+                *(__half2 *)(ovb[u] + (size_t)s_[u] * FL_HD + 2 * lane) = __floats2half2_rn(f[2].x, f[2].y);
+                *(float2 *)(sq + u * FL_HD + 2 * lane) = make_float2((f[0].x * cs[u] - f[0].y * sn[u]) * 0.125f, (f[0].x * sn[u] + f[0].y * cs[u]) * 0.125f);
+            } else *(float2 *)(sq + u * FL_HD + 2 * lane) = make_float2(0.0f, 0.0f);
+        }
     }
     __syncwarp();
     A4_STAMP(0)
