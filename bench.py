@@ -144,7 +144,8 @@ def main():
     ap.add_argument("--ragged", action="store_true",
                     help="also time a batch whose frame counts are drawn from U[60, 140] (SURVEY.md 8d ragged variant)")
     ap.add_argument("--total-prompts", type=int, default=0,
-                    help="configs[4]: also push this many prompts (sharded over the ranks, batches of --batch) through the host-buffer API")
+                    help="configs[4]: also push this many prompts (sharded over the ranks, batches of --sweep-batch) through the host-buffer API")
+    ap.add_argument("--sweep-batch", type=int, default=512, help="utterances per call in the --total-prompts sweep (the engine takes up to 512)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -274,22 +275,29 @@ def main():
         # ---------------- configs[4]: a long prompt list sharded over the ranks, every batch through the host-buffer call
         # (tokens and noise up, PCM down), different prompts in every batch; tokenisation is outside the timed region.
         per_rank = args.total_prompts // world
-        nb = max(1, per_rank // B)
-        allp = pkg.synth.make_prompts(nb * B * world, seed=777)[rank * nb * B:(rank + 1) * nb * B]
+        SB = min(args.sweep_batch, per_rank)
+        nb = max(1, per_rank // SB)
+        allp = pkg.synth.make_prompts(nb * SB * world, seed=777)[rank * nb * SB:(rank + 1) * nb * SB]
         alltok = tokenize_prompts(pkg, md, allp)
-        eng.generate_batch(alltok[:B], voice, F, seeds, None, params, True, audio)   # shapes of this prompt set
+        sseeds = np.arange(SB, dtype=np.int64) + 9000 + rank * nb * SB
+        saudio = torch.empty((SB, F * 1920), dtype=torch.float32).pin_memory().numpy()
+        eng.generate_batch(alltok[:SB], voice, F, sseeds, None, params, True, saudio)   # shapes of this prompt set
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for j in range(nb):
-            eng.generate_batch(alltok[j * B:(j + 1) * B], voice, F, seeds + j * B, None, params, True, audio)
+            eng.generate_batch(alltok[j * SB:(j + 1) * SB], voice, F, sseeds + j * SB, None, params, True, saudio)
         eng.sync()
         sweep_s = max_over_ranks(time.perf_counter() - t0)
         barrier()
+        B_, B = B, SB   # (the summary below reports the sweep's batch size)
         line["sweep"] = {"workload": f"throughput sweep: {nb * B * world} synthetic prompts x {F} frames sharded across {world} B200 (configs[4])",
                          "prompts": nb * B * world, "batches_per_gpu": nb, "seconds": sweep_s,
                          "audio_s_per_s": nb * B * world * F * FRAME_SEC / sweep_s,
+                         "batch_per_call": SB,
                          "note": "host token lists -> host PCM through ptts_b200 generate_batch, H2D / D2H inside"}
+        B = B_
+        eng.stage(toks, voice, F, seeds, None, params)   # restore the staged configs[2] batch for the profile section below
 
     if rank == 0:
         # ---------------- per-class profile of one step. The FlowLM decode loop is ONE launch (k_flow_mega, the
