@@ -145,7 +145,7 @@ def main():
                     help="also time a batch whose frame counts are drawn from U[60, 140] (SURVEY.md 8d ragged variant)")
     ap.add_argument("--total-prompts", type=int, default=0,
                     help="configs[4]: also push this many prompts (sharded over the ranks, batches of --sweep-batch) through the host-buffer API")
-    ap.add_argument("--sweep-batch", type=int, default=512, help="utterances per call in the --total-prompts sweep (the engine takes up to 512)")
+    ap.add_argument("--sweep-batch", type=int, default=1024, help="utterances per call in the --total-prompts sweep (the engine takes up to 1024)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 

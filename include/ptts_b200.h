@@ -88,7 +88,7 @@ typedef struct {
  *   out_frames_used [n]
  *   out_audio [n, frames_cap*1920]   : PCM, zero beyond frames_used*1920 (optional, may be NULL)
  * frames_cap = max over max_frames[]. Host buffers; H2D/D2H copies happen inside the call.
- * n <= 512 per call (larger jobs are sharded by the caller: more calls, more engines, more GPUs); returns -1 otherwise. */
+ * n <= 1024 per call (larger jobs are sharded by the caller: more calls, more engines, more GPUs); returns -1 otherwise. */
 int ptts_b200_generate_batch(ptts_b200_engine *e, int n, const int *tokens_flat, const int *token_offsets,
                              const float *cond_prefix, int cond_len, const int *max_frames,
                              const int64_t *seeds, const int *eos_after, const ptts_b200_gen_params *params,

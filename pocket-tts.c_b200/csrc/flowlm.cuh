@@ -428,7 +428,7 @@ static int prefill_ensure(Engine *e, int rows, int n) {
     for (void **p : bufs) { e->dfree(*p); *p = nullptr; }
     const size_t r = (size_t)rows;
 #define DA(ptr, count) if (e->dalloc(&e->ptr, (count)) != 0) return -1
-    DA(d_row_b, r); DA(d_row_i, r); DA(d_row_start, 1024); DA(pf_x, r * FL_D); DA(pf_qkv, r * 3 * FL_D);
+    DA(d_row_b, r); DA(d_row_i, r); DA(d_row_start, 4096); DA(pf_x, r * FL_D); DA(pf_qkv, r * 3 * FL_D);
     DA(pf_xn_h, r * FL_D); DA(pf_xn_l, r * FL_D); DA(pf_att_h, r * FL_D); DA(pf_att_l, r * FL_D);
     DA(pf_ffh_h, r * FL_FF); DA(pf_ffh_l, r * FL_FF);
 #undef DA

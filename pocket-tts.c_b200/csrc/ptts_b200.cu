@@ -409,7 +409,7 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     const int steps = cap_f;                    // decode iterations (frames); prompts are prefilled in one pass
     const int own_rows = max_tok + 1 + cap_f;   // own-cache rows per utterance
     const int B = n == 1 ? 1 : (n + 15) / 16 * 16;
-    PTTS_CHECK(B <= 512, "batch_stage: at most 512 utterances per call (got %d); shard larger jobs on the host", n);
+    PTTS_CHECK(B <= 1024, "batch_stage: at most 1024 utterances per call (got %d); shard larger jobs on the host", n);
     if (flow_ensure_capacity(e, B, own_rows, max_tok, cap_f, std::max(cond_len, 1)) != 0) return -1;
     if (prefill_ensure(e, std::max(rows, cond_len), n) != 0) return -1;
     if (ensure_rope(e, cond_len + own_rows + 1) != 0) return -1;

@@ -192,8 +192,8 @@ def test_batched_tensor_core_attention_opt_in(pkg, weights, oracle, voice, golde
 
 
 def test_batch_of_512_spot_check(eng, pkg, oracle, voice, golden):
-    """The largest batch one call takes (four row tiles of 128, two attention pairs per warp): a few utterances against the
-    oracle, and the padded tail (n = 500 -> 512 slots) must not disturb them."""
+    """A batch beyond the bench size (four row tiles of 128, two attention pairs per warp): a few utterances against the
+    oracle, and the padded tail (n = 500 -> 512 slots) must not disturb them; more than 1024 utterances are refused."""
     base = [golden["p0_ids"], golden["p1_ids"], golden["p2_ids"], golden["p1_ids"][:9], golden["p2_ids"][2:17]]
     toks = [base[i % 5] for i in range(500)]
     seeds = [3000 + i for i in range(500)]
@@ -202,4 +202,4 @@ def test_batch_of_512_spot_check(eng, pkg, oracle, voice, golden):
         o = oracle.flowlm_generate(toks[i], voice, 3, lsd_steps=1, temp=0.7, seed=seeds[i])
         assert max_rel(out["latents"][i, :3], o["latents"]) < TOL, f"utterance {i}"
     with pytest.raises(pkg.EngineError):
-        eng.generate_batch(toks + toks[:20], voice, 2, seeds=1, params=pkg.default_params(temp=0.7), want_audio=False)
+        eng.generate_batch(toks + toks + toks[:40], voice, 2, seeds=1, params=pkg.default_params(temp=0.7), want_audio=False)
