@@ -203,3 +203,15 @@ def test_batch_of_512_spot_check(eng, pkg, oracle, voice, golden):
         assert max_rel(out["latents"][i, :3], o["latents"]) < TOL, f"utterance {i}"
     with pytest.raises(pkg.EngineError):
         eng.generate_batch(toks + toks + toks[:40], voice, 2, seeds=1, params=pkg.default_params(temp=0.7), want_audio=False)
+
+
+def test_batched_long_prompts_span_several_prefill_tiles(eng, pkg, oracle, voice, golden):
+    """Prompts of 70 and 141 tokens: the tensor-core prefill attention works on 64-row query tiles (two and three tiles here,
+    each appending its own rows to the cache), next to a short prompt in the same batch."""
+    long1 = np.concatenate([golden["p2_ids"]] * 3)[:70].astype(np.int32)
+    long2 = np.concatenate([golden["p0_ids"], golden["p1_ids"], golden["p2_ids"]] * 6)[:141].astype(np.int32)
+    toks = [long1, golden["p1_ids"], long2]
+    out = eng.generate_batch(toks, voice, 4, seeds=[41, 42, 43], params=pkg.default_params(temp=0.7), want_audio=False)
+    for i, t in enumerate(toks):
+        o = oracle.flowlm_generate(t, voice, 4, lsd_steps=1, temp=0.7, seed=41 + i)
+        assert max_rel(out["latents"][i, :4], o["latents"]) < TOL, f"utterance {i} ({len(t)} tokens)"
