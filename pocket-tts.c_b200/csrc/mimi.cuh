@@ -160,12 +160,13 @@ static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const 
     PTTS_CHECK(tiles < (1ll << 31), "resblock_launch: too many tiles");
     p.tiles_total = (int)tiles; p.a_rows = T; p.kb_per_tap = C2 / 64; p.chp = chp;
     const int stage = GEMM_BM * GEMM_BK * 2 + chp * 128, kb2 = chp / 64;
-    const int fixed = kb2 * C2 * 128 + kb2 * GEMM_BM * GEMM_BK * 2 + 256 + (192 + 2 * 768) * 4 + 1024;
+    const int fixed = kb2 * C2 * 128 + kb2 * GEMM_BM * GEMM_BK * 2 + (C2 == 64 ? 2048 : 0) + 256 + (192 + 2 * 768) * 4 + 1024;
     // C2 <= 128: two CTAs per SM (one's output epilogue overlaps the other's contractions) -> at most ~110 KB each
     p.stages = std::min(C2 <= 128 ? 3 : GEMM_MAX_STAGES, (227 * 1024 - fixed) / stage);
     PTTS_CHECK(p.stages >= 2, "resblock_launch: shared memory too small");
     p.idesc1 = umma_idesc_f16(GEMM_BM, chp, false, false);
     p.idesc2 = umma_idesc_f16(GEMM_BM, C2, false, false);
+    p.idesc3 = umma_idesc_f16(GEMM_BM, 16, false, false);
     p.b1 = c1.b; p.b2 = c2.b; p.u = (const uint16_t *)u; p.out = (uint16_t *)vv;
     p.prefetch_u = getenv("PTTS_B200_RB_NO_PREFETCH") == nullptr ? 1 : 0;   // measured: -4 % (64 ch) / -6 % (128 ch) per launch
     if (pcm) {   // last block: the final 64 -> 1 conv is applied in the epilogue, the block's output tensor is never written

@@ -10,7 +10,10 @@
 //               padding) and the matching W1 slices through a shared-memory ring
 //   warp 1    : MMA issuer   - contraction 1 into TMEM D1, then (once the epilogue has staged the middle
 //               tensor) contraction 2 into TMEM D2
-//   warps 2-5 : epilogue     - D1 -> +b1 -> ELU -> fp16 -> shared memory;  D2 -> +b2 +u -> ELU -> fp16 -> HBM
+//   warps 2-9 : epilogue     - D1 -> +b1 -> ELU -> fp16 -> shared memory;  D2 -> +b2 +u -> ELU -> fp16 -> HBM
+// The last block (64 channels) also applies the decoder's final Conv1d 64 -> 1 (k = 3) as a THIRD contraction: its output tile
+// goes back into the `mid` operand buffer, D3[128, 16] = out . W3^T (rows of W3 = the three taps as fp16 hi + lo), and the
+// epilogue only combines three numbers per row with the two rows before it.
 // Persistent over 128-row tiles; contraction 1 of tile i+1 overlaps the output epilogue of tile i.
 #pragma once
 #include "gemm_tc.cuh"
@@ -26,7 +29,7 @@ struct ResParams {
     int chp;                 // middle channels, padded to a multiple of 64
     int stages;
     int prefetch_u;          // 1: L2 prefetch of each tile's residual rows by the producer (A/B switch)
-    uint32_t idesc1, idesc2;
+    uint32_t idesc1, idesc2, idesc3;   // idesc3: the fused final conv (N = 16)
     const float *b1, *b2;    // [chp] (zero padded), [C2]
     const uint16_t *u;       // residual stream, fp16 [rows][C2]
     uint16_t *out;           // fp16 [rows][C2] (NULL when the final conv is fused)
@@ -45,7 +48,8 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const __grid_constant__ CUtensorMap mapW2, const ResParams p) {
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;                 // 16 KB
     constexpr uint32_t D2_COL = C2 == 64 ? 64 : 128;
-    constexpr uint32_t TMEM_COLS = C2 == 64 ? 128 : (C2 == 128 ? 256 : 512);
+    constexpr uint32_t TMEM_COLS = C2 == 64 ? 256 : (C2 == 128 ? 256 : 512);   // C2 == 64: D1 at 0, D2 at 64, D3 (fused final conv, 16 columns) at 128
+    constexpr uint32_t D3_COL = 128;
     extern __shared__ uint8_t rb_smem_raw[];
     uint8_t *smem = rb_smem_raw + ((1024u - (smem_u32(rb_smem_raw) & 1023u)) & 1023u);
     const int chp = p.chp, kb2 = chp / 64;
@@ -53,20 +57,36 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint8_t *ring = smem;
     uint8_t *w2s = ring + p.stages * stage_bytes;                 // [kb2][C2 rows][128 B]
     uint8_t *a2s = w2s + kb2 * C2 * 128;                           // [kb2][128 rows][128 B]
-    uint64_t *bars = (uint64_t *)(a2s + kb2 * A_BYTES);
+    uint8_t *w3s = a2s + kb2 * A_BYTES;                            // [16 rows][128 B]: taps of the fused final conv as a B operand (C2 == 64)
+    uint64_t *bars = (uint64_t *)(w3s + (C2 == 64 ? 2048 : 0));   // the wider blocks sit at the two-CTAs-per-SM limit: no room, no fused conv
     uint64_t *full = bars, *empty = bars + GEMM_MAX_STAGES;
     uint64_t *w2_full = bars + 2 * GEMM_MAX_STAGES, *d1_full = w2_full + 1, *a2_full = w2_full + 2, *d2_full = w2_full + 3,
-             *d2_empty = w2_full + 4;
-    uint32_t *tmem_slot = (uint32_t *)(w2_full + 5);
-    float *dws = (float *)(bars + 32);            // [3][64] final-conv weights
-    float *dpart = dws + 192;                     // [2 buffers][2 column halves][128 rows][3]
+             *d2_empty = w2_full + 4, *a3_full = w2_full + 5, *d3_full = w2_full + 6;
+    uint32_t *tmem_slot = (uint32_t *)(w2_full + 7);
+    float *dpart = (float *)(bars + 32);          // [2 buffers][128 rows][3]: per-row tap sums of the fused final conv
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (C2 == 64 && p.dw && threadIdx.x < 192) dws[(threadIdx.x % 3) * 64 + threadIdx.x / 3] = p.dw[threadIdx.x];
+    const bool fuse_out = C2 == 64 && p.dw != nullptr;
+    if (fuse_out) {
+        // W3[n][c]: rows 0..2 = fp16(w[c][tap n]), rows 3..5 = the rounding remainders (their products are added in the epilogue),
+        // rows 6..15 zero; K-major, 128B swizzle like every other B operand
+        for (int idx = threadIdx.x; idx < 16 * 64; idx += RB_THREADS) {
+            const int k = idx >> 6, c = idx & 63;
+            float w = 0.0f;
+            if (k < 6) {
+                const float wf = p.dw[c * 3 + (k % 3)];
+                const float hi = __half2float(__float2half_rn(wf));
+                w = k < 3 ? hi : wf - hi;
+            }
+            *(__half *)(w3s + k * 128 + ((((c >> 3) ^ (k & 7))) << 4) + (c & 7) * 2) = __float2half_rn(w);
+        }
+        fence_proxy_async();
+    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(w2_full, 1); mbar_init(d1_full, 1); mbar_init(a2_full, RB_EPI_WARPS); mbar_init(d2_full, 1); mbar_init(d2_empty, RB_EPI_WARPS);
+        mbar_init(a3_full, RB_EPI_WARPS); mbar_init(d3_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
@@ -120,6 +140,19 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1; }
             }
+            // contraction 3 of the PREVIOUS tile (fused final conv): D3[128, 16] = out[128, 64] . W3^T, once its output epilogue has
+            // written the tile into the operand buffer; issued here so that contraction 1 of this tile is already running
+            if (fuse_out && lt > 0) {
+                mbar_wait(a3_full, (lt - 1) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t ad = umma_desc_sw128(smem_u32(a2s)), bd = umma_desc_sw128(smem_u32(w3s));
+#pragma unroll
+                    for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base + D3_COL, ad + 2 * k, bd + 2 * k, p.idesc3, k > 0 ? 1u : 0u);
+                    umma_commit(d3_full);
+                }
+                __syncwarp();
+            }
             // contraction 2: D2[128, C2] = mid[128, chp] . W2^T, once the epilogue has staged `mid` and drained the previous D2
             mbar_wait(a2_full, lt & 1);
             mbar_wait(d2_empty, (lt & 1) ^ 1);
@@ -131,6 +164,17 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base + D2_COL, ad + 2 * k, bd + 2 * k, p.idesc2, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(d2_full);
+            }
+            __syncwarp();
+        }
+        if (fuse_out && lt > 0) {   // contraction 3 of the last tile
+            mbar_wait(a3_full, (lt - 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t ad = umma_desc_sw128(smem_u32(a2s)), bd = umma_desc_sw128(smem_u32(w3s));
+#pragma unroll
+                for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base + D3_COL, ad + 2 * k, bd + 2 * k, p.idesc3, k > 0 ? 1u : 0u);
+                umma_commit(d3_full);
             }
             __syncwarp();
         }
@@ -186,7 +230,6 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 const size_t grow = (size_t)batch * p.a_rows + m;
                 const uint16_t *up = p.u + grow * C2;
                 uint16_t *op = p.out ? p.out + grow * C2 : nullptr;
-                float dsum[3] = {0.0f, 0.0f, 0.0f};
                 uint32_t rr[16], rn[16];
                 tmem_ld16(trow + D2_COL + c2_lo, rr); tmem_ld_wait16(rr);
 #pragma unroll 1
@@ -212,14 +255,18 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         uint32_t hw[8], lw[8];
                         act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
                         if (op) st_global_v8(op + c, hw);
-                        if (C2 == 64 && p.dw) {   // final conv on the fp16-rounded block output (what the unfused path reads back)
-#pragma unroll
-                            for (int j = 0; j < 8; j++) {
-                                const float2 f = __half22float2(*(const __half2 *)&hw[j]);
-#pragma unroll
-                                for (int k = 0; k < 3; k++) dsum[k] += f.x * dws[k * 64 + c + 2 * j] + f.y * dws[k * 64 + c + 2 * j + 1];
-                            }
+                        if (fuse_out) {   // final conv on the fp16-rounded block output (what the unfused path reads back): the tile goes
+                                          // back into the operand buffer (contraction 2 is done with it) as the A operand of contraction 3
+                            uint8_t *row = a2s + r * 128;
+                            const int pc = c >> 3;
+                            *(uint4 *)(row + ((pc ^ (r & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                            *(uint4 *)(row + (((pc + 1) ^ (r & 7)) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
                         }
+                    } else if (fuse_out) {   // rows past the end of the utterance: finite operand rows
+                        uint8_t *row = a2s + r * 128;
+                        const int pc = c >> 3;
+                        *(uint4 *)(row + ((pc ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+                        *(uint4 *)(row + (((pc + 1) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                     }
                     if (more) {
                         tmem_ld_wait16(rn);
@@ -227,13 +274,22 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         for (int j = 0; j < 16; j++) rr[j] = rn[j];
                     }
                 }
-                if (C2 == 64 && p.dw) {
-                    float *pb = dpart + (lt & 1) * 768;               // double-buffered: one barrier per tile is enough
-                    float *mine = pb + (cg * 128 + r) * 3;
-                    mine[0] = dsum[0]; mine[1] = dsum[1]; mine[2] = dsum[2];
-                    asm volatile("bar.sync 1, 256;" ::: "memory");    // the 8 epilogue warps
+                if (fuse_out) {
+                    fence_proxy_async();          // generic-proxy writes of the output tile -> visible to the tensor core
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(d2_empty); mbar_arrive(a3_full); }   // D2 is drained; the tile is staged
+                    mbar_wait(d3_full, lt & 1);   // every epilogue warp: the operand buffer is free again after this
+                    tc_fence_after();
                     if (cg == 0) {
-                        auto D = [&](int row, int k) { return pb[row * 3 + k] + pb[(128 + row) * 3 + k]; };
+                        uint32_t y3[16];
+                        tmem_ld16(trow + D3_COL, y3); tmem_ld_wait16(y3);
+                        float *pb = dpart + (lt & 1) * 384;               // double-buffered: one barrier per tile is enough
+                        pb[r * 3 + 0] = __uint_as_float(y3[0]) + __uint_as_float(y3[3]);
+                        pb[r * 3 + 1] = __uint_as_float(y3[1]) + __uint_as_float(y3[4]);
+                        pb[r * 3 + 2] = __uint_as_float(y3[2]) + __uint_as_float(y3[5]);
+                        asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 warps that hold the 128 rows
+                        auto D = [&](int row, int k) { return pb[row * 3 + k]; };
                         float y = p.dbias + D(r, 2);
                         if (r >= 1) y += D(r - 1, 1);
                         if (r >= 2) y += D(r - 2, 0);
@@ -244,7 +300,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(d2_empty);
+            if (lane == 0 && !fuse_out) mbar_arrive(d2_empty);
         }
     }
     tc_fence_before();
