@@ -164,7 +164,7 @@ static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const 
     // C2 <= 128: two CTAs per SM (one's output epilogue overlaps the other's contractions) -> at most ~110 KB each
     p.stages = std::min(C2 <= 128 ? 3 : GEMM_MAX_STAGES, (227 * 1024 - fixed) / stage);
     PTTS_CHECK(p.stages >= 2, "resblock_launch: shared memory too small");
-    p.idesc1 = umma_idesc_f16(GEMM_BM, chp, false, false);
+    p.idesc1 = umma_idesc_f16(GEMM_BM, std::min(chp, C2 / 2), false, false);   // N = the real middle channels (32 for the 64-channel block)
     p.idesc2 = umma_idesc_f16(GEMM_BM, C2, false, false);
     p.idesc3 = umma_idesc_f16(GEMM_BM, 16, false, false);
     p.b1 = c1.b; p.b2 = c2.b; p.u = (const uint16_t *)u; p.out = (uint16_t *)vv;

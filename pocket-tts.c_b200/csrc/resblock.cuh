@@ -160,8 +160,9 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             if (lane == 0) {
                 for (int kb = 0; kb < kb2; kb++) {
                     const uint64_t ad = umma_desc_sw128(smem_u32(a2s + kb * A_BYTES)), bd = umma_desc_sw128(smem_u32(w2s + kb * C2 * 128));
+                    constexpr int KS = (C2 / 2 < GEMM_BK ? C2 / 2 : GEMM_BK) / 16;   // 64-channel block: 32 real middle channels = 2 k-steps
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base + D2_COL, ad + 2 * k, bd + 2 * k, p.idesc2, (kb > 0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < KS; k++) umma_f16(tmem_base + D2_COL, ad + 2 * k, bd + 2 * k, p.idesc2, (kb > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(d2_full);
             }
@@ -180,7 +181,10 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         }
     } else {
         const int quad = warp & 3, cg = (warp - 2) >> 2;   // column half
-        const int c1_lo = cg * (chp / 2), c1_hi = c1_lo + chp / 2, c2_lo = cg * (C2 / 2), c2_hi = c2_lo + C2 / 2;
+        // the middle tensor has C2 / 2 real channels (chp pads them to a multiple of 64 for the operand layout only): contraction 1
+        // produces, epilogue 1 converts and contraction 2 reads just those
+        constexpr int CH = C2 / 2;
+        const int c1_lo = cg * (CH / 2), c1_hi = c1_lo + CH / 2, c2_lo = cg * (C2 / 2), c2_hi = c2_lo + C2 / 2;
         pdl_wait();
         int lt = 0;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, lt++) {
