@@ -42,6 +42,39 @@ VOICE_FRAMES = 125
 WORKLOAD = "batched generation: 256 synthetic ~100-char prompts x 100 frames per GPU, voice alba (configs[2])"
 
 
+def src_sha16() -> str:
+    """Identity of the kernel sources the loaded library was built from (stamped into profiles/*traffic*.json by
+    tools/ncu_traffic.py): an ncu capture of another build is refused instead of silently going stale."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / "pocket-tts.c_b200" / "csrc").glob("*.cu*")):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+# SURVEY.md section 8(d): parameters streamed once per FlowLM frame step at lsd_steps = 1, as bf16
+FLOW_PARAMS_PER_STEP = 75_522_048 + 35_841 + (9_759_008 - 789_760)     # transformer + head/misc + flow net without the constant time embedding
+MIMI_GEMM_FLOP_PER_FRAME = (201.3 + 323.8) * 1e6                        # transformer linears + SEANet / projections (window attention 16.4 M is separate)
+
+
+def flow_step_kernel_work(tok_lens, frames, cond_len):
+    """Algorithmic bytes / FLOPs of ONE launch of the persistent step kernel (all `frames` frame steps of the batch), section
+    8(d) terms only: weights once per step (bf16), every utterance's own K/V rows read once per step (fp16 cache: e = 2), the
+    new K/V row written, the shared voice-prefix K/V (fp32) read once per step. Split-K partial sums, activations and anything
+    else the implementation moves are NOT algorithmic and are not counted."""
+    B = len(tok_lens)
+    own0 = np.asarray(tok_lens, np.float64) + 1.0            # rows the prompt prefill left in each own cache
+    s = np.arange(frames, dtype=np.float64)
+    rows = (own0[:, None] + s[None, :] + 1.0).sum()          # keys each utterance attends to in its own cache, summed over steps
+    w = FLOW_PARAMS_PER_STEP * 2.0 * frames
+    kv_read = 2.0 * rows * 1024 * 6 * 2.0
+    kv_write = 2.0 * 1024 * 6 * 2.0 * B * frames
+    prefix = 2.0 * cond_len * 1024 * 6 * 4.0 * frames
+    flops = 2.0 * FLOW_PARAMS_PER_STEP * B * frames + 4.0 * 1024 * 6 * (rows + cond_len * B * frames)
+    return dict(bytes=w + kv_read + kv_write + prefix, flops=flops, weights=w, kv_read=kv_read, kv_write=kv_write, prefix=prefix)
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -143,8 +176,9 @@ def main():
     ap.add_argument("--skip-mimi-only", action="store_true", help="skip the configs[3] Mimi decode-only measurement")
     ap.add_argument("--ragged", action="store_true",
                     help="also time a batch whose frame counts are drawn from U[60, 140] (SURVEY.md 8d ragged variant)")
-    ap.add_argument("--total-prompts", type=int, default=0,
-                    help="configs[4]: also push this many prompts (sharded over the ranks, batches of --sweep-batch) through the host-buffer API")
+    ap.add_argument("--total-prompts", type=int, default=8192,
+                    help="configs[4]: a FIXED list of this many prompts (sharded over the ranks, calls of --sweep-batch utterances) through the "
+                         "host-buffer API, so that the line carries a strong-scaling point at every N (0 disables)")
     ap.add_argument("--sweep-batch", type=int, default=1024, help="utterances per call in the --total-prompts sweep (the engine takes up to 1024)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -314,44 +348,56 @@ def main():
         line["kernel_classes"] = {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                       "TFLOPs": round(v["flops"] / max(v["ms"], 1e-9) / 1e9, 2),
                                       "GBps": round(v["bytes"] / max(v["ms"], 1e-9) / 1e6, 1)} for k, v in prof.items() if v["launches"]}
-        # dominant kernel = the persistent FlowLM step kernel (one launch per step): time it alone, device events
+        # dominant kernel = the persistent FlowLM step kernel (ONE launch per step). Timed alone: CUDA events recorded on the engine
+        # stream immediately around that launch (ptts_b200_step_kernel_ms: prompt prefill and Mimi excluded), averaged over 3 runs.
         eng.stage(toks, voice, F, seeds, None, params)
         eng.run(False); eng.sync()
-        eng.timer_start()
+        mk = []
         for _ in range(3):
-            eng.run(False)            # prompt prefill (24 small GEMMs + 6 attention launches) + k_flow_mega
-        ms_flow = eng.timer_stop() / 3
-        flow_cls = ("gemm_tc_flowlm", "attn_decode", "rownorm", "flow_misc")
-        flow_bytes = sum(prof[k]["bytes"] for k in flow_cls if k in prof)      # weights once per frame step + K/V rows once per step
-        flow_flops = sum(prof[k]["flops"] for k in flow_cls if k in prof)
-        mem_frac = flow_bytes / (ms_flow / 1e3) / 1e9 / pk["hbm"]
-        flop_frac = flow_flops / (ms_flow / 1e3) / 1e12 / pk["tf_sust"]
-        traffic = None
-        tr = ROOT / "profiles" / "r01_flow_mega_traffic.json"     # dram__bytes_read+write of one k_flow_mega launch (ncu --set full)
-        if tr.exists():
+            eng.run(False)
+            ms_k, steps_k = eng.step_kernel_ms()
+            assert steps_k == F
+            mk.append(ms_k)
+        ms_flow = sum(mk) / len(mk)
+        work = flow_step_kernel_work([len(t) for t in toks], F, int(voice.shape[0]))
+        mem_frac = work["bytes"] / (ms_flow / 1e3) / 1e9 / pk["hbm"]
+        flop_frac = work["flops"] / (ms_flow / 1e3) / 1e12 / pk["tf_sust"]
+        traffic, traffic_note = None, "no ncu --set full capture committed for this build"
+        sha = src_sha16()
+        for tr in sorted((ROOT / "profiles").glob("r*_flow_mega_traffic.json"), reverse=True):
             try:
-                traffic = json.loads(tr.read_text()).get("dram_bytes_per_launch")
+                tj = json.loads(tr.read_text())
             except Exception:
-                traffic = None
-        roof = {"bound": "hbm" if mem_frac >= flop_frac else "tensor",
-                "achieved": flow_bytes / (ms_flow / 1e3) / 1e9 if mem_frac >= flop_frac else flow_flops / (ms_flow / 1e3) / 1e12,
-                "peak": pk["hbm"] if mem_frac >= flop_frac else pk["tf_sust"], "unit": "GB/s" if mem_frac >= flop_frac else "TFLOP/s",
-                "frac": max(mem_frac, flop_frac), "kernel": "k_flow_mega (persistent FlowLM step kernel, incl. the prompt prefill launches before it)",
-                "launches_per_step": 1, "avg_launch_us": 1000.0 * ms_flow, "peak_source": pk["src"], "traffic": traffic,
-                "share_of_step": round(ms_flow / ms_per_step, 4), "tensor_frac": flop_frac, "hbm_frac": mem_frac,
-                "algorithmic_bytes_per_launch": flow_bytes, "algorithmic_flops_per_launch": flow_flops,
-                "timing": "CUDA events on the engine stream around 3 FlowLM-only runs of the staged batch (inputs resident in HBM)"}
+                continue
+            if tj.get("src_sha16") == sha:
+                traffic, traffic_note = tj.get("dram_bytes_per_launch"), f"{tr.name} (ncu --set full, same kernel sources {sha})"
+                break
+            traffic_note = f"{tr.name} is from other kernel sources ({tj.get('src_sha16')} != {sha}): refused as stale"
+        roof = {"bound": "hbm", "achieved": work["bytes"] / (ms_flow / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s", "frac": mem_frac,
+                "kernel": "k_flow_mega (persistent FlowLM step kernel: all frame steps of the batch in one launch)",
+                "launches_per_step": 1, "avg_launch_us": 1000.0 * ms_flow, "us_per_frame_step": 1000.0 * ms_flow / F,
+                "peak_source": pk["src"] + " (sustained: the kernel runs for tens of ms)", "traffic": traffic, "traffic_source": traffic_note,
+                "share_of_step": round(ms_flow / ms_per_step, 4), "tensor_frac": flop_frac,
+                "algorithmic_bytes_per_launch": work["bytes"], "algorithmic_flops_per_launch": work["flops"],
+                "algorithmic_bytes_terms": {k: work[k] for k in ("weights", "kv_read", "kv_write", "prefix")},
+                "timing": "CUDA events on the engine stream around the k_flow_mega launch only, mean of 3 launches"}
         line["roofline"] = roof
-        # second kernel of the step: the Mimi tcgen05 implicit-GEMM kernel (all its launches of one step)
+        # second kernel family of the step: the Mimi tcgen05 kernels (implicit-GEMM convolutions, linears, fused residual blocks)
         if "gemm_tc_mimi" in prof and prof["gemm_tc_mimi"]["launches"]:
             m = prof["gemm_tc_mimi"]
-            line["roofline_mimi_gemm"] = {"bound": "tensor", "achieved": m["flops"] / (m["ms"] / 1e3) / 1e12, "peak": pk["tf_sust"],
-                                          "unit": "TFLOP/s", "frac": m["flops"] / (m["ms"] / 1e3) / 1e12 / pk["tf_sust"],
-                                          "hbm_frac": m["bytes"] / (m["ms"] / 1e3) / 1e9 / pk["hbm"], "launches_per_step": m["launches"],
-                                          "avg_launch_us": 1000.0 * m["ms"] / m["launches"], "share_of_step": shares.get("gemm_tc_mimi")}
+            mflop = MIMI_GEMM_FLOP_PER_FRAME * B * F
+            line["roofline_mimi_gemm"] = {"bound": "tensor", "achieved": mflop / (m["ms"] / 1e3) / 1e12, "peak": pk["tf_sust"],
+                                          "unit": "TFLOP/s", "frac": mflop / (m["ms"] / 1e3) / 1e12 / pk["tf_sust"], "traffic": None,
+                                          "kernel": "gemm_tc_kernel + resblock_kernel (all Mimi tcgen05 launches of one step)",
+                                          "algorithmic_flops_per_step": mflop, "issued_flops_per_step": m["flops"],
+                                          "launches_per_step": m["launches"], "ms_per_step": m["ms"],
+                                          "avg_launch_us": 1000.0 * m["ms"] / m["launches"], "share_of_step": shares.get("gemm_tc_mimi"),
+                                          "timing": "CUDA events around every launch of the class (profile mode, one step)"}
 
-        # ---------------- configs[3]: Mimi decode-only, 64 x 4096 latent frames -> 24 kHz PCM (device-resident timing is not
-        # exposed for this entry: host latents in, host PCM out, copies inside the timed call)
+        # ---------------- configs[3]: Mimi decode-only, 64 x 4096 latent frames -> 24 kHz PCM. Two numbers: host latents -> host PCM
+        # through ptts_b200_mimi_decode_batch (H2D + 2 GB of D2H inside), and the device-resident decode (latents staged, PCM left in
+        # HBM) timed with CUDA events. The whole output is checked for finiteness; tests/test_gpu_measured_configs.py checks slices
+        # of 4096-frame items against the oracle.
         if not args.skip_mimi_only:
             lat = np.random.default_rng(0).standard_normal((64, 4096, 32)).astype(np.float32)
             pcm = torch.empty((64, 4096 * 1920), dtype=torch.float32).pin_memory().numpy()
@@ -359,8 +405,20 @@ def main():
             t0 = time.perf_counter()
             eng.mimi_decode_batch(lat, pcm)
             dt = time.perf_counter() - t0
+            finite = bool(np.isfinite(pcm).all()) and float(np.abs(pcm).max()) > 0.0
+            assert finite, "configs[3]: non-finite or all-zero PCM"
+            eng.mimi_stage(lat)
+            eng.mimi_run(); eng.sync()
+            eng.timer_start()
+            eng.mimi_run()
+            dms = eng.timer_stop()
+            mflop4 = (MIMI_GEMM_FLOP_PER_FRAME + 16.4e6) * 64 * 4096
             line["mimi_decode_only"] = {"workload": "64 x 4096 latent frames (configs[3])", "seconds": dt, "audio_s_per_s": 64 * 4096 * FRAME_SEC / dt,
-                                        "note": "host latents -> host PCM through ptts_b200_mimi_decode_batch (H2D + 2 GB D2H inside)"}
+                                        "device_resident_seconds": dms / 1e3, "device_resident_audio_s_per_s": 64 * 4096 * FRAME_SEC / (dms / 1e3),
+                                        "roofline": {"bound": "tensor", "achieved": mflop4 / (dms / 1e3) / 1e12, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                                                     "frac": mflop4 / (dms / 1e3) / 1e12 / pk["tf_sust"], "traffic": None},
+                                        "output_finite": finite,
+                                        "note": "seconds: host latents -> host PCM (H2D + 2 GB D2H inside); device_resident: ptts_b200_mimi_run between CUDA events"}
             del lat, pcm
 
         # ---------------- batch-1 streaming decode (configs[1]) and first-audio latency
@@ -387,7 +445,10 @@ def main():
         steps1 = 200   # decode iterations; the prompt is prefilled in one batched pass
         line["batch1"] = {"first_audio_ms": statistics.median(lat), "first_audio_stream_api_ms": statistics.median(lat_stream), "first_audio_note": "tokens on host -> first 1920 PCM samples on host, voice prefix KV cached",
                           "decode_200_frames_ms": ms1, "us_per_step": 1000 * ms1 / steps1,
-                          "audio_s_per_s": 200 * FRAME_SEC / (ms1 / 1000), "hbm_frac": 170.6e6 / (ms1 / steps1 / 1000) / 1e9 / pk["hbm"]}
+                          "audio_s_per_s": 200 * FRAME_SEC / (ms1 / 1000),
+                          "roofline": {"bound": "hbm", "achieved": FLOW_PARAMS_PER_STEP * 2.0 / (ms1 / steps1 / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                       "frac": FLOW_PARAMS_PER_STEP * 2.0 / (ms1 / steps1 / 1e3) / 1e9 / pk["hbm"], "traffic": None,
+                                       "kernel": "one CUDA graph of GEMV / attention kernels per frame step (weights streamed once per step)"}}
 
         # ---------------- CPU baseline: the compiled reference on the host cores, bounded sample
         if world == 1 and not args.no_cpu_baseline:

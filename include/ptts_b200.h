@@ -63,11 +63,23 @@ int ptts_b200_flowlm_scale_latents(ptts_b200_engine *e, const float *in_latents,
  * latents [frames,32] (already scaled) -> out_audio [frames*1920], *out_len = frames*1920. */
 int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, int frames, float *out_audio, int *out_len);
 
+/* ---- drop-in for ptts_mimi_forward_one (ptts_mimi.h:20, ptts_mimi.c:550-564), the parity hook behind the reference CLI's
+ * --mimi-test (main.c:444): quantizer projection of one scaled latent[32] + the decoder transformer over that single token
+ * -> out_embed[512]. */
+int ptts_b200_mimi_forward_one(ptts_b200_engine *e, const float *latent, float *out_embed);
+
 /* ---- additive batched entries (the reference is single-utterance, ptts.h:75-76). */
 
 /* Mimi decode of n equal-length latent sequences: latents [n, frames, 32] (scaled) ->
  * out_audio [n, frames*1920]. */
 int ptts_b200_mimi_decode_batch(ptts_b200_engine *e, const float *latents, int n, int frames, float *out_audio);
+
+/* The same decode split in three, so that the middle part can be timed with the latents already resident in HBM and the PCM
+ * left there (configs[3] device-resident timing): stage (H2D), run (kernels only, asynchronous on the engine stream),
+ * fetch (D2H of [n, frames*1920]). mimi_decode_batch == stage + run (PCM chunks overlapped with the decode) + wait. */
+int ptts_b200_mimi_stage(ptts_b200_engine *e, const float *latents, int n, int frames);
+int ptts_b200_mimi_run(ptts_b200_engine *e);
+int ptts_b200_mimi_fetch(ptts_b200_engine *e, float *out_audio);
 
 typedef struct {
     int lsd_steps;        /* ptts_params.num_steps (ptts.h:29) */
@@ -118,6 +130,10 @@ int ptts_b200_stream_next(ptts_b200_engine *e, int want_frames, float *out_pcm, 
 int ptts_b200_sync(ptts_b200_engine *e);
 int ptts_b200_timer_start(ptts_b200_engine *e);
 int ptts_b200_timer_stop(ptts_b200_engine *e, float *out_ms);      /* syncs, returns elapsed ms */
+/* Duration of the most recent launch of the persistent FlowLM step kernel (k_flow_mega: all frames of the last batched run),
+ * CUDA events recorded on the engine stream immediately around that one launch (prompt prefill and Mimi excluded), and the
+ * number of frame steps it executed. Waits for the launch to finish. -1 if no batched run has happened yet. */
+int ptts_b200_step_kernel_ms(ptts_b200_engine *e, float *out_ms, int *out_steps);
 /* Per-kernel-class profiling: when enabled, launches bypass CUDA graphs and each launch is
  * bracketed by events. classes: see ptts_b200_profile_class_name. */
 int ptts_b200_profile_enable(ptts_b200_engine *e, int on);

@@ -43,7 +43,8 @@ EXPORTS = [
     "ptts_b200_generate_batch", "ptts_b200_batch_stage", "ptts_b200_batch_run", "ptts_b200_batch_fetch",
     "ptts_b200_sync", "ptts_b200_timer_start", "ptts_b200_timer_stop", "ptts_b200_profile_enable",
     "ptts_b200_profile_read", "ptts_b200_profile_work", "ptts_b200_profile_class_name", "ptts_b200_launch_count", "ptts_b200_test_gemm",
-    "ptts_b200_stream_begin", "ptts_b200_stream_next",
+    "ptts_b200_stream_begin", "ptts_b200_stream_next", "ptts_b200_mimi_forward_one", "ptts_b200_mimi_stage",
+    "ptts_b200_mimi_run", "ptts_b200_mimi_fetch", "ptts_b200_step_kernel_ms",
 ]
 
 
@@ -81,6 +82,11 @@ def load_library():
     L.ptts_b200_test_gemm.argtypes = [vp, _fp, _fp, _fp] + [C.c_int] * 12
     L.ptts_b200_stream_begin.argtypes = [vp, _ip, C.c_int, _fp, C.c_int, C.c_int, C.c_int64, C.POINTER(GenParams)]
     L.ptts_b200_stream_next.argtypes = [vp, C.c_int, _fp, _ip, _ip]
+    L.ptts_b200_mimi_forward_one.argtypes = [vp, _fp, _fp]
+    L.ptts_b200_mimi_stage.argtypes = [vp, _fp, C.c_int, C.c_int]
+    L.ptts_b200_mimi_run.argtypes = [vp]
+    L.ptts_b200_mimi_fetch.argtypes = [vp, _fp]
+    L.ptts_b200_step_kernel_ms.argtypes = [vp, _fp, _ip]
     return L
 
 
@@ -100,6 +106,7 @@ class Engine:
     """One engine per GPU (weights replicated; utterances shard across engines, no collective)."""
 
     def __init__(self, weights: "dict[str, np.ndarray]", device: int = 0):
+        self.h = None
         self.lib = load_library()
         self._keep = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
         names = [k.encode() for k in self._keep]
@@ -168,7 +175,29 @@ class Engine:
         self._ck(self.lib.ptts_b200_mimi_decode(self.h, _f(latents), F, _f(out), C.byref(n)), "mimi_decode")
         return out[: n.value]
 
+    def mimi_forward_one(self, latent):
+        """ptts_mimi_forward_one (ptts_mimi.c:550-564): one scaled latent[32] -> transformer embedding[512]."""
+        latent = np.ascontiguousarray(latent, np.float32).reshape(32)
+        out = np.zeros(512, np.float32)
+        self._ck(self.lib.ptts_b200_mimi_forward_one(self.h, _f(latent), _f(out)), "mimi_forward_one")
+        return out
+
     # ---- additive batched entries
+    def mimi_stage(self, latents):
+        latents = np.ascontiguousarray(latents, np.float32)
+        self._mimi_staged = (latents.shape[0], latents.shape[1])
+        self._ck(self.lib.ptts_b200_mimi_stage(self.h, _f(latents), latents.shape[0], latents.shape[1]), "mimi_stage")
+
+    def mimi_run(self):
+        self._ck(self.lib.ptts_b200_mimi_run(self.h), "mimi_run")
+
+    def mimi_fetch(self, out=None):
+        n, F = self._mimi_staged
+        if out is None:
+            out = np.zeros((n, F * FRAME_SAMPLES), np.float32)
+        self._ck(self.lib.ptts_b200_mimi_fetch(self.h, _f(out)), "mimi_fetch")
+        return out
+
     def mimi_decode_batch(self, latents, out=None):
         latents = np.ascontiguousarray(latents, np.float32)
         n, F = latents.shape[0], latents.shape[1]
@@ -264,6 +293,12 @@ class Engine:
         self._ck(self.lib.ptts_b200_timer_stop(self.h, C.byref(ms)), "timer_stop")
         return ms.value
 
+    def step_kernel_ms(self):
+        """(ms, frame steps) of the most recent launch of the persistent FlowLM step kernel, events around that launch only."""
+        ms, st = C.c_float(0), C.c_int(0)
+        self._ck(self.lib.ptts_b200_step_kernel_ms(self.h, C.byref(ms), C.byref(st)), "step_kernel_ms")
+        return ms.value, st.value
+
     def profile(self, on: bool):
         self._ck(self.lib.ptts_b200_profile_enable(self.h, 1 if on else 0), "profile_enable")
 
@@ -334,29 +369,3 @@ def estimate_frames(words: int) -> int:
     """ptts_estimate_frames (ptts.c:285-291)."""
     words = max(words, 1)
     return max(int((np.float32(words) * np.float32(1.0) + np.float32(2.0)) * np.float32(12.5)), 1)
-
-
-def smoke():
-    """One small invocation of the hot path on cuda:0 checked against the oracle (test infra)."""
-    import sys
-    sys.path.insert(0, str(PKG_DIR.parent / "oracle"))
-    import pyoracle
-    md = synth.model_dir(0)
-    W = synth.read_safetensors(md / "tts_b6369a24.safetensors")
-    voice = synth.read_safetensors(md / "embeddings" / "alba.safetensors")["audio_prompt"].reshape(-1, 1024)[:8]
-    eng = Engine(W, 0)
-    orc = pyoracle.Oracle(W)
-    ids = np.array([3, 3976, 66, 7, 14], np.int32)
-    g = eng.flowlm_generate_latents(ids, voice, 3, lsd_steps=1, temp=0.0)
-    o = orc.flowlm_generate(ids, voice, 3, lsd_steps=1, temp=0.0)
-    err = np.abs(g["latents"] - o["latents"]).max() / np.abs(o["latents"]).max()
-    assert err < 1e-3, f"FlowLM latents differ from the oracle: {err}"
-    sl = eng.scale_latents(g["latents"])
-    pcm = eng.mimi_decode(sl)
-    ref = orc.mimi_decode(sl)
-    snr = 10 * np.log10((ref ** 2).sum() / ((pcm - ref) ** 2).sum())
-    assert snr > 40.0, f"Mimi PCM SNR {snr:.1f} dB < 40 dB"
-    b = eng.generate_batch([ids, ids[:3]], voice, 2, seeds=[1, 2], params=default_params(temp=0.0))
-    assert b["audio"].shape == (2, 2 * FRAME_SAMPLES) and np.isfinite(b["audio"]).all()
-    print(f"smoke ok: latents max-rel {err:.2e}, pcm snr {snr:.1f} dB, launches {eng.launch_count()}")
-    eng.close()

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <utility>
@@ -50,14 +51,18 @@ struct Prof {
 };
 
 // ---------------------------------------------------------------- TMA host API
+// The one piece of process-wide state: the driver entry point of cuTensorMapEncodeTiled, resolved once (std::call_once, so
+// engines created concurrently from several host threads do not race on it); read-only afterwards.
 TmaApi g_tma;
 int TmaApi::init() {
-    if (encode) return 0;
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    PTTS_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
-    PTTS_CHECK(fn && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
-    encode = (EncodeTiled)fn;
+    static std::once_flag once;
+    std::call_once(once, [this] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && fn && q == cudaDriverEntryPointSuccess)
+            encode = (EncodeTiled)fn;
+    });
+    PTTS_CHECK(encode != nullptr, "cuTensorMapEncodeTiled not available from the driver");
     return 0;
 }
 
@@ -87,9 +92,8 @@ int make_tmap(CUtensorMap *out, const void *base, bool bf16, int k, int rows, in
 // (common.cuh). Stream capture turns these into programmatic edges of the step graph.
 // PTTS_B200_NO_PDL=1 falls back to plain serialized launches (A/B measurements).
 static bool pdl_enabled() {
-    static int v = -1;
-    if (v < 0) v = getenv("PTTS_B200_NO_PDL") == nullptr ? 1 : 0;
-    return v != 0;
+    static const bool v = getenv("PTTS_B200_NO_PDL") == nullptr;   // initialised once, thread-safe
+    return v;
 }
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
@@ -105,11 +109,7 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 // ---------------------------------------------------------------- GEMM dispatch
 template <int BN, int SPLIT>
 static int gemm_launch_t(const GemmOp &op, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    // the dynamic shared-memory attribute is per device: ptts_b200_create sets it for the engine's device (gemm_set_attrs)
     launch_k(gemm_tc_kernel<BN, SPLIT>, op.grid, GEMM_THREADS, op.smem_bytes, st, op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.mapOH, op.mapOR, op.p);
     PTTS_CUDA_OK(cudaGetLastError());
     return 0;
@@ -151,7 +151,6 @@ int gemm_pick_stages(int bn, int split, int iters, bool) {
     (void)iters;
     return s;
 }
-static int g_num_sms = 148;
 
 // Description of one contraction; see gemm_tc.cuh for the operand roles.
 struct GemmDesc {
@@ -166,6 +165,7 @@ struct GemmDesc {
     int bn = 128, split_k = 1;
     bool two_cta = true;
     bool b_static = true;                      // B is a weight matrix (never written by a kernel)
+    int num_sms = 148;                         // SM count of the engine's device (persistent grid size)
     GemmParams epi = {};                       // epilogue fields only
 };
 
@@ -229,7 +229,7 @@ static int gemm_build(GemmOp &op, const GemmDesc &d) {
     (void)out_rows;
     p.idesc = umma_idesc_f16(GEMM_BM, d.bn, d.bf16, d.bf16);
     op.p = p;
-    op.grid = dim3((unsigned)std::min<long long>(tiles, g_num_sms), 1, 1);
+    op.grid = dim3((unsigned)std::min<long long>(tiles, d.num_sms), 1, 1);
     op.smem_bytes = p.stages * stage_bytes(d.bn, op.split) + 1024 + 1024 + (p.tma_store ? GEMM_EPI_WARPS * p.stage_stride : 0);
     return 0;
 }
@@ -296,6 +296,7 @@ static const char *const MIMI_PFX[] = {"mimi.", "model.", nullptr};
 struct FlowLayerW { __nv_bfloat16 *inproj, *outproj, *l1, *l2; float *n1w, *n1b, *n2w, *n2b; };
 struct FlowBlockW { float *lnw, *lnb, *m0b, *m2b; __nv_bfloat16 *m0w, *m2w; };
 struct MimiLayerW { __half *inproj, *outproj, *l1, *l2; float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; };
+struct EngineCaches;   // contraction descriptors + step programs, defined next to their users (ptts_b200.cu)
 struct ConvW { __half *w; float *b; int cin, cout, k, stride, n_rows /*GEMM N*/, k_per_tap; bool transposed_conv; };
 
 
@@ -305,11 +306,15 @@ struct ptts_b200_engine {
     int device = 0;
     cudaStream_t st = nullptr, st_copy = nullptr;   // compute stream; device->host copies of finished PCM chunks
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_chunk = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_m0 = nullptr, ev_m1 = nullptr;   // around the last launch of the persistent step kernel
+    int mega_timed = 0;                             // 1: ev_m0 / ev_m1 have been recorded
+    int mimi_st_n = 0, mimi_st_frames = 0;          // latents staged by ptts_b200_mimi_stage
     const float *pcm_on_host = nullptr;             // host buffer the last run already delivered its PCM to
     std::vector<void *> allocs;
     int64_t launches = 0;
     ptts::Prof prof;
     int num_sms = 148;
+    ptts::EngineCaches *caches = nullptr;
 
     // ---- FlowLM weights
     __nv_bfloat16 *embed = nullptr, *in_lin = nullptr;

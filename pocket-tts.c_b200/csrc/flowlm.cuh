@@ -135,9 +135,12 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
                      (void **)&e->partB, (void **)&e->fx, (void **)&e->ada, (void **)&e->ft, (void **)&e->flow, (void **)&e->sc,
                      (void **)&e->fg, (void **)&e->sc_h, (void **)&e->sc_l, (void **)&e->fh_h, (void **)&e->fh_l,
                      (void **)&e->fg_h, (void **)&e->fg_l, (void **)&e->ok, (void **)&e->ov, (void **)&e->d_own_base};
+    // the recorded capacities drop to zero BEFORE anything is freed: if an allocation below fails, the next call does not
+    // pass the "fits" test above with null buffers but comes back here and re-allocates everything
+    e->capB = e->capS = e->capTok = e->capF = 0;
     for (void **p : bufs) { e->dfree(*p); *p = nullptr; }
     const size_t b = (size_t)B;
-#define DA(ptr, count) if (e->dalloc(&e->ptr, (count)) != 0) return -1
+#define DA(ptr, count) if (e->dalloc(&e->ptr, (count)) != 0) { e->voice_len = -1; return -1; }
     DA(d_own_base, b); DA(d_tokens, b * tok); DA(d_tok_len, b); DA(d_max_frames, b); DA(d_eos_after, b);
     DA(d_noise, b * F * FL_LAT); DA(d_latent, b * FL_LAT); DA(d_out_latents, b * F * FL_LAT);
     DA(d_eos_step, b); DA(d_done, b); DA(d_used, b); DA(d_first_eos, b); DA(d_first_cond, b * FL_D); DA(d_first_flow, b * FL_LAT);
@@ -148,7 +151,9 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
     DA(sc_h, b * FN_D); DA(sc_l, b * FN_D); DA(fh_h, b * FN_D); DA(fh_l, b * FN_D); DA(fg_h, b * FN_D); DA(fg_l, b * FN_D);
     DA(ok, (size_t)FL_L * b * FL_D * S); DA(ov, (size_t)FL_L * b * FL_D * S);
     if (regrow_prefix || !e->pk) {
+        e->capCond = 0; e->voice_len = -1;
         e->dfree(e->pk); e->dfree(e->pv); e->dfree(e->d_cond); e->dfree(e->pk16); e->dfree(e->pv16);
+        e->pk = e->pv = e->d_cond = nullptr; e->pk16 = e->pv16 = nullptr;
         DA(pk, (size_t)FL_L * FL_D * cond + 16); DA(pv, (size_t)FL_L * FL_D * cond + 16); DA(d_cond, (size_t)cond * FL_D + 16);
         DA(pk16, (size_t)FL_L * FL_D * cond + 16); DA(pv16, (size_t)FL_L * FL_D * cond + 16);
         e->voice_len = -1;
@@ -299,16 +304,16 @@ constexpr int FLOW_MAX_SPLIT = 8;   // split-K slices a consumer kernel folds (p
 // Decode-step GEMM: activations [B, K] (bf16 hi + lo, the A operand, M = utterances) x weights
 // [n_w, K] (the B operand), output rows = utterances. The weights are streamed once per M tile; K is
 // split across CTAs until the grid covers the SMs, and the consumer kernel folds the partial sums.
-static int flow_gemm_build(GemmOp &op, const __nv_bfloat16 *W, int n_w, int K, const uint16_t *xh, const uint16_t *xl, int B,
+static int flow_gemm_build(Engine *e, GemmOp &op, const __nv_bfloat16 *W, int n_w, int K, const uint16_t *xh, const uint16_t *xl, int B,
                            int bn, int max_split, const float *bias, float *out_f32, int ldo, size_t split_stride, uint16_t *oh,
                            uint16_t *ol, int ldh, int act) {
     GemmDesc d;
     d.A = xh; d.Alo = xl; d.a_k = K; d.a_rows = B; d.a_batches = 1; d.a_ld = K;
     d.B = W; d.b_k = K; d.b_rows = n_w; d.b_ld = K;
-    d.bf16 = true; d.taps = 1; d.k_per_tap = K;
+    d.bf16 = true; d.taps = 1; d.k_per_tap = K; d.num_sms = e->num_sms;
     d.bn = std::min(bn, std::max(32, n_w));
     const int tiles = ((B + GEMM_BM - 1) / GEMM_BM) * ((n_w + d.bn - 1) / d.bn);
-    d.split_k = std::max(1, std::min(std::min(max_split, g_num_sms / tiles), K / (2 * GEMM_BK)));
+    d.split_k = std::max(1, std::min(std::min(max_split, e->num_sms / tiles), K / (2 * GEMM_BK)));
     d.epi.transposed = 0; d.epi.bias = bias; d.epi.out_f32 = out_f32; d.epi.ldo = ldo; d.epi.split_stride = split_stride;
     d.epi.out_h = oh; d.epi.out_l = ol; d.epi.ldh = ldh; d.epi.out_bf16 = 1; d.epi.act = act;
     return gemm_build(op, d);
@@ -318,29 +323,29 @@ static int flow_gemms_build(Engine *e, FlowGemms &G, int B, int precise, int lsd
     const size_t ps = (size_t)e->capB * FL_D;
     const uint16_t *xl = precise ? e->xn_l : nullptr, *al = precise ? e->att_l : nullptr, *fl = precise ? e->ffh_l : nullptr;
     for (int l = 0; l < FL_L; l++) {
-        if (flow_gemm_build(G.qkv[l], e->L[l].inproj, 3 * FL_D, FL_D, e->xn_h, xl, B, 128, FLOW_MAX_SPLIT, nullptr, e->qkv, 3 * FL_D,
+        if (flow_gemm_build(e, G.qkv[l], e->L[l].inproj, 3 * FL_D, FL_D, e->xn_h, xl, B, 128, FLOW_MAX_SPLIT, nullptr, e->qkv, 3 * FL_D,
                             (size_t)e->capB * 3 * FL_D, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
-        if (flow_gemm_build(G.outp[l], e->L[l].outproj, FL_D, FL_D, e->att_h, al, B, 128, FLOW_MAX_SPLIT, nullptr, e->partA, FL_D, ps,
+        if (flow_gemm_build(e, G.outp[l], e->L[l].outproj, FL_D, FL_D, e->att_h, al, B, 128, FLOW_MAX_SPLIT, nullptr, e->partA, FL_D, ps,
                             nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
-        if (flow_gemm_build(G.ff1[l], e->L[l].l1, FL_FF, FL_D, e->xn_h, xl, B, 64, 1, nullptr, nullptr, 0, 0, e->ffh_h,
+        if (flow_gemm_build(e, G.ff1[l], e->L[l].l1, FL_FF, FL_D, e->xn_h, xl, B, 64, 1, nullptr, nullptr, 0, 0, e->ffh_h,
                             precise ? e->ffh_l : nullptr, FL_FF, ACT_GELU_ERF) != 0) return -1;
-        if (flow_gemm_build(G.ff2[l], e->L[l].l2, FL_D, FL_FF, e->ffh_h, fl, B, 128, FLOW_MAX_SPLIT, nullptr, e->partB, FL_D, ps, nullptr,
+        if (flow_gemm_build(e, G.ff2[l], e->L[l].l2, FL_D, FL_FF, e->ffh_h, fl, B, 128, FLOW_MAX_SPLIT, nullptr, e->partB, FL_D, ps, nullptr,
                             nullptr, 0, ACT_NONE) != 0) return -1;
     }
     G.cond.resize(lsd);
     for (int k = 0; k < lsd; k++)
-        if (flow_gemm_build(G.cond[k], e->cond_w, FN_D, FL_D, e->normed_h, precise ? e->normed_l : nullptr, B, 32, 1,
+        if (flow_gemm_build(e, G.cond[k], e->cond_w, FN_D, FL_D, e->normed_h, precise ? e->normed_l : nullptr, B, 32, 1,
                             cbias + (size_t)k * FN_D, nullptr, 0, 0, e->sc_h, precise ? e->sc_l : nullptr, FN_D, ACT_SILU) != 0)
             return -1;
-    if (flow_gemm_build(G.ada, e->ada_w, FN_ADA, FN_D, e->sc_h, precise ? e->sc_l : nullptr, B, 128, 1, e->ada_b, e->ada, FN_ADA, 0,
+    if (flow_gemm_build(e, G.ada, e->ada_w, FN_ADA, FN_D, e->sc_h, precise ? e->sc_l : nullptr, B, 128, 1, e->ada_b, e->ada, FN_ADA, 0,
                         nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
     for (int b = 0; b < FN_DEPTH; b++) {
-        if (flow_gemm_build(G.m0[b], e->FB[b].m0w, FN_D, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 32, 1, e->FB[b].m0b, nullptr, 0,
+        if (flow_gemm_build(e, G.m0[b], e->FB[b].m0w, FN_D, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 32, 1, e->FB[b].m0b, nullptr, 0,
                             0, e->fg_h, precise ? e->fg_l : nullptr, FN_D, ACT_SILU) != 0) return -1;
-        if (flow_gemm_build(G.m2[b], e->FB[b].m2w, FN_D, FN_D, e->fg_h, precise ? e->fg_l : nullptr, B, 64, FLOW_MAX_SPLIT, e->FB[b].m2b,
+        if (flow_gemm_build(e, G.m2[b], e->FB[b].m2w, FN_D, FN_D, e->fg_h, precise ? e->fg_l : nullptr, B, 64, FLOW_MAX_SPLIT, e->FB[b].m2b,
                             e->ft, FN_D, (size_t)e->capB * FN_D, nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
     }
-    if (flow_gemm_build(G.fin, e->fin_w, FL_LAT, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 32, 1, e->fin_b, e->flow, FL_LAT, 0,
+    if (flow_gemm_build(e, G.fin, e->fin_w, FL_LAT, FN_D, e->fh_h, precise ? e->fh_l : nullptr, B, 32, 1, e->fin_b, e->flow, FL_LAT, 0,
                         nullptr, nullptr, 0, ACT_NONE) != 0) return -1;
     G.B = B; G.precise = precise; G.lsd = lsd; G.gen = e->gen;
     return 0;
@@ -419,9 +424,10 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
 // ---------------------------------------------------------------- batched prefill
 // Grow the packed-row workspace.
 static int prefill_ensure(Engine *e, int rows, int n) {
-    if (rows <= e->capRows && e->d_row_start) return 0;
+    if (rows <= e->capRows && e->d_row_start && e->pf_ffh_l) return 0;
     cudaStreamSynchronize(e->st);
     rows = std::max(rows, e->capRows);
+    e->capRows = 0;   // a failed grow must not leave a capacity that passes the test above with null buffers
     void **bufs[] = {(void **)&e->d_row_b, (void **)&e->d_row_i, (void **)&e->d_row_start, (void **)&e->pf_x, (void **)&e->pf_qkv,
                      (void **)&e->pf_xn_h, (void **)&e->pf_xn_l, (void **)&e->pf_att_h, (void **)&e->pf_att_l,
                      (void **)&e->pf_ffh_h, (void **)&e->pf_ffh_l};
@@ -443,7 +449,7 @@ static int prefill_gemm(Engine *e, const uint16_t *ah, const uint16_t *al, int M
     GemmDesc d;
     d.A = ah; d.Alo = al; d.a_k = K; d.a_rows = M; d.a_batches = 1; d.a_ld = K;
     d.B = W; d.b_k = K; d.b_rows = N; d.b_ld = K;
-    d.bf16 = true; d.taps = 1; d.k_per_tap = K;
+    d.bf16 = true; d.taps = 1; d.k_per_tap = K; d.num_sms = e->num_sms;
     d.bn = M <= 256 ? 64 : (M <= 1024 ? 128 : 256);   // short prompts: more, narrower tiles to spread the weight stream
     d.epi = epi; d.epi.out_bf16 = 1;
     GemmOp op;

@@ -1204,6 +1204,73 @@ __global__ void __launch_bounds__(256) k_dec_out(const __half *e, int T, const f
     pcm[(size_t)b * T + t] = a;
 }
 
+// ---------------------------------------------------------------- ptts_mimi_forward_one (ptts_mimi.c:550-564)
+// The reference's --mimi-test parity hook (main.c:444): quantizer projection of ONE latent, then the decoder transformer over that
+// single token (no upsampling). With one token the softmax is over one key, so the attention output is the value row itself and
+// RoPE at position 0 is the identity: each layer is LN -> v = in_proj[1024:1536] -> out_proj -> layer-scale residual -> LN -> MLP.
+// One CTA of 512 threads; a debug entry, not a hot path.
+struct MimiOneLayer { const __half *inproj, *outproj, *l1, *l2; const float *n1w, *n1b, *n2w, *n2b, *ls1, *ls2; };
+struct MimiOneParams { const float *quant_w /*[32][512]*/; MimiOneLayer L[MI_L]; };
+__device__ __forceinline__ float dot_h16_row(const __half *w, const float *x, int K) {
+    float a = 0.0f;
+    for (int k = 0; k < K; k += 8) {
+        const uint4 u = *(const uint4 *)(w + k);
+        const float2 p0 = __half22float2(*(const __half2 *)&u.x), p1 = __half22float2(*(const __half2 *)&u.y),
+                     p2 = __half22float2(*(const __half2 *)&u.z), p3 = __half22float2(*(const __half2 *)&u.w);
+        a += p0.x * x[k] + p0.y * x[k + 1] + p1.x * x[k + 2] + p1.y * x[k + 3] + p2.x * x[k + 4] + p2.y * x[k + 5] + p3.x * x[k + 6] + p3.y * x[k + 7];
+    }
+    return a;
+}
+__global__ void __launch_bounds__(512) k_mimi_forward_one(const MimiOneParams p, const float *lat, float *out) {
+    __shared__ float x[MI_D], xn[MI_D], hb[MI_FF], red[32], l32[32];
+    const int c = threadIdx.x;
+    if (c < 32) l32[c] = lat[c];
+    __syncthreads();
+    {
+        float a = 0.0f;
+        for (int i = 0; i < 32; i++) a += p.quant_w[i * MI_D + c] * l32[i];
+        x[c] = a;
+    }
+    __syncthreads();
+    for (int l = 0; l < MI_L; l++) {
+        const MimiOneLayer &L = p.L[l];
+        for (int half = 0; half < 2; half++) {
+            // LayerNorm (biased variance, eps 1e-5: ptts_mimi.c:184-206)
+            const float mean = block_sum(x[c], red) / MI_D;
+            const float d = x[c] - mean;
+            const float var = block_sum(d * d, red) / MI_D;
+            xn[c] = d * rsqrtf(var + 1e-5f) * (half ? L.n2w[c] : L.n1w[c]) + (half ? L.n2b[c] : L.n1b[c]);
+            __syncthreads();
+            if (half == 0) {
+                const float v = dot_h16_row(L.inproj + (size_t)(2 * MI_D + c) * MI_D, xn, MI_D);
+                __syncthreads();
+                xn[c] = v;
+                __syncthreads();
+                x[c] += L.ls1[c] * dot_h16_row(L.outproj + (size_t)c * MI_D, xn, MI_D);
+            } else {
+                for (int j = c; j < MI_FF; j += 512) {
+                    const float h = dot_h16_row(L.l1 + (size_t)j * MI_D, xn, MI_D);
+                    hb[j] = 0.5f * h * (1.0f + tanhf(0.79788456f * (h + 0.044715f * h * h * h)));
+                }
+                __syncthreads();
+                x[c] += L.ls2[c] * dot_h16_row(L.l2 + (size_t)c * MI_FF, hb, MI_FF);
+            }
+            __syncthreads();
+        }
+    }
+    out[c] = x[c];
+}
+
+// fp32 -> fp16 copy of the voice prefix K / V (once per voice, ptts_b200.cu set_voice): 8 elements per thread and iteration
+__global__ void __launch_bounds__(256) k_f32_to_f16(const float *src, __half *dst, size_t n8) {
+    pdl_wait(); pdl_trigger();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = *(const float4 *)(src + i * 8), b = *(const float4 *)(src + i * 8 + 4);
+        __half2 h[4] = {__floats2half2_rn(a.x, a.y), __floats2half2_rn(a.z, a.w), __floats2half2_rn(b.x, b.y), __floats2half2_rn(b.z, b.w)};
+        *(uint4 *)(dst + i * 8) = *(const uint4 *)h;
+    }
+}
+
 __global__ void k_f32_to_h16(const float *in, uint16_t *out, size_t n, int bf) {
     pdl_wait(); pdl_trigger();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

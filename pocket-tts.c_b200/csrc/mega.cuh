@@ -46,7 +46,7 @@ struct MegaProgram {
     const AttnDecodeParams *attn;
     AttnDecodeParams attn0;         // layer 0 by value (kernel parameter space); layer l = attn0 + l * the strides below
     size_t attn_prefix_stride, attn_own_stride;
-    int B, pcap, attn_tc;           // padded batch, score-buffer length, 1: tensor-core attention (attn_tc.cuh)
+    int B, pcap;                    // padded batch, score-buffer length
     FlowState st;
     FlowCtrl *ctrl;
     const int *eos_after;
@@ -701,10 +701,6 @@ __device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, in
     }
 }
 
-}  // namespace ptts
-#include "attn_tc.cuh"
-namespace ptts {
-
 // ---------------------------------------------------------------- GEMM phase
 struct MegaPipe {
     int s;          // ring slot (producer and MMA threads keep their own copy)
@@ -843,9 +839,6 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
 }
 
 // ---------------------------------------------------------------- the kernel
-// ATTN_TC: tensor-core attention (attn_tc.cuh) or the scalar one (sequences whose score buffers do not fit next to its
-// block rings); two instantiations, so that each kernel carries one attention only (instruction footprint).
-template <bool ATTN_TC>
 __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_constant__ MegaProgram P) {
     extern __shared__ uint8_t mg_smem_raw[];
     // aligned by pointer + offset (not through an integer round trip): the compiler keeps the shared address space,
@@ -888,23 +881,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
     float *red = scratch + grp * 64, *lat = red + 16;
     const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
     int steps_done = 0;
-
-    // launch constants of the attention phases: prefix length, and own_base of the utterances this CTA works on
-    // (the unit-to-CTA map of attn5_phase with at least one CTA per head) cached in shared memory
-    const int cond_len0 = P.ctrl->cond_len;
-    int *ob_cache = nullptr, ob_first = 0, ob_count = 0;
-    if (ATTN_TC && (int)gridDim.x >= FL_H) {
-        const int cph = (int)gridDim.x / FL_H, hh = (int)blockIdx.x / cph, j = (int)blockIdx.x % cph;
-        if (hh < FL_H) {
-            ob_first = (int)(((long long)j * P.B) / cph);
-            ob_count = (int)(((long long)(j + 1) * P.B) / cph) - ob_first;
-            if (ob_count <= 64) {
-                ob_cache = (int *)(sbase + 768);
-                if (tid < ob_count) ob_cache[tid] = P.attn0.own_base[ob_first + tid];
-                __syncthreads();
-            }
-        }
-    }
 
     // the first contraction's weight tiles can be requested right away
     if (warp == 0 && lane == 0 && P.first_gemm >= 0) {
@@ -981,16 +957,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    if constexpr (ATTN_TC) {
-                        // the layer's parameters are built from the kernel parameter space (no dependent global loads in the phase prologue)
-                        AttnDecodeParams a = P.attn0;
-                        const int l = ph.idx, nl = l + 1 == FL_L ? 0 : l + 1;
-                        a.pk16 += (size_t)l * P.attn_prefix_stride; a.pv16 += (size_t)l * P.attn_prefix_stride;
-                        a.nk = a.ok + (size_t)nl * P.attn_own_stride; a.nv = a.ov + (size_t)nl * P.attn_own_stride; a.n_extra = nl == 0 ? 1 : 0;
-                        a.ok += (size_t)l * P.attn_own_stride; a.ov += (size_t)l * P.attn_own_stride;
-                        a.cond_len_val = cond_len0; a.ob_cache = ob_cache; a.ob_first = ob_first; a.ob_count = ob_count;
-                        attn5_phase(a, P.B, P.pcap, step, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr, P.flags);
-                    } else attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                    attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     break;
                 default: break;
             }
@@ -1122,11 +1089,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
         }
     }
     const int pcap = ((e->capCond + e->capS + 63) / 32) * 32;
-    // The tensor-core attention (attn_tc.cuh) is opt-in (PTTS_B200_ATTN_TC=1): parity-green, but measured slower on the same
-    // box (119.3 vs 113.3 ms per 256 x 100 step) - the phase is bound by the bytes each SM has to pull in (K / V rows, split-K
-    // partial sums), not by instruction issue, and the scalar version already sits on that bound.
-    const int attn_tc = attn5_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA && getenv("PTTS_B200_ATTN_TC") != nullptr ? 1 : 0;
-    PTTS_CHECK(attn_tc || attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA,
+    PTTS_CHECK(attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA,
                "attention score buffers of %zu bytes exceed the persistent kernel's shared memory (sequence too long)",
                attn4_smem_bytes(pcap));
     if (e->dalloc(&M.d_phases, ph.size()) != 0 || e->dalloc(&M.d_gemms, gm.size()) != 0 || e->dalloc(&M.d_rows, rows.size()) != 0 ||
@@ -1137,7 +1100,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
     PTTS_CUDA_OK(cudaMemcpy(M.d_attn, attn.data(), attn.size() * sizeof(AttnDecodeParams), cudaMemcpyHostToDevice));
     MegaProgram &P = M.prog;
     P.phases = M.d_phases; P.n_phases = np; P.gemms = M.d_gemms; P.rows = M.d_rows; P.attn = M.d_attn;
-    P.B = B; P.pcap = pcap; P.attn_tc = attn_tc;
+    P.B = B; P.pcap = pcap;
     P.attn0 = attn[0]; P.attn_prefix_stride = (size_t)FL_D * e->capCond; P.attn_own_stride = (size_t)e->capB * FL_D * e->capS;
     P.st = make_state(e, B, lsd);
     P.ctrl = e->ctrl; P.eos_after = e->d_eos_after;

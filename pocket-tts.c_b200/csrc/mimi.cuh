@@ -121,7 +121,7 @@ static int mimi_gemm(Engine *e, const __half *A, int Bc, int T, int C, const __h
     d.A = A; d.a_k = C; d.a_rows = T; d.a_batches = Bc; d.a_ld = C; d.a_bstride = (size_t)T * C;
     d.B = W; d.b_k = taps * C; d.b_rows = n_rows; d.b_ld = (size_t)taps * C;
     d.bf16 = false; d.taps = taps; d.k_per_tap = C; d.shift0 = shift0; d.step = step; d.a_k_step = 0; d.b_k_step = C;
-    d.bn = bn; d.split_k = 1; d.two_cta = true;
+    d.bn = bn; d.split_k = 1; d.two_cta = true; d.num_sms = e->num_sms;
     d.epi = epi;
     d.epi.fast_act = 1;   // fp16 outputs: hardware exp/tanh approximations are below the rounding error
     GemmOp op;
@@ -138,15 +138,18 @@ static int conv_gemm(Engine *e, const ConvW &c, const __half *A, int Bc, int T, 
     return mimi_gemm(e, A, Bc, T, c.cin, c.w, c.n_rows, c.k, -(c.k - 1), 1, bn, epi);
 }
 
+static int mimi_set_attrs() {
+    PTTS_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTTS_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTTS_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    return 0;
+}
+
 // One fused residual block (resblock.cuh): vv = ELU(u + conv1(ELU(conv3(eu)))) for Bc items of T rows, C2 channels.
 template <int C2>
 static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const __half *eu, const __half *u, __half *vv, int Bc, int T,
                              float *pcm = nullptr, float *edge = nullptr) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        PTTS_CUDA_OK(cudaFuncSetAttribute(resblock_kernel<C2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_done = true;
-    }
+    // (the kernel's dynamic shared-memory attribute is set per device by ptts_b200_create: mimi_set_attrs)
     const int chp = c1.cout;   // padded to a multiple of 64 at load time
     PTTS_CHECK(chp % 64 == 0 && chp <= 128 && c1.cin == C2 && c1.k == 3 && c2.cin == chp && c2.cout == C2 && c2.k == 1,
                "resblock_launch: unexpected block geometry");
@@ -182,7 +185,7 @@ static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const 
     }
     {
         LaunchScope ls(e, KC_GEMM_MIMI);
-        launch_k(resblock_kernel<C2>, dim3((unsigned)std::min<long long>(tiles, (long long)g_num_sms * (C2 <= 128 ? 2 : 1))), dim3(RB_THREADS), (size_t)smem,
+        launch_k(resblock_kernel<C2>, dim3((unsigned)std::min<long long>(tiles, (long long)e->num_sms * (C2 <= 128 ? 2 : 1))), dim3(RB_THREADS), (size_t)smem,
                  e->st, mapA, mapW1, mapW2, p);
     }
     if (e->prof.on && !e->prof.recs.empty()) {
@@ -216,7 +219,8 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
     const size_t need = mimi_ws_per_frame() * (size_t)Bc * F + (1 << 20);
     if (need > e->mimi_ws_bytes) {
         cudaStreamSynchronize(e->st);
-        e->dfree(e->mimi_ws);
+        e->mimi_ws_bytes = 0;
+        e->dfree(e->mimi_ws); e->mimi_ws = nullptr;
         uint8_t *p = nullptr;
         if (e->dalloc(&p, need) != 0) return -1;
         e->mimi_ws = p; e->mimi_ws_bytes = need;
@@ -314,11 +318,10 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
 // chunk i travels to the host on the copy stream while chunk i+1 is being decoded (at least 4 chunks, so that
 // only the last quarter of the device->host transfer is exposed); the caller waits on e->ev_copy.
 static int mimi_run(Engine *e, int n, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm, float *host_out = nullptr) {
-    static size_t budget = 0;
-    if (!budget) {
+    static const size_t budget = [] {   // initialised once, thread-safe
         const char *s = getenv("PTTS_B200_MIMI_WS_GB");
-        budget = (size_t)((s && atof(s) > 0 ? atof(s) : 24.0) * (double)(1ull << 30));
-    }
+        return (size_t)((s && atof(s) > 0 ? atof(s) : 24.0) * (double)(1ull << 30));
+    }();
     int per = (int)(budget / (mimi_ws_per_frame() * (size_t)F));
     if (per < 1) per = 1;
     if (per > n) per = n;

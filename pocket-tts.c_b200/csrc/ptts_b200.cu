@@ -6,7 +6,7 @@
 #include <algorithm>
 #include <thread>
 
-#include "mega1.cuh"
+#include "mega.cuh"
 #include "mimi.cuh"
 
 using namespace ptts;
@@ -43,9 +43,12 @@ static void host_noise(int64_t seed, float temp, float clampv, int frames, float
 }
 
 // ---------------------------------------------------------------- lifetime
-static std::unordered_map<Engine *, std::unordered_map<uint64_t, FlowGemms>> g_gemms;
-static std::unordered_map<Engine *, std::unordered_map<uint64_t, MegaHost>> g_mega;
-static std::unordered_map<Engine *, std::unordered_map<int, Mega1Host>> g_mega1;
+// Per-engine caches of contraction descriptors and step programs (EngineCaches, owned by the engine: nothing here is
+// process-global, so distinct engines can be driven from distinct host threads).
+struct ptts::EngineCaches {
+    std::unordered_map<uint64_t, FlowGemms> gemms;
+    std::unordered_map<uint64_t, MegaHost> mega;
+};
 extern "C" const char *ptts_b200_last_error(void) { return g_last_error; }
 
 static int gemm_set_attrs() {
@@ -70,22 +73,24 @@ extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b
     Engine *e = new Engine();
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
-    g_num_sms = prop.multiProcessorCount;
+    e->caches = new EngineCaches();
     HostWeights hw{tensors, n_tensors};
     if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
         cudaEventCreate(&e->ev1) != cudaSuccess || cudaEventCreateWithFlags(&e->ev_chunk, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&e->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&e->ev_m0) != cudaSuccess || cudaEventCreate(&e->ev_m1) != cudaSuccess) {
         set_error("stream/event creation failed");
         ptts_b200_destroy(e);
         return -1;
     }
-    if (cudaFuncSetAttribute(k_pf_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
+    if (cudaFuncSetAttribute(k_flow_mega, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(k_pf_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-        gemm_set_attrs() != 0 || flow_load_weights(e, hw) != 0 || mimi_load_weights(e, hw) != 0 || ensure_rope(e, 1024) != 0) {
+        gemm_set_attrs() != 0 || mimi_set_attrs() != 0 || flow_load_weights(e, hw) != 0 || mimi_load_weights(e, hw) != 0 || ensure_rope(e, 1024) != 0) {
         ptts_b200_destroy(e);
         return -1;
     }
@@ -103,15 +108,15 @@ extern "C" void ptts_b200_destroy(ptts_b200_engine *e) {
     cudaSetDevice(e->device);
     if (e->st) cudaStreamSynchronize(e->st);
     for (auto &g : e->graphs) cudaGraphExecDestroy(g.second);
-    g_gemms.erase(e);
-    g_mega.erase(e);
-    g_mega1.erase(e);
+    delete e->caches;
     for (void *p : e->allocs) cudaFree(p);
     if (e->pin) cudaFreeHost(e->pin);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_chunk) cudaEventDestroy(e->ev_chunk);
     if (e->ev_copy) cudaEventDestroy(e->ev_copy);
+    if (e->ev_m0) cudaEventDestroy(e->ev_m0);
+    if (e->ev_m1) cudaEventDestroy(e->ev_m1);
     if (e->st_copy) { cudaStreamSynchronize(e->st_copy); cudaStreamDestroy(e->st_copy); }
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
@@ -130,7 +135,7 @@ static int step_launch(Engine *e, int mode, int B, int lsd, int precise) {
     FlowState st = make_state(e, B, lsd);
     if (mode == 1) return flow_step_gemv(e, st, cbias);
     const uint64_t key = gkey(mode, B, lsd, precise);
-    auto &gm = g_gemms[e];
+    auto &gm = e->caches->gemms;
     auto it = gm.find(key);
     if (it == gm.end() || it->second.gen != e->gen) {
         FlowGemms G;
@@ -143,15 +148,14 @@ static int step_launch(Engine *e, int mode, int B, int lsd, int precise) {
 
 // The batched decode loop as ONE cooperative launch of the persistent step kernel (mega.cuh).
 static bool mega_enabled() {
-    static int v = -1;
-    if (v < 0) v = getenv("PTTS_B200_NO_MEGA") == nullptr ? 1 : 0;
-    return v != 0;
+    static const bool v = getenv("PTTS_B200_NO_MEGA") == nullptr;   // initialised once, thread-safe
+    return v;
 }
 static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     float *cb = nullptr;
     if (ensure_cbias(e, lsd, &cb) != 0) return -1;
     const uint64_t key = ((uint64_t)2 << 48) | ((uint64_t)B << 24) | ((uint64_t)lsd << 8) | (uint64_t)precise;
-    auto &gm = g_gemms[e];
+    auto &gm = e->caches->gemms;
     auto gi = gm.find(key);
     if (gi == gm.end() || gi->second.gen != e->gen) {
         FlowGemms G;
@@ -159,16 +163,12 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
         gm[key] = G;
         gi = gm.find(key);
     }
-    MegaHost &M = g_mega[e][key];
+    MegaHost &M = e->caches->mega[key];
     if (M.gen != e->gen || M.B != B || M.lsd != lsd || M.precise != precise) {
         PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
         if (mega_build(e, M, gi->second, B, lsd, precise) != 0) return -1;
     }
-    if (!e->mega_ctl) {
-        if (e->dalloc(&e->mega_ctl, 64) != 0) return -1;
-        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
-        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
-    }
+    if (!e->mega_ctl && e->dalloc(&e->mega_ctl, 64) != 0) return -1;
     PTTS_CUDA_OK(cudaMemsetAsync(e->mega_ctl, 0, 64 * sizeof(unsigned long long), e->st));
     MegaProgram P = M.prog;
     P.bar = (unsigned int *)e->mega_ctl;
@@ -190,8 +190,10 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     e->launches++;
-    if (P.attn_tc) PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega<true>, P));
-    else PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega<false>, P));
+    PTTS_CUDA_OK(cudaEventRecord(e->ev_m0, e->st));
+    PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega, P));
+    PTTS_CUDA_OK(cudaEventRecord(e->ev_m1, e->st));
+    e->mega_timed = 1;
     if (e->prof.on) {
         unsigned long long h[2 * MP_COUNT];
         PTTS_CUDA_OK(cudaMemcpyAsync(h, e->mega_ctl + 8, sizeof h, cudaMemcpyDeviceToHost, e->st));
@@ -201,8 +203,7 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
             PTTS_CUDA_OK(cudaMemcpy(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost));
             static const char *const tn[MP_COUNT] = {"HEAD", "GEMM", "ROW", "MID", "TAIL", "ATTN"};
             const double st_ = (double)h[2 * MP_HEAD + 1];
-            fprintf(stderr, "mega trace: B=%d steps=%.0f phases=%d attention=%s (us per frame: own work of CTA 0 / including barrier)\n", B, st_, P.n_phases,
-                    P.attn_tc ? "mma.sync" : "scalar");
+            fprintf(stderr, "mega trace: B=%d steps=%.0f phases=%d (us per frame: own work of CTA 0 / including barrier)\n", B, st_, P.n_phases);
             for (int i = 0; i < P.n_phases; i++) {
                 const MegaPhase &q = M.phases[i];
                 char extra[96] = "";
@@ -236,65 +237,9 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     return 0;
 }
 
-// Batch-1 streaming decode as one cooperative launch of k_flow_mega1 (mega1.cuh).
-static int run_mega1(Engine *e, int lsd, int nsteps) {
-    float *cb = nullptr;
-    if (ensure_cbias(e, lsd, &cb) != 0) return -1;
-    Mega1Host &M = g_mega1[e][lsd];
-    if (M.gen != e->gen || M.lsd != lsd) {
-        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
-        if (mega1_build(e, M, lsd, cb) != 0) return -1;
-    }
-    if (!e->mega_ctl) {
-        if (e->dalloc(&e->mega_ctl, 64) != 0) return -1;
-        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
-        PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, MG_SMEM_BYTES));
-    }
-    static bool attr1 = false;
-    if (!attr1) { PTTS_CUDA_OK(cudaFuncSetAttribute(k_flow_mega1, cudaFuncAttributeMaxDynamicSharedMemorySize, M1_DYN_SMEM)); attr1 = true; }
-    PTTS_CUDA_OK(cudaMemsetAsync(e->mega_ctl, 0, 64 * sizeof(unsigned long long), e->st));
-    Mega1Program Q = M.prog;
-    MegaProgram &P = Q.base;
-    P.bar = (unsigned int *)e->mega_ctl;
-    P.done_count = (int *)(e->mega_ctl + 1);
-    P.prof = e->prof.on ? e->mega_ctl + 8 : nullptr;
-    P.nsteps = nsteps; P.n_live = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)e->num_sms); cfg.blockDim = dim3(M1_THREADS); cfg.dynamicSmemBytes = M1_DYN_SMEM; cfg.stream = e->st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    e->launches++;
-    PTTS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_flow_mega1, Q));
-    if (e->prof.on) {
-        unsigned long long h[24];
-        PTTS_CUDA_OK(cudaMemcpyAsync(h, e->mega_ctl + 8, sizeof h, cudaMemcpyDeviceToHost, e->st));
-        PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
-        if (getenv("PTTS_B200_MEGA_TRACE"))
-            fprintf(stderr, "batch-1 GEMV phase of CTA 0 (us, cumulative from phase start): prologue %.2f  rows %.2f  look-ahead issued %.2f  phase incl. barrier %.2f\n",
-                    h[16] * 1e-3 / h[2 * M1_GEMV + 1], h[17] * 1e-3 / h[2 * M1_GEMV + 1], h[18] * 1e-3 / h[2 * M1_GEMV + 1],
-                    h[2 * M1_GEMV] * 1e-3 / h[2 * M1_GEMV + 1]);
-        static const int cls_of[M1_COUNT] = {KC_FLOW_MISC, KC_GEMV, KC_ATTN_DECODE, KC_FLOW_MISC, KC_FLOW_MISC};
-        const double steps = (double)h[2 * M1_HEAD + 1];
-        for (int t = 0; t < M1_COUNT; t++) {
-            e->prof.ms[cls_of[t]] += (float)((double)h[2 * t] * 1e-6);
-            e->prof.n[cls_of[t]] += (int64_t)h[2 * t + 1];
-        }
-        e->prof.bytes[KC_GEMV] += M.gemv_bytes * steps;
-        e->prof.flops[KC_GEMV] += M.gemv_bytes * steps;   // 2 FLOP per 2-byte weight
-    }
-    return 0;
-}
-
 static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nsteps, bool poll_done) {
     if (nsteps <= 0) return 0;
     if (mode == 2 && mega_enabled()) return run_mega(e, B, lsd, precise, nsteps);
-    // Batch-1: the persistent kernel (mega1.cuh) is opt-in (PTTS_B200_MEGA1=1). Measured on B200: 6.4 us per GEMV phase
-    // (1.8 grid barrier + 1.8 activation reload / LayerNorm + 2.4 rows + 0.5 look-ahead) x 39 + attention = 335 us per frame,
-    // against 223 us for the 47-node CUDA graph below, whose kernel boundaries cost less than a grid barrier plus a
-    // per-CTA reload of the activation vector. The default stays the graph.
-    if (mode == 1 && mega_enabled() && getenv("PTTS_B200_MEGA1") != nullptr) return run_mega1(e, lsd, nsteps);
     const bool use_graph = !e->prof.on && getenv("PTTS_B200_NO_GRAPH") == nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t gk = 0;
@@ -305,7 +250,7 @@ static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nstep
             float *cb = nullptr;
             if (ensure_cbias(e, lsd, &cb) != 0) return -1;   // allocates: must happen outside capture
             if (mode == 2) {                                   // build tensor maps outside capture too
-                auto &gm = g_gemms[e];
+                auto &gm = e->caches->gemms;
                 auto gi = gm.find(key);
                 if (gi == gm.end() || gi->second.gen != e->gen) {
                     FlowGemms G;
@@ -397,6 +342,7 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     PTTS_CHECK(cond_len >= 0 && (cond_len == 0 || cond_prefix), "batch_stage: cond_prefix missing");
     PTTS_CHECK(gp->lsd_steps >= 1 && gp->lsd_steps <= 64, "batch_stage: lsd_steps %d out of range", gp->lsd_steps);
     PTTS_CUDA_OK(cudaSetDevice(e->device));
+    e->stream_pos = -1;   // a staged batch replaces whatever stream was open (stream_begin re-arms it after staging)
     int max_tok = 0, cap_f = 0, rows = 0;
     for (int i = 0; i < n; i++) {
         const int tl = token_offsets[i + 1] - token_offsets[i];
@@ -410,6 +356,22 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     const int own_rows = max_tok + 1 + cap_f;   // own-cache rows per utterance
     const int B = n == 1 ? 1 : (n + 15) / 16 * 16;
     PTTS_CHECK(B <= 1024, "batch_stage: at most 1024 utterances per call (got %d); shard larger jobs on the host", n);
+    {   // sequence-length limits of the attention kernels, checked against THIS request before any state changes; capacities
+        // left behind by an earlier, longer request are dropped when they alone would push the score buffers over the limit
+        auto fits = [&](int cond, int S) {
+            const int pcap = ((cond + S + 63) / 32) * 32;
+            return (B == 1 ? attn2_smem_bytes(pcap, 1) <= (size_t)200 * 1024 : attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA) &&
+                   pf_attn_smem_bytes(cond, max_tok + 1) <= (size_t)200 * 1024;
+        };
+        const int cond1 = std::max(cond_len, 1);
+        PTTS_CHECK(fits(cond1, own_rows), "batch_stage: voice prefix %d + prompt %d + %d frames = %d cache rows exceed what the %s attention kernel holds",
+                   cond_len, max_tok + 1, cap_f, cond_len + own_rows, B == 1 ? "batch-1" : "batched");
+        if (!fits(std::max(cond1, e->capCond), std::max(own_rows, e->capS))) {
+            PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+            e->capS = 0;
+            if (!fits(std::max(cond1, e->capCond), own_rows)) { e->capCond = 0; e->voice_len = -1; }
+        }
+    }
     if (flow_ensure_capacity(e, B, own_rows, max_tok, cap_f, std::max(cond_len, 1)) != 0) return -1;
     if (prefill_ensure(e, std::max(rows, cond_len), n) != 0) return -1;
     if (ensure_rope(e, cond_len + own_rows + 1) != 0) return -1;
@@ -482,7 +444,8 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
 static int ensure_pcm(Engine *e, size_t samples) {
     if (samples <= e->pcm_cap) return 0;
     cudaStreamSynchronize(e->st);
-    e->dfree(e->d_pcm);
+    e->pcm_cap = 0;
+    e->dfree(e->d_pcm); e->d_pcm = nullptr;
     if (e->dalloc(&e->d_pcm, samples) != 0) return -1;
     e->pcm_cap = samples;
     return 0;
@@ -602,9 +565,11 @@ extern "C" int ptts_b200_mimi_decode_batch(ptts_b200_engine *e, const float *lat
     PTTS_CHECK(e && latents && out_audio && n >= 1 && frames >= 1, "mimi_decode_batch: bad arguments");
     PTTS_CUDA_OK(cudaSetDevice(e->device));
     const size_t nl = (size_t)n * frames * FL_LAT;
+    e->mimi_st_n = 0;
     if (nl > e->mimi_lat_cap) {
         cudaStreamSynchronize(e->st);
-        e->dfree(e->d_mimi_lat);
+        e->mimi_lat_cap = 0;
+        e->dfree(e->d_mimi_lat); e->d_mimi_lat = nullptr;
         if (e->dalloc(&e->d_mimi_lat, nl) != 0) return -1;
         e->mimi_lat_cap = nl;
     }
@@ -615,6 +580,63 @@ extern "C" int ptts_b200_mimi_decode_batch(ptts_b200_engine *e, const float *lat
     PTTS_CUDA_OK(cudaEventSynchronize(e->ev_copy));
     PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     return 0;
+}
+
+extern "C" int ptts_b200_mimi_stage(ptts_b200_engine *e, const float *latents, int n, int frames) {
+    PTTS_CHECK(e && latents && n >= 1 && frames >= 1, "mimi_stage: bad arguments");
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    e->mimi_st_n = 0;
+    const size_t nl = (size_t)n * frames * FL_LAT;
+    if (nl > e->mimi_lat_cap) {
+        cudaStreamSynchronize(e->st);
+        e->mimi_lat_cap = 0;
+        e->dfree(e->d_mimi_lat); e->d_mimi_lat = nullptr;
+        if (e->dalloc(&e->d_mimi_lat, nl) != 0) return -1;
+        e->mimi_lat_cap = nl;
+    }
+    if (ensure_pcm(e, (size_t)n * frames * 1920) != 0) return -1;
+    PTTS_CUDA_OK(cudaMemcpyAsync(e->d_mimi_lat, latents, nl * 4, cudaMemcpyHostToDevice, e->st));
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    e->mimi_st_n = n; e->mimi_st_frames = frames;
+    return 0;
+}
+extern "C" int ptts_b200_mimi_run(ptts_b200_engine *e) {
+    PTTS_CHECK(e && e->mimi_st_n > 0, "mimi_run: nothing staged");
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    return mimi_run(e, e->mimi_st_n, e->mimi_st_frames, e->d_mimi_lat, (size_t)e->mimi_st_frames * FL_LAT, 0, e->d_pcm, nullptr);
+}
+extern "C" int ptts_b200_mimi_fetch(ptts_b200_engine *e, float *out_audio) {
+    PTTS_CHECK(e && out_audio && e->mimi_st_n > 0, "mimi_fetch: nothing staged");
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    PTTS_CUDA_OK(cudaMemcpyAsync(out_audio, e->d_pcm, (size_t)e->mimi_st_n * e->mimi_st_frames * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
+    PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
+    return 0;
+}
+
+extern "C" int ptts_b200_mimi_forward_one(ptts_b200_engine *e, const float *latent, float *out_embed) {
+    PTTS_CHECK(e && latent && out_embed, "mimi_forward_one: bad arguments");   // ptts_mimi.c:551
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    float *d = nullptr;
+    if (e->dalloc(&d, 32 + MI_D) != 0) return -1;
+    MimiOneParams mp;
+    mp.quant_w = e->quant_w;
+    for (int l = 0; l < MI_L; l++) {
+        const MimiLayerW &w = e->ML[l];
+        mp.L[l] = {w.inproj, w.outproj, w.l1, w.l2, w.n1w, w.n1b, w.n2w, w.n2b, w.ls1, w.ls2};
+    }
+    int rc = -1;
+    if (cudaMemcpyAsync(d, latent, 32 * 4, cudaMemcpyHostToDevice, e->st) == cudaSuccess) {
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            k_mimi_forward_one<<<1, 512, 0, e->st>>>(mp, d, d + 32);
+        }
+        if (launch_check("k_mimi_forward_one") == 0 && cudaMemcpyAsync(out_embed, d + 32, MI_D * 4, cudaMemcpyDeviceToHost, e->st) == cudaSuccess &&
+            cudaStreamSynchronize(e->st) == cudaSuccess)
+            rc = 0;
+    }
+    if (rc != 0 && g_last_error[0] == 0) set_error("mimi_forward_one: %s", cudaGetErrorString(cudaGetLastError()));
+    e->dfree(d);
+    return rc;
 }
 
 extern "C" int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, int frames, float *out_audio, int *out_len) {
@@ -686,6 +708,18 @@ extern "C" int ptts_b200_timer_stop(ptts_b200_engine *e, float *out_ms) {
     PTTS_CUDA_OK(cudaEventElapsedTime(out_ms, e->ev0, e->ev1));
     return 0;
 }
+extern "C" int ptts_b200_step_kernel_ms(ptts_b200_engine *e, float *out_ms, int *out_steps) {
+    PTTS_CHECK(e && out_ms, "step_kernel_ms: bad arguments");
+    PTTS_CHECK(e->mega_timed, "step_kernel_ms: the persistent step kernel has not been launched yet (batched runs only)");
+    PTTS_CUDA_OK(cudaEventSynchronize(e->ev_m1));
+    PTTS_CUDA_OK(cudaEventElapsedTime(out_ms, e->ev_m0, e->ev_m1));
+    if (out_steps) {
+        int step = 0;
+        PTTS_CUDA_OK(cudaMemcpy(&step, &e->ctrl->step, 4, cudaMemcpyDeviceToHost));
+        *out_steps = step;
+    }
+    return 0;
+}
 extern "C" int ptts_b200_profile_enable(ptts_b200_engine *e, int on) {
     PTTS_CHECK(e, "profile_enable: null engine");
     PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
@@ -750,7 +784,7 @@ extern "C" int ptts_b200_test_gemm(ptts_b200_engine *e, const float *A, const fl
         d.a_bstride = (size_t)rows * C;
         d.B = dbh; d.Blo = split == 2 ? dbl : nullptr; d.b_k = K; d.b_rows = N; d.b_ld = K;
         d.bf16 = bf16 != 0; d.taps = taps; d.k_per_tap = C; d.shift0 = shift0; d.step = step; d.a_k_step = 0; d.b_k_step = C;
-        d.bn = bn; d.split_k = split_k; d.two_cta = true;
+        d.bn = bn; d.split_k = split_k; d.two_cta = true; d.num_sms = e->num_sms;
         d.epi.transposed = transposed; d.epi.out_f32 = dout; d.epi.ldo = transposed ? rows : N; d.epi.split_stride = no;
         GemmOp op;
         long long *dtrace = nullptr;

@@ -11,10 +11,19 @@
  *                                  ->  ptts_mimi_decode            (ptts.c:1128)  -> ptts_b200_mimi_decode
  *
  * ptts.h, ptts_params, the safetensors layout, tokenizer, voice loading and WAV writer are untouched.
- * The engine is created once per ptts_ctx (keyed by its mmap'd weights file) and lives until exit,
- * which removes the per-call weight reload of ptts.c:1047-1053 and the stale host-pointer weight
- * cache hazard of ptts_cuda.c:617-644.
+ * Engine lifetime.  ptts_generate loads and frees both model handles on EVERY call (ptts.c:1047-1053, 1157-1158), and
+ * ptts_free (ptts.c:414) cannot be hooked without patching ptts.c, so the engine must outlive the handles to keep the
+ * weights resident, yet must never be handed to a different model:
+ *   - every handle (ptts_flowlm / ptts_mimi) holds a reference on its engine; ptts_flowlm_free / ptts_mimi_free drop it;
+ *   - an engine is identified by the CONTENT of the weights file it was built from (file size, tensor count, a hash of the
+ *     safetensors JSON header and of 64 data samples spread over the file), never by the safetensors_file_t address alone:
+ *     ptts_free + ptts_load_dir of another model at a recycled address yields a different fingerprint and a new engine
+ *     (the stale host-pointer cache hazard of ptts_cuda.c:617-644 does not exist here);
+ *   - engines without handles stay cached (weights resident between ptts_generate calls), at most MAX_IDLE of them: the
+ *     least recently used idle engine is destroyed when a new one is needed, and all of them at exit.
  * There is no CPU fallback: every failure propagates as -1 / NULL with the message on stderr.
+ * Threading: like the reference host code (ptts.c has none), this layer is not re-entrant; the engines themselves are
+ * independent of each other (include/ptts_b200.h).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -25,24 +34,78 @@
 #include "ptts_internal.h"
 #include "ptts_mimi.h"
 
-struct ptts_flowlm { ptts_ctx *ctx; ptts_b200_engine *eng; };
-struct ptts_mimi { ptts_ctx *ctx; ptts_b200_engine *eng; };
+typedef struct {
+    ptts_b200_engine *eng;
+    uint64_t fp;            /* content fingerprint of the weights file */
+    size_t file_size;
+    int num_tensors;
+    int refs;               /* live ptts_flowlm / ptts_mimi handles */
+    uint64_t last_use;
+} engine_slot;
+
+struct ptts_flowlm { ptts_ctx *ctx; engine_slot *slot; };
+struct ptts_mimi { ptts_ctx *ctx; engine_slot *slot; };
 
 #define MAX_ENGINES 8
-static struct { const safetensors_file_t *key; ptts_b200_engine *eng; } g_engines[MAX_ENGINES];
-static int g_n_engines = 0, g_atexit = 0;
+#define MAX_IDLE 2
+static engine_slot g_slots[MAX_ENGINES];
+static uint64_t g_clock = 0;
+static int g_atexit = 0;
 
 static void shutdown_engines(void) {
-    for (int i = 0; i < g_n_engines; i++) ptts_b200_destroy(g_engines[i].eng);
-    g_n_engines = 0;
+    for (int i = 0; i < MAX_ENGINES; i++)
+        if (g_slots[i].eng) { ptts_b200_destroy(g_slots[i].eng); g_slots[i].eng = NULL; g_slots[i].refs = 0; }
 }
 
-static ptts_b200_engine *engine_for(ptts_ctx *ctx) {
+static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
+    const unsigned char *b = (const unsigned char *)p;
+    for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+static uint64_t weights_fingerprint(const safetensors_file_t *sf) {
+    uint64_t h = 1469598103934665603ULL;
+    h = fnv1a(h, &sf->file_size, sizeof sf->file_size);
+    h = fnv1a(h, &sf->num_tensors, sizeof sf->num_tensors);
+    if (sf->header_json) h = fnv1a(h, sf->header_json, sf->header_size);
+    const size_t data0 = 8 + sf->header_size;
+    if (sf->data && sf->file_size > data0 + 64) {
+        const size_t span = sf->file_size - data0 - 64;
+        for (int i = 0; i < 64; i++) h = fnv1a(h, (const unsigned char *)sf->data + data0 + (span / 63) * (size_t)i, 64);
+    }
+    return h;
+}
+
+static void drop_idle(int keep) {   /* destroy least recently used idle engines until at most `keep` remain */
+    for (;;) {
+        int idle = 0, lru = -1;
+        for (int i = 0; i < MAX_ENGINES; i++)
+            if (g_slots[i].eng && g_slots[i].refs == 0) {
+                idle++;
+                if (lru < 0 || g_slots[i].last_use < g_slots[lru].last_use) lru = i;
+            }
+        if (idle <= keep || lru < 0) return;
+        ptts_b200_destroy(g_slots[lru].eng);
+        memset(&g_slots[lru], 0, sizeof g_slots[lru]);
+    }
+}
+
+static engine_slot *engine_acquire(ptts_ctx *ctx) {
     if (!ctx || !ctx->weights) return NULL;
-    for (int i = 0; i < g_n_engines; i++)
-        if (g_engines[i].key == ctx->weights) return g_engines[i].eng;
-    if (g_n_engines == MAX_ENGINES) { fprintf(stderr, "[ptts] B200: too many model contexts\n"); return NULL; }
     const safetensors_file_t *sf = ctx->weights;
+    const uint64_t fp = weights_fingerprint(sf);
+    for (int i = 0; i < MAX_ENGINES; i++) {
+        engine_slot *s = &g_slots[i];
+        if (s->eng && s->fp == fp && s->file_size == sf->file_size && s->num_tensors == sf->num_tensors) {
+            s->refs++; s->last_use = ++g_clock;
+            return s;
+        }
+    }
+    drop_idle(MAX_IDLE - 1);   /* room for the new engine's device memory before it is allocated */
+    int slot = -1;
+    for (int i = 0; i < MAX_ENGINES; i++) if (!g_slots[i].eng) { slot = i; break; }
+    if (slot < 0) { drop_idle(0); for (int i = 0; i < MAX_ENGINES; i++) if (!g_slots[i].eng) { slot = i; break; } }
+    if (slot < 0) { fprintf(stderr, "[ptts] B200: %d model contexts are in use at once\n", MAX_ENGINES); return NULL; }
     ptts_b200_tensor *tab = (ptts_b200_tensor *)calloc((size_t)sf->num_tensors, sizeof *tab);
     if (!tab) return NULL;
     int n = 0;
@@ -66,28 +129,45 @@ static ptts_b200_engine *engine_for(ptts_ctx *ctx) {
         return NULL;
     }
     if (!g_atexit) { atexit(shutdown_engines); g_atexit = 1; }
-    g_engines[g_n_engines].key = sf;
-    g_engines[g_n_engines].eng = eng;
-    g_n_engines++;
-    return eng;
+    engine_slot *s = &g_slots[slot];
+    s->eng = eng; s->fp = fp; s->file_size = sf->file_size; s->num_tensors = sf->num_tensors; s->refs = 1; s->last_use = ++g_clock;
+    return s;
+}
+
+static void engine_release(engine_slot *s) {
+    if (!s || s->refs <= 0) return;
+    s->refs--;
+    if (s->refs == 0) drop_idle(MAX_IDLE);
+}
+
+/* test / diagnostics hook: engines currently alive in this process (live + idle) */
+int ptts_b200_host_engine_count(void) {
+    int n = 0;
+    for (int i = 0; i < MAX_ENGINES; i++) n += g_slots[i].eng != NULL;
+    return n;
 }
 
 /* ---- ptts_flowlm.h ---------------------------------------------------------------- */
 ptts_flowlm *ptts_flowlm_load(ptts_ctx *ctx) {
-    ptts_b200_engine *eng = engine_for(ctx);
-    if (!eng) return NULL;
+    engine_slot *s = engine_acquire(ctx);
+    if (!s) return NULL;
     ptts_flowlm *fm = (ptts_flowlm *)calloc(1, sizeof *fm);
-    if (fm) { fm->ctx = ctx; fm->eng = eng; }
+    if (!fm) { engine_release(s); return NULL; }
+    fm->ctx = ctx; fm->slot = s;
     return fm;
 }
-void ptts_flowlm_free(ptts_flowlm *fm) { free(fm); }
+void ptts_flowlm_free(ptts_flowlm *fm) {
+    if (!fm) return;
+    engine_release(fm->slot);
+    free(fm);
+}
 
 int ptts_flowlm_generate_latents(ptts_flowlm *fm, const int *tokens, int token_len, const float *cond_prefix, int cond_len,
                                  int max_frames, int lsd_steps, float temp, float noise_clamp, int64_t seed, int eos_enabled,
                                  float eos_threshold, int eos_min_frames, int eos_after, float *out_latents,
                                  int *out_frames_used, float *out_first_eos_logit, float *out_first_cond, float *out_first_flow) {
     if (!fm) return -1;
-    int rc = ptts_b200_flowlm_generate_latents(fm->eng, tokens, token_len, cond_prefix, cond_len, max_frames, lsd_steps, temp,
+    int rc = ptts_b200_flowlm_generate_latents(fm->slot->eng, tokens, token_len, cond_prefix, cond_len, max_frames, lsd_steps, temp,
                                                noise_clamp, seed, eos_enabled, eos_threshold, eos_min_frames, eos_after,
                                                out_latents, out_frames_used, out_first_eos_logit, out_first_cond, out_first_flow);
     if (rc != 0) fprintf(stderr, "[ptts] B200: %s\n", ptts_b200_last_error());
@@ -108,28 +188,35 @@ int ptts_flowlm_forward_next(ptts_flowlm *fm, const int *tokens, int token_len, 
     if (prev_len == 0 && !prev_latents)
         return ptts_flowlm_forward_one(fm, tokens, token_len, cond_prefix, cond_len, lsd_steps, temp, noise_clamp,
                                        seed_io ? *seed_io : -1, out_latent, out_eos_logit);
-    fprintf(stderr, "[ptts] B200: ptts_flowlm_forward_next (naive non-cached debug path) is not on the accelerated path\n");
+    /* teacher-forced single step over a caller-supplied latent history (ptts_flowlm.c:1027-1127): no caller in the reference
+     * tree (main.c and ptts.c use ptts_flowlm_generate_latents); documented as not provided in INTEGRATION.md */
+    fprintf(stderr, "[ptts] B200: ptts_flowlm_forward_next with a latent history is not provided by the engine\n");
     return -1;
 }
 
 void ptts_flowlm_scale_latents(const ptts_flowlm *fm, const float *in_latents, int frames, float *out_latents) {
     if (!fm || !in_latents || !out_latents || frames <= 0) return;
-    ptts_b200_flowlm_scale_latents(fm->eng, in_latents, frames, out_latents);
+    ptts_b200_flowlm_scale_latents(fm->slot->eng, in_latents, frames, out_latents);
 }
 
 /* ---- ptts_mimi.h ------------------------------------------------------------------ */
 ptts_mimi *ptts_mimi_load(ptts_ctx *ctx) {
-    ptts_b200_engine *eng = engine_for(ctx);
-    if (!eng) return NULL;
+    engine_slot *s = engine_acquire(ctx);
+    if (!s) return NULL;
     ptts_mimi *mm = (ptts_mimi *)calloc(1, sizeof *mm);
-    if (mm) { mm->ctx = ctx; mm->eng = eng; }
+    if (!mm) { engine_release(s); return NULL; }
+    mm->ctx = ctx; mm->slot = s;
     return mm;
 }
-void ptts_mimi_free(ptts_mimi *mm) { free(mm); }
+void ptts_mimi_free(ptts_mimi *mm) {
+    if (!mm) return;
+    engine_release(mm->slot);
+    free(mm);
+}
 
 int ptts_mimi_decode(ptts_mimi *mm, const float *latents, int frames, float *out_audio, int *out_len) {
     if (!mm) return -1;
-    int rc = ptts_b200_mimi_decode(mm->eng, latents, frames, out_audio, out_len);
+    int rc = ptts_b200_mimi_decode(mm->slot->eng, latents, frames, out_audio, out_len);
     if (rc != 0) fprintf(stderr, "[ptts] B200: %s\n", ptts_b200_last_error());
     return rc;
 }
@@ -137,7 +224,8 @@ int ptts_mimi_decode_one(ptts_mimi *mm, const float *latent, float *out_audio, i
     return ptts_mimi_decode(mm, latent, 1, out_audio, out_len);
 }
 int ptts_mimi_forward_one(ptts_mimi *mm, const float *latent, float *out_embed) {
-    (void)mm; (void)latent; (void)out_embed;
-    fprintf(stderr, "[ptts] B200: ptts_mimi_forward_one (--mimi-test debug statistic) is not on the accelerated path\n");
-    return -1;
+    if (!mm) return -1;
+    int rc = ptts_b200_mimi_forward_one(mm->slot->eng, latent, out_embed);   /* the --mimi-test parity hook (main.c:444) */
+    if (rc != 0) fprintf(stderr, "[ptts] B200: %s\n", ptts_b200_last_error());
+    return rc;
 }

@@ -52,10 +52,15 @@ def f32_to_bf16_bits(x: np.ndarray) -> np.ndarray:
     return r.astype(np.uint16).reshape(x.shape)
 
 
-def make_weights(seed: int = 0) -> "dict[str, np.ndarray]":
-    """Return {tensor name: f32 ndarray (bf16-representable)} for FlowLM + Mimi decoder."""
+def make_weights(seed: int = 0, full_mantissa: bool = False) -> "dict[str, np.ndarray]":
+    """Return {tensor name: f32 ndarray} for FlowLM + Mimi decoder.
+
+    Default: every value bf16-representable. full_mantissa=True keeps all 24 significand bits (an F32
+    checkpoint as the reference accepts it, ptts_safetensors.c:294-334): the engine's bf16 / fp16 weight
+    rounding is then visible against an oracle that runs on the unrounded values."""
     rng = np.random.default_rng(seed)
     W: dict[str, np.ndarray] = {}
+    bf16_round = (lambda x: np.ascontiguousarray(x, dtype=np.float32)) if full_mantissa else globals()["bf16_round"]
 
     def lin(name, out, inn, scale=1.0):
         W[name] = bf16_round(rng.standard_normal((out, inn), dtype=np.float32) * (scale / np.sqrt(inn)))

@@ -59,6 +59,13 @@ def max_rel(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
 
 
+def max_rel_per_frame(a, b):
+    """max over frames f of max |a_f - b_f| / max |b_f|: each [32]-latent normalised by ITS OWN peak (tighter than max_rel)."""
+    a = np.asarray(a, np.float64).reshape(-1, 32)
+    b = np.asarray(b, np.float64).reshape(-1, 32)
+    return float((np.abs(a - b).max(axis=1) / np.maximum(np.abs(b).max(axis=1), 1e-30)).max())
+
+
 def snr_db(x, ref):
     x = np.asarray(x, np.float64)
     ref = np.asarray(ref, np.float64)

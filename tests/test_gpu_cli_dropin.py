@@ -32,3 +32,39 @@ def test_reference_cli_on_b200_engine_matches_reference_cpu(model_dir, tmp_path)
     x, y = _wav(a), _wav(b)
     assert x.shape == y.shape == (5 * 1920,)
     assert snr_db(x, y) > 40.0
+
+
+@pytest.mark.skipif(not (CLI.exists() and REF.exists()), reason="prebuilt CLI binaries not present")
+def test_reference_cli_mimi_test_hook_on_b200_engine(model_dir):
+    """--mimi-test (main.c:413-466) calls ptts_mimi_forward_one: the statistic line printed by the drop-in binary must
+    agree with the reference CPU binary's."""
+    import re
+    args = ["-d", str(model_dir), "-p", "Hello world!", "--voice", "alba", "-t", "0", "--mimi-test", "--frames", "3"]
+    a = subprocess.run([str(CLI)] + args, check=True, timeout=300, capture_output=True, text=True).stdout
+    b = subprocess.run([str(REF)] + args, check=True, timeout=300, capture_output=True, text=True).stdout
+    pat = re.compile(r"Mimi decode \(transformer\) stats: mean=(\S+) min=(\S+) max=(\S+)")
+    ma, mb = pat.search(a), pat.search(b)
+    assert ma and mb, (a, b)
+    va, vb = np.array([float(x) for x in ma.groups()]), np.array([float(x) for x in mb.groups()])
+    assert np.abs(va - vb).max() < 2e-3 * max(1.0, np.abs(vb).max())
+
+
+RELOAD = ROOT / "pocket-tts.c_b200" / "build" / "ptts_b200_reload_check"
+
+
+@pytest.mark.skipif(not (RELOAD.exists() and REF.exists()), reason="prebuilt host-layer binaries not present")
+def test_host_layer_engine_lifetime_across_free_and_reload(synth, tmp_path):
+    """ptts_free + ptts_load_dir of ANOTHER model (possibly at a recycled safetensors_file_t address) must never reuse the
+    first model's engine (the stale-pointer cache hazard of ptts_cuda.c:617-644), repeated ptts_generate calls on one
+    context must reuse one engine, and reloads must not accumulate engines (host/ptts_b200_models.c)."""
+    dir_a, dir_b = synth.model_dir(0), synth.model_dir(1)
+    out = subprocess.run([str(RELOAD), str(dir_a), str(dir_b), str(tmp_path)], check=True, timeout=600, capture_output=True, text=True).stdout
+    assert "final engines alive" in out, out
+    args = ["-p", "Hello world!", "--voice", "alba", "-t", "0.7", "-S", "123", "--frames", "5", "--eos-threshold", "1e9", "-q"]
+    subprocess.run([str(REF), "-d", str(dir_a)] + args + ["-o", str(tmp_path / "ref_a.wav")], check=True, timeout=300)
+    subprocess.run([str(REF), "-d", str(dir_b)] + args + ["-o", str(tmp_path / "ref_b.wav")], check=True, timeout=300)
+    a, b, a2 = _wav(tmp_path / "a.wav"), _wav(tmp_path / "b.wav"), _wav(tmp_path / "a2.wav")
+    ra, rb = _wav(tmp_path / "ref_a.wav"), _wav(tmp_path / "ref_b.wav")
+    assert snr_db(a, ra) > 40.0 and snr_db(b, rb) > 40.0      # each context ran on ITS OWN weights
+    assert snr_db(b, ra) < 10.0                                # and the two models really differ
+    assert np.array_equal(a, a2)                               # reloading A reproduces A bit for bit

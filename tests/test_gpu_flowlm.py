@@ -140,57 +140,6 @@ def test_full_batch_of_256_spot_check(eng, pkg, oracle, voice, golden):
         assert max_rel(out["latents"][i, :4], o["latents"]) < TOL, f"utterance {i}"
 
 
-def test_batch1_persistent_kernel_opt_in(pkg, weights, voice, golden, monkeypatch):
-    """PTTS_B200_MEGA1=1 runs the single-utterance decode loop as one cooperative launch (mega1.cuh: GEMV phases with
-    cp.async weight look-ahead, flash-decoding attention chunks); same parity bar as the default graph path."""
-    monkeypatch.setenv("PTTS_B200_MEGA1", "1")
-    e = pkg.Engine(weights, 0)
-    try:
-        for steps in (1, 4):
-            g = e.flowlm_generate_latents(golden["p0_ids"], voice, 8, lsd_steps=steps, temp=0.0)
-            assert g["frames"] == 8
-            assert max_rel(g["latents"], golden[f"hello_s{steps}_latents"]) < TOL
-        g = e.flowlm_generate_latents(golden["p0_ids"], voice, 12, lsd_steps=1, temp=0.0, eos_enabled=1, eos_threshold=-1.2,
-                                      eos_min_frames=1, eos_after=2)
-        assert g["frames"] == int(golden["hello_eos_frames"])
-        assert max_rel(g["latents"], golden["hello_eos_latents"]) < TOL
-    finally:
-        e.close()
-
-
-def test_batched_tensor_core_attention_opt_in(pkg, weights, oracle, voice, golden, monkeypatch):
-    """PTTS_B200_ATTN_TC=1 runs the attention phases of the persistent step kernel on mma.sync (attn_tc.cuh: fp16 hi + lo
-    queries and probabilities, cp.async block ring, ldmatrix fragments): ragged batch, odd batch size (one unit without a
-    partner), 4 Euler steps, and a voice prefix longer than the shared-memory tile (prefix rows streamed through the ring)."""
-    monkeypatch.setenv("PTTS_B200_ATTN_TC", "1")
-    e = pkg.Engine(weights, 0)
-    try:
-        toks = [golden["p0_ids"], golden["p1_ids"], golden["p2_ids"], golden["p1_ids"][:7], golden["p2_ids"][3:20]]
-        frames = [20, 4, 18, 3, 6]
-        seeds = [11, 12, 13, 14, 15]
-        out = e.generate_batch(toks, voice, frames, seeds=seeds, params=pkg.default_params(temp=0.7), want_audio=False)
-        assert list(out["frames"]) == frames
-        for i, (t, f, s) in enumerate(zip(toks, frames, seeds)):
-            o = oracle.flowlm_generate(t, voice, f, lsd_steps=1, temp=0.7, seed=s)
-            assert max_rel(out["latents"][i, :f], o["latents"]) < TOL, f"utterance {i}"
-        out4 = e.generate_batch(toks[:3], voice, 3, seeds=[5, 6, 7], params=pkg.default_params(lsd_steps=4, temp=0.7), want_audio=False)
-        for i in range(3):
-            o = oracle.flowlm_generate(toks[i], voice, 3, lsd_steps=4, temp=0.7, seed=5 + i)
-            assert max_rel(out4["latents"][i, :3], o["latents"]) < TOL, f"utterance {i} (4 steps)"
-        cond = np.concatenate([voice, voice[:60] * 0.7], axis=0).astype(np.float32)
-        outl = e.generate_batch(toks[:4], cond, 5, seeds=[21, 22, 23, 24], params=pkg.default_params(temp=0.7), want_audio=False)
-        for i in range(4):
-            o = oracle.flowlm_generate(toks[i], cond, 5, lsd_steps=1, temp=0.7, seed=21 + i)
-            assert max_rel(outl["latents"][i, :5], o["latents"]) < TOL, f"utterance {i} (long prefix)"
-        outn = e.generate_batch(toks[:2], np.zeros((0, 1024), np.float32), 4, seeds=[31, 32], params=pkg.default_params(temp=0.7),
-                                want_audio=False)
-        for i in range(2):
-            o = oracle.flowlm_generate(toks[i], np.zeros((0, 1024), np.float32), 4, lsd_steps=1, temp=0.7, seed=31 + i)
-            assert max_rel(outn["latents"][i, :4], o["latents"]) < TOL, f"utterance {i} (no prefix)"
-    finally:
-        e.close()
-
-
 def test_batch_of_512_spot_check(eng, pkg, oracle, voice, golden):
     """A batch beyond the bench size (four row tiles of 128, two attention pairs per warp): a few utterances against the
     oracle, and the padded tail (n = 500 -> 512 slots) must not disturb them; more than 1024 utterances are refused."""

@@ -1,0 +1,239 @@
+"""GPU suite: parity AT THE MEASURED CONFIGURATIONS (BASELINE.json configs[1..3]) through the C ABI.
+
+The bench runs 256 utterances x 100 frames with an fp16 own-KV cache and bf16 hi+lo activations in an autoregressive
+loop, batch-1 decodes of 200 frames, and Mimi decodes of 4096-frame items: the horizons where drift would live. These
+tests compare the CUDA path with the oracle (oracle/ptts_oracle.c, pinned to the compiled reference) at exactly those
+sizes. Bars (north star): FlowLM latents <= 1e-3 max-relative at fp32 accumulate - stated twice, normalised by the peak
+of the whole [frames, 32] matrix and, tighter, by the peak of each frame's own 32-vector - and
+PCM >= 40 dB SNR. Reference semantics: ptts_flowlm.c:1138-1251, ptts_mimi.c:570-738.
+"""
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import max_rel, max_rel_per_frame, snr_db
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+SNR_MIN = 40.0
+
+
+@pytest.fixture(scope="module")
+def eng(pkg, weights):
+    e = pkg.Engine(weights, 0)
+    yield e
+    e.close()
+
+
+def _bench_tokens(pkg, model_dir, n, seed=123):
+    """The prompt set bench.py times (synth.make_prompts + ptts_prepare_text + the SentencePiece fixture)."""
+    import sentencepiece as spm
+    sp = spm.SentencePieceProcessor(model_file=str(model_dir / "tokenizer.model"))
+    return [np.asarray(sp.encode(pkg.prepare_text(t)[0]), np.int32) for t in pkg.synth.make_prompts(n, seed=seed)]
+
+
+def test_config2_batch_256_x_100_frames_vs_oracle(eng, pkg, oracle, voice, model_dir):
+    """configs[2] exactly as bench.py runs it (256 prompts of ~100 characters, 125-frame voice prefix, temp 0.7, 100 frames,
+    host buffers in / out): three utterances (first and last slot of the first row tile, last slot of the batch) against
+    the oracle over ALL 100 frames, latents and PCM."""
+    toks = _bench_tokens(pkg, model_dir, 256)
+    seeds = np.arange(256, dtype=np.int64) + 123
+    out = eng.generate_batch(toks, voice, 100, seeds=seeds, params=pkg.default_params(lsd_steps=1, temp=0.7))
+    assert (out["frames"] == 100).all() and np.isfinite(out["audio"]).all()
+    for i in (0, 127, 255):
+        o = oracle.flowlm_generate(toks[i], voice, 100, lsd_steps=1, temp=0.7, seed=int(seeds[i]))
+        g, pf = max_rel(out["latents"][i], o["latents"]), max_rel_per_frame(out["latents"][i], o["latents"])
+        late = max_rel(out["latents"][i, 90:], o["latents"][90:])
+        ref_pcm = oracle.mimi_decode(oracle.scale_latents(o["latents"]))
+        snr = snr_db(out["audio"][i], ref_pcm)
+        print(f"utterance {i}: latents max-rel {g:.2e} (per-frame {pf:.2e}, frames 90..99 {late:.2e}), PCM {snr:.1f} dB")
+        assert g < TOL and pf < TOL, f"utterance {i}: latents {g:.2e} / per-frame {pf:.2e}"
+        assert snr > SNR_MIN, f"utterance {i}: PCM {snr:.1f} dB"
+
+
+def test_config1_batch1_200_frames_vs_oracle(eng, pkg, oracle, voice, model_dir):
+    """configs[1]: single-utterance streaming decode of 200 frames (16 s of audio), latents and PCM against the oracle."""
+    tok = _bench_tokens(pkg, model_dir, 1)[0]
+    o = oracle.flowlm_generate(tok, voice, 200, lsd_steps=1, temp=0.7, seed=123)
+    g = eng.flowlm_generate_latents(tok, voice, 200, lsd_steps=1, temp=0.7, seed=123)
+    assert g["frames"] == o["frames"] == 200
+    a, pf = max_rel(g["latents"], o["latents"]), max_rel_per_frame(g["latents"], o["latents"])
+    pcm = eng.mimi_decode(eng.scale_latents(g["latents"]))
+    snr = snr_db(pcm, oracle.mimi_decode(oracle.scale_latents(o["latents"])))
+    print(f"batch-1, 200 frames: latents max-rel {a:.2e} (per-frame {pf:.2e}), PCM {snr:.1f} dB")
+    assert a < TOL and pf < TOL
+    assert snr > SNR_MIN
+
+
+def test_streamed_pcm_vs_oracle_one_shot(eng, pkg, oracle, voice, model_dir):
+    """The streaming entry against the ORACLE's one-shot decode (not against the engine itself): 48 frames (> the 34-frame
+    receptive field of the Mimi decoder), handed out in chunks of 1, 4, 4, ... frames."""
+    tok = _bench_tokens(pkg, model_dir, 1)[0]
+    o = oracle.flowlm_generate(tok, voice, 48, lsd_steps=1, temp=0.7, seed=9)
+    ref_pcm = oracle.mimi_decode(oracle.scale_latents(o["latents"]))
+    chunks = list(eng.stream(tok, voice, 48, seed=9, params=pkg.default_params(temp=0.7), chunk=4))
+    pcm = np.concatenate(chunks)
+    assert len(chunks[0]) == 1920 and pcm.shape == ref_pcm.shape
+    snr = snr_db(pcm, ref_pcm)
+    tail = snr_db(pcm[40 * 1920:], ref_pcm[40 * 1920:])
+    print(f"streamed 48 frames vs oracle one-shot: {snr:.1f} dB (frames 40..47: {tail:.1f} dB)")
+    assert snr > SNR_MIN and tail > SNR_MIN
+
+
+def test_config3_mimi_4096_frame_items_slices_vs_oracle(eng, oracle):
+    """configs[3] geometry: items of 4096 latent frames (65 536 transformer tokens, 7.86 M samples each). The oracle's
+    attention is O(T^2), so it checks slices: the decoder is causal with a receptive field of 34 frames (two 250-token
+    windows + conv tails) and RoPE scores depend on position differences only, so frames [k, k+8) of the full decode must
+    equal the last 8 frames of the oracle's decode of frames [k-34, k+8); frames [0, 40) are compared directly."""
+    rng = np.random.default_rng(0)
+    lat = rng.standard_normal((2, 4096, 32)).astype(np.float32)
+    pcm = eng.mimi_decode_batch(lat)
+    assert pcm.shape == (2, 4096 * 1920) and np.isfinite(pcm).all()
+    for item in (0, 1):
+        head = oracle.mimi_decode(lat[item, :40])
+        s0 = snr_db(pcm[item, :40 * 1920], head)
+        assert s0 > SNR_MIN, f"item {item} frames [0,40): {s0:.1f} dB"
+        for k in (2000, 4088):
+            win = oracle.mimi_decode(lat[item, k - 34:k + 8])
+            s = snr_db(pcm[item, k * 1920:(k + 8) * 1920], win[34 * 1920:])
+            print(f"item {item}: frames [0,40) {s0:.1f} dB, frames [{k},{k + 8}) {s:.1f} dB")
+            assert s > SNR_MIN, f"item {item} frames [{k},{k + 8}): {s:.1f} dB"
+    # the staged (device-resident) form gives the same samples as the host-to-host call
+    eng.mimi_stage(lat[:, :64])
+    eng.mimi_run()
+    again = eng.mimi_fetch()
+    assert np.array_equal(again, eng.mimi_decode_batch(lat[:, :64]))
+
+
+def test_full_mantissa_f32_checkpoint(pkg, voice, golden):
+    """An F32 checkpoint whose weights use all 24 significand bits (the synthetic default is bf16-representable, which
+    hides the engine's bf16 / fp16 weight rounding from every other test). The engine's contract is bf16 FlowLM weights
+    (north star: 'weights in bf16'): against the oracle on the SAME weights rounded to bf16 the 1e-3 bar holds; against the
+    oracle on the unrounded F32 weights the distance is the weight-rounding error itself, reported and bounded."""
+    import pyoracle
+    Wf = pkg.synth.make_weights(3, full_mantissa=True)
+    Wr = {k: (pkg.synth.bf16_round(v) if k.startswith("flow_lm.") else v) for k, v in Wf.items()}
+    e = pkg.Engine(Wf, 0)
+    try:
+        o_full, o_round = pyoracle.Oracle(Wf), pyoracle.Oracle(Wr)
+        tok = golden["p2_ids"]
+        g = e.flowlm_generate_latents(tok, voice, 24, lsd_steps=1, temp=0.7, seed=7)
+        a = o_round.flowlm_generate(tok, voice, 24, lsd_steps=1, temp=0.7, seed=7)
+        b = o_full.flowlm_generate(tok, voice, 24, lsd_steps=1, temp=0.7, seed=7)
+        r_round, r_full = max_rel(g["latents"], a["latents"]), max_rel(g["latents"], b["latents"])
+        r_oracles = max_rel(a["latents"], b["latents"])
+        print(f"F32 checkpoint: engine vs oracle(bf16-rounded weights) {r_round:.2e}; engine vs oracle(F32 weights) {r_full:.2e}; "
+              f"oracle(bf16-rounded) vs oracle(F32) {r_oracles:.2e}")
+        assert r_round < TOL
+        assert r_full < 5e-2 and r_full < 3 * r_oracles + TOL    # the whole distance is the bf16 rounding of the weights
+        toks = [golden["p0_ids"], golden["p1_ids"], tok]
+        out = e.generate_batch(toks, voice, 12, seeds=[1, 2, 3], params=pkg.default_params(temp=0.7))
+        for i, t in enumerate(toks):
+            ob = o_round.flowlm_generate(t, voice, 12, lsd_steps=1, temp=0.7, seed=1 + i)
+            assert max_rel(out["latents"][i], ob["latents"]) < TOL, f"batched utterance {i}"
+        # Mimi (fp16 weights on the device, fp32 in the oracle): PCM bar unchanged
+        sl = o_full.scale_latents(b["latents"])
+        snr = snr_db(e.mimi_decode(sl), o_full.mimi_decode(sl))
+        print(f"F32 checkpoint: Mimi PCM vs oracle(F32 weights) {snr:.1f} dB")
+        assert snr > SNR_MIN
+    finally:
+        e.close()
+
+
+def test_two_engines_driven_from_two_host_threads(pkg, weights, oracle, voice, golden):
+    """include/ptts_b200.h: 'distinct engines may be driven from distinct host threads'. Two engines (same device - one GPU
+    per box here) run batched and single-utterance generations concurrently from two threads (ctypes drops the GIL inside
+    the C calls); every result is checked against the oracle. Nothing in the library is process-global except the once-only
+    driver entry point."""
+    engines = [pkg.Engine(weights, 0), pkg.Engine(weights, 0)]
+    toks = [[golden["p0_ids"], golden["p1_ids"], golden["p2_ids"]], [golden["p2_ids"][2:17], golden["p1_ids"][:9], golden["p0_ids"]]]
+    results, errors = [None, None], []
+
+    def work(t):
+        try:
+            outs = []
+            for rep in range(4):
+                b = engines[t].generate_batch(toks[t], voice, 6 + t, seeds=[10 * t + 1, 10 * t + 2, 10 * t + 3],
+                                              params=pkg.default_params(temp=0.7))
+                s = engines[t].flowlm_generate_latents(toks[t][0], voice, 5, temp=0.7, seed=77 + t)
+                outs.append((b, s))
+            results[t] = outs
+        except Exception as ex:  # noqa: BLE001
+            errors.append(ex)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    try:
+        assert not errors, errors
+        for t in range(2):
+            for b, s in results[t]:
+                for i, tk in enumerate(toks[t]):
+                    o = oracle.flowlm_generate(tk, voice, 6 + t, lsd_steps=1, temp=0.7, seed=10 * t + 1 + i)
+                    assert max_rel(b["latents"][i], o["latents"]) < TOL, f"thread {t} utterance {i}"
+                    assert snr_db(b["audio"][i], oracle.mimi_decode(oracle.scale_latents(o["latents"]))) > SNR_MIN
+                o = oracle.flowlm_generate(toks[t][0], voice, 5, lsd_steps=1, temp=0.7, seed=77 + t)
+                assert max_rel(s["latents"], o["latents"]) < TOL
+            assert np.array_equal(results[t][0][0]["latents"], results[t][3][0]["latents"])
+    finally:
+        for e in engines:
+            e.close()
+
+
+def test_overlong_request_fails_cleanly_and_the_engine_stays_usable(pkg, weights, oracle, voice, golden):
+    """A batched request whose cache rows (voice prefix + prompt + frames) exceed what the attention phase of the persistent
+    step kernel holds is refused BEFORE any state changes; a normal request on the same engine then works (the sticky
+    capacities of an earlier long request must not poison later calls). Also: a single-utterance stage between stream_next
+    calls closes the stream instead of letting it continue on another utterance's cache."""
+    e = pkg.Engine(weights, 0)
+    try:
+        toks = [golden["p0_ids"], golden["p1_ids"]]
+        with pytest.raises(pkg.EngineError, match="exceed"):
+            e.generate_batch(toks, voice, 900, seeds=[1, 2], params=pkg.default_params(temp=0.7), want_audio=False)
+        out = e.generate_batch(toks, voice, 5, seeds=[1, 2], params=pkg.default_params(temp=0.7), want_audio=False)
+        for i, t in enumerate(toks):
+            o = oracle.flowlm_generate(t, voice, 5, lsd_steps=1, temp=0.7, seed=1 + i)
+            assert max_rel(out["latents"][i], o["latents"]) < TOL
+        # a long single-utterance request (its own, larger limit) leaves big capacities behind; the batched path must still work
+        g = e.flowlm_generate_latents(golden["p0_ids"], voice, 900, lsd_steps=1, temp=0.0)
+        assert g["frames"] == 900 and np.isfinite(g["latents"]).all()
+        out = e.generate_batch(toks, voice, 5, seeds=[1, 2], params=pkg.default_params(temp=0.7), want_audio=False)
+        for i, t in enumerate(toks):
+            o = oracle.flowlm_generate(t, voice, 5, lsd_steps=1, temp=0.7, seed=1 + i)
+            assert max_rel(out["latents"][i], o["latents"]) < TOL
+        # stream interrupted by another single-utterance call
+        e.stream_begin(golden["p0_ids"], voice, 8, 5, pkg.default_params(temp=0.7))
+        pcm, done = e.stream_next(1)
+        assert len(pcm) == 1920 and not done
+        e.flowlm_generate_latents(golden["p1_ids"], voice, 3, temp=0.0)
+        with pytest.raises(pkg.EngineError, match="no stream is open"):
+            e.stream_next(1)
+    finally:
+        e.close()
+
+
+def test_mimi_forward_one_debug_hook(eng, weights):
+    """ptts_mimi_forward_one (ptts_mimi.c:550-564, the statistic behind the reference CLI's --mimi-test): one scaled latent ->
+    quantizer projection -> decoder transformer over that single token, against a float64 restatement."""
+    rng = np.random.default_rng(4)
+    lat = rng.standard_normal(32).astype(np.float32)
+    W = {k[len("mimi."):]: v.astype(np.float64) for k, v in weights.items() if k.startswith("mimi.")}
+    x = W["quantizer.output_proj.weight"].reshape(512, 32) @ lat.astype(np.float64)
+
+    def ln(v, w, b):
+        return (v - v.mean()) / np.sqrt(v.var() + 1e-5) * w + b
+
+    for l in range(2):
+        p = f"decoder_transformer.transformer.layers.{l}."
+        h = ln(x, W[p + "norm1.weight"], W[p + "norm1.bias"])
+        v = W[p + "self_attn.in_proj.weight"][1024:1536] @ h          # one token: softmax over one key -> output = v
+        x = x + W[p + "layer_scale_1.scale"] * (W[p + "self_attn.out_proj.weight"] @ v)
+        h = ln(x, W[p + "norm2.weight"], W[p + "norm2.bias"])
+        u = W[p + "linear1.weight"] @ h
+        u = 0.5 * u * (1.0 + np.tanh(0.79788456 * (u + 0.044715 * u ** 3)))
+        x = x + W[p + "layer_scale_2.scale"] * (W[p + "linear2.weight"] @ u)
+    got = eng.mimi_forward_one(lat)
+    assert max_rel(got, x) < 2e-3     # fp16 weights on the device
