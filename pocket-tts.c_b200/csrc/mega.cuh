@@ -297,409 +297,9 @@ __device__ __forceinline__ void mega_tail(const MegaProgram &P, int b, int tid, 
 }
 
 
-// ---------------------------------------------------------------- decode attention, persistent-kernel version
-// Work unit = one (utterance, head) pair, owned by ONE warp from start to end - no block-level barrier
-// sits between a unit's loads and its math, so the 16 warps of a CTA keep 16 independent streams of
-// 256-bit loads in flight (the per-utterance K / V rows are read exactly once, straight from HBM, and a
-// unit's rows are one contiguous region). Warps draw units from a per-CTA counter, so long and short
-// utterances balance out. The first 128 keys of the shared voice prefix sit in shared memory (one copy per CTA
-// and head); longer prefixes are read from L2 like the own rows.
-// Lane layout everywhere: 8 lanes per key row (32 bytes each), 4 rows per warp instruction.
-// Numerics follow ptts_flowlm.c:465-525: fp32 throughout, max-subtracted softmax, 1/sqrt(64) folded into q.
-constexpr int A4_TILE = 128, A4_WARPS = MG_THREADS / 32;
-__host__ __device__ inline size_t attn4_smem_bytes(int pcap) {
-    return (size_t)(2 * A4_TILE * FL_HD + A4_WARPS * 2 * (pcap + FL_HD) + 8) * sizeof(float);
-}
-__device__ __forceinline__ void ld_global_v8_pred(const float *ptr, bool ok, float (&v)[8]) {
-    if (ok) ld_global_v8(ptr, v);
-    else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = 0.0f;
-    }
-}
-__device__ __forceinline__ float dot8_reduce(const float (&q)[8], const float (&k)[8]) {
-    float a = q[0] * k[0] + q[1] * k[1] + q[2] * k[2] + q[3] * k[3] + q[4] * k[4] + q[5] * k[5] + q[6] * k[6] + q[7] * k[7];
-    a += __shfl_xor_sync(0xffffffffu, a, 1);
-    a += __shfl_xor_sync(0xffffffffu, a, 2);
-    a += __shfl_xor_sync(0xffffffffu, a, 4);
-    return a;
-}
-// scores of rows [0, n) of a global K region (row stride 64 floats) -> sc[0..n); `first` holds rows 0..31 already loaded
-__device__ __forceinline__ void qk_rows_global(const float *kb, int n, const float (&q8)[8], float *sc, int k4, int l8, float (&first)[8][8]) {
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int key = it * 4 + k4;
-        const float a = dot8_reduce(q8, first[it]);
-        if (l8 == 0 && key < n) sc[key] = a;
-    }
-    for (int r0 = 32; r0 < n; r0 += 32) {
-        float kr[8][8];
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            ld_global_v8_pred(kb + (size_t)key * FL_HD + l8 * 8, key < n, kr[it]);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            const float a = dot8_reduce(q8, kr[it]);
-            if (l8 == 0 && key < n) sc[key] = a;
-        }
-    }
-}
-__device__ __forceinline__ void load_rows32(const float *base, int n, int k4, int l8, float (&out)[8][8]) {
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int key = it * 4 + k4;
-        ld_global_v8_pred(base + (size_t)key * FL_HD + l8 * 8, key < n, out[it]);
-    }
-}
-// acc += sum_r sc[r] * V[r] over rows [0, n) of a global V region; `first` holds rows 0..31 already loaded
-__device__ __forceinline__ void pv_rows_global(const float *vb, int n, const float *sc, int k4, int l8, float (&first)[8][8], float (&acc)[8]) {
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int key = it * 4 + k4;
-        const float pw = key < n ? sc[key] : 0.0f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) acc[i] += pw * first[it][i];
-    }
-    for (int r0 = 32; r0 < n; r0 += 32) {
-        float vr[8][8];
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            ld_global_v8_pred(vb + (size_t)key * FL_HD + l8 * 8, key < n, vr[it]);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            const float pw = key < n ? sc[key] : 0.0f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] += pw * vr[it][i];
-        }
-    }
-}
-
-// Own K / V rows are fp16 (128 bytes per row): 8 lanes x 16 bytes per row, 4 rows (512 contiguous bytes) per
-// warp instruction, 32 rows (4 KB) per batch held as raw halves until they are used.
-constexpr int A4_BATCH = 32;
-__device__ __forceinline__ void load_own32(const __half *base, int n, int k4, int l8, uint4 (&raw)[8]) {
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int key = it * 4 + k4;
-        raw[it] = key < n ? *(const uint4 *)(base + (size_t)key * FL_HD + l8 * 8) : make_uint4(0u, 0u, 0u, 0u);
-    }
-}
-__device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
-    const float2 a = __half22float2(*(const __half2 *)&u.x), b = __half22float2(*(const __half2 *)&u.y),
-                 c = __half22float2(*(const __half2 *)&u.z), d = __half22float2(*(const __half2 *)&u.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-}
-
-// A warp works on a PAIR of units (two utterances, same head): the shared-memory prefix tile - the
-// same K / V rows for every utterance - is read once per pair, and each 16-byte chunk fetched from it
-// feeds both utterances' dot products. A lane reads its row's 32 bytes as two 16-byte halves; lanes
-// l8 >= 4 take the upper half first, so the 8 lanes of a quarter-warp cover all 32 banks (no conflict).
-// `qx` holds the query in that (first, second) order, `acc` of the prefix P.V likewise.
-__device__ __forceinline__ void qk_tile2(const float *kt, int k0, int k1, int n_tile, const float (&qx)[2][8], float *sc0, float *sc1,
-                                         int k4, int l8) {
-    const int o1 = l8 * 8 + ((l8 & 4) ? 4 : 0), o2 = l8 * 8 + ((l8 & 4) ? 0 : 4);
-    // branch-free body (rows past the tile are clamped for the loads and only the store is predicated), so the
-    // shuffles sit in uniform control flow and two iterations overlap
-#pragma unroll 2
-    for (int r0 = k0; r0 < k1; r0 += 4) {
-        const int key = r0 + k4, kc = min(key, n_tile - 1);
-        const float4 a = *(const float4 *)(kt + kc * FL_HD + o1);
-        const float4 b = *(const float4 *)(kt + kc * FL_HD + o2);
-        float d0 = qx[0][0] * a.x + qx[0][1] * a.y + qx[0][2] * a.z + qx[0][3] * a.w + qx[0][4] * b.x + qx[0][5] * b.y + qx[0][6] * b.z + qx[0][7] * b.w;
-        float d1 = qx[1][0] * a.x + qx[1][1] * a.y + qx[1][2] * a.z + qx[1][3] * a.w + qx[1][4] * b.x + qx[1][5] * b.y + qx[1][6] * b.z + qx[1][7] * b.w;
-        d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
-        d0 += __shfl_xor_sync(0xffffffffu, d0, 2); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
-        d0 += __shfl_xor_sync(0xffffffffu, d0, 4); d1 += __shfl_xor_sync(0xffffffffu, d1, 4);
-        if (l8 == 0 && key < n_tile) { sc0[key] = d0; sc1[key] = d1; }
-    }
-}
-__device__ __forceinline__ void pv_tile2(const float *vt, int k0, int k1, int n_tile, const float *sc0, const float *sc1, int k4, int l8,
-                                         float (&acc)[2][8]) {
-    const int o1 = l8 * 8 + ((l8 & 4) ? 4 : 0), o2 = l8 * 8 + ((l8 & 4) ? 0 : 4);
-#pragma unroll 2
-    for (int r0 = k0; r0 < k1; r0 += 4) {
-        const int key = r0 + k4, kc = min(key, n_tile - 1);
-        const float p0 = key < n_tile ? sc0[kc] : 0.0f, p1 = key < n_tile ? sc1[kc] : 0.0f;
-        const float4 a = *(const float4 *)(vt + kc * FL_HD + o1), b = *(const float4 *)(vt + kc * FL_HD + o2);
-        acc[0][0] += p0 * a.x; acc[0][1] += p0 * a.y; acc[0][2] += p0 * a.z; acc[0][3] += p0 * a.w;
-        acc[0][4] += p0 * b.x; acc[0][5] += p0 * b.y; acc[0][6] += p0 * b.z; acc[0][7] += p0 * b.w;
-        acc[1][0] += p1 * a.x; acc[1][1] += p1 * a.y; acc[1][2] += p1 * a.z; acc[1][3] += p1 * a.w;
-        acc[1][4] += p1 * b.x; acc[1][5] += p1 * b.y; acc[1][6] += p1 * b.z; acc[1][7] += p1 * b.w;
-    }
-}
-
-// The per-unit pieces are separate (non-inlined) functions: the pair code calls each twice, and the kernel's
-// instruction footprint decides how fast a phase switch is (the whole kernel is far larger than the I-cache).
-__device__ __noinline__ void a4_new_row(const AttnDecodeParams &p, int b, int h, int s, int pos, __half *okb, __half *ovb, float *sqd, int lane) {
-    const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD;
-    const float c = p.rope_cos[pos * 32 + lane], sn = p.rope_sin[pos * 32 + lane];
-    const float2 qq = ld_fold2(row + 2 * lane, p.qkv_nsplit, p.qkv_stride);
-    const float2 kk = ld_fold2(row + FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
-    const float2 vv = ld_fold2(row + 2 * FL_D + 2 * lane, p.qkv_nsplit, p.qkv_stride);
-    *(__half2 *)(okb + (size_t)s * FL_HD + 2 * lane) = __floats2half2_rn(kk.x * c - kk.y * sn, kk.x * sn + kk.y * c);
-    *(__half2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = __floats2half2_rn(vv.x, vv.y);
-    *(float2 *)(sqd + 2 * lane) = make_float2((qq.x * c - qq.y * sn) * 0.125f, (qq.x * sn + qq.y * c) * 0.125f);
-}
-// exp(score - max) in place, returns 1 / sum
-__device__ __forceinline__ float a4_softmax(float *sc, int P, int lane) {
-    float mx = -INFINITY;
-    for (int t = lane; t < P; t += 32) mx = fmaxf(mx, sc[t]);
-    mx = warp_max(mx);
-    float sum = 0.0f;
-    for (int t = lane; t < P; t += 32) { const float e = expf(sc[t] - mx); sc[t] = e; sum += e; }
-    return 1.0f / warp_sum(sum);
-}
-// prefix keys beyond the shared-memory tile (voice prompts longer than 128 frames): straight from L2
-__device__ __noinline__ void a4_far_qk(const float *kb, int n, const float *sqd, float *sc, int k4, int l8) {
-    float q8[8], rows[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) q8[i] = sqd[l8 * 8 + i];
-    load_rows32(kb, n, k4, l8, rows);
-    qk_rows_global(kb, n, q8, sc, k4, l8, rows);
-}
-__device__ __noinline__ void a4_far_pv(const float *vb, int n, const float *sc, int k4, int l8, float (&facc)[8]) {
-    float rows[8][8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) facc[i] = 0.0f;
-    load_rows32(vb, n, k4, l8, rows);
-    pv_rows_global(vb, n, sc, k4, l8, rows, facc);
-}
-
-// Units (b0, h) and - when nlive == 2 - (b0 + 1, h). scw: this warp's scratch, sc[2][pcap] then sq[2][64].
-__device__ __forceinline__ void attn4_pair(const AttnDecodeParams &p, int b0, int nlive, int h, int step, int cond_len, const float *kt,
-                                           const float *vt, float *scw, int pcap, int lane, unsigned long long *tm = nullptr) {
-    const int k4 = lane >> 3, l8 = lane & 7;
-    long long c0 = tm ? clock64() : 0;
-#define A4_STAMP(i) if (tm) { const long long c1 = clock64(); if (lane == 0) tm[i] += (unsigned long long)(c1 - c0); c0 = c1; }
-    const int n_tile = min(cond_len, A4_TILE), n_far = cond_len - n_tile;   // prefix keys in shared memory / beyond the tile
-    const float *pkh = p.pk ? p.pk + (size_t)h * p.pstride * FL_HD : nullptr;
-    const float *pvh = p.pv ? p.pv + (size_t)h * p.pstride * FL_HD : nullptr;
-    float *sc[2] = {scw, scw + pcap};
-    float *sq = scw + 2 * pcap;
-    int n_own[2];
-    __half *okb[2], *ovb[2];
-    // ---- new positions: RoPE(q), RoPE(k) and v appended to the own caches (lane = dimension pair). The partial sums and
-    // RoPE rows of BOTH units are requested before either is used (one global round trip per pair instead of two).
-    {
-        float2 rq[2][3][4];
-        float cs[2], sn[2];
-        int s_[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const bool live = u < nlive;
-            const int b = live ? b0 + u : b0;
-            const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD + 2 * lane;
-#pragma unroll
-            for (int c = 0; c < 3; c++)
-#pragma unroll
-                for (int z = 0; z < 4; z++)
-                    rq[u][c][z] = (z == 0 || z < p.qkv_nsplit) ? *(const float2 *)(row + c * FL_D + z * p.qkv_stride) : make_float2(0.0f, 0.0f);
-            s_[u] = step + p.own_base[b];
-            n_own[u] = live ? s_[u] + 1 : 0;
-            okb[u] = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-            ovb[u] = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int pos = cond_len + s_[u];
-            cs[u] = p.rope_cos[pos * 32 + lane]; sn[u] = p.rope_sin[pos * 32 + lane];
-        }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            if (u < nlive) {
-                float2 f[3];
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    f[c] = make_float2((rq[u][c][0].x + rq[u][c][1].x) + (rq[u][c][2].x + rq[u][c][3].x),
-                                       (rq[u][c][0].y + rq[u][c][1].y) + (rq[u][c][2].y + rq[u][c][3].y));
-                    for (int z = 4; z < p.qkv_nsplit; z++) {   // more than four partial sums (not produced by the step kernel's QKV split)
-                        const float2 e = *(const float2 *)(p.qkv + (size_t)(b0 + u) * 3 * FL_D + h * FL_HD + 2 * lane + c * FL_D + z * p.qkv_stride);
-                        f[c].x += e.x; f[c].y += e.y;
-                    }
-                }
-                *(__half2 *)(okb[u] + (size_t)s_[u] * FL_HD + 2 * lane) = __floats2half2_rn(f[1].x * cs[u] - f[1].y * sn[u], f[1].x * sn[u] + f[1].y * cs[u]);
-                *(__half2 *)(ovb[u] + (size_t)s_[u] * FL_HD + 2 * lane) = __floats2half2_rn(f[2].x, f[2].y);
-                *(float2 *)(sq + u * FL_HD + 2 * lane) = make_float2((f[0].x * cs[u] - f[0].y * sn[u]) * 0.125f, (f[0].x * sn[u] + f[0].y * cs[u]) * 0.125f);
-            } else *(float2 *)(sq + u * FL_HD + 2 * lane) = make_float2(0.0f, 0.0f);
-        }
-    }
-    __syncwarp();
-    A4_STAMP(0)
-    const int nbatch = max(1, (n_own[0] + A4_BATCH - 1) / A4_BATCH + (n_own[1] + A4_BATCH - 1) / A4_BATCH);
-    const int quantum = (((n_tile + nbatch - 1) / nbatch) + 3) & ~3;
-    uint4 raw[8];
-    int pre = 0;
-    {
-        // ---- scores: natural-order query for the own rows, (first, second)-order query for the prefix tile
-        float qn[2][8], qx[2][8];
-        const int sw = (l8 & 4) ? 4 : 0;
-#pragma unroll
-        for (int u = 0; u < 2; u++)
-#pragma unroll
-            for (int i = 0; i < 8; i++) { qn[u][i] = sq[u * FL_HD + l8 * 8 + i]; qx[u][i] = sq[u * FL_HD + l8 * 8 + ((i + sw) & 7)]; }
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            for (int r0 = 0; r0 < n_own[u]; r0 += A4_BATCH) {
-                load_own32(okb[u] + (size_t)r0 * FL_HD, n_own[u] - r0, k4, l8, raw);
-                qk_tile2(kt, pre, min(pre + quantum, n_tile), n_tile, qx, sc[0], sc[1], k4, l8);
-                pre = min(pre + quantum, n_tile);
-#pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    const int key = r0 + it * 4 + k4;
-                    float kf[8];
-                    unpack8(raw[it], kf);
-                    const float a = dot8_reduce(qn[u], kf);
-                    if (l8 == 0 && key < n_own[u]) sc[u][cond_len + key] = a;
-                }
-            }
-        }
-        qk_tile2(kt, pre, n_tile, n_tile, qx, sc[0], sc[1], k4, l8);
-        if (n_far > 0)
-            for (int u = 0; u < 2; u++) a4_far_qk(pkh + (size_t)n_tile * FL_HD, n_far, sq + u * FL_HD, sc[u] + n_tile, k4, l8);
-    }
-    __syncwarp();
-    A4_STAMP(1)
-    // ---- softmax per unit; the first batch of own V rows of unit 0 is requested before it
-    load_own32(ovb[0], n_own[0], k4, l8, raw);
-    float inv[2];
-#pragma unroll
-    for (int u = 0; u < 2; u++) inv[u] = u < nlive ? a4_softmax(sc[u], cond_len + n_own[u], lane) : 0.0f;
-    __syncwarp();
-    A4_STAMP(2)
-    // ---- P.V: prefix accumulators in (first, second) order, own accumulators in natural order
-    float pacc[2][8], oacc[2][8];
-#pragma unroll
-    for (int u = 0; u < 2; u++)
-#pragma unroll
-        for (int i = 0; i < 8; i++) { pacc[u][i] = 0.0f; oacc[u][i] = 0.0f; }
-    pre = 0;
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        for (int r0 = 0; r0 < n_own[u]; r0 += A4_BATCH) {
-            if (u > 0 || r0 > 0) load_own32(ovb[u] + (size_t)r0 * FL_HD, n_own[u] - r0, k4, l8, raw);
-            pv_tile2(vt, pre, min(pre + quantum, n_tile), n_tile, sc[0], sc[1], k4, l8, pacc);
-            pre = min(pre + quantum, n_tile);
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int key = r0 + it * 4 + k4;
-                const float pw = key < n_own[u] ? sc[u][cond_len + key] : 0.0f;
-                float vf[8];
-                unpack8(raw[it], vf);
-#pragma unroll
-                for (int i = 0; i < 8; i++) oacc[u][i] += pw * vf[i];
-            }
-        }
-    }
-    pv_tile2(vt, pre, n_tile, n_tile, sc[0], sc[1], k4, l8, pacc);
-    if (n_far > 0) {
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            float facc[8];
-            a4_far_pv(pvh + (size_t)n_tile * FL_HD, n_far, sc[u] + n_tile, k4, l8, facc);
-#pragma unroll
-            for (int i = 0; i < 8; i++) oacc[u][i] += facc[i];
-        }
-    }
-    A4_STAMP(3)
-    const bool swp = (l8 & 4) != 0;
-#pragma unroll
-    for (int u = 0; u < 2; u++) {
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {   // undo the (first, second) order of the prefix part
-            acc[i] = oacc[u][i] + (swp ? pacc[u][i + 4] : pacc[u][i]);
-            acc[i + 4] = oacc[u][i + 4] + (swp ? pacc[u][i] : pacc[u][i + 4]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-            acc[i] *= inv[u];
-        }
-        if (k4 == 0 && u < nlive) {   // lanes 0..7 hold the 64 outputs, 8 consecutive dimensions each
-            const size_t oi = (size_t)(b0 + u) * FL_D + h * FL_HD + l8 * 8;
-            if (p.out_f32) {
-                *(float4 *)(p.out_f32 + oi) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                *(float4 *)(p.out_f32 + oi + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            }
-            if (p.out_h) {
-                uint4 hv, lv;
-                uint32_t *hp = (uint32_t *)&hv, *lp = (uint32_t *)&lv;
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint16_t h0 = f2h16(acc[2 * i], true), h1 = f2h16(acc[2 * i + 1], true);
-                    hp[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    const uint16_t l0 = f2h16(acc[2 * i] - h162f(h0, true), true), l1 = f2h16(acc[2 * i + 1] - h162f(h1, true), true);
-                    lp[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                }
-                *(uint4 *)(p.out_h + oi) = hv;
-                if (p.out_l) *(uint4 *)(p.out_l + oi) = lv;
-            }
-        }
-    }
-    __syncwarp();   // scratch reusable by this warp's next pair
-    A4_STAMP(4)
-    if (tm && lane == 0) tm[5] += (unsigned long long)nlive;
-#undef A4_STAMP
-}
-
-// Pull a unit's own K / V rows into L2 ahead of its turn (lanes 0, 1 issue one bulk prefetch each).
-__device__ __forceinline__ void attn4_prefetch(const AttnDecodeParams &p, int b, int h, int step, int lane) {
-    if (lane < 2) {
-        const __half *ptr = (lane ? p.ov : p.ok) + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-        const uint32_t bytes = (uint32_t)(step + p.own_base[b]) * FL_HD * 2u;
-        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-    }
-}
-
-// One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b), drawn two at a time.
-__device__ __forceinline__ void attn4_phase(const AttnDecodeParams &p, int B, int pcap, int step, float *sm, int tid, unsigned long long *tmw = nullptr) {
-    float *kt = sm, *vt = kt + A4_TILE * FL_HD, *scw = vt + A4_TILE * FL_HD;
-    int *ctr = (int *)(scw + A4_WARPS * 2 * (pcap + FL_HD));
-    const int w = tid >> 5, lane = tid & 31;
-    float *scr = scw + w * 2 * (pcap + FL_HD);
-    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
-    // units in head-major order (unit = h * B + b). With at least one CTA per head, every CTA stays inside
-    // one head (one prefix tile, no mid-phase reload): gridDim / 16 CTAs share a head's utterances.
-    int u0, u1;
-    const int cph = (int)gridDim.x / FL_H;
-    if (cph >= 1) {
-        const int h = (int)blockIdx.x / cph, j = (int)blockIdx.x % cph;
-        if (h < FL_H) { u0 = h * B + (int)(((long long)j * B) / cph); u1 = h * B + (int)(((long long)(j + 1) * B) / cph); }
-        else { u0 = u1 = 0; }
-    } else {
-        const int units = FL_H * B;
-        u0 = (int)(((long long)blockIdx.x * units) / gridDim.x); u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
-    }
-    for (int ua = u0; ua < u1;) {
-        const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
-        __syncthreads();                                    // previous head's tile no longer in use
-        if (cond_len > 0) {
-            const int nt = min(A4_TILE, cond_len);
-            const float *pkh = p.pk + (size_t)h * p.pstride * FL_HD, *pvh = p.pv + (size_t)h * p.pstride * FL_HD;
-            for (int idx = tid; idx < nt * 16; idx += MG_THREADS) {
-                *(float4 *)(kt + idx * 4) = *(const float4 *)(pkh + idx * 4);
-                *(float4 *)(vt + idx * 4) = *(const float4 *)(pvh + idx * 4);
-            }
-        }
-        if (tid == 0) *ctr = ua;
-        __syncthreads();
-        while (true) {
-            int u = 0;
-            if (lane == 0) u = atomicAdd(ctr, 2);
-            u = __shfl_sync(0xffffffffu, u, 0);
-            if (u >= ub) break;
-            attn4_pair(p, u - h * B, min(2, ub - u), h, step, cond_len, kt, vt, scr, pcap, lane, (tmw && w == 0) ? tmw : nullptr);
-        }
-        ua = ub;
-    }
-}
+}  // namespace ptts
+#include "attn.cuh"
+namespace ptts {
 
 // ---------------------------------------------------------------- GEMM phase
 struct MegaPipe {
@@ -957,7 +557,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    attn4_phase(P.attn[ph.idx], P.B, P.pcap, step, (float *)ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                    attn6_phase(P.attn[ph.idx], P.B, P.pcap, step, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     break;
                 default: break;
             }
@@ -1089,9 +689,9 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
         }
     }
     const int pcap = ((e->capCond + e->capS + 63) / 32) * 32;
-    PTTS_CHECK(attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA,
+    PTTS_CHECK(attn6_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA,
                "attention score buffers of %zu bytes exceed the persistent kernel's shared memory (sequence too long)",
-               attn4_smem_bytes(pcap));
+               attn6_smem_bytes(pcap));
     if (e->dalloc(&M.d_phases, ph.size()) != 0 || e->dalloc(&M.d_gemms, gm.size()) != 0 || e->dalloc(&M.d_rows, rows.size()) != 0 ||
         e->dalloc(&M.d_attn, attn.size()) != 0) return -1;
     PTTS_CUDA_OK(cudaMemcpy(M.d_phases, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));

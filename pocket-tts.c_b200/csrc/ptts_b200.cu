@@ -215,9 +215,10 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
                 fprintf(stderr, "  %3d %-4s %7.2f %7.2f  %s\n", i, tn[q.type], tr[2 * i] * 1e-3 / st_, tr[2 * i + 1] * 1e-3 / st_, extra);
             }
             { const unsigned long long *a = &tr[(size_t)2 * P.n_phases]; const double nu = (double)std::max<unsigned long long>(a[5], 1);
-              fprintf(stderr, "  attention unit (CTA 0 warp 0, cycles per unit over %.0f units): new-row %.0f  scores %.0f  softmax %.0f  PV %.0f  write %.0f\n",
-                      nu, a[0] / nu, a[1] / nu, a[2] / nu, a[3] / nu, a[4] / nu);
-              fprintf(stderr, "    inside new-row (cumulative): loads and ring blocks issued %.0f  new rows stored %.0f\n", a[6] / nu, a[7] / nu); }
+              const double nphase = (double)FL_L * st_, npre = (double)std::max<unsigned long long>(a[7], 1);
+              fprintf(stderr, "  attention, CTA 0 (cycles): new rows of a chunk %.0f per phase; own rows per unit (warp 2, %.0f units): scores %.0f  softmax %.0f  PV %.0f  merge + write %.0f;"
+                              " prefix part of 16 units on the tensor cores (warp 0) %.0f\n",
+                      a[0] / nphase, nu, a[1] / nu, a[2] / nu, a[3] / nu, a[4] / nu, a[6] / npre); }
             e->dfree(d_trace);
         }
         static const int cls_of[MP_COUNT] = {KC_FLOW_MISC, KC_GEMM_FLOW, KC_ROWNORM, KC_FLOW_MISC, KC_FLOW_MISC, KC_ATTN_DECODE};
@@ -360,7 +361,7 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
         // left behind by an earlier, longer request are dropped when they alone would push the score buffers over the limit
         auto fits = [&](int cond, int S) {
             const int pcap = ((cond + S + 63) / 32) * 32;
-            return (B == 1 ? attn2_smem_bytes(pcap, 1) <= (size_t)200 * 1024 : attn4_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA) &&
+            return (B == 1 ? attn2_smem_bytes(pcap, 1) <= (size_t)200 * 1024 : attn6_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA) &&
                    pf_attn_smem_bytes(cond, max_tok + 1) <= (size_t)200 * 1024;
         };
         const int cond1 = std::max(cond_len, 1);

@@ -113,7 +113,15 @@ def test_full_mantissa_f32_checkpoint(pkg, voice, golden):
     oracle on the unrounded F32 weights the distance is the weight-rounding error itself, reported and bounded."""
     import pyoracle
     Wf = pkg.synth.make_weights(3, full_mantissa=True)
-    Wr = {k: (pkg.synth.bf16_round(v) if k.startswith("flow_lm.") else v) for k, v in Wf.items()}
+
+    def engine_keeps_bf16(name):   # the matrices the engine streams as bf16 (csrc/flowlm.cuh flow_load_weights); vectors stay fp32
+        if not name.startswith("flow_lm.") or "time_embed" in name or not name.endswith("weight"):
+            return False
+        return any(t in name for t in ("conditioner.embed", "input_linear", "in_proj", "out_proj", "linear1", "linear2", "cond_embed",
+                                       "input_proj", "mlp.0", "mlp.2", "adaLN_modulation", "final_layer.linear"))
+
+    Wr = {k: (pkg.synth.bf16_round(v) if engine_keeps_bf16(k) else v) for k, v in Wf.items()}
+    assert sum(engine_keeps_bf16(k) for k in Wf) == 4 + 6 * 4 + 6 * 3 + 2
     e = pkg.Engine(Wf, 0)
     try:
         o_full, o_round = pyoracle.Oracle(Wf), pyoracle.Oracle(Wr)
@@ -126,7 +134,7 @@ def test_full_mantissa_f32_checkpoint(pkg, voice, golden):
         print(f"F32 checkpoint: engine vs oracle(bf16-rounded weights) {r_round:.2e}; engine vs oracle(F32 weights) {r_full:.2e}; "
               f"oracle(bf16-rounded) vs oracle(F32) {r_oracles:.2e}")
         assert r_round < TOL
-        assert r_full < 5e-2 and r_full < 3 * r_oracles + TOL    # the whole distance is the bf16 rounding of the weights
+        assert r_full < 2e-2 and r_full < 3 * r_oracles + TOL    # the whole distance is the bf16 rounding of the weights
         toks = [golden["p0_ids"], golden["p1_ids"], tok]
         out = e.generate_batch(toks, voice, 12, seeds=[1, 2, 3], params=pkg.default_params(temp=0.7))
         for i, t in enumerate(toks):
