@@ -7,17 +7,16 @@
 // (unit = one utterance of that head). The two halves of the key set are treated differently:
 //   * voice prefix (the SAME K / V rows for every utterance): a dense contraction over the batch.
 //     S = Q[32 x 64] . Kp^T[64 x <=128] and O = P[32 x 128] . Vp[128 x 64] run on the tensor cores
-//     (mma.sync.m16n8k16, fp16 operands, fp32 accumulate), flash-style inside ONE warp per 16 units: q and the
-//     probabilities are carried as fp16 hi + lo pairs, the prefix K / V as the fp16 copy made once per voice.
-//     The result per unit is an un-normalised (max, sum, O[64]) triple in shared memory.
+//     (mma.sync.m16n8k16, fp16 operands, fp32 accumulate): q and the probabilities are carried as fp16 hi + lo pairs, the
+//     prefix K / V as the fp16 copy made once per voice. The work is cut into (16 units) x (16 keys) slices, one per warp;
+//     each slice leaves an un-normalised (max, sum, O[64]) partial per unit in shared memory.
 //   * own rows (fp16, ~tok_len + 1 + frames rows per utterance, read exactly once): one warp per unit, 8 lanes x 16 B per
-//     128-byte row, 4 rows per warp instruction, register double-buffered batches of 32 rows; fp32 math.
-//   The two partial softmaxes are merged by log-sum-exp (exact in exact arithmetic) and the output is written as bf16
-//   hi + lo (the A operand of the out-projection contraction).
+//     128-byte row, 4 rows per warp instruction; a warp's two units form ONE stream of 32-row blocks (K blocks, V blocks,
+//     next unit's K blocks ...) with two blocks in flight in registers across every stage boundary; fp32 math.
+//   The partial softmaxes (8 prefix slices + own rows) are merged by log-sum-exp (exact in exact arithmetic) and the output is
+//   written as bf16 hi + lo (the A operand of the out-projection contraction).
 // Prefix keys beyond the 128-row tile (voice prompts longer than 128 frames) are read by the unit's own warp from the fp32
 // prefix cache in L2.
-// Warps 0 and 1 first do the prefix part of their 16 units, then join the other 14 warps, which draw units from a per-chunk
-// counter; a unit's warp waits for its prefix triple (a shared-memory flag, release / acquire at CTA scope) only at the merge.
 #pragma once
 
 namespace ptts {
@@ -26,8 +25,9 @@ constexpr int A6_TILE = 128;                 // prefix keys on the tensor-core p
 constexpr int A6_CHUNK = 32;                 // units per chunk = two m16 row tiles
 constexpr int A6_WARPS = MG_THREADS / 32;
 // shared-memory map (bytes from the 1024-aligned ring base)
-constexpr int A6_KP = 0, A6_VP = 16384, A6_QH = 32768, A6_QL = 36864, A6_QF = 40960, A6_PO = 49152, A6_PML = 57344, A6_CTL = 57600,
-              A6_SC = 57664;
+constexpr int A6_SLICES = 8;                 // 16-key slices of the prefix tile, one warp each per row tile
+constexpr int A6_KP = 0, A6_VP = 16384, A6_QH = 32768, A6_QL = 36864, A6_QF = 40960, A6_PO = 49152,
+              A6_PML = A6_PO + A6_CHUNK * A6_SLICES * FL_HD * 4, A6_SC = A6_PML + A6_CHUNK * A6_SLICES * 2 * 4;
 __host__ __device__ inline size_t attn6_smem_bytes(int pcap) { return (size_t)A6_SC + (size_t)A6_WARPS * pcap * sizeof(float); }
 
 __device__ __forceinline__ void ld_global_v8_pred(const float *ptr, bool ok, float (&v)[8]) {
@@ -105,14 +105,6 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
 __device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
-__device__ __forceinline__ void st_release_cta(int *p, int v) {
-    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_cta(const int *p) {
-    int v;
-    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
 // fp32 pair -> fp16 hi pair and fp16 lo pair (lo = value - hi, exactly representable difference rounded once)
 __device__ __forceinline__ void split_hl(float a, float b, uint32_t &hi, uint32_t &lo) {
     const __half2 h = __floats2half2_rn(a, b);
@@ -155,235 +147,259 @@ __device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int
     *(uint32_t *)(sm + A6_QL + off) = lo;
 }
 
-// ---- prefix part of the 16 units of row tile mt (one warp): S = Q.Kp^T, online softmax over two halves of 64 keys,
-// O = P.Vp; un-normalised (max, sum, O) per unit -> shared memory. Rows of absent units hold q = 0 (finite results, unused).
-__device__ __noinline__ void a6_prefix_tile(uint8_t *sm, int mt, int n_tile, int lane) {
+// ---- prefix part, sliced: warp w takes row tile mt = w & 1 (16 units) and the 16 keys [16 ke, 16 ke + 16), ke = w >> 1:
+// S = Q.Kp^T over those keys, a local softmax, O = P.Vp; the un-normalised partial (max, sum, O[64]) per unit and slice goes to
+// shared memory and is merged with the own-row part by log-sum-exp. Rows of absent units hold q = 0 (finite results, unused);
+// a slice past the end of the prefix writes (-inf, 0, 0).
+__device__ __forceinline__ void a6_prefix_slice(uint8_t *sm, int mt, int ke, int n_tile, int lane) {
     const uint32_t kp = smem_u32(sm + A6_KP), vp = smem_u32(sm + A6_VP), qh = smem_u32(sm + A6_QH), ql = smem_u32(sm + A6_QL);
-    const int g = lane >> 2, j = lane & 3;
-    uint32_t ah[4][4], al[4][4];
-    {
-        const int row = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-#pragma unroll
-        for (int ks = 0; ks < 4; ks++) {
-            const uint32_t off = a6_swz(row, ks * 2 + (lane >> 4));
-            ldsm_x4(qh + off, ah[ks]);
-            ldsm_x4(ql + off, al[ks]);
-        }
-    }
-    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    const int g = lane >> 2, j = lane & 3, key0 = ke * 16;
+    float *po = (float *)(sm + A6_PO), *pml = (float *)(sm + A6_PML);
+    const int ua = mt * 16 + g, ub = ua + 8;
     float o[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-        const int key0 = half * 64;
-        if (key0 >= n_tile) break;
-        float s[8][4];
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
+    if (key0 < n_tile) {
+        float s[2][4];
+        {
+            const int qrow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-            uint32_t kb[2][4];
-            const int row = key0 + nt * 8 + (lane & 7);
-            ldsm_x4(kp + a6_swz(row, lane >> 3), kb[0]);        // dims 0..31: b0 / b1 of k-steps 0, 1
-            ldsm_x4(kp + a6_swz(row, 4 + (lane >> 3)), kb[1]);  // dims 32..63: k-steps 2, 3
+            for (int nt = 0; nt < 2; nt++) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+                uint32_t kb[2][4];
+                const int row = key0 + nt * 8 + (lane & 7);
+                ldsm_x4(kp + a6_swz(row, lane >> 3), kb[0]);        // dims 0..31: b0 / b1 of k-steps 0, 1
+                ldsm_x4(kp + a6_swz(row, 4 + (lane >> 3)), kb[1]);  // dims 32..63: k-steps 2, 3
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-                mma_f16_16816(s[nt], ah[ks], kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
-                mma_f16_16816(s[nt], al[ks], kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+                for (int ks = 0; ks < 4; ks++) {
+                    uint32_t ah[4], al[4];
+                    const uint32_t off = a6_swz(qrow, ks * 2 + (lane >> 4));
+                    ldsm_x4(qh + off, ah);
+                    ldsm_x4(ql + off, al);
+                    mma_f16_16816(s[nt], ah, kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+                    mma_f16_16816(s[nt], al, kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+                }
             }
         }
-        float b0 = -INFINITY, b1 = -INFINITY;
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
+        for (int nt = 0; nt < 2; nt++) {
             const int key = key0 + nt * 8 + 2 * j;
             if (key >= n_tile) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
             if (key + 1 >= n_tile) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
-            b0 = fmaxf(b0, fmaxf(s[nt][0], s[nt][1]));
-            b1 = fmaxf(b1, fmaxf(s[nt][2], s[nt][3]));
         }
-        b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, 1)); b0 = fmaxf(b0, __shfl_xor_sync(0xffffffffu, b0, 2));
-        b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, 1)); b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, 2));
-        // key key0 is valid (key0 < n_tile), so the new maxima are finite
-        const float n0 = fmaxf(m0, b0), n1 = fmaxf(m1, b1);
-        const float f0 = expf(m0 - n0), f1 = expf(m1 - n1);   // exp(-inf) = 0 on the first half
-        float r0 = 0.0f, r1 = 0.0f;
+        m0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
+        m1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        // key key0 is valid, so both maxima are finite
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            s[nt][0] = expf(s[nt][0] - n0); s[nt][1] = expf(s[nt][1] - n0);
-            s[nt][2] = expf(s[nt][2] - n1); s[nt][3] = expf(s[nt][3] - n1);
-            r0 += s[nt][0] + s[nt][1];
-            r1 += s[nt][2] + s[nt][3];
-            o[nt][0] *= f0; o[nt][1] *= f0; o[nt][2] *= f1; o[nt][3] *= f1;
+        for (int nt = 0; nt < 2; nt++) {
+            s[nt][0] = expf(s[nt][0] - m0); s[nt][1] = expf(s[nt][1] - m0);
+            s[nt][2] = expf(s[nt][2] - m1); s[nt][3] = expf(s[nt][3] - m1);
+            l0 += s[nt][0] + s[nt][1];
+            l1 += s[nt][2] + s[nt][3];
         }
-        l0 = l0 * f0 + r0; l1 = l1 * f1 + r1;
-        m0 = n0; m1 = n1;
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        uint32_t ph[4], pl[4];   // the two score tiles are the A fragment of P for this 16-key step
+        split_hl(s[0][0], s[0][1], ph[0], pl[0]);
+        split_hl(s[0][2], s[0][3], ph[1], pl[1]);
+        split_hl(s[1][0], s[1][1], ph[2], pl[2]);
+        split_hl(s[1][2], s[1][3], ph[3], pl[3]);
+        const int krow = key0 + ((lane >> 3) & 1) * 8 + (lane & 7);
 #pragma unroll
-        for (int kk = 0; kk < 4; kk++) {   // 16 keys per k-step: score tiles 2 kk and 2 kk + 1 are the A fragment of P
-            uint32_t ph[4], pl[4];
-            split_hl(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
-            split_hl(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
-            split_hl(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
-            split_hl(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
-            const int krow = key0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-#pragma unroll
-            for (int dp = 0; dp < 4; dp++) {   // dimension tiles 2 dp, 2 dp + 1
-                uint32_t vb[4];
-                ldsm_x4_t(vp + a6_swz(krow, dp * 2 + (lane >> 4)), vb);
-                mma_f16_16816(o[2 * dp], ph, vb[0], vb[1]);
-                mma_f16_16816(o[2 * dp], pl, vb[0], vb[1]);
-                mma_f16_16816(o[2 * dp + 1], ph, vb[2], vb[3]);
-                mma_f16_16816(o[2 * dp + 1], pl, vb[2], vb[3]);
-            }
+        for (int dp = 0; dp < 4; dp++) {   // dimension tiles 2 dp, 2 dp + 1
+            uint32_t vb[4];
+            ldsm_x4_t(vp + a6_swz(krow, dp * 2 + (lane >> 4)), vb);
+            mma_f16_16816(o[2 * dp], ph, vb[0], vb[1]);
+            mma_f16_16816(o[2 * dp], pl, vb[0], vb[1]);
+            mma_f16_16816(o[2 * dp + 1], ph, vb[2], vb[3]);
+            mma_f16_16816(o[2 * dp + 1], pl, vb[2], vb[3]);
         }
     }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    float *po = (float *)(sm + A6_PO), *pml = (float *)(sm + A6_PML);
-    const int ua = mt * 16 + g, ub = ua + 8;
-    if (j == 0) { pml[2 * ua] = m0; pml[2 * ua + 1] = l0; pml[2 * ub] = m1; pml[2 * ub + 1] = l1; }
+    if (j == 0) {
+        pml[(ua * A6_SLICES + ke) * 2] = m0; pml[(ua * A6_SLICES + ke) * 2 + 1] = l0;
+        pml[(ub * A6_SLICES + ke) * 2] = m1; pml[(ub * A6_SLICES + ke) * 2 + 1] = l1;
+    }
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
-        *(float2 *)(po + ua * FL_HD + nt * 8 + 2 * j) = make_float2(o[nt][0], o[nt][1]);
-        *(float2 *)(po + ub * FL_HD + nt * 8 + 2 * j) = make_float2(o[nt][2], o[nt][3]);
+        *(float2 *)(po + (size_t)(ua * A6_SLICES + ke) * FL_HD + nt * 8 + 2 * j) = make_float2(o[nt][0], o[nt][1]);
+        *(float2 *)(po + (size_t)(ub * A6_SLICES + ke) * FL_HD + nt * 8 + 2 * j) = make_float2(o[nt][2], o[nt][3]);
     }
 }
 
-// ---- own rows of unit u = (b, h) + the far prefix rows, merged with the unit's prefix triple; one warp.
-__device__ __noinline__ void a6_own_unit(const AttnDecodeParams &p, int b, int h, int u, int step, int cond_len, int n_tile, uint8_t *sm,
-                                            float *sc, int seq, int lane, unsigned long long *tm) {
-    const int k4 = lane >> 3, l8 = lane & 7;
+// ---- own rows of this warp's units (chunk units w and w + 16), as ONE stream of 32-row blocks
+//   unit 0: K blocks, V blocks; unit 1: K blocks, V blocks
+// with two blocks in flight in registers at all times: the V rows of a unit are on their way while its softmax runs, the next
+// unit's K rows while this unit's output is merged and written - HBM never waits for a latency-bound stage of the same warp.
+// (unit descriptors are plain scalars selected with ?: - an indexed array of structs would live in local memory)
+#define A6_SEL(i, a0, a1) ((i) < total0 ? (a0) : (a1))
+#define A6_ISSUE(i, raw)                                                                                              \
+    {                                                                                                                 \
+        const int li_ = (i) < total0 ? (i) : (i) - total0, nb_ = A6_SEL(i, nb0, nb1), no_ = A6_SEL(i, n_own0, n_own1); \
+        const bool isv_ = li_ >= nb_;                                                                                 \
+        const int r0_ = (isv_ ? li_ - nb_ : li_) * 32;                                                                \
+        load_own32((isv_ ? A6_SEL(i, vp0, vp1) : A6_SEL(i, kp0, kp1)) + (size_t)r0_ * FL_HD, no_ - r0_, k4, l8, raw); \
+    }
+
+__device__ __noinline__ void a6_own_stream(const AttnDecodeParams &p, int h, int b0, int nu, int u_first, int step, int cond_len, int n_tile,
+                                           uint8_t *sm, float *sc, int lane, unsigned long long *tm) {
+    const int k4 = lane >> 3, l8 = lane & 7, n_far = cond_len - n_tile;
     long long c0 = tm ? clock64() : 0;
 #define A6_STAMP(i) if (tm) { const long long c1 = clock64(); if (lane == 0) tm[i] += (unsigned long long)(c1 - c0); c0 = c1; }
-    const int n_own = step + p.own_base[b] + 1, n_far = cond_len - n_tile;
-    const __half *okb = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD, *ovb = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-    const float *qf = (const float *)(sm + A6_QF) + u * FL_HD;
+    const int ua0 = u_first, ua1 = u_first + A6_WARPS;
+    const int bb0 = ua0 < nu ? b0 + ua0 : b0, bb1 = ua1 < nu ? b0 + ua1 : b0;
+    const int n_own0 = ua0 < nu ? step + p.own_base[bb0] + 1 : 0, n_own1 = ua1 < nu ? step + p.own_base[bb1] + 1 : 0;
+    const int nb0 = (n_own0 + 31) >> 5, nb1 = (n_own1 + 31) >> 5;
+    const __half *kp0 = p.ok + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD, *vp0 = p.ov + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD;
+    const __half *kp1 = p.ok + ((size_t)h * p.cap_b + bb1) * p.max_s * FL_HD, *vp1 = p.ov + ((size_t)h * p.cap_b + bb1) * p.max_s * FL_HD;
+    const int total0 = 2 * nb0, total = total0 + 2 * nb1;
+    if (total == 0) return;
     uint4 ra[8], rb[8];
-    load_own32(okb, n_own, k4, l8, ra);
-    float q8[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) q8[i] = qf[l8 * 8 + i];
-    // ---- scores: batches of 32 rows, the next batch in flight while this one is reduced
-#define A6_SCORE(raw, r0)                                                   \
-    _Pragma("unroll") for (int it = 0; it < 8; it++) {                      \
-        float kf[8];                                                        \
-        unpack8(raw[it], kf);                                               \
-        const float a = dot8_reduce(q8, kf);                                \
-        const int key = (r0) + it * 4 + k4;                                 \
-        if (l8 == 0 && key < n_own) sc[key] = a;                            \
-    }
+    A6_ISSUE(0, ra)
+    if (total > 1) A6_ISSUE(1, rb)
+    float q8[8], acc[8], mo = 0.0f, lo = 0.0f;
 #pragma unroll 1
-    for (int r0 = 0; r0 < n_own; r0 += 64) {
-        const bool more = r0 + 32 < n_own;
-        if (more) load_own32(okb + (size_t)(r0 + 32) * FL_HD, n_own - r0 - 32, k4, l8, rb);
-        A6_SCORE(ra, r0)
-        if (more) {
-            if (r0 + 64 < n_own) load_own32(okb + (size_t)(r0 + 64) * FL_HD, n_own - r0 - 64, k4, l8, ra);
-            A6_SCORE(rb, r0 + 32)
-        }
-    }
-#undef A6_SCORE
-    if (n_far > 0) a6_far_qk(p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, qf, sc + n_own, k4, l8);
-    load_own32(ovb, n_own, k4, l8, ra);   // first V batch requested before the softmax
-    __syncwarp();
-    A6_STAMP(1)
-    // ---- softmax over [own rows | far prefix rows]: exp(s - max) in place, sum kept for the merge
-    const int np = n_own + n_far;
-    float mo = -INFINITY;
-    for (int t = lane; t < np; t += 32) mo = fmaxf(mo, sc[t]);
-    mo = warp_max(mo);
-    float lo = 0.0f;
-    for (int t = lane; t < np; t += 32) { const float e = expf(sc[t] - mo); sc[t] = e; lo += e; }
-    lo = warp_sum(lo);
-    __syncwarp();
-    A6_STAMP(2)
-    // ---- P.V
-    float acc[8];
+    for (int i = 0; i < total; i++) {
+        const int li = i < total0 ? i : i - total0, x_nb = A6_SEL(i, nb0, nb1), x_n_own = A6_SEL(i, n_own0, n_own1);
+        const int x_u = A6_SEL(i, ua0, ua1), x_b = A6_SEL(i, bb0, bb1);
+        const bool isv = li >= x_nb;
+        const int r0 = (isv ? li - x_nb : li) * 32;
+        const float *qf = (const float *)(sm + A6_QF) + x_u * FL_HD;
+        if (li == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) acc[i] = 0.0f;
-#define A6_PV(raw, r0)                                                      \
-    _Pragma("unroll") for (int it = 0; it < 8; it++) {                      \
-        const int key = (r0) + it * 4 + k4;                                 \
-        const float pw = key < n_own ? sc[key] : 0.0f;                      \
-        float vf[8];                                                        \
-        unpack8(raw[it], vf);                                               \
-        _Pragma("unroll") for (int i = 0; i < 8; i++) acc[i] += pw * vf[i]; \
-    }
-#pragma unroll 1
-    for (int r0 = 0; r0 < n_own; r0 += 64) {
-        const bool more = r0 + 32 < n_own;
-        if (more) load_own32(ovb + (size_t)(r0 + 32) * FL_HD, n_own - r0 - 32, k4, l8, rb);
-        A6_PV(ra, r0)
-        if (more) {
-            if (r0 + 64 < n_own) load_own32(ovb + (size_t)(r0 + 64) * FL_HD, n_own - r0 - 64, k4, l8, ra);
-            A6_PV(rb, r0 + 32)
+            for (int d = 0; d < 8; d++) { q8[d] = qf[l8 * 8 + d]; acc[d] = 0.0f; }
         }
-    }
-#undef A6_PV
-    if (n_far > 0) a6_far_pv(p.pv + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, sc + n_own, k4, l8, acc);
+        // ---- consume block i from the buffer it was loaded into (even blocks: ra, odd blocks: rb), then refill that buffer
+        if (!isv) {
+            if ((i & 1) == 0) {
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-    }
-    A6_STAMP(3)
-    // ---- merge with the prefix triple of this unit (log-sum-exp), write bf16 hi + lo
-    float wa = 0.0f, wb = 1.0f, lp = 0.0f;
-    const float *po = (const float *)(sm + A6_PO) + u * FL_HD + l8 * 8;
-    if (n_tile > 0) {
-        const int *flag = (const int *)(sm + A6_CTL) + 1 + (u >> 4);
-        if (lane == 0) {
-            const long long t0 = clock64();
-            while (ld_acquire_cta(flag) < seq)
-                if (clock64() - t0 > 2000000000LL) { printf("ptts_b200: attention prefix flag timed out (block %d)\n", blockIdx.x); __trap(); }
-        }
-        __syncwarp();
-        const float *pml = (const float *)(sm + A6_PML) + 2 * u;
-        const float mp = pml[0];
-        lp = pml[1];
-        const float m = fmaxf(mp, mo);
-        wa = expf(mp - m); wb = expf(mo - m);
-    }
-    const float inv = 1.0f / (lp * wa + lo * wb);
-    if (k4 == 0) {   // lanes 0..7 hold the 64 outputs, 8 consecutive dimensions each
-        float out[8];
-        if (n_tile > 0) {
-            const float4 pa = *(const float4 *)po, pb = *(const float4 *)(po + 4);
-            out[0] = pa.x; out[1] = pa.y; out[2] = pa.z; out[3] = pa.w; out[4] = pb.x; out[5] = pb.y; out[6] = pb.z; out[7] = pb.w;
-        } else {
+                for (int it = 0; it < 8; it++) {
+                    float kf[8];
+                    unpack8(ra[it], kf);
+                    const float a = dot8_reduce(q8, kf);
+                    const int key = r0 + it * 4 + k4;
+                    if (l8 == 0 && key < x_n_own) sc[key] = a;
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < 8; i++) out[i] = 0.0f;
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) out[i] = (out[i] * wa + acc[i] * wb) * inv;
-        const size_t oi = (size_t)b * FL_D + h * FL_HD + l8 * 8;
-        if (p.out_f32) {
-            *(float4 *)(p.out_f32 + oi) = make_float4(out[0], out[1], out[2], out[3]);
-            *(float4 *)(p.out_f32 + oi + 4) = make_float4(out[4], out[5], out[6], out[7]);
-        }
-        if (p.out_h) {
-            uint4 hv, lv;
-            uint32_t *hp = (uint32_t *)&hv, *lw = (uint32_t *)&lv;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint16_t h0 = f2h16(out[2 * i], true), h1 = f2h16(out[2 * i + 1], true);
-                hp[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                const uint16_t l0 = f2h16(out[2 * i] - h162f(h0, true), true), l1 = f2h16(out[2 * i + 1] - h162f(h1, true), true);
-                lw[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                for (int it = 0; it < 8; it++) {
+                    float kf[8];
+                    unpack8(rb[it], kf);
+                    const float a = dot8_reduce(q8, kf);
+                    const int key = r0 + it * 4 + k4;
+                    if (l8 == 0 && key < x_n_own) sc[key] = a;
+                }
             }
-            *(uint4 *)(p.out_h + oi) = hv;
-            if (p.out_l) *(uint4 *)(p.out_l + oi) = lv;
+        } else {
+            if ((i & 1) == 0) {
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int key = r0 + it * 4 + k4;
+                    const float pw = key < x_n_own ? sc[key] : 0.0f;
+                    float vf[8];
+                    unpack8(ra[it], vf);
+#pragma unroll
+                    for (int d = 0; d < 8; d++) acc[d] += pw * vf[d];
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int key = r0 + it * 4 + k4;
+                    const float pw = key < x_n_own ? sc[key] : 0.0f;
+                    float vf[8];
+                    unpack8(rb[it], vf);
+#pragma unroll
+                    for (int d = 0; d < 8; d++) acc[d] += pw * vf[d];
+                }
+            }
+        }
+        if (i + 2 < total) {
+            if ((i & 1) == 0) A6_ISSUE(i + 2, ra)
+            else A6_ISSUE(i + 2, rb)
+        }
+        if (!isv && li == x_nb - 1) {
+            // ---- all scores of the unit are in: far prefix rows, then softmax over [own rows | far prefix rows]
+            A6_STAMP(1)
+            if (n_far > 0) a6_far_qk(p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, qf, sc + x_n_own, k4, l8);
+            __syncwarp();
+            const int np = x_n_own + n_far;
+            mo = -INFINITY;
+            for (int t = lane; t < np; t += 32) mo = fmaxf(mo, sc[t]);
+            mo = warp_max(mo);
+            lo = 0.0f;
+            for (int t = lane; t < np; t += 32) { const float e = expf(sc[t] - mo); sc[t] = e; lo += e; }
+            lo = warp_sum(lo);
+            __syncwarp();
+            A6_STAMP(2)
+        }
+        if (isv && li == 2 * x_nb - 1) {
+            // ---- unit complete: reduce over the 4 row groups, merge with the prefix partials (log-sum-exp), write bf16 hi + lo
+            A6_STAMP(3)
+            if (n_far > 0) a6_far_pv(p.pv + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, sc + x_n_own, k4, l8, acc);
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+                acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 8);
+                acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 16);
+            }
+            if (k4 == 0) {   // lanes 0..7 hold the 64 outputs, 8 consecutive dimensions each
+                float m = mo;
+                const float *pml = (const float *)(sm + A6_PML) + (size_t)x_u * A6_SLICES * 2;
+                const float *po = (const float *)(sm + A6_PO) + (size_t)x_u * A6_SLICES * FL_HD + l8 * 8;
+                if (n_tile > 0) {
+#pragma unroll
+                    for (int e = 0; e < A6_SLICES; e++) m = fmaxf(m, pml[2 * e]);
+                }
+                const float wb = expf(mo - m);
+                float den = lo * wb, out[8];
+#pragma unroll
+                for (int d = 0; d < 8; d++) out[d] = acc[d] * wb;
+                if (n_tile > 0) {
+#pragma unroll
+                    for (int e = 0; e < A6_SLICES; e++) {
+                        const float we = expf(pml[2 * e] - m);   // exp(-inf) = 0 for slices past the end of the prefix
+                        den += pml[2 * e + 1] * we;
+                        const float4 pa = *(const float4 *)(po + e * FL_HD), pb = *(const float4 *)(po + e * FL_HD + 4);
+                        out[0] += pa.x * we; out[1] += pa.y * we; out[2] += pa.z * we; out[3] += pa.w * we;
+                        out[4] += pb.x * we; out[5] += pb.y * we; out[6] += pb.z * we; out[7] += pb.w * we;
+                    }
+                }
+                const float inv = 1.0f / den;
+#pragma unroll
+                for (int d = 0; d < 8; d++) out[d] *= inv;
+                const size_t oi = (size_t)x_b * FL_D + h * FL_HD + l8 * 8;
+                if (p.out_f32) {
+                    *(float4 *)(p.out_f32 + oi) = make_float4(out[0], out[1], out[2], out[3]);
+                    *(float4 *)(p.out_f32 + oi + 4) = make_float4(out[4], out[5], out[6], out[7]);
+                }
+                if (p.out_h) {
+                    uint4 hv, lv;
+                    uint32_t *hp = (uint32_t *)&hv, *lw = (uint32_t *)&lv;
+#pragma unroll
+                    for (int d = 0; d < 4; d++) {
+                        const uint16_t h0 = f2h16(out[2 * d], true), h1 = f2h16(out[2 * d + 1], true);
+                        hp[d] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                        const uint16_t l0 = f2h16(out[2 * d] - h162f(h0, true), true), l1 = f2h16(out[2 * d + 1] - h162f(h1, true), true);
+                        lw[d] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                    }
+                    *(uint4 *)(p.out_h + oi) = hv;
+                    if (p.out_l) *(uint4 *)(p.out_l + oi) = lv;
+                }
+            }
+            __syncwarp();   // score scratch reusable by the next unit
+            A6_STAMP(4)
+            if (tm && lane == 0) tm[5] += 1;
         }
     }
-    __syncwarp();   // score scratch reusable by this warp's next unit
-    A6_STAMP(4)
-    if (tm && lane == 0) tm[5] += 1;
 #undef A6_STAMP
+#undef A6_ISSUE
+#undef A6_SEL
 }
 
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
 __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int pcap, int step, uint8_t *sm, int tid, unsigned long long *tmw = nullptr) {
     const int w = tid >> 5, lane = tid & 31;
-    int *ctl = (int *)(sm + A6_CTL);
     float *sc = (float *)(sm + A6_SC) + (size_t)w * pcap;
     const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
     const int n_tile = min(cond_len, A6_TILE);
@@ -399,8 +415,6 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
         const int units = FL_H * B;
         u0 = (int)(((long long)blockIdx.x * units) / gridDim.x); u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
     }
-    if (tid == 0) { ctl[1] = 0; ctl[2] = 0; }
-    int seq = 0;
     for (int ua = u0; ua < u1;) {
         const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
         __syncthreads();                                    // previous head's tiles no longer in use
@@ -416,9 +430,7 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
         }
         for (int c0 = ua; c0 < ub; c0 += A6_CHUNK) {
             const int nu = min(A6_CHUNK, ub - c0), b0 = c0 - h * B;
-            if (c0 != ua) __syncthreads();                  // previous chunk's q rows and prefix triples no longer in use
-            if (tid == 0) ctl[0] = 0;
-            seq++;
+            if (c0 != ua) __syncthreads();                  // previous chunk's q rows and prefix partials no longer in use
             long long t0 = (tmw && w == 2) ? clock64() : 0;
             for (int u = w; u < A6_CHUNK; u += A6_WARPS) {
                 if (u < nu) a6_new_row(p, b0 + u, h, u, step, cond_len, sm, lane);
@@ -429,21 +441,13 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
                 }
             }
             __syncthreads();
-            if (tmw && w == 2 && lane == 0) tmw[0] += (unsigned long long)(clock64() - t0);
-            if (w < 2 && n_tile > 0 && w * 16 < nu) {
-                t0 = (tmw && w == 0) ? clock64() : 0;
-                a6_prefix_tile(sm, w, n_tile, lane);
-                __syncwarp();
-                if (lane == 0) st_release_cta(ctl + 1 + w, seq);
-                if (tmw && w == 0 && lane == 0) { tmw[6] += (unsigned long long)(clock64() - t0); tmw[7] += 1; }
+            if (tmw && w == 2 && lane == 0) { const long long t1 = clock64(); tmw[0] += (unsigned long long)(t1 - t0); t0 = t1; }
+            if (n_tile > 0) {
+                if ((w & 1) * 16 < nu) a6_prefix_slice(sm, w & 1, w >> 1, n_tile, lane);
+                __syncthreads();                            // all partials of the chunk are in shared memory
+                if (tmw && w == 2 && lane == 0) { tmw[6] += (unsigned long long)(clock64() - t0); tmw[7] += 1; }
             }
-            while (true) {
-                int u = 0;
-                if (lane == 0) u = atomicAdd(ctl, 1);
-                u = __shfl_sync(0xffffffffu, u, 0);
-                if (u >= nu) break;
-                a6_own_unit(p, b0 + u, h, u, step, cond_len, n_tile, sm, sc, seq, lane, (tmw && w == 2) ? tmw : nullptr);
-            }
+            a6_own_stream(p, h, b0, nu, w, step, cond_len, n_tile, sm, sc, lane, (tmw && w == 2) ? tmw : nullptr);
         }
         ua = ub;
     }

@@ -124,6 +124,9 @@ static int flow_ensure_capacity(Engine *e, int B, int S, int tok, int F, int con
     cudaStreamSynchronize(e->st);
     e->invalidate_graphs();
     const bool regrow_prefix = cond > e->capCond;
+    // capacities grow in steps (32 cache rows, 16 tokens, 8 frames): a sweep over batches whose longest prompt differs by a few
+    // tokens must not re-allocate the caches and rebuild the step program on every call
+    S = (S + 31) / 32 * 32; tok = (tok + 15) / 16 * 16; F = (F + 7) / 8 * 8;
     B = std::max(B, e->capB); S = std::max(S, e->capS); tok = std::max(tok, e->capTok); F = std::max(F, e->capF);
     cond = std::max(cond, e->capCond);
     void **bufs[] = {(void **)&e->d_tokens, (void **)&e->d_tok_len, (void **)&e->d_max_frames, (void **)&e->d_eos_after,
@@ -426,7 +429,7 @@ static int flow_step_tc(Engine *e, const FlowState &st, const FlowGemms &G, int 
 static int prefill_ensure(Engine *e, int rows, int n) {
     if (rows <= e->capRows && e->d_row_start && e->pf_ffh_l) return 0;
     cudaStreamSynchronize(e->st);
-    rows = std::max(rows, e->capRows);
+    rows = std::max((rows + 2047) / 2048 * 2048, e->capRows);
     e->capRows = 0;   // a failed grow must not leave a capacity that passes the test above with null buffers
     void **bufs[] = {(void **)&e->d_row_b, (void **)&e->d_row_i, (void **)&e->d_row_start, (void **)&e->pf_x, (void **)&e->pf_qkv,
                      (void **)&e->pf_xn_h, (void **)&e->pf_xn_l, (void **)&e->pf_att_h, (void **)&e->pf_att_l,

@@ -360,7 +360,7 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     {   // sequence-length limits of the attention kernels, checked against THIS request before any state changes; capacities
         // left behind by an earlier, longer request are dropped when they alone would push the score buffers over the limit
         auto fits = [&](int cond, int S) {
-            const int pcap = ((cond + S + 63) / 32) * 32;
+            const int pcap = ((cond + (S + 31) / 32 * 32 + 63) / 32) * 32;   // S as flow_ensure_capacity rounds it
             return (B == 1 ? attn2_smem_bytes(pcap, 1) <= (size_t)200 * 1024 : attn6_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA) &&
                    pf_attn_smem_bytes(cond, max_tok + 1) <= (size_t)200 * 1024;
         };
