@@ -4,19 +4,24 @@
 // softmax(q.K^T / 8).V per head over [shared voice prefix | the utterance's own rows].
 //
 // A CTA works on one head and a span of utterances (gridDim / 16 CTAs per head), in chunks of up to 32 units
-// (unit = one utterance of that head). The two halves of the key set are treated differently:
+// (unit = one utterance of that head); warp w owns units w and w + 16 of the chunk. The key set has three parts:
+//   * own rows already in the cache (fp16, tok_len + 1 + frames-so-far rows per utterance, ~80 % of the phase's bytes, read
+//     exactly once, straight from HBM): each warp streams its units' K and V rows through a private ring of shared-memory slots
+//     filled by TMA bulk copies (cp.async.bulk, 8 K rows + 8 V rows = 2 KB per slot, completion on an mbarrier per slot). The
+//     old rows depend on nothing computed in this step, so the first copies are issued before anything else happens in the
+//     phase and a slot is refilled the moment it has been consumed: the copies stay in flight across every latency-bound stage
+//     (new rows, prefix part, merge) and no register holds data in flight. The rows are folded with an ONLINE softmax (running
+//     max / sum / accumulator per unit): no score buffer, no separate softmax stage, sequence length not limited by shared memory.
+//   * the new row: k / v of this step, taken from shared memory where the warp that appended them to the cache left them.
 //   * voice prefix (the SAME K / V rows for every utterance): a dense contraction over the batch.
 //     S = Q[32 x 64] . Kp^T[64 x <=128] and O = P[32 x 128] . Vp[128 x 64] run on the tensor cores
 //     (mma.sync.m16n8k16, fp16 operands, fp32 accumulate): q and the probabilities are carried as fp16 hi + lo pairs, the
-//     prefix K / V as the fp16 copy made once per voice. The work is cut into (16 units) x (16 keys) slices, one per warp;
-//     each slice leaves an un-normalised (max, sum, O[64]) partial per unit in shared memory.
-//   * own rows (fp16, ~tok_len + 1 + frames rows per utterance, read exactly once): one warp per unit, 8 lanes x 16 B per
-//     128-byte row, 4 rows per warp instruction; a warp's two units form ONE stream of 32-row blocks (K blocks, V blocks,
-//     next unit's K blocks ...) with two blocks in flight in registers across every stage boundary; fp32 math.
-//   The partial softmaxes (8 prefix slices + own rows) are merged by log-sum-exp (exact in exact arithmetic) and the output is
+//     prefix K / V as the fp16 copy made once per voice. The work is cut into (16 units) x (32 keys) slices, one per warp
+//     (8 warps); each slice leaves an un-normalised (max, sum, O[64]) partial per unit in shared memory.
+//   The partial softmaxes (4 prefix slices + own rows) are merged by log-sum-exp (exact in exact arithmetic) and the output is
 //   written as bf16 hi + lo (the A operand of the out-projection contraction).
 // Prefix keys beyond the 128-row tile (voice prompts longer than 128 frames) are read by the unit's own warp from the fp32
-// prefix cache in L2.
+// prefix cache in L2 and folded into the same online softmax.
 #pragma once
 
 namespace ptts {
@@ -24,11 +29,15 @@ namespace ptts {
 constexpr int A6_TILE = 128;                 // prefix keys on the tensor-core path
 constexpr int A6_CHUNK = 32;                 // units per chunk = two m16 row tiles
 constexpr int A6_WARPS = MG_THREADS / 32;
+constexpr int A6_SLICES = 4;                 // 32-key slices of the prefix tile, one warp each per row tile
+constexpr int A6_ROWS = 8;                   // own rows per ring slot (K rows + V rows)
+constexpr int A6_SLOTS = 3;                  // ring slots per warp
+constexpr int A6_SLOT_BYTES = 2 * A6_ROWS * FL_HD * 2;
 // shared-memory map (bytes from the 1024-aligned ring base)
-constexpr int A6_SLICES = 8;                 // 16-key slices of the prefix tile, one warp each per row tile
-constexpr int A6_KP = 0, A6_VP = 16384, A6_QH = 32768, A6_QL = 36864, A6_QF = 40960, A6_PO = 49152,
-              A6_PML = A6_PO + A6_CHUNK * A6_SLICES * FL_HD * 4, A6_SC = A6_PML + A6_CHUNK * A6_SLICES * 2 * 4;
-__host__ __device__ inline size_t attn6_smem_bytes(int pcap) { return (size_t)A6_SC + (size_t)A6_WARPS * pcap * sizeof(float); }
+constexpr int A6_KP = 0, A6_VP = 16384, A6_QH = 32768, A6_QL = 36864, A6_QF = 40960, A6_KN = 49152, A6_VN = 53248, A6_PML = 57344,
+              A6_PO = A6_PML + A6_CHUNK * A6_SLICES * 2 * 4, A6_RING = A6_PO + A6_CHUNK * A6_SLICES * FL_HD * 4,
+              A6_BARS = A6_RING + A6_WARPS * A6_SLOTS * A6_SLOT_BYTES, A6_END = A6_BARS + A6_WARPS * A6_SLOTS * 8;
+__host__ __device__ inline size_t attn6_smem_bytes(int) { return (size_t)A6_END; }   // independent of the sequence length
 
 __device__ __forceinline__ void ld_global_v8_pred(const float *ptr, bool ok, float (&v)[8]) {
     if (ok) ld_global_v8(ptr, v);
@@ -49,53 +58,7 @@ __device__ __forceinline__ void unpack8(const uint4 &u, float (&f)[8]) {
                  c = __half22float2(*(const __half2 *)&u.z), d = __half22float2(*(const __half2 *)&u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
-// 32 own rows (fp16, 128 B each) starting at `base`: lane (k4 = lane >> 3, l8 = lane & 7) fetches bytes [16 l8, 16 l8 + 16)
-// of rows 4 it + k4; rows past n come back as zeros
-__device__ __forceinline__ void load_own32(const __half *base, int n, int k4, int l8, uint4 (&raw)[8]) {
-#pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int key = it * 4 + k4;
-        raw[it] = key < n ? *(const uint4 *)(base + (size_t)key * FL_HD + l8 * 8) : make_uint4(0u, 0u, 0u, 0u);
-    }
-}
-
-// ---- prefix keys beyond the shared-memory tile: fp32 rows straight from the prefix cache (L2)
-__device__ __noinline__ void a6_far_qk(const float *kb, int n, const float *sqd, float *sc, int k4, int l8) {
-    float q8[8];
-#pragma unroll
-    for (int i = 0; i < 8; i++) q8[i] = sqd[l8 * 8 + i];
-    for (int r0 = 0; r0 < n; r0 += 32) {
-        float kr[8][8];
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            ld_global_v8_pred(kb + (size_t)key * FL_HD + l8 * 8, key < n, kr[it]);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            const float a = dot8_reduce(q8, kr[it]);
-            if (l8 == 0 && key < n) sc[key] = a;
-        }
-    }
-}
-__device__ __noinline__ void a6_far_pv(const float *vb, int n, const float *sc, int k4, int l8, float (&acc)[8]) {
-    for (int r0 = 0; r0 < n; r0 += 32) {
-        float vr[8][8];
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            ld_global_v8_pred(vb + (size_t)key * FL_HD + l8 * 8, key < n, vr[it]);
-        }
-#pragma unroll
-        for (int it = 0; it < 8; it++) {
-            const int key = r0 + it * 4 + k4;
-            const float pw = key < n ? sc[key] : 0.0f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[i] += pw * vr[it][i];
-        }
-    }
-}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) { asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory"); }
 
 // ---- fragment loads. Tiles are [rows][64 halves] with 128-byte rows; the 16-byte chunk c of row r sits at chunk c ^ (r & 7)
 __device__ __forceinline__ uint32_t a6_swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
@@ -114,8 +77,9 @@ __device__ __forceinline__ void split_hl(float a, float b, uint32_t &hi, uint32_
     lo = *(const uint32_t *)&l;
 }
 
-// ---- new position of unit (b, h): fold the split-K partial sums of q / k / v, RoPE, append k / v to the own cache, q -> smem
-// (fp32 for the own-row part, fp16 hi + lo in the fragment tile for the prefix part). Lane = dimension pair.
+// ---- new position of unit (b, h): fold the split-K partial sums of q / k / v, RoPE, append k / v to the own cache; q -> smem
+// (fp32 for the own-row part, fp16 hi + lo in the fragment tile for the prefix part), the fp16-rounded k / v of the new row -> smem
+// (exactly the values later steps read back from the cache). Lane = dimension pair.
 __device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int h, int u, int step, int cond_len, uint8_t *sm, int lane) {
     const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD + 2 * lane;
     float2 rq[3][4];
@@ -136,8 +100,11 @@ __device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int
         }
     }
     __half *okb = p.ok + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD, *ovb = p.ov + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-    *(__half2 *)(okb + (size_t)s * FL_HD + 2 * lane) = __floats2half2_rn(f[1].x * cs - f[1].y * sn, f[1].x * sn + f[1].y * cs);
-    *(__half2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = __floats2half2_rn(f[2].x, f[2].y);
+    const __half2 kh = __floats2half2_rn(f[1].x * cs - f[1].y * sn, f[1].x * sn + f[1].y * cs), vh = __floats2half2_rn(f[2].x, f[2].y);
+    *(__half2 *)(okb + (size_t)s * FL_HD + 2 * lane) = kh;
+    *(__half2 *)(ovb + (size_t)s * FL_HD + 2 * lane) = vh;
+    *(__half2 *)(sm + A6_KN + (u * FL_HD + 2 * lane) * 2) = kh;
+    *(__half2 *)(sm + A6_VN + (u * FL_HD + 2 * lane) * 2) = vh;
     const float qx = (f[0].x * cs - f[0].y * sn) * 0.125f, qy = (f[0].x * sn + f[0].y * cs) * 0.125f;   // 1 / sqrt(64) folded into q
     *(float2 *)((float *)(sm + A6_QF) + u * FL_HD + 2 * lane) = make_float2(qx, qy);
     uint32_t hi, lo;
@@ -147,13 +114,13 @@ __device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int
     *(uint32_t *)(sm + A6_QL + off) = lo;
 }
 
-// ---- prefix part, sliced: warp w takes row tile mt = w & 1 (16 units) and the 16 keys [16 ke, 16 ke + 16), ke = w >> 1:
-// S = Q.Kp^T over those keys, a local softmax, O = P.Vp; the un-normalised partial (max, sum, O[64]) per unit and slice goes to
-// shared memory and is merged with the own-row part by log-sum-exp. Rows of absent units hold q = 0 (finite results, unused);
-// a slice past the end of the prefix writes (-inf, 0, 0).
+// ---- prefix part, sliced: a warp takes row tile mt (16 units) and the 32 keys [32 ke, 32 ke + 32): S = Q.Kp^T over those keys, a
+// local softmax, O = P.Vp; the un-normalised partial (max, sum, O[64]) per unit and slice goes to shared memory and is merged
+// with the own-row part by log-sum-exp. Rows of absent units hold q = 0 (finite results, unused); a slice past the end of the
+// prefix writes (-inf, 0, 0).
 __device__ __forceinline__ void a6_prefix_slice(uint8_t *sm, int mt, int ke, int n_tile, int lane) {
     const uint32_t kp = smem_u32(sm + A6_KP), vp = smem_u32(sm + A6_VP), qh = smem_u32(sm + A6_QH), ql = smem_u32(sm + A6_QL);
-    const int g = lane >> 2, j = lane & 3, key0 = ke * 16;
+    const int g = lane >> 2, j = lane & 3, key0 = ke * 32;
     float *po = (float *)(sm + A6_PO), *pml = (float *)(sm + A6_PML);
     const int ua = mt * 16 + g, ub = ua + 8;
     float o[8][4];
@@ -161,40 +128,42 @@ __device__ __forceinline__ void a6_prefix_slice(uint8_t *sm, int mt, int ke, int
     for (int nt = 0; nt < 8; nt++) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.0f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     if (key0 < n_tile) {
-        float s[2][4];
+        float s[4][4];
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
         {
             const int qrow = mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
 #pragma unroll
-            for (int nt = 0; nt < 2; nt++) {
-                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
-                uint32_t kb[2][4];
-                const int row = key0 + nt * 8 + (lane & 7);
-                ldsm_x4(kp + a6_swz(row, lane >> 3), kb[0]);        // dims 0..31: b0 / b1 of k-steps 0, 1
-                ldsm_x4(kp + a6_swz(row, 4 + (lane >> 3)), kb[1]);  // dims 32..63: k-steps 2, 3
+            for (int ks = 0; ks < 4; ks++) {   // 16 dimensions per step
+                uint32_t ah[4], al[4];
+                const uint32_t off = a6_swz(qrow, ks * 2 + (lane >> 4));
+                ldsm_x4(qh + off, ah);
+                ldsm_x4(ql + off, al);
 #pragma unroll
-                for (int ks = 0; ks < 4; ks++) {
-                    uint32_t ah[4], al[4];
-                    const uint32_t off = a6_swz(qrow, ks * 2 + (lane >> 4));
-                    ldsm_x4(qh + off, ah);
-                    ldsm_x4(ql + off, al);
-                    mma_f16_16816(s[nt], ah, kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
-                    mma_f16_16816(s[nt], al, kb[ks >> 1][(ks & 1) * 2], kb[ks >> 1][(ks & 1) * 2 + 1]);
+                for (int np = 0; np < 2; np++) {   // key tiles 2 np, 2 np + 1: one x4 load = (b0, b1) of both for this k-step
+                    uint32_t kb[4];
+                    const int row = key0 + np * 16 + ((lane >> 4) & 1) * 8 + (lane & 7);
+                    ldsm_x4(kp + a6_swz(row, ks * 2 + ((lane >> 3) & 1)), kb);
+                    mma_f16_16816(s[2 * np], ah, kb[0], kb[1]);
+                    mma_f16_16816(s[2 * np], al, kb[0], kb[1]);
+                    mma_f16_16816(s[2 * np + 1], ah, kb[2], kb[3]);
+                    mma_f16_16816(s[2 * np + 1], al, kb[2], kb[3]);
                 }
             }
         }
 #pragma unroll
-        for (int nt = 0; nt < 2; nt++) {
+        for (int nt = 0; nt < 4; nt++) {
             const int key = key0 + nt * 8 + 2 * j;
             if (key >= n_tile) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
             if (key + 1 >= n_tile) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+            m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+            m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
         }
-        m0 = fmaxf(fmaxf(s[0][0], s[0][1]), fmaxf(s[1][0], s[1][1]));
-        m1 = fmaxf(fmaxf(s[0][2], s[0][3]), fmaxf(s[1][2], s[1][3]));
         m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
         m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
         // key key0 is valid, so both maxima are finite
 #pragma unroll
-        for (int nt = 0; nt < 2; nt++) {
+        for (int nt = 0; nt < 4; nt++) {
             s[nt][0] = expf(s[nt][0] - m0); s[nt][1] = expf(s[nt][1] - m0);
             s[nt][2] = expf(s[nt][2] - m1); s[nt][3] = expf(s[nt][3] - m1);
             l0 += s[nt][0] + s[nt][1];
@@ -202,20 +171,23 @@ __device__ __forceinline__ void a6_prefix_slice(uint8_t *sm, int mt, int ke, int
         }
         l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
         l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        uint32_t ph[4], pl[4];   // the two score tiles are the A fragment of P for this 16-key step
-        split_hl(s[0][0], s[0][1], ph[0], pl[0]);
-        split_hl(s[0][2], s[0][3], ph[1], pl[1]);
-        split_hl(s[1][0], s[1][1], ph[2], pl[2]);
-        split_hl(s[1][2], s[1][3], ph[3], pl[3]);
-        const int krow = key0 + ((lane >> 3) & 1) * 8 + (lane & 7);
 #pragma unroll
-        for (int dp = 0; dp < 4; dp++) {   // dimension tiles 2 dp, 2 dp + 1
-            uint32_t vb[4];
-            ldsm_x4_t(vp + a6_swz(krow, dp * 2 + (lane >> 4)), vb);
-            mma_f16_16816(o[2 * dp], ph, vb[0], vb[1]);
-            mma_f16_16816(o[2 * dp], pl, vb[0], vb[1]);
-            mma_f16_16816(o[2 * dp + 1], ph, vb[2], vb[3]);
-            mma_f16_16816(o[2 * dp + 1], pl, vb[2], vb[3]);
+        for (int kk = 0; kk < 2; kk++) {   // 16 keys per step: score tiles 2 kk and 2 kk + 1 are the A fragment of P
+            uint32_t ph[4], pl[4];
+            split_hl(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+            split_hl(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+            split_hl(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+            split_hl(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+            const int krow = key0 + kk * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+            for (int dp = 0; dp < 4; dp++) {   // dimension tiles 2 dp, 2 dp + 1
+                uint32_t vb[4];
+                ldsm_x4_t(vp + a6_swz(krow, dp * 2 + (lane >> 4)), vb);
+                mma_f16_16816(o[2 * dp], ph, vb[0], vb[1]);
+                mma_f16_16816(o[2 * dp], pl, vb[0], vb[1]);
+                mma_f16_16816(o[2 * dp + 1], ph, vb[2], vb[3]);
+                mma_f16_16816(o[2 * dp + 1], pl, vb[2], vb[3]);
+            }
         }
     }
     if (j == 0) {
@@ -229,178 +201,178 @@ __device__ __forceinline__ void a6_prefix_slice(uint8_t *sm, int mt, int ke, int
     }
 }
 
-// ---- own rows of this warp's units (chunk units w and w + 16), as ONE stream of 32-row blocks
-//   unit 0: K blocks, V blocks; unit 1: K blocks, V blocks
-// with two blocks in flight in registers at all times: the V rows of a unit are on their way while its softmax runs, the next
-// unit's K rows while this unit's output is merged and written - HBM never waits for a latency-bound stage of the same warp.
-// (unit descriptors are plain scalars selected with ?: - an indexed array of structs would live in local memory)
-#define A6_SEL(i, a0, a1) ((i) < total0 ? (a0) : (a1))
-#define A6_ISSUE(i, raw)                                                                                              \
-    {                                                                                                                 \
-        const int li_ = (i) < total0 ? (i) : (i) - total0, nb_ = A6_SEL(i, nb0, nb1), no_ = A6_SEL(i, n_own0, n_own1); \
-        const bool isv_ = li_ >= nb_;                                                                                 \
-        const int r0_ = (isv_ ? li_ - nb_ : li_) * 32;                                                                \
-        load_own32((isv_ ? A6_SEL(i, vp0, vp1) : A6_SEL(i, kp0, kp1)) + (size_t)r0_ * FL_HD, no_ - r0_, k4, l8, raw); \
-    }
+// ---- own rows. Online softmax state of the unit in flight: m (uniform over the warp), l and acc[8] per lane (partial over the rows
+// the lane's row group k4 has seen; reduced over the four groups when the unit is complete). Lane (k4 = lane >> 3, l8 = lane & 7)
+// handles rows 4 it + k4 of a block and dimensions [8 l8, 8 l8 + 8).
+struct A6Acc { float m, l, acc[8]; };
 
-__device__ __noinline__ void a6_own_stream(const AttnDecodeParams &p, int h, int b0, int nu, int u_first, int step, int cond_len, int n_tile,
-                                           uint8_t *sm, float *sc, int lane, unsigned long long *tm) {
+// fold NIT x 4 rows whose K / V values are given as fp32 registers; rows >= nvalid are ignored
+template <int NIT>
+__device__ __forceinline__ void a6_fold(A6Acc &st, const float (&q8)[8], const float (&kf)[NIT][8], const float (&vf)[NIT][8], int nvalid, int k4) {
+    float sc[NIT], cm = -INFINITY;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const float a = dot8_reduce(q8, kf[it]);
+        sc[it] = it * 4 + k4 < nvalid ? a : -INFINITY;
+        cm = fmaxf(cm, sc[it]);
+    }
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
+    cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
+    const float mn = fmaxf(st.m, cm);               // finite whenever nvalid >= 1 (row 0 belongs to some lane group)
+    const float f = expf(st.m - mn);                // exp(-inf) = 0 on the first block
+    st.l *= f;
+#pragma unroll
+    for (int d = 0; d < 8; d++) st.acc[d] *= f;
+#pragma unroll
+    for (int it = 0; it < NIT; it++) {
+        const bool ok = it * 4 + k4 < nvalid;
+        const float pw = ok ? expf(sc[it] - mn) : 0.0f;
+        st.l += pw;
+#pragma unroll
+        for (int d = 0; d < 8; d++) st.acc[d] += pw * (ok ? vf[it][d] : 0.0f);   // stale shared memory beyond nvalid may hold NaN patterns
+    }
+    st.m = mn;
+}
+
+// far prefix rows [0, n) of fp32 K / V regions in L2 (voice prompts longer than the shared-memory tile)
+__device__ __noinline__ void a6_far(A6Acc &st, const float *kb, const float *vb, int n, const float *qf, int k4, int l8) {
+    float q8[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) q8[i] = qf[l8 * 8 + i];
+    for (int r0 = 0; r0 < n; r0 += 16) {
+        float kf[4][8], vf[4][8];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int key = r0 + it * 4 + k4;
+            ld_global_v8_pred(kb + (size_t)key * FL_HD + l8 * 8, key < n, kf[it]);
+            ld_global_v8_pred(vb + (size_t)key * FL_HD + l8 * 8, key < n, vf[it]);
+        }
+        a6_fold<4>(st, q8, kf, vf, n - r0, k4);
+    }
+}
+
+// One warp, its units u_first and u_first + 16 of the chunk: the stream of ring slots (slot c of the stream = 8 old rows of K and V
+// of one unit), then per unit the new row, the far prefix rows, the merge with the prefix partials and the write-out.
+struct A6Stream {
+    const __half *k0, *v0;      // unit 0 cache rows; unit 1 = + unit_stride
+    size_t unit_stride;
+    int n_old0, n_old1, nch0, total;
+};
+__device__ __forceinline__ void a6_issue(const A6Stream &S, int c, uint8_t *ring, uint64_t *bars) {   // one lane
+    const bool second = c >= S.nch0;
+    const int r0 = (second ? c - S.nch0 : c) * A6_ROWS, n_old = second ? S.n_old1 : S.n_old0;
+    const uint32_t bytes = (uint32_t)min(A6_ROWS, n_old - r0) * FL_HD * 2;
+    const size_t off = (second ? S.unit_stride : 0) + (size_t)r0 * FL_HD;
+    const int slot = c % A6_SLOTS;
+    uint8_t *dst = ring + slot * A6_SLOT_BYTES;
+    mbar_expect_tx(&bars[slot], 2 * bytes);
+    bulk_load_1d(dst, S.k0 + off, bytes, &bars[slot]);
+    bulk_load_1d(dst + A6_SLOT_BYTES / 2, S.v0 + off, bytes, &bars[slot]);
+}
+
+__device__ __noinline__ void a6_own_stream(const AttnDecodeParams &p, const A6Stream &S, int h, int b0, int u_first, int cond_len, int n_tile,
+                                           uint8_t *sm, uint8_t *ring, uint64_t *bars, int lane, unsigned long long *tm) {
     const int k4 = lane >> 3, l8 = lane & 7, n_far = cond_len - n_tile;
     long long c0 = tm ? clock64() : 0;
 #define A6_STAMP(i) if (tm) { const long long c1 = clock64(); if (lane == 0) tm[i] += (unsigned long long)(c1 - c0); c0 = c1; }
-    const int ua0 = u_first, ua1 = u_first + A6_WARPS;
-    const int bb0 = ua0 < nu ? b0 + ua0 : b0, bb1 = ua1 < nu ? b0 + ua1 : b0;
-    const int n_own0 = ua0 < nu ? step + p.own_base[bb0] + 1 : 0, n_own1 = ua1 < nu ? step + p.own_base[bb1] + 1 : 0;
-    const int nb0 = (n_own0 + 31) >> 5, nb1 = (n_own1 + 31) >> 5;
-    const __half *kp0 = p.ok + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD, *vp0 = p.ov + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD;
-    const __half *kp1 = p.ok + ((size_t)h * p.cap_b + bb1) * p.max_s * FL_HD, *vp1 = p.ov + ((size_t)h * p.cap_b + bb1) * p.max_s * FL_HD;
-    const int total0 = 2 * nb0, total = total0 + 2 * nb1;
-    if (total == 0) return;
-    uint4 ra[8], rb[8];
-    A6_ISSUE(0, ra)
-    if (total > 1) A6_ISSUE(1, rb)
-    float q8[8], acc[8], mo = 0.0f, lo = 0.0f;
+    A6Acc st;
+    float q8[8];
+    int c = 0;
 #pragma unroll 1
-    for (int i = 0; i < total; i++) {
-        const int li = i < total0 ? i : i - total0, x_nb = A6_SEL(i, nb0, nb1), x_n_own = A6_SEL(i, n_own0, n_own1);
-        const int x_u = A6_SEL(i, ua0, ua1), x_b = A6_SEL(i, bb0, bb1);
-        const bool isv = li >= x_nb;
-        const int r0 = (isv ? li - x_nb : li) * 32;
-        const float *qf = (const float *)(sm + A6_QF) + x_u * FL_HD;
-        if (li == 0) {
+    for (int x = 0; x < 2; x++) {
+        const int u = u_first + x * A6_WARPS, nch = x ? S.total - S.nch0 : S.nch0, n_old = x ? S.n_old1 : S.n_old0;
+        if (x == 1 && S.n_old1 < 0) break;   // no second unit
+        const float *qf = (const float *)(sm + A6_QF) + u * FL_HD;
+        st.m = -INFINITY; st.l = 0.0f;
 #pragma unroll
-            for (int d = 0; d < 8; d++) { q8[d] = qf[l8 * 8 + d]; acc[d] = 0.0f; }
+        for (int d = 0; d < 8; d++) { st.acc[d] = 0.0f; q8[d] = qf[l8 * 8 + d]; }
+#pragma unroll 1
+        for (int i = 0; i < nch; i++, c++) {
+            const int slot = c % A6_SLOTS;
+            mbar_wait(&bars[slot], (uint32_t)(c / A6_SLOTS) & 1u);
+            const uint8_t *src = ring + slot * A6_SLOT_BYTES + (k4 * FL_HD + l8 * 8) * 2;
+            float kf[2][8], vf[2][8];
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                unpack8(*(const uint4 *)(src + it * 4 * FL_HD * 2), kf[it]);
+                unpack8(*(const uint4 *)(src + A6_SLOT_BYTES / 2 + it * 4 * FL_HD * 2), vf[it]);
+            }
+            __syncwarp();                                                   // every lane has read the slot
+            if (lane == 0 && c + A6_SLOTS < S.total) a6_issue(S, c + A6_SLOTS, ring, bars);
+            a6_fold<2>(st, q8, kf, vf, n_old - i * A6_ROWS, k4);
         }
-        // ---- consume block i from the buffer it was loaded into (even blocks: ra, odd blocks: rb), then refill that buffer
-        if (!isv) {
-            if ((i & 1) == 0) {
+        A6_STAMP(1)
+        {   // the new row of this step, from shared memory (row group 0 takes it)
+            float kf[1][8], vf[1][8];
+            unpack8(*(const uint4 *)(sm + A6_KN + (u * FL_HD + l8 * 8) * 2), kf[0]);
+            unpack8(*(const uint4 *)(sm + A6_VN + (u * FL_HD + l8 * 8) * 2), vf[0]);
+            a6_fold<1>(st, q8, kf, vf, 1, k4);
+        }
+        if (n_far > 0) a6_far(st, p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD, p.pv + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, qf, k4, l8);
+        // ---- unit complete: reduce over the four row groups, merge with the prefix partials (log-sum-exp), write bf16 hi + lo
+        st.l += __shfl_xor_sync(0xffffffffu, st.l, 8);
+        st.l += __shfl_xor_sync(0xffffffffu, st.l, 16);
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    float kf[8];
-                    unpack8(ra[it], kf);
-                    const float a = dot8_reduce(q8, kf);
-                    const int key = r0 + it * 4 + k4;
-                    if (l8 == 0 && key < x_n_own) sc[key] = a;
-                }
-            } else {
+        for (int d = 0; d < 8; d++) {
+            st.acc[d] += __shfl_xor_sync(0xffffffffu, st.acc[d], 8);
+            st.acc[d] += __shfl_xor_sync(0xffffffffu, st.acc[d], 16);
+        }
+        A6_STAMP(3)
+        if (k4 == 0) {   // lanes 0..7 hold the 64 outputs, 8 consecutive dimensions each
+            float m = st.m;
+            const float *pml = (const float *)(sm + A6_PML) + (size_t)u * A6_SLICES * 2;
+            const float *po = (const float *)(sm + A6_PO) + (size_t)u * A6_SLICES * FL_HD + l8 * 8;
+            if (n_tile > 0) {
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    float kf[8];
-                    unpack8(rb[it], kf);
-                    const float a = dot8_reduce(q8, kf);
-                    const int key = r0 + it * 4 + k4;
-                    if (l8 == 0 && key < x_n_own) sc[key] = a;
+                for (int e = 0; e < A6_SLICES; e++) m = fmaxf(m, pml[2 * e]);
+            }
+            const float wb = expf(st.m - m);
+            float den = st.l * wb, out[8];
+#pragma unroll
+            for (int d = 0; d < 8; d++) out[d] = st.acc[d] * wb;
+            if (n_tile > 0) {
+#pragma unroll
+                for (int e = 0; e < A6_SLICES; e++) {
+                    const float we = expf(pml[2 * e] - m);   // exp(-inf) = 0 for slices past the end of the prefix
+                    den += pml[2 * e + 1] * we;
+                    const float4 pa = *(const float4 *)(po + e * FL_HD), pb = *(const float4 *)(po + e * FL_HD + 4);
+                    out[0] += pa.x * we; out[1] += pa.y * we; out[2] += pa.z * we; out[3] += pa.w * we;
+                    out[4] += pb.x * we; out[5] += pb.y * we; out[6] += pb.z * we; out[7] += pb.w * we;
                 }
             }
-        } else {
-            if ((i & 1) == 0) {
+            const float inv = 1.0f / den;
 #pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    const int key = r0 + it * 4 + k4;
-                    const float pw = key < x_n_own ? sc[key] : 0.0f;
-                    float vf[8];
-                    unpack8(ra[it], vf);
+            for (int d = 0; d < 8; d++) out[d] *= inv;
+            const size_t oi = (size_t)(b0 + u) * FL_D + h * FL_HD + l8 * 8;
+            if (p.out_f32) {
+                *(float4 *)(p.out_f32 + oi) = make_float4(out[0], out[1], out[2], out[3]);
+                *(float4 *)(p.out_f32 + oi + 4) = make_float4(out[4], out[5], out[6], out[7]);
+            }
+            if (p.out_h) {
+                uint4 hv, lv;
+                uint32_t *hp = (uint32_t *)&hv, *lw = (uint32_t *)&lv;
 #pragma unroll
-                    for (int d = 0; d < 8; d++) acc[d] += pw * vf[d];
+                for (int d = 0; d < 4; d++) {
+                    const uint16_t h0 = f2h16(out[2 * d], true), h1 = f2h16(out[2 * d + 1], true);
+                    hp[d] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                    const uint16_t l0 = f2h16(out[2 * d] - h162f(h0, true), true), l1 = f2h16(out[2 * d + 1] - h162f(h1, true), true);
+                    lw[d] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                 }
-            } else {
-#pragma unroll
-                for (int it = 0; it < 8; it++) {
-                    const int key = r0 + it * 4 + k4;
-                    const float pw = key < x_n_own ? sc[key] : 0.0f;
-                    float vf[8];
-                    unpack8(rb[it], vf);
-#pragma unroll
-                    for (int d = 0; d < 8; d++) acc[d] += pw * vf[d];
-                }
+                *(uint4 *)(p.out_h + oi) = hv;
+                if (p.out_l) *(uint4 *)(p.out_l + oi) = lv;
             }
         }
-        if (i + 2 < total) {
-            if ((i & 1) == 0) A6_ISSUE(i + 2, ra)
-            else A6_ISSUE(i + 2, rb)
-        }
-        if (!isv && li == x_nb - 1) {
-            // ---- all scores of the unit are in: far prefix rows, then softmax over [own rows | far prefix rows]
-            A6_STAMP(1)
-            if (n_far > 0) a6_far_qk(p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, qf, sc + x_n_own, k4, l8);
-            __syncwarp();
-            const int np = x_n_own + n_far;
-            mo = -INFINITY;
-            for (int t = lane; t < np; t += 32) mo = fmaxf(mo, sc[t]);
-            mo = warp_max(mo);
-            lo = 0.0f;
-            for (int t = lane; t < np; t += 32) { const float e = expf(sc[t] - mo); sc[t] = e; lo += e; }
-            lo = warp_sum(lo);
-            __syncwarp();
-            A6_STAMP(2)
-        }
-        if (isv && li == 2 * x_nb - 1) {
-            // ---- unit complete: reduce over the 4 row groups, merge with the prefix partials (log-sum-exp), write bf16 hi + lo
-            A6_STAMP(3)
-            if (n_far > 0) a6_far_pv(p.pv + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, sc + x_n_own, k4, l8, acc);
-#pragma unroll
-            for (int d = 0; d < 8; d++) {
-                acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 8);
-                acc[d] += __shfl_xor_sync(0xffffffffu, acc[d], 16);
-            }
-            if (k4 == 0) {   // lanes 0..7 hold the 64 outputs, 8 consecutive dimensions each
-                float m = mo;
-                const float *pml = (const float *)(sm + A6_PML) + (size_t)x_u * A6_SLICES * 2;
-                const float *po = (const float *)(sm + A6_PO) + (size_t)x_u * A6_SLICES * FL_HD + l8 * 8;
-                if (n_tile > 0) {
-#pragma unroll
-                    for (int e = 0; e < A6_SLICES; e++) m = fmaxf(m, pml[2 * e]);
-                }
-                const float wb = expf(mo - m);
-                float den = lo * wb, out[8];
-#pragma unroll
-                for (int d = 0; d < 8; d++) out[d] = acc[d] * wb;
-                if (n_tile > 0) {
-#pragma unroll
-                    for (int e = 0; e < A6_SLICES; e++) {
-                        const float we = expf(pml[2 * e] - m);   // exp(-inf) = 0 for slices past the end of the prefix
-                        den += pml[2 * e + 1] * we;
-                        const float4 pa = *(const float4 *)(po + e * FL_HD), pb = *(const float4 *)(po + e * FL_HD + 4);
-                        out[0] += pa.x * we; out[1] += pa.y * we; out[2] += pa.z * we; out[3] += pa.w * we;
-                        out[4] += pb.x * we; out[5] += pb.y * we; out[6] += pb.z * we; out[7] += pb.w * we;
-                    }
-                }
-                const float inv = 1.0f / den;
-#pragma unroll
-                for (int d = 0; d < 8; d++) out[d] *= inv;
-                const size_t oi = (size_t)x_b * FL_D + h * FL_HD + l8 * 8;
-                if (p.out_f32) {
-                    *(float4 *)(p.out_f32 + oi) = make_float4(out[0], out[1], out[2], out[3]);
-                    *(float4 *)(p.out_f32 + oi + 4) = make_float4(out[4], out[5], out[6], out[7]);
-                }
-                if (p.out_h) {
-                    uint4 hv, lv;
-                    uint32_t *hp = (uint32_t *)&hv, *lw = (uint32_t *)&lv;
-#pragma unroll
-                    for (int d = 0; d < 4; d++) {
-                        const uint16_t h0 = f2h16(out[2 * d], true), h1 = f2h16(out[2 * d + 1], true);
-                        hp[d] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                        const uint16_t l0 = f2h16(out[2 * d] - h162f(h0, true), true), l1 = f2h16(out[2 * d + 1] - h162f(h1, true), true);
-                        lw[d] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                    }
-                    *(uint4 *)(p.out_h + oi) = hv;
-                    if (p.out_l) *(uint4 *)(p.out_l + oi) = lv;
-                }
-            }
-            __syncwarp();   // score scratch reusable by the next unit
-            A6_STAMP(4)
-            if (tm && lane == 0) tm[5] += 1;
-        }
+        A6_STAMP(4)
+        if (tm && lane == 0) tm[5] += 1;
     }
 #undef A6_STAMP
-#undef A6_ISSUE
-#undef A6_SEL
 }
 
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
-__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int pcap, int step, uint8_t *sm, int tid, unsigned long long *tmw = nullptr) {
+__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, uint8_t *sm, int tid, unsigned long long *tmw = nullptr) {
     const int w = tid >> 5, lane = tid & 31;
-    float *sc = (float *)(sm + A6_SC) + (size_t)w * pcap;
+    uint8_t *ring = sm + A6_RING + w * A6_SLOTS * A6_SLOT_BYTES;
+    uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
     const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
     const int n_tile = min(cond_len, A6_TILE);
     // with at least one CTA per head, every CTA stays inside one head (one prefix tile per phase): gridDim / 16 CTAs share
@@ -415,22 +387,43 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
         const int units = FL_H * B;
         u0 = (int)(((long long)blockIdx.x * units) / gridDim.x); u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
     }
+    int last_h = -1;
     for (int ua = u0; ua < u1;) {
         const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
-        __syncthreads();                                    // previous head's tiles no longer in use
-        if (n_tile > 0) {   // fp16 prefix tiles of head h, rows past the prefix zero-filled (P = 0 times garbage must stay 0)
-            const __half *pkh = p.pk16 + (size_t)h * p.pstride * FL_HD, *pvh = p.pv16 + (size_t)h * p.pstride * FL_HD;
-            for (int idx = tid; idx < A6_TILE * 8; idx += MG_THREADS) {
-                const int row = idx >> 3, c = idx & 7;
-                uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-                if (row < n_tile) { kv = *(const uint4 *)(pkh + (size_t)row * FL_HD + c * 8); vv = *(const uint4 *)(pvh + (size_t)row * FL_HD + c * 8); }
-                *(uint4 *)(sm + A6_KP + a6_swz(row, c)) = kv;
-                *(uint4 *)(sm + A6_VP + a6_swz(row, c)) = vv;
-            }
-        }
         for (int c0 = ua; c0 < ub; c0 += A6_CHUNK) {
             const int nu = min(A6_CHUNK, ub - c0), b0 = c0 - h * B;
-            if (c0 != ua) __syncthreads();                  // previous chunk's q rows and prefix partials no longer in use
+            __syncthreads();   // the previous chunk (or the previous phase's use of the ring memory) is over for every warp
+            // ---- this warp's stream of old own rows: set up the ring barriers and get the first copies going
+            A6Stream S;
+            {
+                const int ua0 = w, ua1 = w + A6_WARPS;
+                const int bb0 = b0 + min(ua0, nu - 1);
+                S.n_old0 = ua0 < nu ? step + p.own_base[bb0] : -1;
+                S.n_old1 = ua1 < nu ? step + p.own_base[b0 + ua1] : -1;
+                S.k0 = p.ok + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD;
+                S.v0 = p.ov + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD;
+                S.unit_stride = (size_t)A6_WARPS * p.max_s * FL_HD;
+                S.nch0 = S.n_old0 > 0 ? (S.n_old0 + A6_ROWS - 1) / A6_ROWS : 0;
+                S.total = S.nch0 + (S.n_old1 > 0 ? (S.n_old1 + A6_ROWS - 1) / A6_ROWS : 0);
+            }
+            if (lane == 0) {
+                for (int s = 0; s < A6_SLOTS; s++) mbar_init(&bars[s], 1);
+                fence_barrier_init();
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring memory was last touched through the generic proxy
+                for (int c = 0; c < A6_SLOTS && c < S.total; c++) a6_issue(S, c, ring, bars);
+            }
+            __syncwarp();
+            if (h != last_h && n_tile > 0) {   // fp16 prefix tiles of head h, rows past the prefix zero-filled (P = 0 times garbage must stay 0)
+                const __half *pkh = p.pk16 + (size_t)h * p.pstride * FL_HD, *pvh = p.pv16 + (size_t)h * p.pstride * FL_HD;
+                for (int idx = tid; idx < A6_TILE * 8; idx += MG_THREADS) {
+                    const int row = idx >> 3, cc = idx & 7;
+                    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
+                    if (row < n_tile) { kv = *(const uint4 *)(pkh + (size_t)row * FL_HD + cc * 8); vv = *(const uint4 *)(pvh + (size_t)row * FL_HD + cc * 8); }
+                    *(uint4 *)(sm + A6_KP + a6_swz(row, cc)) = kv;
+                    *(uint4 *)(sm + A6_VP + a6_swz(row, cc)) = vv;
+                }
+            }
+            last_h = h;
             long long t0 = (tmw && w == 2) ? clock64() : 0;
             for (int u = w; u < A6_CHUNK; u += A6_WARPS) {
                 if (u < nu) a6_new_row(p, b0 + u, h, u, step, cond_len, sm, lane);
@@ -443,11 +436,14 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
             __syncthreads();
             if (tmw && w == 2 && lane == 0) { const long long t1 = clock64(); tmw[0] += (unsigned long long)(t1 - t0); t0 = t1; }
             if (n_tile > 0) {
-                if ((w & 1) * 16 < nu) a6_prefix_slice(sm, w & 1, w >> 1, n_tile, lane);
+                if (w < 2 * A6_SLICES && (w & 1) * 16 < nu) a6_prefix_slice(sm, w & 1, w >> 1, n_tile, lane);
                 __syncthreads();                            // all partials of the chunk are in shared memory
                 if (tmw && w == 2 && lane == 0) { tmw[6] += (unsigned long long)(clock64() - t0); tmw[7] += 1; }
             }
-            a6_own_stream(p, h, b0, nu, w, step, cond_len, n_tile, sm, sc, lane, (tmw && w == 2) ? tmw : nullptr);
+            if (S.n_old0 >= 0) a6_own_stream(p, S, h, b0, w, cond_len, n_tile, sm, ring, bars, lane, (tmw && w == 2) ? tmw : nullptr);
+            __syncwarp();
+            if (lane == 0)
+                for (int s = 0; s < A6_SLOTS; s++) mbar_inval(&bars[s]);
         }
         ua = ub;
     }

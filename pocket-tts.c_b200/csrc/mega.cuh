@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    attn6_phase(P.attn[ph.idx], P.B, P.pcap, step, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                    attn6_phase(P.attn[ph.idx], P.B, step, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     break;
                 default: break;
             }

@@ -192,10 +192,12 @@ def test_two_engines_driven_from_two_host_threads(pkg, weights, oracle, voice, g
 
 
 def test_overlong_request_fails_cleanly_and_the_engine_stays_usable(pkg, weights, oracle, voice, golden):
-    """A batched request whose cache rows (voice prefix + prompt + frames) exceed what the attention phase of the persistent
-    step kernel holds is refused BEFORE any state changes; a normal request on the same engine then works (the sticky
-    capacities of an earlier long request must not poison later calls). Also: a single-utterance stage between stream_next
-    calls closes the stream instead of letting it continue on another utterance's cache."""
+    """A request the attention kernels cannot hold (here: a prompt whose rows, with the voice prefix, exceed the shared-memory
+    tile of the prompt-prefill attention) is refused BEFORE any state changes; a normal request on the same engine then works,
+    also after a very long single-utterance request has left large capacities behind (sticky capacities must not poison later
+    calls; the batched decode itself has no sequence limit: its own rows stream through TMA rings with an online softmax).
+    Also: a single-utterance stage between stream_next calls closes the stream instead of letting it continue on another
+    utterance's cache."""
     e = pkg.Engine(weights, 0)
     try:
         toks = [golden["p0_ids"], golden["p1_ids"]]
