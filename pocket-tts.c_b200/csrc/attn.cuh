@@ -368,16 +368,9 @@ __device__ __noinline__ void a6_own_stream(const AttnDecodeParams &p, const A6St
 #undef A6_STAMP
 }
 
-// One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
-__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, uint8_t *sm, int tid, unsigned long long *tmw = nullptr) {
-    const int w = tid >> 5, lane = tid & 31;
-    uint8_t *ring = sm + A6_RING + w * A6_SLOTS * A6_SLOT_BYTES;
-    uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
-    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
-    const int n_tile = min(cond_len, A6_TILE);
-    // with at least one CTA per head, every CTA stays inside one head (one prefix tile per phase): gridDim / 16 CTAs share
-    // a head's utterances
-    int u0, u1;
+// Units [u0, u1) of this CTA in head-major order (unit = h * B + b): with at least one CTA per head, every CTA stays inside one
+// head (one prefix tile per phase) and gridDim / 16 CTAs share a head's utterances.
+__device__ __forceinline__ void attn6_units(int B, int &u0, int &u1) {
     const int cph = (int)gridDim.x / FL_H;
     if (cph >= 1) {
         const int h = (int)blockIdx.x / cph, j = (int)blockIdx.x % cph;
@@ -387,7 +380,33 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
         const int units = FL_H * B;
         u0 = (int)(((long long)blockIdx.x * units) / gridDim.x); u1 = (int)(((long long)(blockIdx.x + 1) * units) / gridDim.x);
     }
+}
+
+// Pull the own K / V rows this CTA will stream in a coming attention phase into L2 (one bulk prefetch per unit and tensor; each
+// unit's rows are one contiguous region). Issued by the two warps that have no role in a GEMM phase, while HBM is nearly idle
+// (a GEMM phase streams ~8 MB of weights; an attention phase needs 84 MB of rows): the attention phase then streams from L2.
+__device__ __forceinline__ void attn6_prefetch_l2(const AttnDecodeParams &p, int B, int step, int t, int nthreads) {
+    int u0, u1;
+    attn6_units(B, u0, u1);
+    for (int i = t; i < 2 * (u1 - u0); i += nthreads) {
+        const int unit = u0 + (i >> 1), h = unit / B, b = unit - h * B;
+        const __half *ptr = ((i & 1) ? p.ov : p.ok) + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
+        const uint32_t bytes = (uint32_t)(step + p.own_base[b]) * FL_HD * 2u;
+        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
+    }
+}
+
+// One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
+__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, uint8_t *sm, int tid, unsigned long long *tmw = nullptr) {
+    const int w = tid >> 5, lane = tid & 31;
+    uint8_t *ring = sm + A6_RING + w * A6_SLOTS * A6_SLOT_BYTES;
+    uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
+    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
+    const int n_tile = min(cond_len, A6_TILE);
+    int u0, u1;
+    attn6_units(B, u0, u1);
     int last_h = -1;
+    const long long t_entry = (tmw && w == 2) ? clock64() : 0;
     for (int ua = u0; ua < u1;) {
         const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
         for (int c0 = ua; c0 < ub; c0 += A6_CHUNK) {
@@ -425,6 +444,7 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
             }
             last_h = h;
             long long t0 = (tmw && w == 2) ? clock64() : 0;
+            if (tmw && w == 2 && lane == 0 && c0 == u0) tmw[2] += (unsigned long long)(t0 - t_entry);
             for (int u = w; u < A6_CHUNK; u += A6_WARPS) {
                 if (u < nu) a6_new_row(p, b0 + u, h, u, step, cond_len, sm, lane);
                 else {   // absent unit: a zero query keeps the row tile's arithmetic finite

@@ -216,9 +216,9 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
             }
             { const unsigned long long *a = &tr[(size_t)2 * P.n_phases]; const double nu = (double)std::max<unsigned long long>(a[5], 1);
               const double nphase = (double)FL_L * st_, npre = (double)std::max<unsigned long long>(a[7], 1);
-              fprintf(stderr, "  attention, CTA 0 (cycles): new rows of a chunk %.0f per phase; own rows per unit (warp 2, %.0f units): scores %.0f  softmax %.0f  PV %.0f  merge + write %.0f;"
-                              " prefix part of 16 units on the tensor cores (warp 0) %.0f\n",
-                      a[0] / nphase, nu, a[1] / nu, a[2] / nu, a[3] / nu, a[4] / nu, a[6] / npre); }
+              fprintf(stderr, "  attention, CTA 0 warp 2 (cycles per phase): ring set-up + prefix tile staging %.0f  new rows %.0f  prefix slice + barrier %.0f;"
+                              " per unit (%.0f units): TMA-fed own-row stream %.0f  new row + reduce %.0f  merge + write %.0f\n",
+                      a[2] / nphase, a[0] / nphase, a[6] / npre, nu, a[1] / nu, a[3] / nu, a[4] / nu); }
             e->dfree(d_trace);
         }
         static const int cls_of[MP_COUNT] = {KC_FLOW_MISC, KC_GEMM_FLOW, KC_ROWNORM, KC_FLOW_MISC, KC_FLOW_MISC, KC_ATTN_DECODE};
