@@ -30,13 +30,17 @@ constexpr int A6_TILE = 128;                 // prefix keys on the tensor-core p
 constexpr int A6_CHUNK = 32;                 // units per chunk = two m16 row tiles
 constexpr int A6_WARPS = MG_THREADS / 32;
 constexpr int A6_SLICES = 4;                 // 32-key slices of the prefix tile, one warp each per row tile
-constexpr int A6_ROWS = 8;                   // own rows per ring slot (K rows + V rows)
-constexpr int A6_SLOTS = 3;                  // ring slots per warp
+constexpr int A6_ROWS = 16;                  // own rows per ring slot (K rows + V rows): 2 KB per bulk copy - the TMA unit's rate of
+                                             // small copies, not bytes, bounds the stream (1 KB copies: 17 B/clk per SM measured)
+constexpr int A6_SLOTS = 2;                  // ring slots per warp
 constexpr int A6_SLOT_BYTES = 2 * A6_ROWS * FL_HD * 2;
-// shared-memory map (bytes from the 1024-aligned ring base)
-constexpr int A6_KP = 0, A6_VP = 16384, A6_QH = 32768, A6_QL = 36864, A6_QF = 40960, A6_KN = 49152, A6_VN = 53248, A6_PML = 57344,
-              A6_PO = A6_PML + A6_CHUNK * A6_SLICES * 2 * 4, A6_RING = A6_PO + A6_CHUNK * A6_SLICES * FL_HD * 4,
-              A6_BARS = A6_RING + A6_WARPS * A6_SLOTS * A6_SLOT_BYTES, A6_END = A6_BARS + A6_WARPS * A6_SLOTS * 8;
+// shared-memory map (bytes from the 1024-aligned ring base). Slot 0 of every warp sits in ring A, slot 1 in ring B; the fp16 prefix
+// tiles and the fp16 query fragments (dead after the prefix slices) alias ring B, whose first copies are issued after them.
+constexpr int A6_QF = 0, A6_KN = 8192, A6_VN = 12288, A6_PML = 16384, A6_PO = A6_PML + A6_CHUNK * A6_SLICES * 2 * 4,
+              A6_RING_A = A6_PO + A6_CHUNK * A6_SLICES * FL_HD * 4, A6_RING_B = A6_RING_A + A6_WARPS * A6_SLOT_BYTES,
+              A6_KP = A6_RING_B, A6_VP = A6_KP + 16384, A6_QH = A6_VP + 16384, A6_QL = A6_QH + 4096,
+              A6_BARS = A6_RING_B + A6_WARPS * A6_SLOT_BYTES, A6_END = A6_BARS + A6_WARPS * A6_SLOTS * 8;
+static_assert(A6_QL + 4096 <= A6_BARS, "prefix tiles must fit inside ring B");
 __host__ __device__ inline size_t attn6_smem_bytes(int) { return (size_t)A6_END; }   // independent of the sequence length
 
 __device__ __forceinline__ void ld_global_v8_pred(const float *ptr, bool ok, float (&v)[8]) {
@@ -258,13 +262,14 @@ struct A6Stream {
     size_t unit_stride;
     int n_old0, n_old1, nch0, total;
 };
+__device__ __forceinline__ uint8_t *a6_slot(uint8_t *ring, int slot) { return ring + slot * (A6_RING_B - A6_RING_A); }
 __device__ __forceinline__ void a6_issue(const A6Stream &S, int c, uint8_t *ring, uint64_t *bars) {   // one lane
     const bool second = c >= S.nch0;
     const int r0 = (second ? c - S.nch0 : c) * A6_ROWS, n_old = second ? S.n_old1 : S.n_old0;
     const uint32_t bytes = (uint32_t)min(A6_ROWS, n_old - r0) * FL_HD * 2;
     const size_t off = (second ? S.unit_stride : 0) + (size_t)r0 * FL_HD;
     const int slot = c % A6_SLOTS;
-    uint8_t *dst = ring + slot * A6_SLOT_BYTES;
+    uint8_t *dst = a6_slot(ring, slot);
     mbar_expect_tx(&bars[slot], 2 * bytes);
     bulk_load_1d(dst, S.k0 + off, bytes, &bars[slot]);
     bulk_load_1d(dst + A6_SLOT_BYTES / 2, S.v0 + off, bytes, &bars[slot]);
@@ -290,16 +295,17 @@ __device__ __noinline__ void a6_own_stream(const AttnDecodeParams &p, const A6St
         for (int i = 0; i < nch; i++, c++) {
             const int slot = c % A6_SLOTS;
             mbar_wait(&bars[slot], (uint32_t)(c / A6_SLOTS) & 1u);
-            const uint8_t *src = ring + slot * A6_SLOT_BYTES + (k4 * FL_HD + l8 * 8) * 2;
-            float kf[2][8], vf[2][8];
+            const uint8_t *src = a6_slot(ring, slot) + (k4 * FL_HD + l8 * 8) * 2;
+            constexpr int NIT = A6_ROWS / 4;
+            float kf[NIT][8], vf[NIT][8];
 #pragma unroll
-            for (int it = 0; it < 2; it++) {
+            for (int it = 0; it < NIT; it++) {
                 unpack8(*(const uint4 *)(src + it * 4 * FL_HD * 2), kf[it]);
                 unpack8(*(const uint4 *)(src + A6_SLOT_BYTES / 2 + it * 4 * FL_HD * 2), vf[it]);
             }
             __syncwarp();                                                   // every lane has read the slot
             if (lane == 0 && c + A6_SLOTS < S.total) a6_issue(S, c + A6_SLOTS, ring, bars);
-            a6_fold<2>(st, q8, kf, vf, n_old - i * A6_ROWS, k4);
+            a6_fold<NIT>(st, q8, kf, vf, n_old - i * A6_ROWS, k4);
         }
         A6_STAMP(1)
         {   // the new row of this step, from shared memory (row group 0 takes it)
@@ -399,13 +405,12 @@ __device__ __forceinline__ void attn6_prefetch_l2(const AttnDecodeParams &p, int
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
 __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, uint8_t *sm, int tid, unsigned long long *tmw = nullptr) {
     const int w = tid >> 5, lane = tid & 31;
-    uint8_t *ring = sm + A6_RING + w * A6_SLOTS * A6_SLOT_BYTES;
+    uint8_t *ring = sm + A6_RING_A + w * A6_SLOT_BYTES;   // slot 0; slot 1 is the same offset inside ring B
     uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
     const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
     const int n_tile = min(cond_len, A6_TILE);
     int u0, u1;
     attn6_units(B, u0, u1);
-    int last_h = -1;
     const long long t_entry = (tmw && w == 2) ? clock64() : 0;
     for (int ua = u0; ua < u1;) {
         const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
@@ -429,10 +434,10 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
                 for (int s = 0; s < A6_SLOTS; s++) mbar_init(&bars[s], 1);
                 fence_barrier_init();
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the ring memory was last touched through the generic proxy
-                for (int c = 0; c < A6_SLOTS && c < S.total; c++) a6_issue(S, c, ring, bars);
+                if (S.total > 0) a6_issue(S, 0, ring, bars);                   // slot 1 (ring B) holds the prefix tiles until the slices are done
             }
             __syncwarp();
-            if (h != last_h && n_tile > 0) {   // fp16 prefix tiles of head h, rows past the prefix zero-filled (P = 0 times garbage must stay 0)
+            if (n_tile > 0) {   // (re-staged for every chunk: ring B overwrites them)   // fp16 prefix tiles of head h, rows past the prefix zero-filled (P = 0 times garbage must stay 0)
                 const __half *pkh = p.pk16 + (size_t)h * p.pstride * FL_HD, *pvh = p.pv16 + (size_t)h * p.pstride * FL_HD;
                 for (int idx = tid; idx < A6_TILE * 8; idx += MG_THREADS) {
                     const int row = idx >> 3, cc = idx & 7;
@@ -442,7 +447,6 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
                     *(uint4 *)(sm + A6_VP + a6_swz(row, cc)) = vv;
                 }
             }
-            last_h = h;
             long long t0 = (tmw && w == 2) ? clock64() : 0;
             if (tmw && w == 2 && lane == 0 && c0 == u0) tmw[2] += (unsigned long long)(t0 - t_entry);
             for (int u = w; u < A6_CHUNK; u += A6_WARPS) {
@@ -457,9 +461,14 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
             if (tmw && w == 2 && lane == 0) { const long long t1 = clock64(); tmw[0] += (unsigned long long)(t1 - t0); t0 = t1; }
             if (n_tile > 0) {
                 if (w < 2 * A6_SLICES && (w & 1) * 16 < nu) a6_prefix_slice(sm, w & 1, w >> 1, n_tile, lane);
-                __syncthreads();                            // all partials of the chunk are in shared memory
+                __syncthreads();                            // all partials of the chunk are in shared memory, ring B is free
                 if (tmw && w == 2 && lane == 0) { tmw[6] += (unsigned long long)(clock64() - t0); tmw[7] += 1; }
             }
+            if (lane == 0 && S.total > 1) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                a6_issue(S, 1, ring, bars);
+            }
+            __syncwarp();
             if (S.n_old0 >= 0) a6_own_stream(p, S, h, b0, w, cond_len, n_tile, sm, ring, bars, lane, (tmw && w == 2) ? tmw : nullptr);
             __syncwarp();
             if (lane == 0)

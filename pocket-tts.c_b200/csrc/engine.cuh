@@ -386,6 +386,10 @@ struct ptts_b200_engine {
     size_t mimi_ws_bytes = 0;
     float *d_mimi_lat = nullptr, *d_pcm = nullptr;
     size_t mimi_lat_cap = 0, pcm_cap = 0;
+    // streaming decode state of the open stream (mimi.cuh): q scratch and per-layer K / V caches [8][ms_cap][64] fp16,
+    // transformer outputs [ms_cap][512] fp16 (source of the SEANet conv tails)
+    __half *ms_q = nullptr, *ms_xn = nullptr, *ms_k[ptts::MI_L] = {nullptr, nullptr}, *ms_v[ptts::MI_L] = {nullptr, nullptr};
+    int ms_cap = 0;
 
     template <typename T>
     int dalloc(T **p, size_t count) {

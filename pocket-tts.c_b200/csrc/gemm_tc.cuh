@@ -65,6 +65,8 @@ struct GemmParams {
     uint16_t *rope_q, *rope_k, *rope_v;
     const float *rope_cos, *rope_sin;   // [T][32]
     int rope_pos0;           // position of row 0 (streaming decode of a window that starts mid-utterance)
+    int rope_rows;           // rows per head of the rope_q / rope_k / rope_v buffers (0: a_rows) and
+    int rope_row0;           // destination row of A row 0: the streaming decoder appends a chunk's K / V to per-utterance caches
     int tma_store;           // 1: 16-bit outputs (out_h, out_raw) leave through shared-memory staging + TMA tensor stores
                              // (whole 128-byte lines) instead of one 32-byte store per thread and chunk
     int stage_off;           // byte offset (multiple of 1024) of the per-warp staging buffers from the aligned shared-memory base
@@ -327,7 +329,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                                 for (int j = 0; j < 8; j++) { const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]); hw[j] = *(const uint32_t *)&h2; }
                             }
                             uint16_t *dst = (which == 0 ? p.rope_q : which == 1 ? p.rope_k : p.rope_v) +
-                                            (((size_t)t.batch * 8 + head) * p.a_rows + m) * 64 + d0;
+                                            (((size_t)t.batch * 8 + head) * (p.rope_rows ? p.rope_rows : p.a_rows) + m + p.rope_row0) * 64 + d0;
                             st_global_v8(dst, hw);
                         }
                         if (rs && m_ok) {

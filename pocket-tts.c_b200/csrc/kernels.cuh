@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(512) k_time_embed(const float *l0w, const floa
 __global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32], item stride lat_stride*/, size_t lat_stride, int F,
                                                     const float *emb_std, const float *emb_mean,
                                                     int apply_scale, const float *quant_wt /*[32,512] transposed*/,
-                                                    const float *ups_t /*[32,512] transposed*/, float *x /*[B,16F,512]*/) {
+                                                    const float *ups_t /*[32,512] transposed*/, float *x /*[B,16F,512]*/, int prev_ok) {
     pdl_wait(); pdl_trigger();
     __shared__ float l0[32], l1[32];
     const int t = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
@@ -779,8 +779,8 @@ __global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32],
         l0[c] = v;
     } else if (c < 64) {
         float v = 0.0f;
-        if (t > 0) {
-            v = lat[(size_t)b * lat_stride + (size_t)(t - 1) * 32 + (c - 32)];
+        if (t > 0 || prev_ok) {   // prev_ok: `lat` points into the middle of an utterance (streaming), frame -1 exists
+            v = lat[(size_t)b * lat_stride + (size_t)t * 32 - 32 + (c - 32)];
             if (apply_scale) v = v * emb_std[c - 32] + emb_mean[c - 32];
         }
         l1[c - 32] = v;
@@ -797,7 +797,7 @@ __global__ void __launch_bounds__(512) k_mimi_front(const float *lat /*[B,F,32],
 #pragma unroll
     for (int r = 0; r < 16; r++) {
         float v = ups_t[r * MI_D + c] * q0;
-        if (t > 0) v += ups_t[(16 + r) * MI_D + c] * q1;
+        if (t > 0 || prev_ok) v += ups_t[(16 + r) * MI_D + c] * q1;
         xo[(size_t)r * MI_D] = v;
     }
 }
@@ -876,13 +876,16 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *(const uint32_t *)&h;
 }
+// Streaming form: queries are rows [t_begin, T) of buffers that hold t_stride rows per head (the K / V caches of the utterance so
+// far); out row 0 = query t_begin. One-shot form: t_begin = 0, t_stride = T.
 __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __half *k, const __half *v, int T,
-                                                       __half *out /*[B*T, 512]*/) {
+                                                       __half *out /*[B*(T - t_begin), 512]*/, int t_begin, int t_stride) {
     pdl_wait(); pdl_trigger();
     __shared__ __align__(16) __half sQ[64 * FA_LD], sKb[2][64 * FA_LD], sVb[2][64 * FA_LD];   // K / V blocks double-buffered (cp.async)
-    const int q0 = blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
+    const int q0 = t_begin + blockIdx.x * 64, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-    const size_t base = ((size_t)b * MI_H + h) * T;
+    const size_t base = ((size_t)b * MI_H + h) * t_stride;
+    const int kb_end = min(T, q0 + 64);   // keys beyond the tile's last query are never visible
     const int kb_start = max(0, q0 - (MI_CTX - 1)) & ~63;
     // K / V block kb -> buffer `buf` with cp.async (rows past T are zero-filled); one commit group per block
     auto stage = [&](int kb, int buf) {
@@ -922,8 +925,8 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.0f, l1 = 0.0f;
     const int tq0 = q0 + warp * 16 + g, tq1 = tq0 + 8;
     int buf = 0;
-    for (int kb = kb_start; kb <= q0 && kb < T; kb += 64, buf ^= 1) {
-        const bool more = kb + 64 <= q0 && kb + 64 < T;
+    for (int kb = kb_start; kb < kb_end; kb += 64, buf ^= 1) {
+        const bool more = kb + 64 < kb_end;
         if (more) stage(kb + 64, buf ^ 1);          // the next block lands while this one is multiplied
         if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
@@ -989,8 +992,8 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
     const float i0 = l0 > 0.0f ? 1.0f / l0 : 0.0f, i1 = l1 > 0.0f ? 1.0f / l1 : 0.0f;
 #pragma unroll
     for (int nd = 0; nd < 8; nd++) {
-        if (tq0 < T) *(__half2 *)(out + ((size_t)b * T + tq0) * MI_D + h * 64 + nd * 8 + 2 * t) = __floats2half2_rn(o[nd][0] * i0, o[nd][1] * i0);
-        if (tq1 < T) *(__half2 *)(out + ((size_t)b * T + tq1) * MI_D + h * 64 + nd * 8 + 2 * t) = __floats2half2_rn(o[nd][2] * i1, o[nd][3] * i1);
+        if (tq0 < T) *(__half2 *)(out + ((size_t)b * (T - t_begin) + tq0 - t_begin) * MI_D + h * 64 + nd * 8 + 2 * t) = __floats2half2_rn(o[nd][0] * i0, o[nd][1] * i0);
+        if (tq1 < T) *(__half2 *)(out + ((size_t)b * (T - t_begin) + tq1 - t_begin) * MI_D + h * 64 + nd * 8 + 2 * t) = __floats2half2_rn(o[nd][2] * i1, o[nd][3] * i1);
     }
 }
 

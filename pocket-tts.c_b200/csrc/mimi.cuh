@@ -210,68 +210,9 @@ static int resblock_launch(Engine *e, const ConvW &c1, const ConvW &c2, const __
     return -1;
 }
 
-// Decode Bc equal-length items. d_lat [Bc,F,32] fp32 on the device; d_pcm [Bc, F*1920].
-// pos0 = token position of the first row (RoPE is absolute: ptts_mimi.c:341).
-static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm, int pos0 = 0) {
-    const int T = 16 * F;
-    const size_t R = (size_t)Bc * T;
-    if (ensure_rope(e, T + pos0) != 0) return -1;
-    const size_t need = mimi_ws_per_frame() * (size_t)Bc * F + (1 << 20);
-    if (need > e->mimi_ws_bytes) {
-        cudaStreamSynchronize(e->st);
-        e->mimi_ws_bytes = 0;
-        e->dfree(e->mimi_ws); e->mimi_ws = nullptr;
-        uint8_t *p = nullptr;
-        if (e->dalloc(&p, need) != 0) return -1;
-        e->mimi_ws = p; e->mimi_ws_bytes = need;
-    }
-    Bump ws{(uint8_t *)e->mimi_ws};
-    float *x = ws.take<float>(R * MI_D);
-    __half *xn = ws.take<__half>(R * MI_D);
-    __half *q = ws.take<__half>(R * MI_D), *k = ws.take<__half>(R * MI_D), *v = ws.take<__half>(R * MI_D);
-    __half *att = ws.take<__half>(R * MI_D);
-    __half *hb = ws.take<__half>(R * MI_FF);
-    __half *d0 = ws.take<__half>(R * MI_D);
-    {
-        LaunchScope ls(e, KC_MIMI_MISC);
-        launch_k(k_mimi_front, dim3(F, Bc), 512, 0, e->st, d_lat, lat_stride, F, e->emb_std, e->emb_mean, apply_scale, e->quant_w, e->ups_w, x);
-        if (launch_check("k_mimi_front") != 0) return -1;
-    }
-    for (int l = 0; l < MI_L; l++) {
-        {
-            LaunchScope ls(e, KC_MIMI_MISC);
-            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n1w, e->ML[l].n1b, 1e-5f, xn);
-            if (launch_check("k_ln512_f16") != 0) return -1;
-        }
-        GemmParams g = {};
-        g.rope_q = (uint16_t *)q; g.rope_k = (uint16_t *)k; g.rope_v = (uint16_t *)v;   // RoPE + head split fused in the epilogue
-        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_pos0 = pos0;
-        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
-        {
-            if (e->prof.on) {   // banded attention: <= 250 keys per query, QK^T and PV
-                double pairs = 0.0;
-                for (int t = 0; t < T; t++) pairs += std::min(t + 1, MI_CTX);
-                e->prof.flops[KC_MIMI_ATTN] += 4.0 * 64.0 * MI_H * pairs * Bc;
-                e->prof.bytes[KC_MIMI_ATTN] += (double)R * MI_D * 2.0 * 4.0;
-            }
-            LaunchScope ls(e, KC_MIMI_ATTN);
-            launch_k(k_mimi_win_attn, dim3((T + 63) / 64, MI_H, Bc), 128, 0, e->st, q, k, v, T, att);
-            if (launch_check("k_mimi_win_attn") != 0) return -1;
-        }
-        g = {}; g.scale = e->ML[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls1 * out_proj(att)
-        if (mimi_gemm(e, att, Bc, T, MI_D, e->ML[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
-        {
-            LaunchScope ls(e, KC_MIMI_MISC);
-            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n2w, e->ML[l].n2b, 1e-5f, xn);
-            if (launch_check("k_ln512_f16") != 0) return -1;
-        }
-        g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
-        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].l1, MI_FF, 1, 0, 0, 256, g) != 0) return -1;
-        g = {}; g.scale = e->ML[l].ls2; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls2 * linear2(h)
-        if (l == MI_L - 1) { g.out_h = (uint16_t *)xn; g.ldh = MI_D; g.act = ACT_NONE; }   // fp16 copy feeds dec_in
-        if (mimi_gemm(e, hb, Bc, T, MI_FF, e->ML[l].l2, MI_D, 1, 0, 0, 256, g) != 0) return -1;
-    }
-    // ---- SEANet (ptts_mimi.c:676-737)
+// SEANet conv stack (ptts_mimi.c:676-737) over Bc items of T transformer-output rows xn [Bc][T][512] fp16 -> d_pcm [Bc][T*120].
+// d0 = scratch for the first conv's output; the other intermediates come from the bump allocator.
+static int mimi_seanet(Engine *e, Bump &ws, int Bc, int T, const __half *xn, __half *d0, float *d_pcm) {
     GemmParams g = {};
     g.out_h = (uint16_t *)d0; g.ldh = MI_D; g.act = ACT_ELU;                               // ELU(dec_in(x))
     if (conv_gemm(e, e->dec_in, xn, Bc, T, 256, g) != 0) return -1;
@@ -310,6 +251,163 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         launch_k(k_dec_out, dim3((Tc + 255) / 256, Bc), 256, 0, e->st, last, Tc, e->dec_out_w, e->dec_out_b, d_pcm);
         if (launch_check("k_dec_out") != 0) return -1;
     }
+    return 0;
+}
+
+
+// Decode Bc equal-length items. d_lat [Bc,F,32] fp32 on the device; d_pcm [Bc, F*1920].
+// pos0 = token position of the first row (RoPE is absolute: ptts_mimi.c:341).
+static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm, int pos0 = 0) {
+    const int T = 16 * F;
+    const size_t R = (size_t)Bc * T;
+    if (ensure_rope(e, T + pos0) != 0) return -1;
+    const size_t need = mimi_ws_per_frame() * (size_t)Bc * F + (1 << 20);
+    if (need > e->mimi_ws_bytes) {
+        cudaStreamSynchronize(e->st);
+        e->mimi_ws_bytes = 0;
+        e->dfree(e->mimi_ws); e->mimi_ws = nullptr;
+        uint8_t *p = nullptr;
+        if (e->dalloc(&p, need) != 0) return -1;
+        e->mimi_ws = p; e->mimi_ws_bytes = need;
+    }
+    Bump ws{(uint8_t *)e->mimi_ws};
+    float *x = ws.take<float>(R * MI_D);
+    __half *xn = ws.take<__half>(R * MI_D);
+    __half *q = ws.take<__half>(R * MI_D), *k = ws.take<__half>(R * MI_D), *v = ws.take<__half>(R * MI_D);
+    __half *att = ws.take<__half>(R * MI_D);
+    __half *hb = ws.take<__half>(R * MI_FF);
+    __half *d0 = ws.take<__half>(R * MI_D);
+    {
+        LaunchScope ls(e, KC_MIMI_MISC);
+        launch_k(k_mimi_front, dim3(F, Bc), 512, 0, e->st, d_lat, lat_stride, F, e->emb_std, e->emb_mean, apply_scale, e->quant_w, e->ups_w, x, 0);
+        if (launch_check("k_mimi_front") != 0) return -1;
+    }
+    for (int l = 0; l < MI_L; l++) {
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n1w, e->ML[l].n1b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
+        }
+        GemmParams g = {};
+        g.rope_q = (uint16_t *)q; g.rope_k = (uint16_t *)k; g.rope_v = (uint16_t *)v;   // RoPE + head split fused in the epilogue
+        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_pos0 = pos0;
+        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        {
+            if (e->prof.on) {   // banded attention: <= 250 keys per query, QK^T and PV
+                double pairs = 0.0;
+                for (int t = 0; t < T; t++) pairs += std::min(t + 1, MI_CTX);
+                e->prof.flops[KC_MIMI_ATTN] += 4.0 * 64.0 * MI_H * pairs * Bc;
+                e->prof.bytes[KC_MIMI_ATTN] += (double)R * MI_D * 2.0 * 4.0;
+            }
+            LaunchScope ls(e, KC_MIMI_ATTN);
+            launch_k(k_mimi_win_attn, dim3((T + 63) / 64, MI_H, Bc), 128, 0, e->st, q, k, v, T, att, 0, T);
+            if (launch_check("k_mimi_win_attn") != 0) return -1;
+        }
+        g = {}; g.scale = e->ML[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls1 * out_proj(att)
+        if (mimi_gemm(e, att, Bc, T, MI_D, e->ML[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n2w, e->ML[l].n2b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
+        }
+        g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
+        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].l1, MI_FF, 1, 0, 0, 256, g) != 0) return -1;
+        g = {}; g.scale = e->ML[l].ls2; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls2 * linear2(h)
+        if (l == MI_L - 1) { g.out_h = (uint16_t *)xn; g.ldh = MI_D; g.act = ACT_NONE; }   // fp16 copy feeds dec_in
+        if (mimi_gemm(e, hb, Bc, T, MI_FF, e->ML[l].l2, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+    }
+    return mimi_seanet(e, ws, Bc, T, xn, d0, d_pcm);
+}
+
+// ---------------------------------------------------------------- streaming decode (single utterance, carried state)
+// The decoder is causal, so a chunk of nf new latent frames needs only state from the past (README.md:162-167 roadmap item,
+// SURVEY.md section 8 f2):
+//   * the previous latent frame (second tap of the k = 32 / s = 16 depthwise upsampler, ptts_mimi.c:588-593): read in place from
+//     the utterance's latent buffer;
+//   * per transformer layer, the RoPE'd K / V rows of the last 249 tokens (window 250, ptts_mimi.c:264-299): the chunk's QKV
+//     epilogue appends its rows at their absolute positions to per-utterance caches ms_k / ms_v (RoPE positions are absolute);
+//     the banded attention kernel runs for the chunk's query rows only;
+//   * the causal conv tails of the SEANet stack (ptts_kernels.c:128-153, 172-204): its receptive field is exactly 8 transformer
+//     rows (dec_in k = 7: 6 rows; each ConvTranspose k = 2s: one input row; each residual block's k = 3 conv: two rows of its own
+//     rate; the final k = 3 conv: two samples - 2 rows in total after the three up-sampling stages), so the stack is run over
+//     [8 carried transformer-output rows | the chunk's rows] and only the chunk's samples are kept. The 8 rows are the conv
+//     tails' source; recomputing the tails from them costs half a frame of conv work per chunk and keeps one copy of the state.
+// A chunk therefore costs nf (+ 0.5 conv) frames of Mimi work whatever the position in the utterance, and the samples equal the
+// one-shot decode (same kernels, same operands; tests/test_gpu_measured_configs.py checks against the oracle's one-shot PCM).
+static int mimi_stream_reserve(Engine *e, int frames) {
+    const int cap = (16 * frames + 63) / 64 * 64;
+    if (cap <= e->ms_cap) return 0;
+    cudaStreamSynchronize(e->st);
+    e->ms_cap = 0;
+    e->dfree(e->ms_q); e->dfree(e->ms_xn); e->ms_q = nullptr; e->ms_xn = nullptr;
+    for (int l = 0; l < MI_L; l++) { e->dfree(e->ms_k[l]); e->dfree(e->ms_v[l]); e->ms_k[l] = e->ms_v[l] = nullptr; }
+    if (e->dalloc(&e->ms_q, (size_t)cap * MI_D) != 0 || e->dalloc(&e->ms_xn, (size_t)cap * MI_D) != 0) return -1;
+    for (int l = 0; l < MI_L; l++)
+        if (e->dalloc(&e->ms_k[l], (size_t)cap * MI_D) != 0 || e->dalloc(&e->ms_v[l], (size_t)cap * MI_D) != 0) return -1;
+    e->ms_cap = cap;
+    return 0;
+}
+
+constexpr int MIMI_CONV_HALO = 8;   // transformer rows the SEANet stack looks back (derivation above)
+
+// Decode latent frames [f0, f0 + nf) of the streamed utterance; d_lat points at frame f0 of its latent buffer (raw FlowLM latents
+// when apply_scale). *pcm_out = device pointer to the chunk's nf * 1920 samples (inside the workspace, valid until the next call).
+static int mimi_stream_chunk(Engine *e, int f0, int nf, const float *d_lat, int apply_scale, float **pcm_out) {
+    const int pos0 = 16 * f0, Tn = 16 * nf, T_end = pos0 + Tn;
+    PTTS_CHECK(T_end <= e->ms_cap, "mimi_stream_chunk: stream state holds %d tokens, chunk ends at %d", e->ms_cap, T_end);
+    if (ensure_rope(e, T_end) != 0) return -1;
+    const int w0 = std::max(0, pos0 - MIMI_CONV_HALO), Tw = T_end - w0;
+    const size_t need = mimi_ws_per_frame() * (size_t)(nf + 1) + (size_t)Tw * 120 * 4 + (1 << 20);
+    if (need > e->mimi_ws_bytes) {
+        cudaStreamSynchronize(e->st);
+        e->mimi_ws_bytes = 0;
+        e->dfree(e->mimi_ws); e->mimi_ws = nullptr;
+        uint8_t *p = nullptr;
+        if (e->dalloc(&p, need) != 0) return -1;
+        e->mimi_ws = p; e->mimi_ws_bytes = need;
+    }
+    Bump ws{(uint8_t *)e->mimi_ws};
+    const size_t R = (size_t)Tn;
+    float *x = ws.take<float>(R * MI_D);
+    __half *xn = ws.take<__half>(R * MI_D), *att = ws.take<__half>(R * MI_D), *hb = ws.take<__half>(R * MI_FF);
+    __half *d0 = ws.take<__half>((size_t)Tw * MI_D);
+    float *pcm = ws.take<float>((size_t)Tw * 120);
+    {
+        LaunchScope ls(e, KC_MIMI_MISC);
+        launch_k(k_mimi_front, dim3(nf, 1), 512, 0, e->st, d_lat, (size_t)0, nf, e->emb_std, e->emb_mean, apply_scale, e->quant_w, e->ups_w, x, f0 > 0 ? 1 : 0);
+        if (launch_check("k_mimi_front") != 0) return -1;
+    }
+    for (int l = 0; l < MI_L; l++) {
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n1w, e->ML[l].n1b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
+        }
+        GemmParams g = {};
+        g.rope_q = (uint16_t *)e->ms_q; g.rope_k = (uint16_t *)e->ms_k[l]; g.rope_v = (uint16_t *)e->ms_v[l];
+        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_pos0 = pos0; g.rope_rows = e->ms_cap; g.rope_row0 = pos0;
+        if (mimi_gemm(e, xn, 1, Tn, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        {
+            LaunchScope ls(e, KC_MIMI_ATTN);
+            launch_k(k_mimi_win_attn, dim3((Tn + 63) / 64, MI_H, 1), 128, 0, e->st, (const __half *)e->ms_q, (const __half *)e->ms_k[l],
+                     (const __half *)e->ms_v[l], T_end, att, pos0, e->ms_cap);
+            if (launch_check("k_mimi_win_attn") != 0) return -1;
+        }
+        g = {}; g.scale = e->ML[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;
+        if (mimi_gemm(e, att, 1, Tn, MI_D, e->ML[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n2w, e->ML[l].n2b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
+        }
+        g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
+        if (mimi_gemm(e, xn, 1, Tn, MI_D, e->ML[l].l1, MI_FF, 1, 0, 0, 256, g) != 0) return -1;
+        g = {}; g.scale = e->ML[l].ls2; g.resid = x; g.out_f32 = x; g.ldo = MI_D;
+        if (l == MI_L - 1) { g.out_h = (uint16_t *)(e->ms_xn + (size_t)pos0 * MI_D); g.ldh = MI_D; g.act = ACT_NONE; }   // carried: feeds dec_in
+        if (mimi_gemm(e, hb, 1, Tn, MI_FF, e->ML[l].l2, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+    }
+    if (mimi_seanet(e, ws, 1, Tw, e->ms_xn + (size_t)w0 * MI_D, d0, pcm) != 0) return -1;
+    *pcm_out = pcm + (size_t)(pos0 - w0) * 120;
     return 0;
 }
 

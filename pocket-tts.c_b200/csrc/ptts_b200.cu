@@ -648,16 +648,16 @@ extern "C" int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, 
 }
 
 // ---------------------------------------------------------------- streaming (single utterance)
-// Mimi's receptive field in latent frames: two stacked 250-token attention windows (500 tokens = 31.25
-// frames, ptts_mimi.c:264-299), the 7-tap input conv (6 tokens) and the k=32/s=16 upsampler (1 frame).
-static const int STREAM_CTX_FRAMES = 34;
-
+// FlowLM: the batch-1 decode loop, k frames per call. Mimi: carried-state streaming decode (mimi.cuh mimi_stream_chunk): a call
+// that hands out k frames costs k frames of decoder work (+ half a frame of conv-tail recomputation), wherever it is in the
+// utterance.
 extern "C" int ptts_b200_stream_begin(ptts_b200_engine *e, const int *tokens, int token_len, const float *cond_prefix, int cond_len,
                                       int max_frames, int64_t seed, const ptts_b200_gen_params *params) {
     PTTS_CHECK(e && tokens && token_len > 0 && params && max_frames >= 1, "stream_begin: bad arguments");
     e->stream_pos = -1;
     const int offs[2] = {0, token_len};
     if (stage_impl(e, 1, tokens, offs, cond_prefix, cond_len, &max_frames, &seed, nullptr, params) != 0) return -1;
+    if (mimi_stream_reserve(e, max_frames) != 0) return -1;
     if (run_begin(e) != 0) return -1;
     e->stream_pos = 0;
     return 0;
@@ -678,10 +678,9 @@ extern "C" int ptts_b200_stream_next(ptts_b200_engine *e, int want_frames, float
     PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     const int newf = h[0] - e->stream_pos;   // frames past the stop point are not part of the utterance
     if (newf > 0) {
-        const int f0 = std::max(0, e->stream_pos - STREAM_CTX_FRAMES), nwin = e->stream_pos + newf - f0;
-        if (ensure_pcm(e, (size_t)nwin * 1920) != 0) return -1;
-        if (mimi_run_chunk(e, 1, nwin, e->d_out_latents + (size_t)f0 * FL_LAT, (size_t)e->capF * FL_LAT, 1, e->d_pcm, 16 * f0) != 0) return -1;
-        PTTS_CUDA_OK(cudaMemcpyAsync(out_pcm, e->d_pcm + (size_t)(e->stream_pos - f0) * 1920, (size_t)newf * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
+        float *pcm = nullptr;
+        if (mimi_stream_chunk(e, e->stream_pos, newf, e->d_out_latents + (size_t)e->stream_pos * FL_LAT, 1, &pcm) != 0) return -1;
+        PTTS_CUDA_OK(cudaMemcpyAsync(out_pcm, pcm, (size_t)newf * 1920 * 4, cudaMemcpyDeviceToHost, e->st));
         PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
     }
     e->stream_pos += newf;

@@ -201,15 +201,16 @@ def test_overlong_request_fails_cleanly_and_the_engine_stays_usable(pkg, weights
     e = pkg.Engine(weights, 0)
     try:
         toks = [golden["p0_ids"], golden["p1_ids"]]
+        huge = np.tile(golden["p2_ids"], 40)[:600].astype(np.int32)
         with pytest.raises(pkg.EngineError, match="exceed"):
-            e.generate_batch(toks, voice, 900, seeds=[1, 2], params=pkg.default_params(temp=0.7), want_audio=False)
+            e.generate_batch([huge, golden["p1_ids"]], voice, 4, seeds=[1, 2], params=pkg.default_params(temp=0.7), want_audio=False)
         out = e.generate_batch(toks, voice, 5, seeds=[1, 2], params=pkg.default_params(temp=0.7), want_audio=False)
         for i, t in enumerate(toks):
             o = oracle.flowlm_generate(t, voice, 5, lsd_steps=1, temp=0.7, seed=1 + i)
             assert max_rel(out["latents"][i], o["latents"]) < TOL
         # a long single-utterance request (its own, larger limit) leaves big capacities behind; the batched path must still work
-        g = e.flowlm_generate_latents(golden["p0_ids"], voice, 900, lsd_steps=1, temp=0.0)
-        assert g["frames"] == 900 and np.isfinite(g["latents"]).all()
+        g = e.flowlm_generate_latents(golden["p0_ids"], voice, 1500, lsd_steps=1, temp=0.0)
+        assert g["frames"] == 1500 and np.isfinite(g["latents"]).all()
         out = e.generate_batch(toks, voice, 5, seeds=[1, 2], params=pkg.default_params(temp=0.7), want_audio=False)
         for i, t in enumerate(toks):
             o = oracle.flowlm_generate(t, voice, 5, lsd_steps=1, temp=0.7, seed=1 + i)
