@@ -115,13 +115,31 @@ int ptts_b200_batch_stage(ptts_b200_engine *e, int n, const int *tokens_flat, co
 int ptts_b200_batch_run(ptts_b200_engine *e, int with_mimi);
 int ptts_b200_batch_fetch(ptts_b200_engine *e, float *out_latents, int *out_frames_used, float *out_audio);
 
+/* ---- additive multi-GPU entry: a pool = one engine per device, weights replicated, one host thread per
+ * device inside pool_generate. The utterance list is sorted by max_frames (the caller's ptts_estimate_frames value, ptts.c:285-291),
+ * cut into calls of at most max_batch utterances (<= 0: 1024; at least one call per device when there is enough work), the calls
+ * are dealt to the devices longest-first, and latents / frames_used / PCM are gathered in the ORIGINAL order with the layout of
+ * ptts_b200_generate_batch (frames_cap = max over max_frames[]). No collective and no peer traffic on the data path.
+ * devices == NULL: every visible device. */
+typedef struct ptts_b200_pool ptts_b200_pool;
+int ptts_b200_pool_create(ptts_b200_pool **out, const int *devices, int n_devices, const ptts_b200_tensor *tensors, int n_tensors);
+void ptts_b200_pool_destroy(ptts_b200_pool *p);
+int ptts_b200_pool_size(const ptts_b200_pool *p);
+ptts_b200_engine *ptts_b200_pool_engine(ptts_b200_pool *p, int i);   /* engine of pool slot i (single-utterance entries, measurement hooks) */
+int ptts_b200_pool_generate(ptts_b200_pool *p, int n, const int *tokens_flat, const int *token_offsets, const float *cond_prefix,
+                            int cond_len, const int *max_frames, const int64_t *seeds, const int *eos_after,
+                            const ptts_b200_gen_params *params, int max_batch, float *out_latents, int *out_frames_used,
+                            float *out_audio);
+
 /* ---- additive streaming entry (roadmap item of the reference, README.md:162-167):
  * single utterance, audio handed out as it is generated, so first-audio latency is observable
  * through the API. begin = stage + prompt prefill; next = up to want_frames more FlowLM frames, then
- * the Mimi decoder over those frames plus a left context that covers its whole receptive field
- * (2 x 250-token attention windows + the causal conv tails = 33 latent frames, RoPE at absolute
- * positions), so the PCM equals the one-shot decode of the full utterance. out_pcm receives
- * *out_frames * 1920 samples; *out_done != 0 after the last frame (EOS rule or max_frames). */
+ * the Mimi decoder over those frames ONLY, with carried state: per-layer K / V caches of the 250-token
+ * attention window (RoPE at absolute positions), the previous latent frame for the upsampler and the 8
+ * transformer-output rows the causal conv tails of the SEANet stack are rebuilt from. A call costs
+ * want_frames (+ 0.5) frames of decoder work wherever it is in the utterance, and the PCM equals the
+ * one-shot decode. out_pcm receives *out_frames * 1920 samples; *out_done != 0 after the last frame
+ * (EOS rule or max_frames). */
 int ptts_b200_stream_begin(ptts_b200_engine *e, const int *tokens, int token_len, const float *cond_prefix, int cond_len,
                            int max_frames, int64_t seed, const ptts_b200_gen_params *params);
 int ptts_b200_stream_next(ptts_b200_engine *e, int want_frames, float *out_pcm, int *out_frames, int *out_done);

@@ -44,7 +44,8 @@ EXPORTS = [
     "ptts_b200_sync", "ptts_b200_timer_start", "ptts_b200_timer_stop", "ptts_b200_profile_enable",
     "ptts_b200_profile_read", "ptts_b200_profile_work", "ptts_b200_profile_class_name", "ptts_b200_launch_count", "ptts_b200_test_gemm",
     "ptts_b200_stream_begin", "ptts_b200_stream_next", "ptts_b200_mimi_forward_one", "ptts_b200_mimi_stage",
-    "ptts_b200_mimi_run", "ptts_b200_mimi_fetch", "ptts_b200_step_kernel_ms",
+    "ptts_b200_mimi_run", "ptts_b200_mimi_fetch", "ptts_b200_step_kernel_ms", "ptts_b200_pool_create", "ptts_b200_pool_destroy",
+    "ptts_b200_pool_size", "ptts_b200_pool_engine", "ptts_b200_pool_generate",
 ]
 
 
@@ -87,6 +88,13 @@ def load_library():
     L.ptts_b200_mimi_run.argtypes = [vp]
     L.ptts_b200_mimi_fetch.argtypes = [vp, _fp]
     L.ptts_b200_step_kernel_ms.argtypes = [vp, _fp, _ip]
+    L.ptts_b200_pool_create.argtypes = [C.POINTER(vp), _ip, C.c_int, C.POINTER(_Tensor), C.c_int]
+    L.ptts_b200_pool_destroy.argtypes = [vp]
+    L.ptts_b200_pool_destroy.restype = None
+    L.ptts_b200_pool_size.argtypes = [vp]
+    L.ptts_b200_pool_engine.argtypes = [vp, C.c_int]
+    L.ptts_b200_pool_engine.restype = vp
+    L.ptts_b200_pool_generate.argtypes = [vp] + stage_args[1:] + [C.c_int, _fp, _ip, _fp]
     return L
 
 
@@ -325,6 +333,55 @@ class Engine:
         self._ck(self.lib.ptts_b200_test_gemm(self.h, _f(A), _f(B), _f(out), batches, rows, N, K, taps, shift0, step,
                                               1 if bf16 else 0, split, 1 if transposed else 0, bn, split_k), "test_gemm")
         return out.reshape(N, batches * rows) if transposed else out.reshape(batches * rows, N)
+
+
+class Pool:
+    """ptts_b200_pool: one engine per device, utterances bucketed by length and sharded by the C library (one host thread per
+    device), results gathered in the original order. devices=None: every visible device."""
+
+    def __init__(self, weights: "dict[str, np.ndarray]", devices=None):
+        self.h = None
+        self.lib = load_library()
+        keep = {k: np.ascontiguousarray(v, dtype=np.float32) for k, v in weights.items()}
+        names = [k.encode() for k in keep]
+        tab = (_Tensor * len(names))()
+        for i, (k, v) in enumerate(keep.items()):
+            tab[i] = _Tensor(names[i], v.ctypes.data, 0, v.size)
+        dv = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        h = C.c_void_p()
+        if self.lib.ptts_b200_pool_create(C.byref(h), _i(dv), 0 if dv is None else len(dv), tab, len(names)) != 0:
+            raise EngineError("ptts_b200_pool_create: " + (self.lib.ptts_b200_last_error() or b"").decode())
+        self.h = h
+
+    @property
+    def size(self) -> int:
+        return int(self.lib.ptts_b200_pool_size(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ptts_b200_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def generate(self, token_lists, cond, max_frames, seeds=123, eos_after=None, params: "GenParams | None" = None, max_batch=0,
+                 want_audio=True, audio_out=None, want_latents=True):
+        params = params or default_params()
+        cond = np.ascontiguousarray(cond, dtype=np.float32).reshape(-1, 1024)
+        n, flat, offs, mf, sd, ea = Engine._pack(token_lists, max_frames, seeds, eos_after)
+        F = int(mf.max())
+        lat = np.zeros((n, F, 32), np.float32) if want_latents else None
+        used = np.zeros(n, np.int32)
+        pcm = audio_out if audio_out is not None else (np.zeros((n, F * FRAME_SAMPLES), np.float32) if want_audio else None)
+        rc = self.lib.ptts_b200_pool_generate(self.h, n, _i(flat), _i(offs), _f(cond) if cond.shape[0] else None, cond.shape[0], _i(mf),
+                                              sd.ctypes.data_as(_lp), _i(ea), C.byref(params), int(max_batch), _f(lat), _i(used), _f(pcm))
+        if rc != 0:
+            raise EngineError("pool_generate: " + (self.lib.ptts_b200_last_error() or b"").decode())
+        return dict(latents=lat, frames=used, audio=pcm)
 
 
 def default_params(lsd_steps=1, temp=0.0, noise_clamp=0.0, eos_enabled=0, eos_threshold=-4.0, eos_min_frames=1,

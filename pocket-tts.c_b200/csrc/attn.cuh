@@ -84,7 +84,7 @@ __device__ __forceinline__ void split_hl(float a, float b, uint32_t &hi, uint32_
 // ---- new position of unit (b, h): fold the split-K partial sums of q / k / v, RoPE, append k / v to the own cache; q -> smem
 // (fp32 for the own-row part, fp16 hi + lo in the fragment tile for the prefix part), the fp16-rounded k / v of the new row -> smem
 // (exactly the values later steps read back from the cache). Lane = dimension pair.
-__device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int h, int u, int step, int cond_len, uint8_t *sm, int lane) {
+__device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int h, int u, int s, int cond_len, uint8_t *sm, int lane) {
     const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD + 2 * lane;
     float2 rq[3][4];
 #pragma unroll
@@ -92,7 +92,7 @@ __device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int
 #pragma unroll
         for (int z = 0; z < 4; z++)
             rq[c][z] = (z == 0 || z < p.qkv_nsplit) ? *(const float2 *)(row + c * FL_D + z * p.qkv_stride) : make_float2(0.0f, 0.0f);
-    const int s = step + p.own_base[b], pos = cond_len + s;
+    const int pos = cond_len + s;   // s = rows already in the own cache = index of the new row
     const float cs = p.rope_cos[pos * 32 + lane], sn = p.rope_sin[pos * 32 + lane];
     float2 f[3];
 #pragma unroll
@@ -403,7 +403,7 @@ __device__ __forceinline__ void attn6_prefetch_l2(const AttnDecodeParams &p, int
 }
 
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
-__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, uint8_t *sm, int tid, unsigned long long *tmw = nullptr) {
+__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, uint8_t *sm, int tid, int flags, unsigned long long *tmw = nullptr) {
     const int w = tid >> 5, lane = tid & 31;
     uint8_t *ring = sm + A6_RING_A + w * A6_SLOT_BYTES;   // slot 0; slot 1 is the same offset inside ring B
     uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
@@ -450,13 +450,14 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
             long long t0 = (tmw && w == 2) ? clock64() : 0;
             if (tmw && w == 2 && lane == 0 && c0 == u0) tmw[2] += (unsigned long long)(t0 - t_entry);
             for (int u = w; u < A6_CHUNK; u += A6_WARPS) {
-                if (u < nu) a6_new_row(p, b0 + u, h, u, step, cond_len, sm, lane);
+                if (u < nu) a6_new_row(p, b0 + u, h, u, u == w ? S.n_old0 : S.n_old1, cond_len, sm, lane);
                 else {   // absent unit: a zero query keeps the row tile's arithmetic finite
                     const uint32_t off = a6_swz(u, lane >> 2) + (lane & 3) * 4;
                     *(uint32_t *)(sm + A6_QH + off) = 0u;
                     *(uint32_t *)(sm + A6_QL + off) = 0u;
                 }
             }
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             if (tmw && w == 2 && lane == 0) { const long long t1 = clock64(); tmw[0] += (unsigned long long)(t1 - t0); t0 = t1; }
             if (n_tile > 0) {

@@ -70,7 +70,7 @@ struct MegaProgram {
     int *done_count;                // utterances that reached their stop point, zeroed by the host
     int n_live, nsteps, first_gemm;
     int n_gemms;                    // contractions per frame (parity of the ring-state slots below)
-    int flags;                      // experiment bits: 2 = light grid barrier, 8 = L2 prefetch of the next attention phase's rows by the idle warps of a
+    int flags;                      // experiment bits: 2 = light grid barrier, 16 = no L2 prefetch at the start of an attention phase, 8 = L2 prefetch of the next attention phase's rows by the idle warps of a
                                     // GEMM phase (measured: attention phases -1.5 us, GEMM phases +17 %: off by default)
     int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
                                     // (only when the loop cannot stop early, i.e. EOS detection is off)
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    attn6_phase(P.attn[ph.idx], P.B, step, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                    attn6_phase(P.attn[ph.idx], P.B, step, ring, tid, P.flags, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     break;
                 default: break;
             }

@@ -690,6 +690,8 @@ extern "C" int ptts_b200_stream_next(ptts_b200_engine *e, int want_frames, float
     return 0;
 }
 
+#include "pool.cuh"
+
 // ---------------------------------------------------------------- measurement hooks
 extern "C" int ptts_b200_sync(ptts_b200_engine *e) {
     PTTS_CHECK(e, "sync: null engine");
