@@ -35,7 +35,8 @@
 #include "ptts_mimi.h"
 
 typedef struct {
-    ptts_b200_engine *eng;
+    ptts_b200_pool *pool;   /* one engine per device of PTTS_B200_DEVICES ("all" or "0,1,..."); default: the single device PTTS_B200_DEVICE */
+    ptts_b200_engine *eng;  /* engine of pool slot 0: the single-utterance drop-in entries run here */
     uint64_t fp;            /* content fingerprint of the weights file */
     size_t file_size;
     int num_tensors;
@@ -54,7 +55,7 @@ static int g_atexit = 0;
 
 static void shutdown_engines(void) {
     for (int i = 0; i < MAX_ENGINES; i++)
-        if (g_slots[i].eng) { ptts_b200_destroy(g_slots[i].eng); g_slots[i].eng = NULL; g_slots[i].refs = 0; }
+        if (g_slots[i].eng) { ptts_b200_pool_destroy(g_slots[i].pool); g_slots[i].pool = NULL; g_slots[i].eng = NULL; g_slots[i].refs = 0; }
 }
 
 static uint64_t fnv1a(uint64_t h, const void *p, size_t n) {
@@ -85,7 +86,7 @@ static void drop_idle(int keep) {   /* destroy least recently used idle engines 
                 if (lru < 0 || g_slots[i].last_use < g_slots[lru].last_use) lru = i;
             }
         if (idle <= keep || lru < 0) return;
-        ptts_b200_destroy(g_slots[lru].eng);
+        ptts_b200_pool_destroy(g_slots[lru].pool);
         memset(&g_slots[lru], 0, sizeof g_slots[lru]);
     }
 }
@@ -120,9 +121,20 @@ static engine_slot *engine_acquire(ptts_ctx *ctx) {
         tab[n].numel = numel;
         n++;
     }
-    const char *dev = getenv("PTTS_B200_DEVICE");
-    ptts_b200_engine *eng = NULL;
-    int rc = ptts_b200_create(&eng, dev ? atoi(dev) : 0, tab, n);
+    /* devices: PTTS_B200_DEVICES = "all" | "0,1,2" (utterance sharding of ptts_generate_batch); default one device, PTTS_B200_DEVICE */
+    int devs[64], nd = 0, all = 0;
+    const char *dl = getenv("PTTS_B200_DEVICES"), *dev = getenv("PTTS_B200_DEVICE");
+    if (dl && strcmp(dl, "all") == 0) all = 1;
+    else if (dl && *dl) {
+        for (const char *q = dl; *q && nd < 64;) {
+            devs[nd++] = atoi(q);
+            while (*q && *q != ',') q++;
+            if (*q == ',') q++;
+        }
+    }
+    if (!all && nd == 0) devs[nd++] = dev ? atoi(dev) : 0;
+    ptts_b200_pool *pool = NULL;
+    int rc = ptts_b200_pool_create(&pool, all ? NULL : devs, all ? 0 : nd, tab, n);
     free(tab);
     if (rc != 0) {
         fprintf(stderr, "[ptts] B200 engine creation failed: %s\n", ptts_b200_last_error());
@@ -130,7 +142,7 @@ static engine_slot *engine_acquire(ptts_ctx *ctx) {
     }
     if (!g_atexit) { atexit(shutdown_engines); g_atexit = 1; }
     engine_slot *s = &g_slots[slot];
-    s->eng = eng; s->fp = fp; s->file_size = sf->file_size; s->num_tensors = sf->num_tensors; s->refs = 1; s->last_use = ++g_clock;
+    s->pool = pool; s->eng = ptts_b200_pool_engine(pool, 0); s->fp = fp; s->file_size = sf->file_size; s->num_tensors = sf->num_tensors; s->refs = 1; s->last_use = ++g_clock;
     return s;
 }
 
@@ -145,6 +157,87 @@ int ptts_b200_host_engine_count(void) {
     int n = 0;
     for (int i = 0; i < MAX_ENGINES; i++) n += g_slots[i].eng != NULL;
     return n;
+}
+
+/* ---- additive batched entry at the ptts.h level ------------------------------------------------------------------------
+ * ptts.h is single-utterance (ptts_generate, ptts.h:75-76); configs 3-5 need a batch. ptts_generate_batch mirrors ptts_generate
+ * (ptts.c:1011-1161) step by step with the reference's own host functions - ptts_prepare_text (ptts.c:219-283), ptts_tokenize
+ * (the reference SentencePiece reader), ptts_estimate_frames (ptts.c:285-291), ptts_load_voice_conditioning (ptts.c:293-364) - then
+ * hands ALL utterances to the engine pool: bucketed by estimated frames, sharded over the visible devices (one host thread +
+ * engine per device), PCM gathered in the original order. Utterance i draws its noise from seed params->seed + i
+ * (params->seed == -1: time based, as ptts_flowlm.c:1188). Returns n ptts_audio objects (free with ptts_audio_batch_free), NULL on
+ * failure. ptts.h, ptts_params and every existing symbol are untouched. */
+ptts_audio **ptts_generate_batch(ptts_ctx *ctx, const char *const *texts, int n, const char *voice_path, const ptts_params *params);
+void ptts_audio_batch_free(ptts_audio **audio, int n);
+
+#include <time.h>
+#include "ptts.h"
+
+void ptts_audio_batch_free(ptts_audio **audio, int n) {
+    if (!audio) return;
+    for (int i = 0; i < n; i++) ptts_audio_free(audio[i]);
+    free(audio);
+}
+
+ptts_audio **ptts_generate_batch(ptts_ctx *ctx, const char *const *texts, int n, const char *voice_path, const ptts_params *params) {
+    if (!ctx || !texts || n < 1) return NULL;
+    ptts_params p = PTTS_PARAMS_DEFAULT;
+    if (params) p = *params;
+    if (p.sample_rate <= 0) p.sample_rate = 24000;
+    if (p.num_steps <= 0) p.num_steps = 1;
+    engine_slot *slot = engine_acquire(ctx);
+    if (!slot) return NULL;
+    int *offs = (int *)calloc((size_t)n + 1, sizeof(int)), *frames = (int *)calloc((size_t)n, sizeof(int));
+    int *eos_after = (int *)calloc((size_t)n, sizeof(int)), *used = (int *)calloc((size_t)n, sizeof(int));
+    int64_t *seeds = (int64_t *)calloc((size_t)n, sizeof(int64_t));
+    int *flat = NULL, flat_cap = 0, fcap = 0, ok = offs && frames && eos_after && used && seeds;
+    float *voice = NULL, *pcm = NULL;
+    int voice_len = 0;
+    ptts_audio **out = NULL;
+    const int64_t seed0 = p.seed == -1 ? (int64_t)time(NULL) : p.seed;
+    for (int i = 0; ok && i < n; i++) {
+        int words = 0, guess = 0, *ids = NULL, len = 0;
+        char *prep = ptts_prepare_text(texts[i], &words, &guess);
+        if (!prep || ptts_tokenize(ctx, prep, &ids, &len) != 0 || len <= 0) { fprintf(stderr, "[ptts] B200: cannot tokenize utterance %d\n", i); free(prep); free(ids); ok = 0; break; }
+        free(prep);
+        if (offs[i] + len > flat_cap) {
+            flat_cap = (offs[i] + len) * 2 + 64;
+            int *nf = (int *)realloc(flat, (size_t)flat_cap * sizeof(int));
+            if (!nf) { free(ids); ok = 0; break; }
+            flat = nf;
+        }
+        memcpy(flat + offs[i], ids, (size_t)len * sizeof(int));
+        free(ids);
+        offs[i + 1] = offs[i] + len;
+        frames[i] = p.num_frames > 0 ? p.num_frames : ptts_estimate_frames(words);
+        eos_after[i] = p.eos_after > 0 ? p.eos_after : guess;
+        seeds[i] = seed0 + i;
+        if (frames[i] > fcap) fcap = frames[i];
+    }
+    if (ok && ptts_load_voice_conditioning(ctx, voice_path, &voice, &voice_len) != 0) ok = 0;
+    if (ok) {
+        pcm = (float *)malloc((size_t)n * fcap * 1920 * sizeof(float));
+        ok = pcm != NULL;
+    }
+    if (ok) {
+        ptts_b200_gen_params gp = {p.num_steps, p.temp, p.noise_clamp, p.eos_enabled, p.eos_threshold, p.eos_min_frames > 0 ? p.eos_min_frames : 1,
+                                   p.eos_after > 0 ? p.eos_after : 3, 1};
+        if (ptts_b200_pool_generate(slot->pool, n, flat, offs, voice, voice_len, frames, seeds, eos_after, &gp, 0, NULL, used, pcm) != 0) {
+            fprintf(stderr, "[ptts] B200: %s\n", ptts_b200_last_error());
+            ok = 0;
+        }
+    }
+    if (ok) {
+        out = (ptts_audio **)calloc((size_t)n, sizeof *out);
+        for (int i = 0; out && i < n; i++) {
+            out[i] = ptts_audio_create(p.sample_rate, 1, used[i] * 1920);
+            if (!out[i]) { ptts_audio_batch_free(out, n); out = NULL; break; }
+            memcpy(out[i]->samples, pcm + (size_t)i * fcap * 1920, (size_t)used[i] * 1920 * sizeof(float));
+        }
+    }
+    free(pcm); free(voice); free(flat); free(offs); free(frames); free(eos_after); free(used); free(seeds);
+    engine_release(slot);
+    return out;
 }
 
 /* ---- ptts_flowlm.h ---------------------------------------------------------------- */
