@@ -84,16 +84,23 @@ __device__ __forceinline__ void split_hl(float a, float b, uint32_t &hi, uint32_
 // ---- new position of unit (b, h): fold the split-K partial sums of q / k / v, RoPE, append k / v to the own cache; q -> smem
 // (fp32 for the own-row part, fp16 hi + lo in the fragment tile for the prefix part), the fp16-rounded k / v of the new row -> smem
 // (exactly the values later steps read back from the cache). Lane = dimension pair.
-__device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int h, int u, int s, int cond_len, uint8_t *sm, int lane) {
+// The loads of a warp's two units (partial sums, RoPE rows) are issued together: one L2 round trip instead of two (the L1 is cold
+// after every grid barrier).
+struct A6NewRowIn { float2 rq[3][4]; float cs, sn; };
+__device__ __forceinline__ void a6_new_row_load(const AttnDecodeParams &p, int b, int h, int s, int cond_len, int lane, A6NewRowIn &in) {
     const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD + 2 * lane;
-    float2 rq[3][4];
 #pragma unroll
     for (int c = 0; c < 3; c++)
 #pragma unroll
         for (int z = 0; z < 4; z++)
-            rq[c][z] = (z == 0 || z < p.qkv_nsplit) ? *(const float2 *)(row + c * FL_D + z * p.qkv_stride) : make_float2(0.0f, 0.0f);
+            in.rq[c][z] = (z == 0 || z < p.qkv_nsplit) ? *(const float2 *)(row + c * FL_D + z * p.qkv_stride) : make_float2(0.0f, 0.0f);
     const int pos = cond_len + s;   // s = rows already in the own cache = index of the new row
-    const float cs = p.rope_cos[pos * 32 + lane], sn = p.rope_sin[pos * 32 + lane];
+    in.cs = p.rope_cos[pos * 32 + lane]; in.sn = p.rope_sin[pos * 32 + lane];
+}
+__device__ __forceinline__ void a6_new_row(const AttnDecodeParams &p, int b, int h, int u, int s, uint8_t *sm, int lane, const A6NewRowIn &in) {
+    const float *row = p.qkv + (size_t)b * 3 * FL_D + h * FL_HD + 2 * lane;
+    const float2 (&rq)[3][4] = in.rq;
+    const float cs = in.cs, sn = in.sn;
     float2 f[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -388,26 +395,14 @@ __device__ __forceinline__ void attn6_units(int B, int &u0, int &u1) {
     }
 }
 
-// Pull the own K / V rows this CTA will stream in a coming attention phase into L2 (one bulk prefetch per unit and tensor; each
-// unit's rows are one contiguous region). Issued by the two warps that have no role in a GEMM phase, while HBM is nearly idle
-// (a GEMM phase streams ~8 MB of weights; an attention phase needs 84 MB of rows): the attention phase then streams from L2.
-__device__ __forceinline__ void attn6_prefetch_l2(const AttnDecodeParams &p, int B, int step, int t, int nthreads) {
-    int u0, u1;
-    attn6_units(B, u0, u1);
-    for (int i = t; i < 2 * (u1 - u0); i += nthreads) {
-        const int unit = u0 + (i >> 1), h = unit / B, b = unit - h * B;
-        const __half *ptr = ((i & 1) ? p.ov : p.ok) + ((size_t)h * p.cap_b + b) * p.max_s * FL_HD;
-        const uint32_t bytes = (uint32_t)(step + p.own_base[b]) * FL_HD * 2u;
-        if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
-    }
-}
-
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
-__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, uint8_t *sm, int tid, int flags, unsigned long long *tmw = nullptr) {
+// ob_cache: own_base of this CTA's units [u0, u1) in shared memory (or NULL: read p.own_base), cond_len: the prefix length of the launch.
+// flags bit 16 (experiment): no L2 prefetch of the warp's remaining rows at the start of the phase.
+__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, int cond_len, const int *ob_cache, uint8_t *sm, int tid,
+                                            int flags, unsigned long long *tmw = nullptr) {
     const int w = tid >> 5, lane = tid & 31;
     uint8_t *ring = sm + A6_RING_A + w * A6_SLOT_BYTES;   // slot 0; slot 1 is the same offset inside ring B
     uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
-    const int cond_len = p.ctrl_cond_len ? *p.ctrl_cond_len : 0;
     const int n_tile = min(cond_len, A6_TILE);
     int u0, u1;
     attn6_units(B, u0, u1);
@@ -422,8 +417,8 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
             {
                 const int ua0 = w, ua1 = w + A6_WARPS;
                 const int bb0 = b0 + min(ua0, nu - 1);
-                S.n_old0 = ua0 < nu ? step + p.own_base[bb0] : -1;
-                S.n_old1 = ua1 < nu ? step + p.own_base[b0 + ua1] : -1;
+                S.n_old0 = ua0 < nu ? step + (ob_cache ? ob_cache[c0 - u0 + ua0] : p.own_base[bb0]) : -1;
+                S.n_old1 = ua1 < nu ? step + (ob_cache ? ob_cache[c0 - u0 + ua1] : p.own_base[b0 + ua1]) : -1;
                 S.k0 = p.ok + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD;
                 S.v0 = p.ov + ((size_t)h * p.cap_b + bb0) * p.max_s * FL_HD;
                 S.unit_stride = (size_t)A6_WARPS * p.max_s * FL_HD;
@@ -437,25 +432,45 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
                 if (S.total > 0) a6_issue(S, 0, ring, bars);                   // slot 1 (ring B) holds the prefix tiles until the slices are done
             }
             __syncwarp();
-            if (n_tile > 0) {   // (re-staged for every chunk: ring B overwrites them)   // fp16 prefix tiles of head h, rows past the prefix zero-filled (P = 0 times garbage must stay 0)
+            if (!(flags & 16) && lane < 4) {
+                // the rest of this warp's rows -> L2 while the prologue below runs (new rows, prefix slices: several us without HBM
+                // traffic otherwise). One bulk prefetch per unit and tensor, beyond the first ring slot.
+                const bool second = lane >= 2;
+                const int n_old = second ? S.n_old1 : S.n_old0;
+                const __half *src = ((lane & 1) ? S.v0 : S.k0) + (second ? S.unit_stride : 0);
+                const int skip = second ? 0 : A6_ROWS;   // chunk 0 of unit 0 is already on its way into the ring
+                if (n_old > skip)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)skip * FL_HD), "r"((uint32_t)(n_old - skip) * FL_HD * 2u) : "memory");
+            }
+            if (n_tile > 0) {   // fp16 prefix tiles of head h (re-staged for every chunk: ring B overwrites them) with cp.async: in flight
+                                // while the new rows are computed; rows past the prefix zero-filled (P = 0 times garbage must stay 0)
                 const __half *pkh = p.pk16 + (size_t)h * p.pstride * FL_HD, *pvh = p.pv16 + (size_t)h * p.pstride * FL_HD;
+                const uint32_t kpa = smem_u32(sm + A6_KP), vpa = smem_u32(sm + A6_VP);
                 for (int idx = tid; idx < A6_TILE * 8; idx += MG_THREADS) {
                     const int row = idx >> 3, cc = idx & 7;
-                    uint4 kv = make_uint4(0u, 0u, 0u, 0u), vv = kv;
-                    if (row < n_tile) { kv = *(const uint4 *)(pkh + (size_t)row * FL_HD + cc * 8); vv = *(const uint4 *)(pvh + (size_t)row * FL_HD + cc * 8); }
-                    *(uint4 *)(sm + A6_KP + a6_swz(row, cc)) = kv;
-                    *(uint4 *)(sm + A6_VP + a6_swz(row, cc)) = vv;
+                    const bool ok = row < n_tile;
+                    const size_t so = ok ? (size_t)row * FL_HD + cc * 8 : 0;
+                    const uint32_t sz = ok ? 16u : 0u, off = a6_swz(row, cc);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(kpa + off), "l"(pkh + so), "r"(sz) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(vpa + off), "l"(pvh + so), "r"(sz) : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
             }
             long long t0 = (tmw && w == 2) ? clock64() : 0;
             if (tmw && w == 2 && lane == 0 && c0 == u0) tmw[2] += (unsigned long long)(t0 - t_entry);
-            for (int u = w; u < A6_CHUNK; u += A6_WARPS) {
-                if (u < nu) a6_new_row(p, b0 + u, h, u, u == w ? S.n_old0 : S.n_old1, cond_len, sm, lane);
-                else {   // absent unit: a zero query keeps the row tile's arithmetic finite
-                    const uint32_t off = a6_swz(u, lane >> 2) + (lane & 3) * 4;
-                    *(uint32_t *)(sm + A6_QH + off) = 0u;
-                    *(uint32_t *)(sm + A6_QL + off) = 0u;
-                }
+            {
+                A6NewRowIn in0, in1;
+                const bool live0 = w < nu, live1 = w + A6_WARPS < nu;
+                if (live0) a6_new_row_load(p, b0 + w, h, S.n_old0, cond_len, lane, in0);
+                if (live1) a6_new_row_load(p, b0 + w + A6_WARPS, h, S.n_old1, cond_len, lane, in1);
+                if (live0) a6_new_row(p, b0 + w, h, w, S.n_old0, sm, lane, in0);
+                if (live1) a6_new_row(p, b0 + w + A6_WARPS, h, w + A6_WARPS, S.n_old1, sm, lane, in1);
+                for (int u = w; u < A6_CHUNK; u += A6_WARPS)
+                    if (u >= nu) {   // absent unit: a zero query keeps the row tile's arithmetic finite
+                        const uint32_t off = a6_swz(u, lane >> 2) + (lane & 3) * 4;
+                        *(uint32_t *)(sm + A6_QH + off) = 0u;
+                        *(uint32_t *)(sm + A6_QL + off) = 0u;
+                    }
             }
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();

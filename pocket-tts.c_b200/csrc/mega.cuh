@@ -36,8 +36,6 @@ struct MegaPhase {
     int type;
     int idx;         // GEMM / ROW / ATTN: index into the respective array; MID: LSD step k just finished
     int next_gemm;   // GEMM whose first weight tiles the producer fetches after this phase's own loads (-1: none)
-    int pf_attn;     // GEMM phases: attention layer whose own K / V rows the two idle warps pull into L2 during this phase (-1: none)
-    int pf_extra;    // 1: that attention phase belongs to the NEXT frame step (one more row per utterance)
 };
 
 struct MegaProgram {
@@ -70,8 +68,7 @@ struct MegaProgram {
     int *done_count;                // utterances that reached their stop point, zeroed by the host
     int n_live, nsteps, first_gemm;
     int n_gemms;                    // contractions per frame (parity of the ring-state slots below)
-    int flags;                      // experiment bits: 2 = light grid barrier, 16 = no L2 prefetch at the start of an attention phase, 8 = L2 prefetch of the next attention phase's rows by the idle warps of a
-                                    // GEMM phase (measured: attention phases -1.5 us, GEMM phases +17 %: off by default)
+    int flags;                      // experiment bits: 2 = light grid barrier, 16 = no L2 prefetch at the start of an attention phase
     int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
                                     // (only when the loop cannot stop early, i.e. EOS detection is off)
     unsigned long long *prof;       // optional [MP_COUNT][2]: ns and phase count per type (written by CTA 0)
@@ -485,6 +482,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
     const bool prof = P.prof != nullptr && blockIdx.x == 0 && tid == 0;
     int steps_done = 0;
 
+    // launch constants of the attention phases: the prefix length, and own_base of this CTA's units (fixed for the whole launch)
+    // cached in shared memory - every grid barrier leaves the L1 cold, and a phase must not start with dependent L2 round trips
+    const int cond_len0 = P.ctrl->cond_len;
+    int *ob_cache = nullptr;
+    {
+        int au0, au1;
+        attn6_units(P.B, au0, au1);
+        if (au1 - au0 <= 64 && au1 > au0 && au0 / P.B == (au1 - 1) / P.B) {
+            ob_cache = (int *)(sbase + 768);
+            if (tid < au1 - au0) ob_cache[tid] = P.attn0.own_base[au0 - (au0 / P.B) * P.B + tid];
+            __syncthreads();
+        }
+    }
+
     // the first contraction's weight tiles can be requested right away
     if (warp == 0 && lane == 0 && P.first_gemm >= 0) {
         const GemmOp &g0 = P.gemms[P.first_gemm];
@@ -518,8 +529,6 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                     if (warp == 0) { pipe.s = rd[0]; pipe.ph = (uint32_t)rd[1]; pipe.pre = rd[2]; }
                     else if (warp == 1) { pipe.s = rd[4]; pipe.ph = (uint32_t)rd[5]; pipe.lt = rd[6]; }
                     else pipe.lt = rd[8];
-                    if (warp >= 2 + MG_EPI_WARPS && ph.pf_attn >= 0 && (P.flags & 8))
-                        attn6_prefetch_l2(P.attn[ph.pf_attn], P.B, step + ph.pf_extra, tid - 32 * (2 + MG_EPI_WARPS), MG_THREADS - 32 * (2 + MG_EPI_WARPS));
                     mega_gemm(P.gemms[ph.idx], nx, pipe, ring, full, empty, tfull, tempty, tmem_base);
                     if (lane == 0) {
                         if (warp == 0) { wr[0] = pipe.s; wr[1] = (int)pipe.ph; wr[2] = pipe.pre; }
@@ -562,7 +571,14 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    attn6_phase(P.attn[ph.idx], P.B, step, ring, tid, P.flags, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                    {   // the layer's parameters are built from the kernel parameter space: no dependent global loads in the phase prologue
+                        AttnDecodeParams a = P.attn0;
+                        const int l = ph.idx;
+                        a.pk += (size_t)l * P.attn_prefix_stride; a.pv += (size_t)l * P.attn_prefix_stride;
+                        a.pk16 += (size_t)l * P.attn_prefix_stride; a.pv16 += (size_t)l * P.attn_prefix_stride;
+                        a.ok += (size_t)l * P.attn_own_stride; a.ov += (size_t)l * P.attn_own_stride;
+                        attn6_phase(a, P.B, step, cond_len0, ob_cache, ring, tid, P.flags, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                    }
                     break;
                 default: break;
             }
@@ -638,14 +654,14 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
             return -1;
         }
         gm.push_back(op);
-        ph.push_back({MP_GEMM, (int)gm.size() - 1, -1, -1, 0});
+        ph.push_back({MP_GEMM, (int)gm.size() - 1, -1});
         const double rows_ = op.p.a_rows, n = op.p.n_total, k = (double)op.p.kblocks_per_tap * GEMM_BK;
         M.flops[MP_GEMM] += 2.0 * rows_ * n * k;
         M.bytes[MP_GEMM] += 2.0 * n * k;   // weights once; activations stay in L2
         return 0;
     };
-    auto add_row = [&](const RowNormParams &r) { rows.push_back(r); ph.push_back({MP_ROW, (int)rows.size() - 1, -1, -1, 0}); };
-    ph.push_back({MP_HEAD, 0, -1, -1, 0});
+    auto add_row = [&](const RowNormParams &r) { rows.push_back(r); ph.push_back({MP_ROW, (int)rows.size() - 1, -1}); };
+    ph.push_back({MP_HEAD, 0, -1});
     for (int k = 0; k < lsd; k++) {
         if (add_gemm(G.cond[k]) != 0 || add_gemm(G.ada) != 0) return -1;
         for (int b = 0; b <= FN_DEPTH; b++) {
@@ -659,10 +675,9 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
             if (b < FN_DEPTH && (add_gemm(G.m0[b]) != 0 || add_gemm(G.m2[b]) != 0)) return -1;
         }
         if (add_gemm(G.fin) != 0) return -1;
-        if (k + 1 == lsd) ph.back().pf_attn = 0;   // ~25 us ahead of layer 0's attention phase (TAIL and the QKV contraction in between)
-        if (k + 1 < lsd) ph.push_back({MP_MID, k, -1, -1, 0});
+        if (k + 1 < lsd) ph.push_back({MP_MID, k, -1});
     }
-    ph.push_back({MP_TAIL, 0, -1, -1, 0});
+    ph.push_back({MP_TAIL, 0, -1});
     for (int l = 0; l < FL_L; l++) {
         RowNormParams r = {};
         if (l > 0) {
@@ -673,16 +688,14 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
         }
         if (add_gemm(G.qkv[l]) != 0) return -1;
         attn.push_back(make_attn_params(e, l, true, G.qkv[l].p.split_k));
-        ph.push_back({MP_ATTN, (int)attn.size() - 1, -1, -1, 0});
+        ph.push_back({MP_ATTN, (int)attn.size() - 1, -1});
         if (add_gemm(G.outp[l]) != 0) return -1;
         r = {};
         r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
         r.part = e->partA; r.nsplit = (int)G.outp[l].p.split_k; r.split_stride = ps;
         r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
         add_row(r);
-        if (add_gemm(G.ff1[l]) != 0) return -1;
-        if (l + 1 < FL_L) ph.back().pf_attn = l + 1;   // FF1, FF2, the row phase and the QKV contraction (~35 us) cover the 84 MB of rows
-        if (add_gemm(G.ff2[l]) != 0) return -1;
+        if (add_gemm(G.ff1[l]) != 0 || add_gemm(G.ff2[l]) != 0) return -1;
     }
     // next contraction reachable without an attention phase in between (attention aliases the ring)
     const int np = (int)ph.size();

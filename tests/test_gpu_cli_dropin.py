@@ -68,3 +68,26 @@ def test_host_layer_engine_lifetime_across_free_and_reload(synth, tmp_path):
     assert snr_db(a, ra) > 40.0 and snr_db(b, rb) > 40.0      # each context ran on ITS OWN weights
     assert snr_db(b, ra) < 10.0                                # and the two models really differ
     assert np.array_equal(a, a2)                               # reloading A reproduces A bit for bit
+
+
+BATCH = ROOT / "pocket-tts.c_b200" / "build" / "ptts_b200_batch_check"
+
+
+@pytest.mark.skipif(not (BATCH.exists() and REF.exists()), reason="prebuilt host-layer binaries not present")
+def test_host_layer_generate_batch_matches_reference_cli_per_text(model_dir, synth, tmp_path):
+    """ptts_generate_batch (the additive ptts.h-level entry of host/ptts_b200_models.c): texts of different lengths are prepared and
+    tokenised by the reference's own host code, bucketed by ptts_estimate_frames, run through the engine pool and returned in the
+    ORIGINAL order; each WAV must match the reference CPU CLI run on that text alone (same seed, frames from the same estimate)."""
+    texts = ["Hello world!", synth.make_prompts(1, seed=5)[0], "One two three four five six seven.", "Short one.",
+             synth.make_prompts(1, seed=6, lo=40, hi=50)[0]]
+    subprocess.run([str(BATCH), str(model_dir), str(tmp_path)] + texts, check=True, timeout=600)
+    lengths = set()
+    for i, t in enumerate(texts):
+        ref = tmp_path / f"ref{i}.wav"
+        subprocess.run([str(REF), "-d", str(model_dir), "-p", t, "--voice", "alba", "-t", "0.7", "-S", str(123 + i), "--eos-threshold", "1e9",
+                        "-q", "-o", str(ref)], check=True, timeout=600)
+        x, y = _wav(tmp_path / f"b{i}.wav"), _wav(ref)
+        assert x.shape == y.shape, f"utterance {i}: {x.shape} vs {y.shape}"
+        assert snr_db(x, y) > 40.0, f"utterance {i}"
+        lengths.add(x.shape[0])
+    assert len(lengths) >= 3      # the batch really was ragged

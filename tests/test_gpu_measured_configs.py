@@ -248,3 +248,38 @@ def test_mimi_forward_one_debug_hook(eng, weights):
         x = x + W[p + "layer_scale_2.scale"] * (W[p + "linear2.weight"] @ u)
     got = eng.mimi_forward_one(lat)
     assert max_rel(got, x) < 2e-3     # fp16 weights on the device
+
+
+def test_pool_shards_buckets_and_gathers_in_original_order(pkg, weights, oracle, voice, golden):
+    """ptts_b200_pool_generate (SURVEY.md section 8e host driver): a ragged list (frames 3..30) goes through a pool of two engines (the
+    same device twice on a 1-GPU box: two engines, two host threads, the sharding / bucketing / gather logic is device-agnostic).
+    The list is sorted by length, cut into calls, dealt to the engines; every utterance must come back at ITS index with ITS
+    length, equal to the oracle run one at a time, and equal to a single-engine run of the same list."""
+    import torch
+    nd = torch.cuda.device_count()
+    pool = pkg.Pool(weights, devices=[0, 1 % nd])
+    try:
+        assert pool.size == 2
+        base = [golden["p0_ids"], golden["p1_ids"], golden["p2_ids"], golden["p1_ids"][:9], golden["p2_ids"][2:17]]
+        n = 70
+        toks = [base[i % 5] for i in range(n)]
+        frames = [3 + (i * 7) % 28 for i in range(n)]
+        seeds = [500 + i for i in range(n)]
+        out = pool.generate(toks, voice, frames, seeds=seeds, params=pkg.default_params(temp=0.7), max_batch=32)
+        assert list(out["frames"]) == frames
+        F = max(frames)
+        assert out["audio"].shape == (n, F * 1920)
+        for i in (0, 1, 13, 34, 69):
+            o = oracle.flowlm_generate(toks[i], voice, frames[i], lsd_steps=1, temp=0.7, seed=seeds[i])
+            assert max_rel(out["latents"][i, :frames[i]], o["latents"]) < TOL, f"utterance {i}"
+            assert not out["latents"][i, frames[i]:].any() and not out["audio"][i, frames[i] * 1920:].any()
+            ref = oracle.mimi_decode(oracle.scale_latents(o["latents"]))
+            assert snr_db(out["audio"][i, :frames[i] * 1920], ref) > SNR_MIN, f"utterance {i}"
+        e = pkg.Engine(weights, 0)
+        try:
+            one = e.generate_batch(toks, voice, frames, seeds=seeds, params=pkg.default_params(temp=0.7))
+            assert np.abs(one["latents"] - out["latents"]).max() < 1e-4 * np.abs(one["latents"]).max()
+        finally:
+            e.close()
+    finally:
+        pool.close()
