@@ -282,7 +282,10 @@ __device__ __forceinline__ void a6_issue(const A6Stream &S, int c, uint8_t *ring
     bulk_load_1d(dst + A6_SLOT_BYTES / 2, S.v0 + off, bytes, &bars[slot]);
 }
 
-__device__ __noinline__ void a6_own_stream(const AttnDecodeParams &p, const A6Stream &S, int h, int b0, int u_first, int cond_len, int n_tile,
+// (arguments by value: a reference to a struct built from kernel parameters would force that struct into local memory, and every field
+// access of the callee into an L1-cold local load)
+struct A6Out { uint16_t *out_h, *out_l; float *out_f32; const float *pk_far, *pv_far; };
+__device__ __noinline__ void a6_own_stream(const A6Out p, const A6Stream S, int h, int b0, int u_first, int cond_len, int n_tile,
                                            uint8_t *sm, uint8_t *ring, uint64_t *bars, int lane, unsigned long long *tm) {
     const int k4 = lane >> 3, l8 = lane & 7, n_far = cond_len - n_tile;
     long long c0 = tm ? clock64() : 0;
@@ -321,7 +324,7 @@ __device__ __noinline__ void a6_own_stream(const AttnDecodeParams &p, const A6St
             unpack8(*(const uint4 *)(sm + A6_VN + (u * FL_HD + l8 * 8) * 2), vf[0]);
             a6_fold<1>(st, q8, kf, vf, 1, k4);
         }
-        if (n_far > 0) a6_far(st, p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD, p.pv + ((size_t)h * p.pstride + n_tile) * FL_HD, n_far, qf, k4, l8);
+        if (n_far > 0) a6_far(st, p.pk_far, p.pv_far, n_far, qf, k4, l8);
         // ---- unit complete: reduce over the four row groups, merge with the prefix partials (log-sum-exp), write bf16 hi + lo
         st.l += __shfl_xor_sync(0xffffffffu, st.l, 8);
         st.l += __shfl_xor_sync(0xffffffffu, st.l, 16);
@@ -397,9 +400,10 @@ __device__ __forceinline__ void attn6_units(int B, int &u0, int &u1) {
 
 // One attention phase: units [u0, u1) of this CTA in head-major order (unit = h * B + b).
 // ob_cache: own_base of this CTA's units [u0, u1) in shared memory (or NULL: read p.own_base), cond_len: the prefix length of the launch.
-// flags bit 16 (experiment): no L2 prefetch of the warp's remaining rows at the start of the phase.
+// (L2 prefetches of the rows - cp.async.bulk.prefetch.L2 at the start of the phase, or from the idle warps of the preceding GEMM
+// phases - were measured and lose: issuing them costs more than they save, profiles/r02_attention_experiments.txt.)
 __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, int cond_len, const int *ob_cache, uint8_t *sm, int tid,
-                                            int flags, unsigned long long *tmw = nullptr) {
+                                            unsigned long long *tmw = nullptr) {
     const int w = tid >> 5, lane = tid & 31;
     uint8_t *ring = sm + A6_RING_A + w * A6_SLOT_BYTES;   // slot 0; slot 1 is the same offset inside ring B
     uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
@@ -432,16 +436,6 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
                 if (S.total > 0) a6_issue(S, 0, ring, bars);                   // slot 1 (ring B) holds the prefix tiles until the slices are done
             }
             __syncwarp();
-            if (!(flags & 16) && lane < 4) {
-                // the rest of this warp's rows -> L2 while the prologue below runs (new rows, prefix slices: several us without HBM
-                // traffic otherwise). One bulk prefetch per unit and tensor, beyond the first ring slot.
-                const bool second = lane >= 2;
-                const int n_old = second ? S.n_old1 : S.n_old0;
-                const __half *src = ((lane & 1) ? S.v0 : S.k0) + (second ? S.unit_stride : 0);
-                const int skip = second ? 0 : A6_ROWS;   // chunk 0 of unit 0 is already on its way into the ring
-                if (n_old > skip)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + (size_t)skip * FL_HD), "r"((uint32_t)(n_old - skip) * FL_HD * 2u) : "memory");
-            }
             if (n_tile > 0) {   // fp16 prefix tiles of head h (re-staged for every chunk: ring B overwrites them) with cp.async: in flight
                                 // while the new rows are computed; rows past the prefix zero-filled (P = 0 times garbage must stay 0)
                 const __half *pkh = p.pk16 + (size_t)h * p.pstride * FL_HD, *pvh = p.pv16 + (size_t)h * p.pstride * FL_HD;
@@ -485,7 +479,11 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
                 a6_issue(S, 1, ring, bars);
             }
             __syncwarp();
-            if (S.n_old0 >= 0) a6_own_stream(p, S, h, b0, w, cond_len, n_tile, sm, ring, bars, lane, (tmw && w == 2) ? tmw : nullptr);
+            if (S.n_old0 >= 0) {
+                const A6Out o = {p.out_h, p.out_l, p.out_f32, p.pk ? p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD : nullptr,
+                                 p.pv ? p.pv + ((size_t)h * p.pstride + n_tile) * FL_HD : nullptr};
+                a6_own_stream(o, S, h, b0, w, cond_len, n_tile, sm, ring, bars, lane, (tmw && w == 2) ? tmw : nullptr);
+            }
             __syncwarp();
             if (lane == 0)
                 for (int s = 0; s < A6_SLOTS; s++) mbar_inval(&bars[s]);

@@ -68,7 +68,7 @@ struct MegaProgram {
     int *done_count;                // utterances that reached their stop point, zeroed by the host
     int n_live, nsteps, first_gemm;
     int n_gemms;                    // contractions per frame (parity of the ring-state slots below)
-    int flags;                      // experiment bits: 2 = light grid barrier, 16 = no L2 prefetch at the start of an attention phase
+    int flags;                      // experiment bits: 2 = light grid barrier
     int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
                                     // (only when the loop cannot stop early, i.e. EOS detection is off)
     unsigned long long *prof;       // optional [MP_COUNT][2]: ns and phase count per type (written by CTA 0)
@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         a.pk += (size_t)l * P.attn_prefix_stride; a.pv += (size_t)l * P.attn_prefix_stride;
                         a.pk16 += (size_t)l * P.attn_prefix_stride; a.pv16 += (size_t)l * P.attn_prefix_stride;
                         a.ok += (size_t)l * P.attn_own_stride; a.ov += (size_t)l * P.attn_own_stride;
-                        attn6_phase(a, P.B, step, cond_len0, ob_cache, ring, tid, P.flags, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                        attn6_phase(a, P.B, step, cond_len0, ob_cache, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     }
                     break;
                 default: break;
