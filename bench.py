@@ -468,6 +468,30 @@ def main():
             except Exception as ex:  # the baseline is reported, never required for the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": "audio-s/s", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"unavailable: {ex}"}
+        # ---------------- second baseline: the reference's OWN GPU backend (`make cuda-opt`: ptts_cuda.c on cuBLAS + NVRTC kernels, unmodified,
+        # built by oracle/Makefile) on this same B200: one prompt x 100 frames, timings as the reference prints them (PTTS_TIMING=1)
+        if world == 1 and not args.no_cpu_baseline:
+            exe = ROOT / "oracle" / "_ref" / "ptts_ref_cuda"
+            try:
+                import re
+                wav = Path(tempfile.gettempdir()) / "ptts_ref_cuda.wav"
+                cmd = [str(exe), "-d", str(md), "-p", prompts[0], "--voice", "alba", "-t", "0.7", "-S", "123", "--frames", str(F), "--eos-threshold", "1e9",
+                       "-o", str(wav)]
+                env = dict(os.environ, PTTS_TIMING="1")
+                t0 = time.perf_counter()
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+                wall = time.perf_counter() - t0
+                fm = re.search(r"FlowLM latents: ([0-9.]+) ms", r.stderr)
+                mm = re.search(r"Mimi decode: ([0-9.]+) ms", r.stderr)
+                if r.returncode == 0 and fm and mm:
+                    gen_s = (float(fm.group(1)) + float(mm.group(1))) / 1e3
+                    line["reference_cuda_baseline"] = {"value": F * FRAME_SEC / gen_s, "unit": "audio-s/s", "flowlm_ms": float(fm.group(1)), "mimi_ms": float(mm.group(1)),
+                                                       "wall_s_incl_load_and_nvrtc": wall, "kind": "reference (make cuda-opt: cuBLAS + NVRTC, unmodified)",
+                                                       "sample": f"1 prompt x {F} frames, single utterance (the reference has no batching)"}
+                else:
+                    line["reference_cuda_baseline"] = {"value": None, "sample": f"failed: rc={r.returncode} {r.stderr[-200:]}"}
+            except Exception as ex:
+                line["reference_cuda_baseline"] = {"value": None, "sample": f"unavailable: {ex}"}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
