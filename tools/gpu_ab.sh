@@ -1,17 +1,8 @@
-# usage: bash tools/gpu_ab.sh TAG "flagsA flagsB ..." -- phase trace of the persistent step kernel under each PTTS_B200_MEGA_FLAGS value
-# (same box, back to back), then a short bench with the default flags
-TAG=${1:-ab}; FLAGS=${2:-"0"}
-mkdir -p gpurun_out
-for f in $FLAGS; do
-  echo "== PTTS_B200_MEGA_FLAGS=$f"
-  PTTS_B200_MEGA_FLAGS=$f timeout 600 python tools/mega_trace.py 256 100 2> gpurun_out/${TAG}_trace_f$f.txt | tail -1 | cut -c1-400
-  grep -E " ATTN |attention" gpurun_out/${TAG}_trace_f$f.txt | head -8
+# usage: bash tools/gpu_ab.sh [FLAGS_NEW]  - same-box A/B of the persistent step kernel: build_ab/base.so vs build_ab/new.so (+ optional PTTS_B200_MEGA_FLAGS for new)
+L=pocket-tts.c_b200/libptts_b200.so
+for rep in 1 2; do
+  cp build_ab/base.so $L; echo -n "base: "; timeout 200 python tools/step_time.py 256 100 3 2>&1 | tail -1
+  cp build_ab/new.so $L;  echo -n "new : "; timeout 200 python tools/step_time.py 256 100 3 2>&1 | tail -1
+  if [ -n "$1" ]; then echo -n "new flags=$1: "; PTTS_B200_MEGA_FLAGS=$1 timeout 200 python tools/step_time.py 256 100 3 2>&1 | tail -1; fi
 done
-timeout 900 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --skip-mimi-only --total-prompts 0 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
-python - <<PY
-import json
-d=json.load(open('gpurun_out/${TAG}_bench.json'))
-print("value",round(d["value"],1),"ms/step",round(d["ms_per_step"],2),"e2e",round(d["e2e"]["value"],1))
-print("roofline",{k:v for k,v in d.get("roofline",{}).items() if k in ("achieved","frac","avg_launch_us","us_per_frame_step","share_of_step")})
-for k,v in d.get("kernel_classes",{}).items(): print(k,v)
-PY
+cp build_ab/new.so $L

@@ -17,17 +17,16 @@ __device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t ph) {
     while (!ok) asm volatile("{.reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0,1,0,p;}" : "=r"(ok) : "r"(s32(b)), "r"(ph) : "memory");
 }
 template <int CL>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128, 1) probe(const uint8_t *src, int iters, int mode, long long *out) {
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128, 1) probe(const uint8_t *src, int iters, int mode, long long *out, int same) {
     extern __shared__ __align__(1024) uint8_t sm[];
     uint64_t *full = (uint64_t *)(sm + STAGES * TILE);
     uint32_t rank; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
     if (threadIdx.x == 0) { for (int s = 0; s < STAGES; s++) mb_init(&full[s], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     asm volatile("barrier.cluster.arrive.release.aligned; barrier.cluster.wait.acquire.aligned;" ::: "memory");
-    const uint8_t *base = src + (size_t)(blockIdx.x / CL) * (size_t)iters * TILE;   // one stream per cluster
+    const uint8_t *base = src + (same ? 0 : (size_t)(blockIdx.x / CL) * (size_t)iters * TILE);   // one stream per cluster, or ONE stream for the whole grid (same = 1: the A operand of a GEMM whose CTAs differ in N)
     long long t0 = clock64();
-    if (threadIdx.x == 0) {
-        // no slot reuse handshake across CTAs is needed for the measurement if every CTA consumes in lock step: use a cluster barrier per round of STAGES tiles
-        for (int it0 = 0; it0 < iters; it0 += STAGES) {
+    for (int it0 = 0; it0 < iters; it0 += STAGES) {
+        if (threadIdx.x == 0) {
             for (int s = 0; s < STAGES; s++) {
                 const uint8_t *g = base + (size_t)(it0 + s) * TILE;
                 mb_expect(&full[s], TILE);
@@ -41,20 +40,26 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128, 1) probe(const
             }
             for (int s = 0; s < STAGES; s++) mb_wait(&full[s], (it0 / STAGES) & 1);
         }
+        // a peer must not multicast round r + 1 into this CTA's slots before this CTA has armed them: one cluster barrier per round
+        if (CL > 1 && mode == 1) {
+            __syncthreads();
+            asm volatile("barrier.cluster.arrive.release.aligned; barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
     }
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release.aligned; barrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = clock64() - t0;
 }
-template <int CL> void run(const uint8_t *d, long long *dout, int grid, int iters) {
+template <int CL> void run(const uint8_t *d, long long *dout, int grid, int iters, int same = 0) {
     CK(cudaFuncSetAttribute(probe<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * TILE + 1024));
     for (int mode = 0; mode < 2; mode++) {
-        for (int rep = 0; rep < 2; rep++) { probe<CL><<<grid, 128, STAGES * TILE + 1024>>>(d, iters, mode, dout); CK(cudaDeviceSynchronize()); }
+        for (int rep = 0; rep < 2; rep++) { probe<CL><<<grid, 128, STAGES * TILE + 1024>>>(d, iters, mode, dout, same); CK(cudaDeviceSynchronize()); }
         long long cyc; CK(cudaMemcpy(&cyc, dout, 8, cudaMemcpyDeviceToHost));
-        printf("cluster %d grid %d %s: %.1f bytes landed per SM per clock (%lld cycles for %d tiles)\n", CL, grid, mode ? "multicast" : "unicast  ", (double)iters * TILE / cyc, cyc, iters);
+        printf("%s cluster %d grid %d %s: %.1f bytes landed per SM per clock (%lld cycles for %d tiles)\n", same ? "one stream " : "per cluster", CL, grid, mode ? "multicast" : "unicast  ", (double)iters * TILE / cyc, cyc, iters);
     }
 }
 int main() {
+    setvbuf(stdout, NULL, _IOLBF, 0);
     const int iters = 256;   // 8 MB per cluster stream: L2 resident after the first pass
     uint8_t *d; long long *dout;
     CK(cudaMalloc(&d, (size_t)148 * iters * TILE)); CK(cudaMemset(d, 1, (size_t)148 * iters * TILE)); CK(cudaMalloc(&dout, 8));
@@ -63,5 +68,9 @@ int main() {
     run<4>(d, dout, 148, iters);
     run<2>(d, dout, 32, iters);
     run<4>(d, dout, 32, iters);
+    // every CTA of the grid wants the SAME L2-resident stream (8 MB)
+    run<1>(d, dout, 148, iters, 1); run<1>(d, dout, 64, iters, 1); run<1>(d, dout, 16, iters, 1);
+    run<2>(d, dout, 148, iters, 1); run<4>(d, dout, 148, iters, 1);
+    run<2>(d, dout, 64, iters, 1); run<4>(d, dout, 64, iters, 1);
     return 0;
 }
