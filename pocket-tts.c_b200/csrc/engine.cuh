@@ -105,6 +105,33 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);   // errors are picked up by launch_check / cudaGetLastError
 }
+// The same launch with an L2 access-policy window over [win, win + win_bytes): lines of the window are kept in the persisting
+// part of L2 with probability hit_ratio (the rest streams). Used by the batch-1 GEMV path for the weight matrix each launch
+// streams; a launch attribute, so it is recorded into the node when the step is captured into a CUDA graph.
+template <typename... KArgs, typename... Args>
+static void launch_k_window(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const void *win, size_t win_bytes,
+                            float hit_ratio, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (pdl_enabled()) {
+        at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    if (win && win_bytes > 0 && hit_ratio > 0.0f) {
+        at[na].id = cudaLaunchAttributeAccessPolicyWindow;
+        at[na].val.accessPolicyWindow.base_ptr = const_cast<void *>(win);
+        at[na].val.accessPolicyWindow.num_bytes = win_bytes;
+        at[na].val.accessPolicyWindow.hitRatio = hit_ratio;
+        at[na].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        at[na].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        na++;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
+    (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // ---------------------------------------------------------------- GEMM dispatch
 template <int BN, int SPLIT>
@@ -314,6 +341,10 @@ struct ptts_b200_engine {
     int64_t launches = 0;
     ptts::Prof prof;
     int num_sms = 148;
+    // batch-1 decode: share of the GEMV weight stream kept in the persisting part of L2 (0: no access-policy windows) and the
+    // largest window a launch may name (cudaDevAttrMaxAccessPolicyWindowSize)
+    float l2_hit_ratio = 0.0f;
+    size_t l2_max_window = 0;
     ptts::EngineCaches *caches = nullptr;
 
     // ---- FlowLM weights

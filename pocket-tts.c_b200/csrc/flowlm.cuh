@@ -191,7 +191,8 @@ static int gemv(Engine *e, const __nv_bfloat16 *W, int N, const float *x, GemvPa
     constexpr int THREADS = K / 8 < 128 ? K / 8 : 128;
     if (e->prof.on) { e->prof.bytes[KC_GEMV] += 2.0 * N * K + 4.0 * (K + N); e->prof.flops[KC_GEMV] += 2.0 * N * K; }
     LaunchScope ls(e, KC_GEMV);
-    launch_k(k_gemv<K, RPC, PRO>, (N + RPC - 1) / RPC, THREADS, 0, e->st, p);
+    launch_k_window(k_gemv<K, RPC, PRO>, (N + RPC - 1) / RPC, THREADS, 0, e->st, (const void *)W, std::min((size_t)N * K * 2, e->l2_max_window),
+                    e->l2_hit_ratio, p);
     return launch_check("k_gemv");
 }
 

@@ -74,6 +74,26 @@ extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
     e->caches = new EngineCaches();
+    {   // L2 residency of the batch-1 weight stream (north star: "L2-resident pinned weights"). The set-aside is a per-device limit
+        // that also shrinks the L2 every other kernel sees, so it is opt-in: PTTS_B200_L2_PERSIST_MB = megabytes to set aside
+        // (clamped to cudaDevAttrMaxPersistingL2CacheSize); the GEMV launches then name their weight matrix as a persisting window
+        // with hit ratio = set-aside / 171 MB of streamed weights.
+        const char *pm = getenv("PTTS_B200_L2_PERSIST_MB");
+        int max_persist = 0, max_win = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        if (pm && atoi(pm) > 0 && max_persist > 0 && max_win > 0) {
+            const size_t want = std::min((size_t)atoi(pm) << 20, (size_t)max_persist);
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                e->l2_hit_ratio = std::min(1.0f, (float)((double)want / 170.6e6));
+                e->l2_max_window = (size_t)max_win;
+                if (getenv("PTTS_B200_L2_VERBOSE"))
+                    fprintf(stderr, "ptts_b200: L2 %d MB, persisting set-aside %zu MB (max %d MB), window max %d MB, hit ratio %.2f\n",
+                            prop.l2CacheSize >> 20, want >> 20, max_persist >> 20, max_win >> 20, e->l2_hit_ratio);
+            }
+        }
+        cudaGetLastError();
+    }
     HostWeights hw{tensors, n_tensors};
     if (cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&e->st_copy, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&e->ev0) != cudaSuccess ||
