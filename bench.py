@@ -174,8 +174,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast", type=int, default=0, help="1: activations as single bf16 (precise=0); default hi+lo pairs")
     ap.add_argument("--skip-mimi-only", action="store_true", help="skip the configs[3] Mimi decode-only measurement")
-    ap.add_argument("--ragged", action="store_true",
-                    help="also time a batch whose frame counts are drawn from U[60, 140] (SURVEY.md 8d ragged variant)")
+    ap.add_argument("--ragged", action="store_true", default=True,
+                    help="also time the ragged variants (SURVEY.md 8d): one lock-step batch whose frame counts are drawn from U[60, 140], "
+                         "and a ragged prompt list through the product's length-bucketing pool driver (default: on)")
+    ap.add_argument("--no-ragged", dest="ragged", action="store_false")
     ap.add_argument("--total-prompts", type=int, default=8192,
                     help="configs[4]: a FIXED list of this many prompts (sharded over the ranks, calls of --sweep-batch utterances) through the "
                          "host-buffer API, so that the line carries a strong-scaling point at every N (0 disables)")
@@ -331,6 +333,30 @@ def main():
                          "batch_per_call": SB,
                          "note": "host token lists -> host PCM through ptts_b200 generate_batch, H2D / D2H inside"}
         B = B_
+        if args.ragged:
+            # ---------------- the same kind of list with RAGGED lengths (frames ~ U[60, 140]) through ptts_b200_pool_generate: the
+            # product's host driver sorts the utterances by length and cuts the sorted list into calls, so every lock-step call
+            # (and its Mimi decode) runs only to its own longest utterance. Efficiency = produced audio-s/s vs the uniform sweep.
+            nr = min(nb, 4) * SB
+            rfr = np.random.default_rng(4242 + rank).integers(60, 141, size=nr).astype(np.int32)
+            Wp = pkg.synth.read_safetensors(md / "tts_b6369a24.safetensors")
+            pool = pkg.Pool(Wp, [local_rank])
+            del Wp
+            rpcm = torch.empty((nr, int(rfr.max()) * 1920), dtype=torch.float32).pin_memory().numpy()
+            rseeds = np.arange(nr, dtype=np.int64) + 70000 + rank * nr
+            pool.generate(alltok[:nr], voice, rfr, rseeds, None, params, SB, True, rpcm, False)   # shapes / capacities
+            barrier()
+            t0 = time.perf_counter()
+            out = pool.generate(alltok[:nr], voice, rfr, rseeds, None, params, SB, True, rpcm, False)
+            rs = max_over_ranks(time.perf_counter() - t0)
+            assert (out["frames"] == rfr).all()
+            pool.close()
+            uniform_rate = line["sweep"]["audio_s_per_s"]
+            ragged_rate = world * float(rfr.sum()) * FRAME_SEC / rs
+            line["ragged_sweep"] = {"workload": f"{nr * world} prompts, frames ~ U[60, 140], ptts_b200_pool_generate (length bucketing, calls of <= {SB})",
+                                    "seconds": rs, "audio_s_per_s": ragged_rate, "vs_uniform_sweep": ragged_rate / uniform_rate,
+                                    "note": "host token lists -> host PCM; audio seconds count produced frames only"}
+            barrier()
         eng.stage(toks, voice, F, seeds, None, params)   # restore the staged configs[2] batch for the profile section below
 
     if rank == 0:

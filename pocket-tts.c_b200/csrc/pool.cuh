@@ -22,6 +22,11 @@ struct PoolCall {
 struct ptts_b200_pool {
     std::vector<ptts_b200_engine *> eng;
     std::vector<int> dev;
+    // per device: two pinned PCM staging buffers (grow-only, kept for the life of the pool). A call whose utterances are not one
+    // contiguous index range of full length lands in a staging buffer; its rows are copied to their final places by a helper
+    // thread while the device already runs the next call into the other buffer.
+    struct Stage { float *buf[2] = {nullptr, nullptr}; size_t cap[2] = {0, 0}; };
+    std::vector<Stage> stage;
 };
 
 extern "C" int ptts_b200_pool_create(ptts_b200_pool **out, const int *devices, int n_devices, const ptts_b200_tensor *tensors, int n_tensors) {
@@ -40,6 +45,7 @@ extern "C" int ptts_b200_pool_create(ptts_b200_pool **out, const int *devices, i
     ptts_b200_pool *p = new ptts_b200_pool();
     p->dev = dev;
     p->eng.assign(dev.size(), nullptr);
+    p->stage.assign(dev.size(), ptts_b200_pool::Stage());
     std::vector<std::string> err(dev.size());
     std::vector<std::thread> th;
     for (size_t i = 0; i < dev.size(); i++)   // weight conversion and upload of the replicas run side by side
@@ -60,6 +66,11 @@ extern "C" int ptts_b200_pool_create(ptts_b200_pool **out, const int *devices, i
 
 extern "C" void ptts_b200_pool_destroy(ptts_b200_pool *p) {
     if (!p) return;
+    for (size_t d = 0; d < p->eng.size(); d++) {
+        if (p->eng[d]) cudaSetDevice(p->eng[d]->device);
+        for (int k = 0; k < 2; k++)
+            if (p->stage[d].buf[k]) cudaFreeHost(p->stage[d].buf[k]);
+    }
     for (auto *e : p->eng) ptts_b200_destroy(e);
     delete p;
 }
@@ -109,15 +120,19 @@ extern "C" int ptts_b200_pool_generate(ptts_b200_pool *p, int n, const int *toke
     std::vector<std::string> err(nd);
     auto worker = [&](int d) {
         ptts_b200_engine *e = p->eng[d];
-        std::vector<int> tok, offs, mf, ea, used;
+        ptts_b200_pool::Stage &sg = p->stage[d];
+        std::vector<int> tok, offs, mf, ea;
         std::vector<int64_t> sd;
-        std::vector<float> lat;
-        float *pin = nullptr;
-        size_t pin_cap = 0;
+        // per staging buffer: the latents / frame counts of the call it holds and the thread gathering them
+        std::vector<float> lat[2];
+        std::vector<int> used[2];
+        std::thread gather[2];
+        int which = 0;
         for (const PoolCall &c : calls) {
             if (c.device != d || !err[d].empty()) continue;
-            const int m = (int)c.idx.size();
-            tok.clear(); offs.assign(1, 0); mf.resize(m); sd.resize(m); ea.resize(m); used.assign(m, 0);
+            const int m = (int)c.idx.size(), w = which;
+            if (gather[w].joinable()) gather[w].join();   // the previous user of this buffer has been copied out
+            tok.clear(); offs.assign(1, 0); mf.resize(m); sd.resize(m); ea.resize(m); used[w].assign(m, 0);
             for (int k = 0; k < m; k++) {
                 const int i = c.idx[k];
                 tok.insert(tok.end(), tokens_flat + token_offsets[i], tokens_flat + token_offsets[i + 1]);
@@ -129,39 +144,45 @@ extern "C" int ptts_b200_pool_generate(ptts_b200_pool *p, int n, const int *toke
                 lat_dst = out_latents ? out_latents + (size_t)c.idx[0] * F * FL_LAT : nullptr;
                 pcm_dst = out_audio ? out_audio + (size_t)c.idx[0] * F * 1920 : nullptr;
             } else {
-                if (out_latents) { lat.resize((size_t)m * c.cap * FL_LAT); lat_dst = lat.data(); }
+                if (out_latents) { lat[w].resize((size_t)m * c.cap * FL_LAT); lat_dst = lat[w].data(); }
                 if (out_audio) {
                     const size_t need = (size_t)m * c.cap * 1920;
-                    if (need > pin_cap) {
+                    if (need > sg.cap[w]) {
                         cudaSetDevice(e->device);
-                        if (pin) cudaFreeHost(pin);
-                        pin = nullptr; pin_cap = 0;
-                        if (cudaMallocHost(&pin, need * sizeof(float)) != cudaSuccess) { err[d] = "pool_generate: pinned staging allocation failed"; break; }
-                        pin_cap = need;
+                        if (sg.buf[w]) cudaFreeHost(sg.buf[w]);
+                        sg.buf[w] = nullptr; sg.cap[w] = 0;
+                        if (cudaMallocHost(&sg.buf[w], need * sizeof(float)) != cudaSuccess) { err[d] = "pool_generate: pinned staging allocation failed"; break; }
+                        sg.cap[w] = need;
                     }
-                    pcm_dst = pin;
+                    pcm_dst = sg.buf[w];
                 }
             }
             if (ptts_b200_generate_batch(e, m, tok.data(), offs.data(), cond_prefix, cond_len, mf.data(), sd.data(), ea.data(), params, lat_dst,
-                                         used.data(), pcm_dst) != 0) {
+                                         used[w].data(), pcm_dst) != 0) {
                 err[d] = ptts_b200_last_error();
                 break;
             }
-            for (int k = 0; k < m; k++) {   // gather in the original order
-                const int i = c.idx[k];
-                if (out_frames_used) out_frames_used[i] = used[k];
-                if (c.direct) continue;
-                if (out_latents) {
-                    memcpy(out_latents + (size_t)i * F * FL_LAT, lat_dst + (size_t)k * c.cap * FL_LAT, (size_t)c.cap * FL_LAT * sizeof(float));
-                    memset(out_latents + ((size_t)i * F + c.cap) * FL_LAT, 0, (size_t)(F - c.cap) * FL_LAT * sizeof(float));
+            auto scatter = [&, w, lat_dst, pcm_dst](const PoolCall *cc) {   // results to their places in the original order
+                const int mm = (int)cc->idx.size();
+                for (int k = 0; k < mm; k++) {
+                    const int i = cc->idx[k];
+                    if (out_frames_used) out_frames_used[i] = used[w][k];
+                    if (cc->direct) continue;
+                    if (out_latents) {
+                        memcpy(out_latents + (size_t)i * F * FL_LAT, lat_dst + (size_t)k * cc->cap * FL_LAT, (size_t)cc->cap * FL_LAT * sizeof(float));
+                        memset(out_latents + ((size_t)i * F + cc->cap) * FL_LAT, 0, (size_t)(F - cc->cap) * FL_LAT * sizeof(float));
+                    }
+                    if (out_audio) {
+                        memcpy(out_audio + (size_t)i * F * 1920, pcm_dst + (size_t)k * cc->cap * 1920, (size_t)cc->cap * 1920 * sizeof(float));
+                        memset(out_audio + ((size_t)i * F + cc->cap) * 1920, 0, (size_t)(F - cc->cap) * 1920 * sizeof(float));
+                    }
                 }
-                if (out_audio) {
-                    memcpy(out_audio + (size_t)i * F * 1920, pcm_dst + (size_t)k * c.cap * 1920, (size_t)c.cap * 1920 * sizeof(float));
-                    memset(out_audio + ((size_t)i * F + c.cap) * 1920, 0, (size_t)(F - c.cap) * 1920 * sizeof(float));
-                }
-            }
+            };
+            if (c.direct) scatter(&c);
+            else { gather[w] = std::thread(scatter, &c); which ^= 1; }
         }
-        if (pin) { cudaSetDevice(e->device); cudaFreeHost(pin); }
+        for (int k = 0; k < 2; k++)
+            if (gather[k].joinable()) gather[k].join();
     };
     std::vector<std::thread> th;
     for (int d = 1; d < nd; d++) th.emplace_back(worker, d);
