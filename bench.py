@@ -337,7 +337,7 @@ def main():
             # ---------------- the same kind of list with RAGGED lengths (frames ~ U[60, 140]) through ptts_b200_pool_generate: the
             # product's host driver sorts the utterances by length and cuts the sorted list into calls, so every lock-step call
             # (and its Mimi decode) runs only to its own longest utterance. Efficiency = produced audio-s/s vs the uniform sweep.
-            nr = min(nb, 4) * SB
+            nr = min(nb, 8) * SB
             rfr = np.random.default_rng(4242 + rank).integers(60, 141, size=nr).astype(np.int32)
             Wp = pkg.synth.read_safetensors(md / "tts_b6369a24.safetensors")
             pool = pkg.Pool(Wp, [local_rank])

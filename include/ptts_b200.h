@@ -68,6 +68,15 @@ int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, int frames,
  * -> out_embed[512]. */
 int ptts_b200_mimi_forward_one(ptts_b200_engine *e, const float *latent, float *out_embed);
 
+/* ---- additive: voice-cloning encoder. 24 kHz mono PCM -> conditioning rows out_cond [frames, 1024]
+ * at 12.5 Hz (frames = ceil(n_samples / 1920), the input is zero padded to whole frames), i.e. the tensor the reference loads
+ * from a voice file as "audio_prompt" (ptts.c:293-364) and passes to ptts_flowlm_generate_latents as cond_prefix. The reference
+ * itself only shape-checks the tensors involved (ptts.c:914-944: encoder.model.*, encoder_transformer.*, downsample.conv) and
+ * loads flow_lm.speaker_proj_weight without using it (ptts_flowlm.c:874); this entry runs them: SEANet encoder (causal Conv1d,
+ * ptts_kernels.c:114-156; ResBlock, ptts_mimi.c:160-177) -> encoder transformer (ptts_mimi.c:301-376) -> stride-16 downsampler
+ * -> speaker projection. Fails (-1) when the checkpoint has no encoder tensors or frames > max_frames. */
+int ptts_b200_voice_encode(ptts_b200_engine *e, const float *pcm, int n_samples, float *out_cond, int max_frames, int *out_frames);
+
 /* ---- additive batched entries (the reference is single-utterance, ptts.h:75-76). */
 
 /* Mimi decode of n equal-length latent sequences: latents [n, frames, 32] (scaled) ->

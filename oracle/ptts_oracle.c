@@ -47,6 +47,11 @@ struct orc_model {
     struct { const float *inproj, *outproj, *n1w, *n1b, *n2w, *n2b, *l1, *l2, *ls1, *ls2; } M[ML];
     conv_t dec_in, res1[3], res2[3], dec_out;
     conv_t up[3];
+    /* voice-cloning encoder (optional tensors; shapes ptts.c:914-944, speaker projection ptts_flowlm.c:874) */
+    int has_encoder;
+    conv_t enc_in, eres1[3], eres2[3], edown[3], enc_out, down;
+    struct { const float *inproj, *outproj, *n1w, *n1b, *n2w, *n2b, *l1, *l2, *ls1, *ls2; } E[ML];
+    const float *spk;
 };
 
 /* ---------------------------------------------------------------- lookup */
@@ -192,6 +197,43 @@ orc_model *orc_create(const orc_tensor *t, int n) {
             if ((G[i].tr ? relay_convtr(c) : relay_conv(c)) != 0) goto fail;
         }
     }
+    /* optional: encoder side. Present only when the checkpoint carries the tensors the reference's --verify expects. */
+    m->spk = find(t, n, FLOW_PFX, "speaker_proj_weight", D * MD, 0);
+    if (m->spk && find(t, n, MIMI_PFX, "encoder.model.0.conv.weight", 64 * 7, 0)) {
+        struct { conv_t *c; const char *nm; int cin, cout, k, s, bias; } G[] = {
+            {&m->enc_in, "encoder.model.0.conv", 1, 64, 7, 1, 1},
+            {&m->eres1[0], "encoder.model.1.block.1.conv", 64, 32, 3, 1, 1},
+            {&m->eres2[0], "encoder.model.1.block.3.conv", 32, 64, 1, 1, 1},
+            {&m->edown[0], "encoder.model.3.conv", 64, 128, 8, 4, 1},
+            {&m->eres1[1], "encoder.model.4.block.1.conv", 128, 64, 3, 1, 1},
+            {&m->eres2[1], "encoder.model.4.block.3.conv", 64, 128, 1, 1, 1},
+            {&m->edown[1], "encoder.model.6.conv", 128, 256, 10, 5, 1},
+            {&m->eres1[2], "encoder.model.7.block.1.conv", 256, 128, 3, 1, 1},
+            {&m->eres2[2], "encoder.model.7.block.3.conv", 128, 256, 1, 1, 1},
+            {&m->edown[2], "encoder.model.9.conv", 256, 512, 12, 6, 1},
+            {&m->enc_out, "encoder.model.11.conv", 512, 512, 3, 1, 1},
+            {&m->down, "downsample.conv.conv", 512, 512, 32, 16, 0},
+        };
+        for (size_t i = 0; i < sizeof G / sizeof G[0]; i++) {
+            conv_t *c = G[i].c;
+            c->cin = G[i].cin; c->cout = G[i].cout; c->k = G[i].k; c->stride = G[i].s;
+            snprintf(nm, sizeof nm, "%s.weight", G[i].nm);
+            MGET(c->w, nm, (int64_t)c->cin * c->cout * c->k);
+            c->b = NULL;
+            if (G[i].bias) { snprintf(nm, sizeof nm, "%s.bias", G[i].nm); MGET(c->b, nm, c->cout); }
+        }
+        for (int l = 0; l < ML; l++) {
+#define EL_(field, suffix, ne) snprintf(nm, sizeof nm, "encoder_transformer.transformer.layers.%d." suffix, l); MGET(m->E[l].field, nm, ne)
+            EL_(inproj, "self_attn.in_proj.weight", 3 * MD * MD);
+            EL_(outproj, "self_attn.out_proj.weight", MD * MD);
+            EL_(n1w, "norm1.weight", MD); EL_(n1b, "norm1.bias", MD);
+            EL_(n2w, "norm2.weight", MD); EL_(n2b, "norm2.bias", MD);
+            EL_(l1, "linear1.weight", MFF * MD); EL_(l2, "linear2.weight", MD * MFF);
+            EL_(ls1, "layer_scale_1.scale", MD); EL_(ls2, "layer_scale_2.scale", MD);
+#undef EL_
+        }
+        m->has_encoder = 1;
+    }
     return m;
 fail:
     orc_destroy(m);
@@ -225,6 +267,7 @@ void orc_linear(float *y, const float *x, const float *w, const float *b, int n,
 void orc_conv1d(float *y, const float *x, const float *w, const float *b,
                 int in_ch, int out_ch, int T, int k, int stride, int groups) {
     int out_len = T / stride, ipg = in_ch / groups, opg = out_ch / groups, pad = k - stride;
+#pragma omp parallel for schedule(static)
     for (int oc = 0; oc < out_ch; oc++) {
         int g = oc / opg;
         for (int t = 0; t < out_len; t++) {
@@ -541,7 +584,10 @@ static void convtr_tm(const conv_t *c, const float *x, int T, float *y) {
 static void elu_copy(const float *x, size_t n, float *y) { for (size_t i = 0; i < n; i++) y[i] = elu(x[i]); }
 
 /* Mimi transformer_forward, ptts_mimi.c:301-376 (window ptts_mimi.c:279) */
-static int mimi_transformer(const orc_model *m, float *x, int T) {
+typedef struct { const float *inproj, *outproj, *n1w, *n1b, *n2w, *n2b, *l1, *l2, *ls1, *ls2; } mimi_layer_t;
+static int mimi_transformer_w(const mimi_layer_t *Lw, float *x, int T);
+static int mimi_transformer(const orc_model *m, float *x, int T) { return mimi_transformer_w((const mimi_layer_t *)m->M, x, T); }
+static int mimi_transformer_w(const mimi_layer_t *Lw, float *x, int T) {
     float *xn = (float *)malloc(sizeof(float) * (size_t)T * MD);
     float *qkv = (float *)malloc(sizeof(float) * (size_t)T * 3 * MD);
     float *K = (float *)malloc(sizeof(float) * (size_t)T * MD);
@@ -550,8 +596,8 @@ static int mimi_transformer(const orc_model *m, float *x, int T) {
     float *h1 = (float *)malloc(sizeof(float) * (size_t)T * MFF);
     if (!xn || !qkv || !K || !V || !att || !h1) { free(xn); free(qkv); free(K); free(V); free(att); free(h1); return -1; }
     for (int l = 0; l < ML; l++) {
-        for (int t = 0; t < T; t++) layernorm(x + (size_t)t * MD, MD, m->M[l].n1w, m->M[l].n1b, 1e-5f, xn + (size_t)t * MD);
-        orc_linear(qkv, xn, m->M[l].inproj, NULL, T, MD, 3 * MD);
+        for (int t = 0; t < T; t++) layernorm(x + (size_t)t * MD, MD, Lw[l].n1w, Lw[l].n1b, 1e-5f, xn + (size_t)t * MD);
+        orc_linear(qkv, xn, Lw[l].inproj, NULL, T, MD, 3 * MD);
         for (int t = 0; t < T; t++) {
             float *row = qkv + (size_t)t * 3 * MD;
             rope(row, row + MD, MH, t);
@@ -567,13 +613,13 @@ static int mimi_transformer(const orc_model *m, float *x, int T) {
                 attend(qkv + (size_t)t * 3 * MD, K, V, MH, lo, t, sc, att + (size_t)t * MD);
             }
         }
-        orc_linear(xn, att, m->M[l].outproj, NULL, T, MD, MD);
-        for (size_t i = 0; i < (size_t)T * MD; i++) x[i] += m->M[l].ls1[i % MD] * xn[i];
-        for (int t = 0; t < T; t++) layernorm(x + (size_t)t * MD, MD, m->M[l].n2w, m->M[l].n2b, 1e-5f, xn + (size_t)t * MD);
-        orc_linear(h1, xn, m->M[l].l1, NULL, T, MD, MFF);
+        orc_linear(xn, att, Lw[l].outproj, NULL, T, MD, MD);
+        for (size_t i = 0; i < (size_t)T * MD; i++) x[i] += Lw[l].ls1[i % MD] * xn[i];
+        for (int t = 0; t < T; t++) layernorm(x + (size_t)t * MD, MD, Lw[l].n2w, Lw[l].n2b, 1e-5f, xn + (size_t)t * MD);
+        orc_linear(h1, xn, Lw[l].l1, NULL, T, MD, MFF);
         for (size_t i = 0; i < (size_t)T * MFF; i++) h1[i] = gelu_tanh(h1[i]);
-        orc_linear(xn, h1, m->M[l].l2, NULL, T, MFF, MD);
-        for (size_t i = 0; i < (size_t)T * MD; i++) x[i] += m->M[l].ls2[i % MD] * xn[i];
+        orc_linear(xn, h1, Lw[l].l2, NULL, T, MFF, MD);
+        for (size_t i = 0; i < (size_t)T * MD; i++) x[i] += Lw[l].ls2[i % MD] * xn[i];
     }
     free(xn); free(qkv); free(K); free(V); free(att); free(h1);
     return 0;
@@ -636,5 +682,71 @@ int orc_mimi_decode(orc_model *m, const float *latents, int frames, float *out_a
     }
     free(x);
     *out_len = T;
+    return 0;
+}
+
+/* ---------------------------------------------------------------- voice-cloning encoder
+ * PARITY UNPINNED END TO END: the reference only shape-checks these tensors (ptts.c:914-944) and loads speaker_proj_weight
+ * without using it (ptts_flowlm.c:874); it has no forward pass to compare with. The composition below is the mirror image of
+ * the decoder the reference does implement, built from the reference's own primitives, each of which IS pinned against the
+ * compiled reference (tests/test_oracle_vs_reference.py):
+ *   Conv1d, causal, any stride: left pad k - stride, out_len = T / stride            (ptts_kernels.c:114-156 -> orc_conv1d)
+ *   ResBlock: x + conv_k1(ELU(conv_k3(ELU(x))))                                       (ptts_mimi.c:160-177)
+ *   transformer: 2 layers, window 250, RoPE from position 0, layer scale              (ptts_mimi.c:301-376)
+ * order of the modules: ptts.c:919-944 (model.0 conv, then per ratio 4, 5, 6: resblock, ELU, strided conv; ELU, conv k3),
+ * encoder_transformer, downsample.conv (k 32, stride 16, no bias, ptts.c:914), speaker projection [1024,512]. */
+int orc_voice_encode(orc_model *m, const float *pcm, int n_samples, float *out_cond, int max_frames, int *out_frames) {
+    if (!m || !pcm || !out_cond || !out_frames || n_samples < 1) return -1;
+    if (!m->has_encoder) { snprintf(g_err, sizeof g_err, "checkpoint has no encoder tensors"); return -1; }
+    const int F = (n_samples + 1919) / 1920;       /* whole 12.5 Hz frames, zero padded on the right */
+    if (F > max_frames) { snprintf(g_err, sizeof g_err, "voice_encode: %d frames exceed the output capacity %d", F, max_frames); return -1; }
+    int T = F * 1920, C = 64;
+    float *x = (float *)calloc((size_t)T, sizeof(float)), *y = NULL;
+    if (!x) return -1;
+    memcpy(x, pcm, sizeof(float) * (size_t)n_samples);
+    y = (float *)malloc(sizeof(float) * (size_t)C * T);
+    orc_conv1d(y, x, m->enc_in.w, m->enc_in.b, 1, 64, T, 7, 1, 1);          /* channel-major [C,T] from here */
+    free(x); x = y;
+    for (int st = 0; st < 3; st++) {
+        const size_t n = (size_t)C * T;
+        float *e = (float *)malloc(sizeof(float) * n), *h = (float *)malloc(sizeof(float) * n / 2), *r = (float *)malloc(sizeof(float) * n);
+        elu_copy(x, n, e);
+        orc_conv1d(h, e, m->eres1[st].w, m->eres1[st].b, C, C / 2, T, 3, 1, 1);
+        elu_copy(h, n / 2, h);
+        orc_conv1d(r, h, m->eres2[st].w, m->eres2[st].b, C / 2, C, T, 1, 1, 1);
+        for (size_t i = 0; i < n; i++) x[i] += r[i];
+        elu_copy(x, n, e);
+        const int s = m->edown[st].stride, T2 = T / s, C2 = 2 * C;
+        float *d = (float *)malloc(sizeof(float) * (size_t)C2 * T2);
+        orc_conv1d(d, e, m->edown[st].w, m->edown[st].b, C, C2, T, m->edown[st].k, s, 1);
+        free(e); free(h); free(r); free(x);
+        x = d; T = T2; C = C2;
+    }
+    {   /* ELU, conv k3 512 -> 512 */
+        const size_t n = (size_t)C * T;
+        float *e = (float *)malloc(sizeof(float) * n), *o = (float *)malloc(sizeof(float) * n);
+        elu_copy(x, n, e);
+        orc_conv1d(o, e, m->enc_out.w, m->enc_out.b, 512, 512, T, 3, 1, 1);
+        free(e); free(x); x = o;
+    }
+    /* [512,T] -> [T,512] (ptts_mimi.c:134-150), encoder transformer, back */
+    float *tm = (float *)malloc(sizeof(float) * (size_t)T * MD);
+    for (int c = 0; c < MD; c++) for (int t = 0; t < T; t++) tm[(size_t)t * MD + c] = x[(size_t)c * T + t];
+    if (mimi_transformer_w((const mimi_layer_t *)m->E, tm, T) != 0) { free(tm); free(x); return -1; }
+    for (int c = 0; c < MD; c++) for (int t = 0; t < T; t++) x[(size_t)c * T + t] = tm[(size_t)t * MD + c];
+    free(tm);
+    /* learnt downsample 200 Hz -> 12.5 Hz */
+    float *lat = (float *)malloc(sizeof(float) * (size_t)MD * F);
+    orc_conv1d(lat, x, m->down.w, NULL, 512, 512, T, 32, 16, 1);
+    free(x);
+    /* speaker projection: cond[t, :] = W[1024,512] . lat[:, t] */
+    for (int t = 0; t < F; t++)
+        for (int o = 0; o < D; o++) {
+            float a = 0.0f;
+            for (int c = 0; c < MD; c++) a += m->spk[(size_t)o * MD + c] * lat[(size_t)c * F + t];
+            out_cond[(size_t)t * D + o] = a;
+        }
+    free(lat);
+    *out_frames = F;
     return 0;
 }

@@ -58,6 +58,8 @@ class Oracle:
         L.orc_scale_latents.argtypes = [C.c_void_p, _fp, C.c_int, _fp]
         L.orc_mimi_decode.restype = C.c_int
         L.orc_mimi_decode.argtypes = [C.c_void_p, _fp, C.c_int, _fp, _ip]
+        L.orc_voice_encode.restype = C.c_int
+        L.orc_voice_encode.argtypes = [C.c_void_p, _fp, C.c_int, _fp, C.c_int, _ip]
         L.orc_linear.argtypes = [_fp, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int]
         L.orc_conv1d.argtypes = [_fp, _fp, _fp, _fp] + [C.c_int] * 6
         L.orc_convtr1d.argtypes = [_fp, _fp, _fp, _fp] + [C.c_int] * 6
@@ -127,6 +129,17 @@ class Oracle:
         rc = self.lib.orc_mimi_decode(self.h, _f(latents), F, _f(out), C.byref(n))
         if rc != 0 or n.value != F * 1920:
             raise RuntimeError("orc_mimi_decode failed")
+        return out
+
+
+    def voice_encode(self, pcm):
+        """24 kHz mono PCM -> conditioning rows [frames, 1024] (orc_voice_encode)."""
+        pcm = np.ascontiguousarray(pcm, np.float32).reshape(-1)
+        F = (pcm.size + 1919) // 1920
+        out = np.zeros((F, 1024), np.float32)
+        n = C.c_int(0)
+        if self.lib.orc_voice_encode(self.h, _f(pcm), pcm.size, _f(out), F, C.byref(n)) != 0 or n.value != F:
+            raise RuntimeError("orc_voice_encode: " + self.lib.orc_last_error().decode())
         return out
 
 

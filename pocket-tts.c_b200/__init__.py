@@ -45,7 +45,7 @@ EXPORTS = [
     "ptts_b200_profile_read", "ptts_b200_profile_work", "ptts_b200_profile_class_name", "ptts_b200_launch_count", "ptts_b200_test_gemm",
     "ptts_b200_stream_begin", "ptts_b200_stream_next", "ptts_b200_mimi_forward_one", "ptts_b200_mimi_stage",
     "ptts_b200_mimi_run", "ptts_b200_mimi_fetch", "ptts_b200_step_kernel_ms", "ptts_b200_pool_create", "ptts_b200_pool_destroy",
-    "ptts_b200_pool_size", "ptts_b200_pool_engine", "ptts_b200_pool_generate",
+    "ptts_b200_pool_size", "ptts_b200_pool_engine", "ptts_b200_pool_generate", "ptts_b200_voice_encode",
 ]
 
 
@@ -65,6 +65,7 @@ def load_library():
     L.ptts_b200_flowlm_scale_latents.argtypes = [vp, _fp, C.c_int, _fp]
     L.ptts_b200_mimi_decode.argtypes = [vp, _fp, C.c_int, _fp, _ip]
     L.ptts_b200_mimi_decode_batch.argtypes = [vp, _fp, C.c_int, C.c_int, _fp]
+    L.ptts_b200_voice_encode.argtypes = [vp, _fp, C.c_int, _fp, C.c_int, _ip]
     stage_args = [vp, C.c_int, _ip, _ip, _fp, C.c_int, _ip, _lp, _ip, C.POINTER(GenParams)]
     L.ptts_b200_generate_batch.argtypes = stage_args + [_fp, _ip, _fp]
     L.ptts_b200_batch_stage.argtypes = stage_args
@@ -191,6 +192,15 @@ class Engine:
         return out
 
     # ---- additive batched entries
+    def voice_encode(self, pcm):
+        """24 kHz mono PCM -> conditioning rows [frames, 1024] (ptts_b200_voice_encode): a cond_prefix for generate calls."""
+        pcm = np.ascontiguousarray(pcm, np.float32).reshape(-1)
+        F = (pcm.size + FRAME_SAMPLES - 1) // FRAME_SAMPLES
+        out = np.zeros((F, 1024), np.float32)
+        n = C.c_int(0)
+        self._ck(self.lib.ptts_b200_voice_encode(self.h, _f(pcm), pcm.size, _f(out), F, C.byref(n)), "voice_encode")
+        return out[:n.value]
+
     def mimi_stage(self, latents):
         latents = np.ascontiguousarray(latents, np.float32)
         self._mimi_staged = (latents.shape[0], latents.shape[1])

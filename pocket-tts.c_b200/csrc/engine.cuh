@@ -366,6 +366,12 @@ struct ptts_b200_engine {
     float h_dec_out_b = 0.0f;
     ptts::MimiLayerW ML[ptts::MI_L];
     ptts::ConvW dec_in, up[3], res1[3], res2[3];
+    // ---- voice-cloning encoder (optional: present when the checkpoint carries the encoder tensors, enc.cuh)
+    bool has_encoder = false;
+    float *enc_in_w = nullptr, *enc_in_b = nullptr;          // Conv1d 1 -> 64, k 7: [64][7] fp32
+    ptts::ConvW eres1[3], eres2[3], edown[3], enc_out, down;  // resblocks (64, 128, 256 channels), strided convs, conv k3, downsampler
+    ptts::MimiLayerW EL[ptts::MI_L];                          // encoder_transformer
+    __half *spk16 = nullptr;                                  // speaker_proj_weight [1024, 512]
 
     // ---- FlowLM run state (capacity-sized)
     int capB = 0, capS = 0, capTok = 0, capF = 0, capCond = 0;

@@ -255,6 +255,48 @@ static int mimi_seanet(Engine *e, Bump &ws, int Bc, int T, const __half *xn, __h
 }
 
 
+// The 2-layer windowed transformer (ptts_mimi.c:301-376) over x [Bc][T][512] fp32 (residual stream, updated in place) with the
+// layer weights Lw (decoder_transformer, or encoder_transformer for the voice-cloning encoder). Leaves an fp16 copy of the result in xn.
+static int mimi_transformer_layers(Engine *e, const MimiLayerW *Lw, float *x, __half *xn, __half *q, __half *k, __half *v, __half *att, __half *hb,
+                                   int Bc, int T, int pos0) {
+    const size_t R = (size_t)Bc * T;
+    for (int l = 0; l < MI_L; l++) {
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, Lw[l].n1w, Lw[l].n1b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
+        }
+        GemmParams g = {};
+        g.rope_q = (uint16_t *)q; g.rope_k = (uint16_t *)k; g.rope_v = (uint16_t *)v;   // RoPE + head split fused in the epilogue
+        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_pos0 = pos0;
+        if (mimi_gemm(e, xn, Bc, T, MI_D, Lw[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        {
+            if (e->prof.on) {   // banded attention: <= 250 keys per query, QK^T and PV
+                double pairs = 0.0;
+                for (int t = 0; t < T; t++) pairs += std::min(t + 1, MI_CTX);
+                e->prof.flops[KC_MIMI_ATTN] += 4.0 * 64.0 * MI_H * pairs * Bc;
+                e->prof.bytes[KC_MIMI_ATTN] += (double)R * MI_D * 2.0 * 4.0;
+            }
+            LaunchScope ls(e, KC_MIMI_ATTN);
+            launch_k(k_mimi_win_attn, dim3((T + 63) / 64, MI_H, Bc), 128, 0, e->st, q, k, v, T, att, 0, T);
+            if (launch_check("k_mimi_win_attn") != 0) return -1;
+        }
+        g = {}; g.scale = Lw[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls1 * out_proj(att)
+        if (mimi_gemm(e, att, Bc, T, MI_D, Lw[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+        {
+            LaunchScope ls(e, KC_MIMI_MISC);
+            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, Lw[l].n2w, Lw[l].n2b, 1e-5f, xn);
+            if (launch_check("k_ln512_f16") != 0) return -1;
+        }
+        g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
+        if (mimi_gemm(e, xn, Bc, T, MI_D, Lw[l].l1, MI_FF, 1, 0, 0, 256, g) != 0) return -1;
+        g = {}; g.scale = Lw[l].ls2; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls2 * linear2(h)
+        if (l == MI_L - 1) { g.out_h = (uint16_t *)xn; g.ldh = MI_D; g.act = ACT_NONE; }   // fp16 copy feeds dec_in
+        if (mimi_gemm(e, hb, Bc, T, MI_FF, Lw[l].l2, MI_D, 1, 0, 0, 256, g) != 0) return -1;
+    }
+    return 0;
+}
+
 // Decode Bc equal-length items. d_lat [Bc,F,32] fp32 on the device; d_pcm [Bc, F*1920].
 // pos0 = token position of the first row (RoPE is absolute: ptts_mimi.c:341).
 static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t lat_stride, int apply_scale, float *d_pcm, int pos0 = 0) {
@@ -282,40 +324,7 @@ static int mimi_run_chunk(Engine *e, int Bc, int F, const float *d_lat, size_t l
         launch_k(k_mimi_front, dim3(F, Bc), 512, 0, e->st, d_lat, lat_stride, F, e->emb_std, e->emb_mean, apply_scale, e->quant_w, e->ups_w, x, 0);
         if (launch_check("k_mimi_front") != 0) return -1;
     }
-    for (int l = 0; l < MI_L; l++) {
-        {
-            LaunchScope ls(e, KC_MIMI_MISC);
-            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n1w, e->ML[l].n1b, 1e-5f, xn);
-            if (launch_check("k_ln512_f16") != 0) return -1;
-        }
-        GemmParams g = {};
-        g.rope_q = (uint16_t *)q; g.rope_k = (uint16_t *)k; g.rope_v = (uint16_t *)v;   // RoPE + head split fused in the epilogue
-        g.rope_cos = e->rope_cos; g.rope_sin = e->rope_sin; g.rope_pos0 = pos0;
-        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].inproj, 3 * MI_D, 1, 0, 0, 256, g) != 0) return -1;
-        {
-            if (e->prof.on) {   // banded attention: <= 250 keys per query, QK^T and PV
-                double pairs = 0.0;
-                for (int t = 0; t < T; t++) pairs += std::min(t + 1, MI_CTX);
-                e->prof.flops[KC_MIMI_ATTN] += 4.0 * 64.0 * MI_H * pairs * Bc;
-                e->prof.bytes[KC_MIMI_ATTN] += (double)R * MI_D * 2.0 * 4.0;
-            }
-            LaunchScope ls(e, KC_MIMI_ATTN);
-            launch_k(k_mimi_win_attn, dim3((T + 63) / 64, MI_H, Bc), 128, 0, e->st, q, k, v, T, att, 0, T);
-            if (launch_check("k_mimi_win_attn") != 0) return -1;
-        }
-        g = {}; g.scale = e->ML[l].ls1; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls1 * out_proj(att)
-        if (mimi_gemm(e, att, Bc, T, MI_D, e->ML[l].outproj, MI_D, 1, 0, 0, 256, g) != 0) return -1;
-        {
-            LaunchScope ls(e, KC_MIMI_MISC);
-            launch_k(k_ln512_f16, (unsigned)((R + 7) / 8), 256, 0, e->st, x, R, e->ML[l].n2w, e->ML[l].n2b, 1e-5f, xn);
-            if (launch_check("k_ln512_f16") != 0) return -1;
-        }
-        g = {}; g.out_h = (uint16_t *)hb; g.ldh = MI_FF; g.act = ACT_GELU_TANH;
-        if (mimi_gemm(e, xn, Bc, T, MI_D, e->ML[l].l1, MI_FF, 1, 0, 0, 256, g) != 0) return -1;
-        g = {}; g.scale = e->ML[l].ls2; g.resid = x; g.out_f32 = x; g.ldo = MI_D;          // x += ls2 * linear2(h)
-        if (l == MI_L - 1) { g.out_h = (uint16_t *)xn; g.ldh = MI_D; g.act = ACT_NONE; }   // fp16 copy feeds dec_in
-        if (mimi_gemm(e, hb, Bc, T, MI_FF, e->ML[l].l2, MI_D, 1, 0, 0, 256, g) != 0) return -1;
-    }
+    if (mimi_transformer_layers(e, e->ML, x, xn, q, k, v, att, hb, Bc, T, pos0) != 0) return -1;
     return mimi_seanet(e, ws, Bc, T, xn, d0, d_pcm);
 }
 

@@ -8,6 +8,7 @@
 
 #include "mega.cuh"
 #include "mimi.cuh"
+#include "enc.cuh"
 
 using namespace ptts;
 
@@ -110,7 +111,7 @@ extern "C" int ptts_b200_create(ptts_b200_engine **out, int device, const ptts_b
         cudaFuncSetAttribute(k_attn_decode2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
         cudaFuncSetAttribute(k_attn_decode2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess ||
-        gemm_set_attrs() != 0 || mimi_set_attrs() != 0 || flow_load_weights(e, hw) != 0 || mimi_load_weights(e, hw) != 0 || ensure_rope(e, 1024) != 0) {
+        gemm_set_attrs() != 0 || mimi_set_attrs() != 0 || flow_load_weights(e, hw) != 0 || mimi_load_weights(e, hw) != 0 || enc_load_weights(e, hw) != 0 || ensure_rope(e, 1024) != 0) {
         ptts_b200_destroy(e);
         return -1;
     }
@@ -665,6 +666,30 @@ extern "C" int ptts_b200_mimi_decode(ptts_b200_engine *e, const float *latents, 
     if (ptts_b200_mimi_decode_batch(e, latents, 1, frames, out_audio) != 0) return -1;
     *out_len = frames * 1920;
     return 0;
+}
+
+// ---------------------------------------------------------------- voice-cloning encoder
+extern "C" int ptts_b200_voice_encode(ptts_b200_engine *e, const float *pcm, int n_samples, float *out_cond, int max_frames, int *out_frames) {
+    PTTS_CHECK(e && pcm && out_cond && out_frames && n_samples >= 1, "voice_encode: bad arguments");
+    PTTS_CHECK(e->has_encoder, "voice_encode: the checkpoint has no encoder tensors (mimi.encoder.*, mimi.encoder_transformer.*, mimi.downsample.*)");
+    const int frames = (n_samples + 1919) / 1920;   // whole 12.5 Hz frames, zero padded on the right
+    PTTS_CHECK(frames <= max_frames, "voice_encode: %d frames exceed the output capacity %d", frames, max_frames);
+    PTTS_CHECK(frames <= 4096, "voice_encode: at most 4096 frames (%d requested)", frames);
+    PTTS_CUDA_OK(cudaSetDevice(e->device));
+    e->stream_pos = -1;   // the decoder workspace is shared: an open stream does not survive
+    float *d_pcm = nullptr, *d_cond = nullptr;
+    int rc = -1;
+    if (e->dalloc(&d_pcm, (size_t)frames * 1920) == 0 && e->dalloc(&d_cond, (size_t)frames * FL_D) == 0 &&
+        cudaMemsetAsync(d_pcm, 0, (size_t)frames * 1920 * 4, e->st) == cudaSuccess &&
+        cudaMemcpyAsync(d_pcm, pcm, (size_t)n_samples * 4, cudaMemcpyHostToDevice, e->st) == cudaSuccess &&
+        enc_run(e, d_pcm, frames, d_cond) == 0 &&
+        cudaMemcpyAsync(out_cond, d_cond, (size_t)frames * FL_D * 4, cudaMemcpyDeviceToHost, e->st) == cudaSuccess &&
+        cudaStreamSynchronize(e->st) == cudaSuccess)
+        rc = 0;
+    if (rc != 0 && g_last_error[0] == 0) set_error("voice_encode: %s", cudaGetErrorString(cudaGetLastError()));
+    e->dfree(d_pcm); e->dfree(d_cond);
+    if (rc == 0) *out_frames = frames;
+    return rc;
 }
 
 // ---------------------------------------------------------------- streaming (single utterance)

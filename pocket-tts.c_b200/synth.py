@@ -160,6 +160,34 @@ def make_weights(seed: int = 0, full_mantissa: bool = False) -> "dict[str, np.nd
         lin(q + "linear2.weight", MIMI_D, MIMI_FFN)
         vec(q + "layer_scale_1.scale", MIMI_D, 0.1, 0.01)
         vec(q + "layer_scale_2.scale", MIMI_D, 0.1, 0.01)
+    # Voice-cloning side (shapes from ptts.c:914-944, 973): SEANet encoder, encoder transformer,
+    # learnt stride-16 downsampler. Appended AFTER everything else so the tensors above keep their values.
+    en = m + "encoder.model."
+    conv(en + "0.conv", 64, 1, 7)
+    idx, ch = 1, 64
+    for ratio in (4, 5, 6):
+        conv(f"{en}{idx}.block.1.conv", ch // 2, ch, 3)
+        conv(f"{en}{idx}.block.3.conv", ch, ch // 2, 1, 0.5)
+        idx += 2
+        conv(f"{en}{idx}.conv", 2 * ch, ch, 2 * ratio)
+        idx += 1
+        ch *= 2
+    idx += 1
+    conv(f"{en}{idx}.conv", 512, 512, 3)
+    for l in range(MIMI_LAYERS):
+        q = f"{m}encoder_transformer.transformer.layers.{l}."
+        lin(q + "self_attn.in_proj.weight", 3 * MIMI_D, MIMI_D)
+        lin(q + "self_attn.out_proj.weight", MIMI_D, MIMI_D)
+        vec(q + "norm1.weight", MIMI_D, 1.0, 0.05)
+        vec(q + "norm1.bias", MIMI_D, 0.0, 0.05)
+        vec(q + "norm2.weight", MIMI_D, 1.0, 0.05)
+        vec(q + "norm2.bias", MIMI_D, 0.0, 0.05)
+        lin(q + "linear1.weight", MIMI_FFN, MIMI_D)
+        lin(q + "linear2.weight", MIMI_D, MIMI_FFN)
+        vec(q + "layer_scale_1.scale", MIMI_D, 0.1, 0.01)
+        vec(q + "layer_scale_2.scale", MIMI_D, 0.1, 0.01)
+    W[m + "downsample.conv.conv.weight"] = bf16_round(
+        rng.standard_normal((MIMI_D, MIMI_D, 32), dtype=np.float32) / np.sqrt(MIMI_D * 32))
     return W
 
 
@@ -285,7 +313,7 @@ def model_dir(seed: int = 0, voice_frames: int = 125, root=None) -> Path:
     embeddings/alba.safetensors.
     """
     root = Path(root or os.environ.get("PTTS_B200_MODEL_CACHE", "/tmp/ptts_b200_models"))
-    d = root / f"synth_s{seed}_v{voice_frames}"
+    d = root / f"synth2_s{seed}_v{voice_frames}"   # synth2: + voice-cloning encoder tensors
     done = d / ".complete"
     if done.exists():
         return d
