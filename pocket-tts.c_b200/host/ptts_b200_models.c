@@ -240,6 +240,28 @@ ptts_audio **ptts_generate_batch(ptts_ctx *ctx, const char *const *texts, int n,
     return out;
 }
 
+/* ---- additive voice-cloning entry at the ptts.h level -------------------------------------------------
+ * 24 kHz mono PCM -> conditioning rows [*out_len][1024] (malloc'd, caller frees), the tensor ptts_load_voice_conditioning
+ * (ptts.c:293-364) otherwise reads from a voice file as "audio_prompt". The reference loads the tensors involved
+ * (encoder.*, encoder_transformer.*, downsample.conv, speaker_proj_weight) only to shape-check them (ptts.c:914-944,
+ * ptts_flowlm.c:874); the engine runs them (ptts_b200_voice_encode). Returns 0, or -1 (message on stderr). */
+int ptts_voice_from_pcm(ptts_ctx *ctx, const float *pcm, int n_samples, float **out_cond, int *out_len) {
+    if (!ctx || !pcm || n_samples < 1 || !out_cond || !out_len) return -1;
+    engine_slot *slot = engine_acquire(ctx);
+    if (!slot) return -1;
+    const int frames = (n_samples + 1919) / 1920;
+    float *cond = (float *)malloc((size_t)frames * 1024 * sizeof(float));
+    int got = 0, rc = -1;
+    if (cond && ptts_b200_voice_encode(slot->eng, pcm, n_samples, cond, frames, &got) == 0) {
+        *out_cond = cond; *out_len = got; rc = 0;
+    } else {
+        fprintf(stderr, "[ptts] B200: %s\n", cond ? ptts_b200_last_error() : "out of memory");
+        free(cond);
+    }
+    engine_release(slot);
+    return rc;
+}
+
 /* ---- ptts_flowlm.h ---------------------------------------------------------------- */
 ptts_flowlm *ptts_flowlm_load(ptts_ctx *ctx) {
     engine_slot *s = engine_acquire(ctx);

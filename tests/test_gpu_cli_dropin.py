@@ -91,3 +91,25 @@ def test_host_layer_generate_batch_matches_reference_cli_per_text(model_dir, syn
         assert snr_db(x, y) > 40.0, f"utterance {i}"
         lengths.add(x.shape[0])
     assert len(lengths) >= 3      # the batch really was ragged
+
+
+@pytest.mark.skipif(not (CLI.exists() and REF.exists()), reason="prebuilt CLIs not present")
+def test_cloned_voice_file_works_with_the_unmodified_reference(pkg, model_dir, synth, weights, tmp_path):
+    """Voice cloning end to end: PCM -> ptts_b200_voice_encode -> a voice file in the reference's own layout
+    ("audio_prompt" [1, T, 1024], ptts.c:293-364). The UNMODIFIED reference CPU CLI and the reference CLI on the B200 engine both
+    load it through the reference's voice loader (--voice <path>) and must produce the same audio."""
+    import shutil
+    md = tmp_path / "model"
+    shutil.copytree(model_dir, md)
+    t = np.arange(24000 * 2) / 24000.0
+    pcm = (0.3 * np.sin(2 * np.pi * 180.0 * t) * (1.0 + 0.5 * np.sin(2 * np.pi * 3.0 * t))).astype(np.float32)
+    eng = pkg.Engine(weights, 0)
+    cond = eng.voice_encode(pcm)
+    eng.close()
+    assert cond.shape == (25, 1024) and np.isfinite(cond).all()
+    synth.write_safetensors(md / "embeddings" / "cloned.safetensors", {"audio_prompt": cond[None]}, "F32")
+    args = ["-d", str(md), "-p", "Hello cloned world!", "--voice", "cloned", "-t", "0.7", "-S", "5", "--frames", "4", "--eos-threshold", "1e9", "-q"]
+    subprocess.run([str(CLI)] + args + ["-o", str(tmp_path / "b200.wav")], check=True, timeout=600)
+    subprocess.run([str(REF)] + args + ["-o", str(tmp_path / "ref.wav")], check=True, timeout=600)
+    x, y = _wav(tmp_path / "b200.wav"), _wav(tmp_path / "ref.wav")
+    assert x.shape == y.shape and snr_db(x, y) > 40.0
