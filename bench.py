@@ -75,6 +75,32 @@ def flow_step_kernel_work(tok_lens, frames, cond_len):
     return dict(bytes=w + kv_read + kv_write + prefix, flops=flops, weights=w, kv_read=kv_read, kv_write=kv_write, prefix=prefix)
 
 
+# ---- sharding of the work over the ranks (one process per GPU, no collective on the data path). Pure functions, also exercised
+# by the world_size-2 gloo test on CPU (tests/test_dist_gloo.py).
+def rank_slice(rank: int, per_rank: int):
+    """Utterances [lo, hi) of a list of world * per_rank that rank `rank` processes (weak scaling: per_rank is fixed)."""
+    return rank * per_rank, (rank + 1) * per_rank
+
+
+def sweep_plan(total_prompts: int, world: int, sweep_batch: int):
+    """configs[4]: a fixed list of total_prompts is dealt to the ranks (strong scaling) and cut into calls of at most sweep_batch
+    utterances: returns (utterances per call, calls per rank)."""
+    per_rank = total_prompts // world
+    sb = min(sweep_batch, per_rank)
+    return sb, max(1, per_rank // sb)
+
+
+def reduce_max(value: float, world: int, device: str) -> float:
+    """MAX over the ranks of a host scalar (device-timed milliseconds / seconds): the job is as slow as its slowest rank."""
+    if world == 1:
+        return value
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -212,11 +238,7 @@ def main():
             dist.barrier()
 
     def max_over_ranks(v: float) -> float:
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return reduce_max(v, world, "cuda")
 
     if rank == 0:
         md = pkg.synth.model_dir(0, VOICE_FRAMES)
@@ -228,7 +250,8 @@ def main():
     del W
 
     B, F = args.batch, args.frames
-    prompts = pkg.synth.make_prompts(B * world, seed=123)[rank * B:(rank + 1) * B]
+    lo, hi = rank_slice(rank, B)
+    prompts = pkg.synth.make_prompts(B * world, seed=123)[lo:hi]
     toks = tokenize_prompts(pkg, md, prompts)
     seeds = np.arange(B, dtype=np.int64) + 123 + rank * B
     params = pkg.default_params(lsd_steps=1, temp=0.7, eos_enabled=0, precise=0 if args.fast else 1)
@@ -310,10 +333,9 @@ def main():
     if args.total_prompts > 0:
         # ---------------- configs[4]: a long prompt list sharded over the ranks, every batch through the host-buffer call
         # (tokens and noise up, PCM down), different prompts in every batch; tokenisation is outside the timed region.
-        per_rank = args.total_prompts // world
-        SB = min(args.sweep_batch, per_rank)
-        nb = max(1, per_rank // SB)
-        allp = pkg.synth.make_prompts(nb * SB * world, seed=777)[rank * nb * SB:(rank + 1) * nb * SB]
+        SB, nb = sweep_plan(args.total_prompts, world, args.sweep_batch)
+        lo, hi = rank_slice(rank, nb * SB)
+        allp = pkg.synth.make_prompts(nb * SB * world, seed=777)[lo:hi]
         alltok = tokenize_prompts(pkg, md, allp)
         sseeds = np.arange(SB, dtype=np.int64) + 9000 + rank * nb * SB
         saudio = torch.empty((SB, F * 1920), dtype=torch.float32).pin_memory().numpy()
