@@ -236,16 +236,14 @@ static int rownorm(Engine *e, int rows, RowNormParams p, int cls = KC_ROWNORM) {
 
 // One decode iteration, batch-1 path: head (frame j) then transformer body for frame j+1.
 static int flow_step_gemv(Engine *e, const FlowState &st, const float *cbias) {
-    RowNormParams r = {};
-    r.x = e->x; r.D = FL_D; r.w = e->onorm_w; r.b = e->onorm_b; r.eps = 1e-5f; r.do_norm = 1; r.out_f32 = e->normed;
-    if (rownorm(e, 1, r) != 0) return -1;
-    {
+    {   // out_norm + EOS rule + noise -> latent + flow input projection of LSD step 0: one node instead of three
         LaunchScope ls(e, KC_FLOW_MISC);
-        launch_k(k_eos_state, 1, 256, 0, e->st, st, e->ctrl, e->d_eos_after, e->normed, e->eos_w, e->eos_b);
-        if (launch_check("k_eos_state") != 0) return -1;
+        launch_k(k_b1_head, 1, 256, 0, e->st, st, e->ctrl, (const float *)e->x, (const float *)e->onorm_w, (const float *)e->onorm_b,
+                 (const float *)e->eos_w, (const float *)e->eos_b, (const __nv_bfloat16 *)e->inp_w, (const float *)e->inp_b, e->normed, e->fx);
+        if (launch_check("k_b1_head") != 0) return -1;
     }
     for (int k = 0; k < st.lsd_steps; k++) {
-        {
+        if (k > 0) {
             LaunchScope ls(e, KC_FLOW_MISC);
             launch_k(k_flow_init, 1, 512, 0, e->st, st, k, e->inp_w, e->inp_b, e->fx);
             if (launch_check("k_flow_init") != 0) return -1;
@@ -266,16 +264,16 @@ static int flow_step_gemv(Engine *e, const FlowState &st, const float *cbias) {
         const float *ad = e->ada + (size_t)FN_DEPTH * 3 * FN_D;
         g = {}; g.eps = 1e-6f; g.shift = ad; g.scale = ad + FN_D; g.bias = e->fin_b; g.out = e->flow;
         if (gemv<FN_D, 4, 2>(e, e->fin_w, FL_LAT, e->fx, g) != 0) return -1;
-        {
+        if (k + 1 < st.lsd_steps) {
             LaunchScope ls(e, KC_FLOW_MISC);
             launch_k(k_flow_update, 1, 32, 0, e->st, st, e->ctrl, e->d_eos_after, k, e->flow);
             if (launch_check("k_flow_update") != 0) return -1;
         }
     }
-    {
+    {   // last Euler update + frame record + stop rule + x = input_linear . latent: one node instead of two
         LaunchScope ls(e, KC_FLOW_MISC);
-        launch_k(k_prepare_x, 1, 256, 0, e->st, st, e->in_lin, e->x);
-        if (launch_check("k_prepare_x") != 0) return -1;
+        launch_k(k_b1_tail, 1, 256, 0, e->st, st, (const int *)e->d_eos_after, (const float *)e->flow, (const __nv_bfloat16 *)e->in_lin, e->x);
+        if (launch_check("k_b1_tail") != 0) return -1;
     }
     for (int l = 0; l < FL_L; l++) {
         GemvParams g = {};
@@ -287,11 +285,11 @@ static int flow_step_gemv(Engine *e, const FlowState &st, const float *cbias) {
         g = {}; g.ln_w = e->L[l].n2w; g.ln_b = e->L[l].n2b; g.eps = 1e-5f; g.act = ACT_GELU_ERF; g.out = e->ffh;
         if (gemv<FL_D, 8, 1>(e, e->L[l].l1, FL_FF, e->x, g) != 0) return -1;
         g = {}; g.acc_out = e->x;
+        if (l == FL_L - 1) g.inc = &e->ctrl->step;   // the frame counter moves with the last kernel of the step (every reader of this
+                                                     // step's value - the attention kernels above - has finished by then)
         if (gemv<FL_FF, 4, 0>(e, e->L[l].l2, FL_D, e->ffh, g) != 0) return -1;
     }
-    LaunchScope ls(e, KC_FLOW_MISC);
-    launch_k(k_advance_step, 1, 1, 0, e->st, &e->ctrl->step);
-    return launch_check("k_advance_step");
+    return 0;
 }
 
 // ---------------------------------------------------------------- batched tcgen05 path

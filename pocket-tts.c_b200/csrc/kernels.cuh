@@ -128,6 +128,7 @@ struct GemvParams {
     const float *gate;         // y *= gate[n]
     float *acc_out;            // acc_out[n] += y   (residual stream), or
     float *out;                // out[n] = y
+    int *inc;                  // optional: *inc += 1 by one thread of the grid (the frame counter, after the last GEMV of a step)
 };
 
 template <int K, int RPC, int PRO>
@@ -213,6 +214,7 @@ __global__ void __launch_bounds__((K / 8 < 128 ? K / 8 : 128)) k_gemv(const Gemv
         if (p.gate) y *= p.gate[n];
         if (p.acc_out) p.acc_out[n] += y; else p.out[n] = y;
     }
+    if (p.inc && blockIdx.x == 0 && tid == 0) *p.inc += 1;
 }
 
 // =====================================================================================
@@ -347,6 +349,94 @@ __global__ void __launch_bounds__(32) k_flow_update(const FlowState st, const Fl
 }
 __global__ void k_advance_step(int *step) {
     pdl_wait(); pdl_trigger(); *step += 1; }
+
+// Batch-1 decode: the three single-CTA kernels at the start of a frame step as ONE graph node - out_norm (ptts_flowlm.c:1197),
+// EOS logit + stop rule (:1202-1209), noise -> latent and the flow input projection of LSD step 0 (:1211-1231, 710).
+// grid 1, block 256. x [1024] -> normed [1024] (input of the cond_embed GEMV), fx [512].
+__global__ void __launch_bounds__(256) k_b1_head(const FlowState st, const FlowCtrl *ctrl, const float *x, const float *nw, const float *nb,
+                                                 const float *eos_w, const float *eos_b, const __nv_bfloat16 *inp_w, const float *inp_b,
+                                                 float *normed, float *fx) {
+    pdl_wait(); pdl_trigger();
+    __shared__ float red[32];
+    __shared__ float lat[FL_LAT];
+    const int tid = threadIdx.x, i = *st.step;
+    const float4 v = *(const float4 *)(x + tid * 4);
+    const float4 w4 = *(const float4 *)(nw + tid * 4), b4 = *(const float4 *)(nb + tid * 4), e4 = *(const float4 *)(eos_w + tid * 4);
+    if (tid < FL_LAT) {   // noise of this frame -> running latent (LSD step 0)
+        const int fi = min(max(i, 0), st.max_frames_cap - 1);
+        const float z = st.noise[(size_t)fi * FL_LAT + tid];
+        st.latent[tid] = z;
+        lat[tid] = z;
+    }
+    const float mean = block_sum(v.x + v.y + v.z + v.w, red) / (float)FL_D;
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    const float inv = 1.0f / sqrtf(block_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3, red) / (float)FL_D + 1e-5f);
+    const float4 y = make_float4(d0 * inv * w4.x + b4.x, d1 * inv * w4.y + b4.y, d2 * inv * w4.z + b4.z, d3 * inv * w4.w + b4.w);
+    *(float4 *)(normed + tid * 4) = y;
+    const float eos = block_sum(e4.x * y.x + e4.y * y.y + e4.z * y.z + e4.w * y.w, red) + eos_b[0];
+    const bool valid = i < st.max_frames[0] && !st.done[0];
+    if (valid) {
+        if (i == 0) *(float4 *)(st.first_cond + tid * 4) = y;
+        if (tid == 0) {
+            if (i == 0) st.first_eos[0] = eos;
+            if (st.eos_log) st.eos_log[i] = eos;
+            if (ctrl->eos_enabled && i + 1 >= ctrl->eos_min_frames && eos >= ctrl->eos_threshold && st.eos_step[0] < 0) st.eos_step[0] = i;
+        }
+    }
+    // (block_sum's barriers made lat[] visible)
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int n = tid + r * 256;
+        const uint4 *wr = (const uint4 *)(inp_w + (size_t)n * FL_LAT);
+        float a = inp_b[n];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 u = wr[c];
+            const float *l = lat + c * 8;
+            a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] + bf16lo(u.z) * l[4] +
+                 bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
+        }
+        fx[n] = a;
+    }
+}
+
+// Batch-1 decode: the three kernels at the end of the flow head as ONE graph node - Euler update of the last LSD step + frame record +
+// stop rule (ptts_flowlm.c:775-777, 1235-1238), x = input_linear . latent (:1240-1241). grid 1, block 256.
+__global__ void __launch_bounds__(256) k_b1_tail(const FlowState st, const int *eos_after, const float *flow, const __nv_bfloat16 *in_lin, float *x) {
+    pdl_wait(); pdl_trigger();
+    __shared__ float lat[FL_LAT];
+    const int tid = threadIdx.x, i = *st.step, k = st.lsd_steps - 1;
+    if (tid < FL_LAT) {
+        const bool valid = i < st.max_frames[0] && !st.done[0];
+        const float f = flow[tid];
+        const float v = st.latent[tid] + f / (float)st.lsd_steps;
+        st.latent[tid] = v;
+        lat[tid] = v;
+        if (valid) {
+            if (i == 0 && k == 0) st.first_flow[tid] = f;
+            st.out_latents[(size_t)i * FL_LAT + tid] = v;
+        }
+        __syncwarp();
+        if (tid == 0 && valid) {
+            st.used[0] = i + 1;
+            const int es = st.eos_step[0];
+            if ((es >= 0 && i >= es + eos_after[0]) || i + 1 >= st.max_frames[0]) st.done[0] = 1;
+        }
+    }
+    __syncthreads();
+    for (int n = tid; n < FL_D; n += 256) {
+        const uint4 *wr = (const uint4 *)(in_lin + (size_t)n * FL_LAT);
+        float a = 0.0f;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const uint4 u = wr[c];
+            const float *l = lat + c * 8;
+            a += bf16lo(u.x) * l[0] + bf16hi(u.x) * l[1] + bf16lo(u.y) * l[2] + bf16hi(u.y) * l[3] + bf16lo(u.z) * l[4] +
+                 bf16hi(u.z) * l[5] + bf16lo(u.w) * l[6] + bf16hi(u.w) * l[7];
+        }
+        x[n] = a;
+    }
+}
 
 // =====================================================================================
 // RoPE + KV append + single-query attention over [shared voice prefix | own positions]
