@@ -3,6 +3,7 @@
 TAG=${1:-r02}; TESTS=${2:-tests}; NCU=${3:-ncu}
 mkdir -p gpurun_out
 python -c "import bench; print(bench.src_sha16())" > gpurun_out/${TAG}_src_sha16.txt 2>/dev/null
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?" > gpurun_out/${TAG}_summary0.txt; tail -1 gpurun_out/${TAG}_smoke.log
 if [ "$TESTS" = tests ]; then
   timeout 1800 python -m pytest tests -m gpu -q -x -p no:cacheprovider -s > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest exit $?" > gpurun_out/${TAG}_summary.txt
   grep -E "max-rel|dB|passed|failed|error|Error" gpurun_out/${TAG}_pytest_gpu.log | tail -40
