@@ -417,6 +417,11 @@ struct ptts_b200_engine {
     // pinned staging
     void *pin = nullptr;
     size_t pin_bytes = 0;
+    // one-shot batched call: the per-utterance noise (data-independent, generated on host threads) is produced and uploaded AFTER
+    // the prompt prefill has been launched, so the host work runs under the prefill's device time
+    float *pin_noise = nullptr;
+    size_t pin_noise_cap = 0;
+    struct { int n = 0, cap_f = 0; float temp = 0.0f, clamp = 0.0f; std::vector<int64_t> seeds; std::vector<int> frames; } pend_noise;
 
     // ---- Mimi workspace
     void *mimi_ws = nullptr;

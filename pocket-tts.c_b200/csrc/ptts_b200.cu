@@ -132,6 +132,7 @@ extern "C" void ptts_b200_destroy(ptts_b200_engine *e) {
     delete e->caches;
     for (void *p : e->allocs) cudaFree(p);
     if (e->pin) cudaFreeHost(e->pin);
+    if (e->pin_noise) cudaFreeHost(e->pin_noise);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
     if (e->ev_chunk) cudaEventDestroy(e->ev_chunk);
@@ -358,8 +359,43 @@ static int set_voice(Engine *e, const float *cond, int cond_len) {
 }
 
 // ---------------------------------------------------------------- batch stage / run / fetch
+// Host noise of utterances [0, n): one xorshift64* generator per seed, spread over host threads (the utterances are independent).
+static void fill_noise(int n, int cap_f, const int64_t *seeds, const int *max_frames, float temp, float clampv, float *out) {
+    auto fill = [&](int i0, int i1) {
+        for (int i = i0; i < i1; i++) {
+            host_noise(seeds[i], temp, clampv, max_frames[i], out + (size_t)i * cap_f * FL_LAT);
+            for (size_t j = (size_t)max_frames[i] * FL_LAT; j < (size_t)cap_f * FL_LAT; j++) out[(size_t)i * cap_f * FL_LAT + j] = 0.0f;
+        }
+    };
+    const int nt = temp > 0.0f ? (int)std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u),
+                                                       (size_t)n * cap_f / 2048 + 1) : 1;
+    if (nt <= 1) { fill(0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(fill, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
+    for (auto &t : th) t.join();
+}
+
+// The noise a deferred stage left pending: generated into pinned memory and uploaded behind whatever is already queued on the stream.
+static int upload_pending_noise(Engine *e) {
+    auto &pn = e->pend_noise;
+    if (pn.n <= 0) return 0;
+    const size_t need = (size_t)pn.n * pn.cap_f * FL_LAT;
+    if (need > e->pin_noise_cap) {
+        if (e->pin_noise) cudaFreeHost(e->pin_noise);
+        e->pin_noise = nullptr; e->pin_noise_cap = 0;
+        PTTS_CUDA_OK(cudaMallocHost(&e->pin_noise, need * sizeof(float)));
+        e->pin_noise_cap = need;
+    }
+    fill_noise(pn.n, pn.cap_f, pn.seeds.data(), pn.frames.data(), pn.temp, pn.clamp, e->pin_noise);
+    PTTS_CUDA_OK(cudaMemcpy2DAsync(e->d_noise, (size_t)e->capF * FL_LAT * 4, e->pin_noise, (size_t)pn.cap_f * FL_LAT * 4,
+                                   (size_t)pn.cap_f * FL_LAT * 4, pn.n, cudaMemcpyHostToDevice, e->st));
+    pn.n = 0;
+    return 0;
+}
+
 static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token_offsets, const float *cond_prefix, int cond_len,
-                      const int *max_frames, const int64_t *seeds, const int *eos_after, const ptts_b200_gen_params *gp) {
+                      const int *max_frames, const int64_t *seeds, const int *eos_after, const ptts_b200_gen_params *gp,
+                      bool defer_noise = false) {
     PTTS_CHECK(e && n >= 1 && tokens_flat && token_offsets && max_frames && seeds && gp, "batch_stage: bad arguments");
     PTTS_CHECK(cond_len >= 0 && (cond_len == 0 || cond_prefix), "batch_stage: cond_prefix missing");
     PTTS_CHECK(gp->lsd_steps >= 1 && gp->lsd_steps <= 64, "batch_stage: lsd_steps %d out of range", gp->lsd_steps);
@@ -401,24 +437,17 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     // host staging
     const int capTok = e->capTok, capF = e->capF;
     std::vector<int> h_tok((size_t)B * capTok, 0), h_tl(B, 1), h_mf(B, 0), h_ea(B, 0), h_done(B, 1), h_es(B, -1), h_used(B, 0);
-    std::vector<float> h_noise((size_t)n * cap_f * FL_LAT);
+    std::vector<float> h_noise;
     std::vector<int> h_rb(rows), h_ri(rows), h_rs(n + 1, 0), h_ob(B, 0);
     double mean_ob = 0.0;
-    {   // the noise of different utterances is independent (one generator per seed): spread it over host threads
-        auto fill = [&](int i0, int i1) {
-            for (int i = i0; i < i1; i++) {
-                host_noise(seeds[i], gp->temp, gp->noise_clamp, max_frames[i], &h_noise[(size_t)i * cap_f * FL_LAT]);
-                for (size_t j = (size_t)max_frames[i] * FL_LAT; j < (size_t)cap_f * FL_LAT; j++) h_noise[(size_t)i * cap_f * FL_LAT + j] = 0.0f;
-            }
-        };
-        const int nt = gp->temp > 0.0f ? (int)std::min<size_t>(std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u),
-                                                                (size_t)n * cap_f / 2048 + 1) : 1;
-        if (nt <= 1) fill(0, n);
-        else {
-            std::vector<std::thread> th;
-            for (int t = 0; t < nt; t++) th.emplace_back(fill, (int)((long long)n * t / nt), (int)((long long)n * (t + 1) / nt));
-            for (auto &t : th) t.join();
-        }
+    e->pend_noise.n = 0;
+    if (defer_noise) {   // generated and uploaded by upload_pending_noise() once the prefill is on its way
+        auto &pn = e->pend_noise;
+        pn.n = n; pn.cap_f = cap_f; pn.temp = gp->temp; pn.clamp = gp->noise_clamp;
+        pn.seeds.assign(seeds, seeds + n); pn.frames.assign(max_frames, max_frames + n);
+    } else {
+        h_noise.resize((size_t)n * cap_f * FL_LAT);
+        fill_noise(n, cap_f, seeds, max_frames, gp->temp, gp->noise_clamp, h_noise.data());
     }
     for (int i = 0, r = 0; i < n; i++) {
         const int tl = token_offsets[i + 1] - token_offsets[i];
@@ -447,8 +476,9 @@ static int stage_impl(Engine *e, int n, const int *tokens_flat, const int *token
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_done, h_done.data(), B * 4, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_eos_step, h_es.data(), B * 4, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaMemcpyAsync(e->d_used, h_used.data(), B * 4, cudaMemcpyHostToDevice, st));
-    PTTS_CUDA_OK(cudaMemcpy2DAsync(e->d_noise, (size_t)capF * FL_LAT * 4, h_noise.data(), (size_t)cap_f * FL_LAT * 4,
-                                   (size_t)cap_f * FL_LAT * 4, n, cudaMemcpyHostToDevice, st));
+    if (!defer_noise)
+        PTTS_CUDA_OK(cudaMemcpy2DAsync(e->d_noise, (size_t)capF * FL_LAT * 4, h_noise.data(), (size_t)cap_f * FL_LAT * 4,
+                                       (size_t)cap_f * FL_LAT * 4, n, cudaMemcpyHostToDevice, st));
     PTTS_CUDA_OK(cudaMemsetAsync(e->d_out_latents, 0, (size_t)B * capF * FL_LAT * 4, st));
     PTTS_CUDA_OK(cudaMemsetAsync(e->d_first_eos, 0, (size_t)B * 4, st));
     PTTS_CUDA_OK(cudaMemsetAsync(e->d_first_cond, 0, (size_t)B * FL_D * 4, st));
@@ -495,6 +525,7 @@ static int run_begin(Engine *e) {
 static int run_impl(Engine *e, int with_mimi, float *host_audio = nullptr) {
     e->pcm_on_host = nullptr;
     if (run_begin(e) != 0) return -1;
+    if (upload_pending_noise(e) != 0) return -1;   // host noise generation runs while the device works through the prompt prefill
     const int B = e->curB, n = e->st_n;
     const int mode = B == 1 ? 1 : 2;
     if (run_steps(e, mode, B, e->st_lsd, e->st_precise, e->st_steps, e->st_eos != 0) != 0) return -1;
@@ -541,9 +572,16 @@ extern "C" int ptts_b200_generate_batch(ptts_b200_engine *e, int n, const int *t
                                         const float *cond_prefix, int cond_len, const int *max_frames, const int64_t *seeds,
                                         const int *eos_after, const ptts_b200_gen_params *params, float *out_latents,
                                         int *out_frames_used, float *out_audio) {
-    if (stage_impl(e, n, tokens_flat, token_offsets, cond_prefix, cond_len, max_frames, seeds, eos_after, params) != 0) return -1;
+    static const bool trace = getenv("PTTS_B200_E2E_TRACE") != nullptr;   // host-side timeline of the call (stderr)
+    auto now = [] { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e3 + t.tv_nsec * 1e-6; };
+    const double t0 = trace ? now() : 0.0;
+    if (stage_impl(e, n, tokens_flat, token_offsets, cond_prefix, cond_len, max_frames, seeds, eos_after, params, /*defer_noise=*/true) != 0) return -1;
+    const double t1 = trace ? now() : 0.0;
     if (run_impl(e, out_audio != nullptr, out_audio) != 0) return -1;
-    return fetch_impl(e, out_latents, out_frames_used, out_audio);
+    const double t2 = trace ? now() : 0.0;
+    const int rc = fetch_impl(e, out_latents, out_frames_used, out_audio);
+    if (trace) fprintf(stderr, "generate_batch n=%d: stage %.2f ms, run (enqueue) %.2f ms, fetch (wait + copies) %.2f ms\n", n, t1 - t0, t2 - t1, now() - t2);
+    return rc;
 }
 
 // ---------------------------------------------------------------- drop-in single-utterance entries
