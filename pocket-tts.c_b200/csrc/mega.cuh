@@ -34,16 +34,52 @@ enum MegaPhaseType : int { MP_HEAD = 0, MP_GEMM, MP_ROW, MP_MID, MP_TAIL, MP_ATT
 
 struct MegaPhase {
     int type;
-    int idx;         // GEMM / ROW / ATTN: index into the respective array; MID: LSD step k just finished
+    int idx;         // GEMM / ROW / ATTN: index into the respective table; MID: LSD step k just finished
     int next_gemm;   // GEMM whose first weight tiles the producer fetches after this phase's own loads (-1: none)
+    int seq;         // GEMM phases: ordinal of the contraction within the frame (parity of the ring-state slots)
+    int wraps;       // GEMM phases: next_gemm belongs to the NEXT frame
 };
 
+// What a contraction phase needs of a GemmOp: the three operand maps and the GemmParams fields the roles read (same names).
+struct MegaGemmParams {
+    int m_tiles_per_batch, m_tiles_total, n_tiles, iters_per_split, total_tiles, taps, kblocks_per_tap, a_rows, n_total, act, ldo, ldh, split_k;
+    uint32_t idesc;
+    const float *bias;
+    float *out_f32;
+    size_t split_stride;
+    uint16_t *out_h, *out_l;
+};
+struct MegaGemm {
+    CUtensorMap mapA, mapAlo, mapB;
+    MegaGemmParams p;
+    int bn, split;
+};
+__device__ __forceinline__ TileCoord mega_tile(const MegaGemmParams &p, int tile, int BN) {   // gemm_tile() on the compact record
+    TileCoord t;
+    const int nt = tile % p.n_tiles;
+    int r = tile / p.n_tiles;
+    const int mt = r % p.m_tiles_total;
+    t.z = r / p.m_tiles_total;
+    t.batch = mt / p.m_tiles_per_batch;
+    t.m0 = (mt - t.batch * p.m_tiles_per_batch) * GEMM_BM;
+    t.n0 = nt * BN;
+    t.it0 = t.z * p.iters_per_split;
+    t.it1 = min(p.taps * p.kblocks_per_tap, t.it0 + p.iters_per_split);
+    return t;
+}
+// Table capacities of the kernel parameter space (32 KB in all): lsd_steps <= 6 (the flow-head contractions and row programs of the
+// LSD steps share their entries; only cond_embed, whose bias carries the time embedding, differs per step)
+constexpr int MG_PHASES_C = 208, MG_ROWS_C = 20, MG_GEMMS_C = 44;
+
+// The whole program travels in the kernel parameter space: a phase starts with its table entries, and a global load behind the grid
+// barrier (the L1 is cold there) costs an L2 round trip 65 times per frame - the constant bank answers in a few cycles (measured
+// 718 -> 697 us per frame, profiles/r02_step_kernel_experiments.txt). TMA reads its tensor maps from the parameter space as well.
 struct MegaProgram {
-    const MegaPhase *phases;
+    MegaPhase phases[MG_PHASES_C];
+    RowNormParams rows[MG_ROWS_C];
+    MegaGemm gemms[MG_GEMMS_C];
     int n_phases;
-    const GemmOp *gemms;
-    const RowNormParams *rows;
-    const AttnDecodeParams *attn;
+    int n_gemm_phases;              // contraction phases per frame (parity of the ring-state slots)
     AttnDecodeParams attn0;         // layer 0 by value (kernel parameter space); layer l = attn0 + l * the strides below
     size_t attn_prefix_stride, attn_own_stride;
     int B, pcap;                    // padded batch, score-buffer length
@@ -67,13 +103,14 @@ struct MegaProgram {
     unsigned int *bar;              // grid barrier counter, zeroed by the host before the launch
     int *done_count;                // utterances that reached their stop point, zeroed by the host
     int n_live, nsteps, first_gemm;
-    int n_gemms;                    // contractions per frame (parity of the ring-state slots below)
     int flags;                      // experiment bits: 2 = light grid barrier
     int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
                                     // (only when the loop cannot stop early, i.e. EOS detection is off)
     unsigned long long *prof;       // optional [MP_COUNT][2]: ns and phase count per type (written by CTA 0)
     unsigned long long *trace;      // optional [n_phases][2]: ns of CTA 0's own work / ns including the barrier, summed over frames
 };
+
+static_assert(sizeof(MegaProgram) <= 32764, "the step program must fit the kernel parameter space");
 
 // ---------------------------------------------------------------- sync primitives
 __device__ __forceinline__ void group_bar(int id) { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
@@ -309,14 +346,14 @@ struct MegaPipe {
     int pre;        // producer: leading items of the coming GEMM whose B tile is already in flight
 };
 
-__device__ __forceinline__ uint32_t mg_stage_bytes(const GemmOp &g) {
+__device__ __forceinline__ uint32_t mg_stage_bytes(const MegaGemm &g) {
     return (uint32_t)(MG_A_BYTES * (g.split == 1 ? 2 : 1) + g.bn * GEMM_BK * 2);
 }
 
-__device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, MegaPipe &pipe, uint8_t *ring, uint64_t *full,
+__device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *next, MegaPipe &pipe, uint8_t *ring, uint64_t *full,
                                           uint64_t *empty, uint64_t *tfull, uint64_t *tempty, uint32_t tmem_base) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const GemmParams &p = g.p;
+    const MegaGemmParams &p = g.p;
     const int BN = g.bn;
     const bool lo = g.split == 1;
     if (warp == 0) {
@@ -326,7 +363,7 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
             const uint32_t sb = mg_stage_bytes(g);
             int n = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = gemm_tile(p, tile, BN);
+                const TileCoord t = mega_tile(p, tile, BN);
                 for (int it = t.it0; it < t.it1; it++, n++) {
                     uint8_t *st = ring + pipe.s * MG_SLOT_BYTES;
                     if (n >= pipe.pre) {
@@ -345,7 +382,7 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
                 const uint32_t sbn = mg_stage_bytes(*next);
                 int s2 = pipe.s; uint32_t ph2 = pipe.ph;
                 for (int tile = blockIdx.x; tile < next->p.total_tiles && pipe.pre < MG_STAGES; tile += gridDim.x) {
-                    const TileCoord t = gemm_tile(next->p, tile, next->bn);
+                    const TileCoord t = mega_tile(next->p, tile, next->bn);
                     for (int it = t.it0; it < t.it1 && pipe.pre < MG_STAGES; it++, pipe.pre++) {
                         mbar_wait(&empty[s2], ph2 ^ 1);
                         mbar_expect_tx(&full[s2], sbn);
@@ -358,7 +395,7 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (one elected lane)
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, pipe.lt++) {
-            const TileCoord t = gemm_tile(p, tile, BN);
+            const TileCoord t = mega_tile(p, tile, BN);
             const int acc = pipe.lt & 1;
             mbar_wait(&tempty[acc], ((pipe.lt >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -390,7 +427,7 @@ __device__ __forceinline__ void mega_gemm(const GemmOp &g, const GemmOp *next, M
         const float *bias = p.bias;
         uint16_t *out_h = p.out_h, *out_l = p.out_l;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, pipe.lt++) {
-            const TileCoord t = gemm_tile(p, tile, BN);
+            const TileCoord t = mega_tile(p, tile, BN);
             const int acc = pipe.lt & 1;
             mbar_wait(&tfull[acc], (pipe.lt >> 1) & 1);
             tc_fence_after();
@@ -498,17 +535,17 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
 
     // the first contraction's weight tiles can be requested right away
     if (warp == 0 && lane == 0 && P.first_gemm >= 0) {
-        const GemmOp &g0 = P.gemms[P.first_gemm];
+        const MegaGemm &g0 = P.gemms[P.first_gemm];
         const uint32_t sb0 = mg_stage_bytes(g0);
         int pre = 0;
         for (int tile = blockIdx.x; tile < g0.p.total_tiles && pre < MG_STAGES; tile += gridDim.x) {
-            const TileCoord t = gemm_tile(g0.p, tile, g0.bn);
+            const TileCoord t = mega_tile(g0.p, tile, g0.bn);
             for (int it = t.it0; it < t.it1 && pre < MG_STAGES; it++, pre++) {
                 mbar_expect_tx(&full[pre], sb0);
                 tma_load_3d(ring + pre * MG_SLOT_BYTES + 2 * MG_A_BYTES, &g0.mapB, &full[pre], it * GEMM_BK, t.n0, 0);
             }
         }
-        pst[(P.first_gemm & 1) * 16 + 2] = pre;   // read by the first contraction (parity of 0 * n_gemms + first_gemm)
+        pst[2] = pre;   // read by the first contraction of the launch (slot parity 0)
     }
 
     for (int si = 0; si < P.nsteps; si++) {
@@ -520,9 +557,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
             switch (ph.type) {
                 case MP_GEMM: {
                     // a fetch that wraps into the next frame must be consumed: never past the end of the launch
-                    const bool wraps = ph.next_gemm >= 0 && ph.next_gemm <= ph.idx;
-                    const GemmOp *nx = ph.next_gemm >= 0 && !(wraps && (!P.wrap_prefetch || si + 1 == P.nsteps)) ? &P.gemms[ph.next_gemm] : nullptr;
-                    const int par = (si * P.n_gemms + ph.idx) & 1;
+                    const bool wraps = ph.wraps != 0;
+                    const MegaGemm *nx = ph.next_gemm >= 0 && !(wraps && (!P.wrap_prefetch || si + 1 == P.nsteps)) ? &P.gemms[ph.next_gemm] : nullptr;
+                    const int par = (si * P.n_gemm_phases + ph.seq) & 1;
                     const int *rd = pst + par * 16;
                     int *wr = pst + (par ^ 1) * 16;
                     MegaPipe pipe = {0, 0u, 0, 0};
@@ -611,10 +648,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
 struct MegaHost {
     uint64_t gen = ~0ull;
     int B = 0, lsd = 0, precise = -1;
-    MegaPhase *d_phases = nullptr;
-    GemmOp *d_gemms = nullptr;
-    RowNormParams *d_rows = nullptr;
-    AttnDecodeParams *d_attn = nullptr;
+    bool fits = false;              // the program fits the parameter-space tables (otherwise the caller runs the multi-kernel path)
     MegaProgram prog = {};
     std::vector<MegaPhase> phases;
     std::vector<GemmOp> gemms;
@@ -639,45 +673,65 @@ static AttnDecodeParams make_attn_params(Engine *e, int layer, bool out16, int q
     return a;
 }
 
+// Returns 0 (M.fits tells whether the program can run as k_flow_mega) or -1 on error.
 static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd, int precise) {
-    void *old[] = {M.d_phases, M.d_gemms, M.d_rows, M.d_attn};
-    for (void *q : old) e->dfree(q);
     M = MegaHost();
     std::vector<RowNormParams> rows;
     std::vector<AttnDecodeParams> attn;
     auto &ph = M.phases;
     auto &gm = M.gemms;
     const size_t ps = (size_t)e->capB * FL_D;
-    auto add_gemm = [&](const GemmOp &op) -> int {
-        if (op.bn > MG_MAX_BN || op.split == 2 || op.p.taps != 1 || op.p.transposed) {
+    // Table entries are shared where the work is identical: the flow-head contractions and row programs of every LSD step use
+    // the same buffers and weights (only cond_embed differs, its bias carries the time embedding of the step).
+    auto new_gemm = [&](const GemmOp &op) -> int {
+        if (op.bn > MG_MAX_BN || op.split == 2 || op.p.taps != 1 || op.p.transposed || op.p.m_tiles_per_batch != op.p.m_tiles_total) {
             set_error("mega_build: contraction shape not supported by the persistent step kernel");
             return -1;
         }
         gm.push_back(op);
-        ph.push_back({MP_GEMM, (int)gm.size() - 1, -1});
+        return (int)gm.size() - 1;
+    };
+    auto gemm_phase = [&](int idx) {
+        ph.push_back({MP_GEMM, idx, -1, 0, 0});
+        const GemmOp &op = gm[idx];
         const double rows_ = op.p.a_rows, n = op.p.n_total, k = (double)op.p.kblocks_per_tap * GEMM_BK;
         M.flops[MP_GEMM] += 2.0 * rows_ * n * k;
         M.bytes[MP_GEMM] += 2.0 * n * k;   // weights once; activations stay in L2
+    };
+    auto add_gemm = [&](const GemmOp &op) -> int {
+        const int idx = new_gemm(op);
+        if (idx < 0) return -1;
+        gemm_phase(idx);
         return 0;
     };
-    auto add_row = [&](const RowNormParams &r) { rows.push_back(r); ph.push_back({MP_ROW, (int)rows.size() - 1, -1}); };
-    ph.push_back({MP_HEAD, 0, -1});
+    auto new_row = [&](const RowNormParams &r) { rows.push_back(r); return (int)rows.size() - 1; };
+    auto row_phase = [&](int idx) { ph.push_back({MP_ROW, idx, -1, 0, 0}); };
+    auto add_row = [&](const RowNormParams &r) { row_phase(new_row(r)); };
+    ph.push_back({MP_HEAD, 0, -1, 0, 0});
+    int i_ada = -1, i_m0[FN_DEPTH], i_m2[FN_DEPTH], i_fin = -1, i_row[FN_DEPTH + 1];
     for (int k = 0; k < lsd; k++) {
-        if (add_gemm(G.cond[k]) != 0 || add_gemm(G.ada) != 0) return -1;
+        if (add_gemm(G.cond[k]) != 0) return -1;
+        if (k == 0 && (i_ada = new_gemm(G.ada)) < 0) return -1;
+        gemm_phase(i_ada);
         for (int b = 0; b <= FN_DEPTH; b++) {
-            RowNormParams r = {};
-            r.x = e->fx; r.D = FN_D; r.eps = 1e-6f; r.do_norm = 1; r.ldmod = FN_ADA;
-            if (b > 0) { r.part = e->ft; r.nsplit = G.m2[b - 1].p.split_k; r.split_stride = (size_t)e->capB * FN_D; r.gate = e->ada + (size_t)(b - 1) * 3 * FN_D + 2 * FN_D; }
-            if (b < FN_DEPTH) { r.w = e->FB[b].lnw; r.b = e->FB[b].lnb; }
-            r.shift = e->ada + (size_t)b * 3 * FN_D; r.scale = r.shift + FN_D;
-            r.out_h = e->fh_h; r.out_l = precise ? e->fh_l : nullptr; r.out_bf16 = 1;
-            add_row(r);
-            if (b < FN_DEPTH && (add_gemm(G.m0[b]) != 0 || add_gemm(G.m2[b]) != 0)) return -1;
+            if (k == 0) {
+                RowNormParams r = {};
+                r.x = e->fx; r.D = FN_D; r.eps = 1e-6f; r.do_norm = 1; r.ldmod = FN_ADA;
+                if (b > 0) { r.part = e->ft; r.nsplit = G.m2[b - 1].p.split_k; r.split_stride = (size_t)e->capB * FN_D; r.gate = e->ada + (size_t)(b - 1) * 3 * FN_D + 2 * FN_D; }
+                if (b < FN_DEPTH) { r.w = e->FB[b].lnw; r.b = e->FB[b].lnb; }
+                r.shift = e->ada + (size_t)b * 3 * FN_D; r.scale = r.shift + FN_D;
+                r.out_h = e->fh_h; r.out_l = precise ? e->fh_l : nullptr; r.out_bf16 = 1;
+                i_row[b] = new_row(r);
+                if (b < FN_DEPTH && ((i_m0[b] = new_gemm(G.m0[b])) < 0 || (i_m2[b] = new_gemm(G.m2[b])) < 0)) return -1;
+            }
+            row_phase(i_row[b]);
+            if (b < FN_DEPTH) { gemm_phase(i_m0[b]); gemm_phase(i_m2[b]); }
         }
-        if (add_gemm(G.fin) != 0) return -1;
-        if (k + 1 < lsd) ph.push_back({MP_MID, k, -1});
+        if (k == 0 && (i_fin = new_gemm(G.fin)) < 0) return -1;
+        gemm_phase(i_fin);
+        if (k + 1 < lsd) ph.push_back({MP_MID, k, -1, 0, 0});
     }
-    ph.push_back({MP_TAIL, 0, -1});
+    ph.push_back({MP_TAIL, 0, -1, 0, 0});
     for (int l = 0; l < FL_L; l++) {
         RowNormParams r = {};
         if (l > 0) {
@@ -688,7 +742,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
         }
         if (add_gemm(G.qkv[l]) != 0) return -1;
         attn.push_back(make_attn_params(e, l, true, G.qkv[l].p.split_k));
-        ph.push_back({MP_ATTN, (int)attn.size() - 1, -1});
+        ph.push_back({MP_ATTN, (int)attn.size() - 1, -1, 0, 0});
         if (add_gemm(G.outp[l]) != 0) return -1;
         r = {};
         r.x = e->x; r.D = FL_D; r.w = e->L[l].n2w; r.b = e->L[l].n2b; r.eps = 1e-5f; r.do_norm = 1;
@@ -697,30 +751,40 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
         add_row(r);
         if (add_gemm(G.ff1[l]) != 0 || add_gemm(G.ff2[l]) != 0) return -1;
     }
-    // next contraction reachable without an attention phase in between (attention aliases the ring)
+    // per contraction phase: its ordinal within the frame, and the next contraction reachable without an attention phase in between
+    // (attention aliases the ring) - whose first weight tiles the producer requests early
     const int np = (int)ph.size();
-    int first_gemm = -1;
+    int first_gemm = -1, n_gp = 0;
     for (int i = 0; i < np; i++) {
         if (ph[i].type != MP_GEMM) continue;
         if (first_gemm < 0) first_gemm = ph[i].idx;
+        ph[i].seq = n_gp++;
         for (int d = 1; d < np; d++) {
             const MegaPhase &q = ph[(i + d) % np];
             if (q.type == MP_ATTN) break;
-            if (q.type == MP_GEMM) { ph[i].next_gemm = q.idx; break; }
+            if (q.type == MP_GEMM) { ph[i].next_gemm = q.idx; ph[i].wraps = i + d >= np ? 1 : 0; break; }
         }
     }
     const int pcap = ((e->capCond + e->capS + 63) / 32) * 32;
     PTTS_CHECK(attn6_smem_bytes(pcap) <= (size_t)MG_RING_BYTES + MG_ATTN_EXTRA,
                "attention score buffers of %zu bytes exceed the persistent kernel's shared memory (sequence too long)",
                attn6_smem_bytes(pcap));
-    if (e->dalloc(&M.d_phases, ph.size()) != 0 || e->dalloc(&M.d_gemms, gm.size()) != 0 || e->dalloc(&M.d_rows, rows.size()) != 0 ||
-        e->dalloc(&M.d_attn, attn.size()) != 0) return -1;
-    PTTS_CUDA_OK(cudaMemcpy(M.d_phases, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
-    PTTS_CUDA_OK(cudaMemcpy(M.d_gemms, gm.data(), gm.size() * sizeof(GemmOp), cudaMemcpyHostToDevice));
-    PTTS_CUDA_OK(cudaMemcpy(M.d_rows, rows.data(), rows.size() * sizeof(RowNormParams), cudaMemcpyHostToDevice));
-    PTTS_CUDA_OK(cudaMemcpy(M.d_attn, attn.data(), attn.size() * sizeof(AttnDecodeParams), cudaMemcpyHostToDevice));
+    M.gen = e->gen; M.B = B; M.lsd = lsd; M.precise = precise;
+    M.fits = np <= MG_PHASES_C && (int)rows.size() <= MG_ROWS_C && (int)gm.size() <= MG_GEMMS_C;
+    if (!M.fits) return 0;
     MegaProgram &P = M.prog;
-    P.phases = M.d_phases; P.n_phases = np; P.gemms = M.d_gemms; P.rows = M.d_rows; P.attn = M.d_attn;
+    for (int i = 0; i < np; i++) P.phases[i] = ph[i];
+    for (size_t i = 0; i < rows.size(); i++) P.rows[i] = rows[i];
+    for (size_t i = 0; i < gm.size(); i++) {
+        MegaGemm &g = P.gemms[i];
+        const GemmParams &q = gm[i].p;
+        g.mapA = gm[i].mapA; g.mapAlo = gm[i].mapAlo; g.mapB = gm[i].mapB; g.bn = gm[i].bn; g.split = gm[i].split;
+        g.p.m_tiles_per_batch = q.m_tiles_per_batch; g.p.m_tiles_total = q.m_tiles_total; g.p.n_tiles = q.n_tiles;
+        g.p.iters_per_split = q.iters_per_split; g.p.total_tiles = q.total_tiles; g.p.taps = q.taps; g.p.kblocks_per_tap = q.kblocks_per_tap;
+        g.p.a_rows = q.a_rows; g.p.n_total = q.n_total; g.p.act = q.act; g.p.ldo = q.ldo; g.p.ldh = q.ldh; g.p.split_k = q.split_k;
+        g.p.idesc = q.idesc; g.p.bias = q.bias; g.p.out_f32 = q.out_f32; g.p.split_stride = q.split_stride; g.p.out_h = q.out_h; g.p.out_l = q.out_l;
+    }
+    P.n_phases = np; P.n_gemm_phases = n_gp;
     P.B = B; P.pcap = pcap;
     P.attn0 = attn[0]; P.attn_prefix_stride = (size_t)FL_D * e->capCond; P.attn_own_stride = (size_t)e->capB * FL_D * e->capS;
     P.st = make_state(e, B, lsd);
@@ -737,8 +801,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
     r.x = e->x; r.D = FL_D; r.w = e->L[0].n1w; r.b = e->L[0].n1b; r.eps = 1e-5f; r.do_norm = 1;
     r.out_h = e->xn_h; r.out_l = precise ? e->xn_l : nullptr; r.out_bf16 = 1;
     P.ln0 = r;
-    P.first_gemm = first_gemm; P.n_gemms = (int)gm.size();
-    M.gen = e->gen; M.B = B; M.lsd = lsd; M.precise = precise;
+    P.first_gemm = first_gemm;
     return 0;
 }
 

@@ -190,6 +190,7 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
         PTTS_CUDA_OK(cudaStreamSynchronize(e->st));
         if (mega_build(e, M, gi->second, B, lsd, precise) != 0) return -1;
     }
+    if (!M.fits) return 1;   // program too long for the kernel parameter space (lsd_steps > 6): the caller runs the multi-kernel path
     if (!e->mega_ctl && e->dalloc(&e->mega_ctl, 64) != 0) return -1;
     PTTS_CUDA_OK(cudaMemsetAsync(e->mega_ctl, 0, 64 * sizeof(unsigned long long), e->st));
     MegaProgram P = M.prog;
@@ -262,7 +263,10 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
 
 static int run_steps(Engine *e, int mode, int B, int lsd, int precise, int nsteps, bool poll_done) {
     if (nsteps <= 0) return 0;
-    if (mode == 2 && mega_enabled()) return run_mega(e, B, lsd, precise, nsteps);
+    if (mode == 2 && mega_enabled()) {
+        const int rc = run_mega(e, B, lsd, precise, nsteps);
+        if (rc <= 0) return rc;   // 1: the step program does not fit the persistent kernel - one CUDA graph per frame step instead
+    }
     const bool use_graph = !e->prof.on && getenv("PTTS_B200_NO_GRAPH") == nullptr;
     cudaGraphExec_t exec = nullptr;
     int64_t gk = 0;
