@@ -80,8 +80,7 @@ struct MegaProgram {
     MegaGemm gemms[MG_GEMMS_C];
     int n_phases;
     int n_gemm_phases;              // contraction phases per frame (parity of the ring-state slots)
-    AttnDecodeParams attn0;         // layer 0 by value (kernel parameter space); layer l = attn0 + l * the strides below
-    size_t attn_prefix_stride, attn_own_stride;
+    AttnDecodeParams attn[FL_L];    // per layer, by value: the attention phase reads its parameters straight from the constant bank
     int B, pcap;                    // padded batch, score-buffer length
     FlowState st;
     FlowCtrl *ctrl;
@@ -528,7 +527,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
         attn6_units(P.B, au0, au1);
         if (au1 - au0 <= 64 && au1 > au0 && au0 / P.B == (au1 - 1) / P.B) {
             ob_cache = (int *)(sbase + 768);
-            if (tid < au1 - au0) ob_cache[tid] = P.attn0.own_base[au0 - (au0 / P.B) * P.B + tid];
+            if (tid < au1 - au0) ob_cache[tid] = P.attn[0].own_base[au0 - (au0 / P.B) * P.B + tid];
             __syncthreads();
         }
     }
@@ -608,14 +607,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_ATTN:
-                    {   // the layer's parameters are built from the kernel parameter space: no dependent global loads in the phase prologue
-                        AttnDecodeParams a = P.attn0;
-                        const int l = ph.idx;
-                        a.pk += (size_t)l * P.attn_prefix_stride; a.pv += (size_t)l * P.attn_prefix_stride;
-                        a.pk16 += (size_t)l * P.attn_prefix_stride; a.pv16 += (size_t)l * P.attn_prefix_stride;
-                        a.ok += (size_t)l * P.attn_own_stride; a.ov += (size_t)l * P.attn_own_stride;
-                        attn6_phase(a, P.B, step, cond_len0, ob_cache, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
-                    }
+                    attn6_phase(P.attn[ph.idx], P.B, step, cond_len0, ob_cache, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     break;
                 default: break;
             }
@@ -786,7 +778,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
     }
     P.n_phases = np; P.n_gemm_phases = n_gp;
     P.B = B; P.pcap = pcap;
-    P.attn0 = attn[0]; P.attn_prefix_stride = (size_t)FL_D * e->capCond; P.attn_own_stride = (size_t)e->capB * FL_D * e->capS;
+    for (int l = 0; l < FL_L; l++) P.attn[l] = attn[l];
     P.st = make_state(e, B, lsd);
     P.ctrl = e->ctrl; P.eos_after = e->d_eos_after;
     RowNormParams r = {};
