@@ -138,6 +138,14 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void 
                  "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_3d_s(const CUtensorMap *map, uint32_t smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(smem_src), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }   // sources reusable
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }              // stores complete
@@ -230,8 +238,9 @@ __device__ __forceinline__ float act_t(float x) {
 template <int ACT, bool FAST, bool BF, bool LO>
 __device__ __forceinline__ void act_pack16(const float (&v)[16], uint32_t (&hw)[8], uint32_t (&lw)[8]) {
     if constexpr (ACT == ACT_ELU && FAST && !BF && !LO) {
-        // fp16 output: ELU evaluated on packed halves, ELU(x) = max(x,0) + (2^(min(x,0)*log2 e) - 1): six
-        // instructions per PAIR, one packed MUFU.EX2 (the result is rounded to fp16 anyway)
+        // fp16 output: ELU evaluated on packed halves, ELU(x) = max(x,0) + (2^(min(x,0)*log2 e) - 1). h2exp2 goes through fp32
+        // (two MUFU.EX2 and conversions per pair); ex2.approx.f16x2 would save 4 instructions per pair but costs 1-1.7 dB of PCM
+        // parity for -1 % of the decode time (profiles/r02_step_kernel_experiments.txt, experiment 14)
         const __half2 zero = __float2half2_rn(0.0f), one = __float2half2_rn(1.0f), l2e = __float2half2_rn(1.4426950408889634f);
 #pragma unroll
         for (int j = 0; j < 8; j++) {

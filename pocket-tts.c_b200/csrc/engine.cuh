@@ -134,15 +134,19 @@ static void launch_k_window(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 }
 
 // ---------------------------------------------------------------- GEMM dispatch
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int EPI = EPI_GENERIC>
 static int gemm_launch_t(const GemmOp &op, cudaStream_t st) {
     // the dynamic shared-memory attribute is per device: ptts_b200_create sets it for the engine's device (gemm_set_attrs)
-    launch_k(gemm_tc_kernel<BN, SPLIT>, op.grid, GEMM_THREADS, op.smem_bytes, st, op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.mapOH, op.mapOR, op.p);
+    launch_k(gemm_tc_kernel<BN, SPLIT, EPI>, op.grid, GEMM_THREADS, op.smem_bytes, st, op.mapA, op.mapAlo, op.mapB, op.mapBlo, op.mapOH, op.mapOR, op.p);
     PTTS_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 int gemm_launch(const GemmOp &op, cudaStream_t st) {
+    if (op.epi == EPI_CONV && op.split == 0) {
+        if (op.bn == 128) return gemm_launch_t<128, 0, EPI_CONV>(op, st);
+        if (op.bn == 256) return gemm_launch_t<256, 0, EPI_CONV>(op, st);
+    }
 #define GL(BN_, SP_) if (op.bn == BN_ && op.split == SP_) return gemm_launch_t<BN_, SP_>(op, st);
     GL(32, 0) GL(64, 0) GL(128, 0) GL(256, 0)
     GL(32, 1) GL(64, 1) GL(128, 1) GL(256, 1)
@@ -255,6 +259,11 @@ static int gemm_build(GemmOp &op, const GemmDesc &d) {
     }
     (void)out_rows;
     p.idesc = umma_idesc_f16(GEMM_BM, d.bn, d.bf16, d.bf16);
+    // the SEANet convolutions take the specialised epilogue (gemm_tc.cuh EPI_CONV)
+    op.epi = (p.tma_store && p.out_h && p.bias && !p.scale && !p.resid && !p.resid_h && !p.out_f32 && !p.out_l && !p.rope_q && !p.out_bf16 &&
+              p.fast_act && (p.act == ACT_ELU || p.act == ACT_NONE) && op.split == 0 && split_k == 1 && (d.bn == 128 || d.bn == 256) &&
+              d.b_rows % 64 == 0 && (p.bias_mask == 0 || (p.bias_mask + 1) % 64 == 0) && getenv("PTTS_B200_NO_EPI_CONV") == nullptr)
+                 ? EPI_CONV : EPI_GENERIC;
     op.p = p;
     op.grid = dim3((unsigned)std::min<long long>(tiles, d.num_sms), 1, 1);
     op.smem_bytes = p.stages * stage_bytes(d.bn, op.split) + 1024 + 1024 + (p.tma_store ? GEMM_EPI_WARPS * p.stage_stride : 0);

@@ -117,7 +117,15 @@ __device__ __forceinline__ TileCoord gemm_tile(const GemmParams &p, int tile, in
 // Persistent: each CTA loops over tiles (tile = blockIdx.x + i*gridDim.x). The shared-memory ring
 // keeps streaming across tile boundaries and the accumulator is double-buffered in TMEM, so the
 // epilogue of tile i overlaps the main loop of tile i+1.
-template <int BN, int SPLIT>
+// EPI selects the epilogue at compile time:
+//   EPI_GENERIC - every fused form, chosen by the run-time fields of GemmParams;
+//   EPI_CONV    - the SEANet convolutions (Conv1d / ConvTranspose1d, ptts_kernels.c:128-204): + bias -> fp16 (optional copy of the
+//                 pre-activation value) -> ELU or identity -> fp16, both leaving through the staging buffers as TMA tensor stores.
+//                 Straight-line code per 64-column group, accumulator chunks in two alternating register sets, shared-space stores:
+//                 the generic path spends ~320 instructions per 16-column chunk on these GEMMs, which are bound by exactly that.
+constexpr int EPI_GENERIC = 0, EPI_CONV = 1;
+
+template <int BN, int SPLIT, int EPI = EPI_GENERIC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapAlo,
                const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapBlo,
@@ -273,7 +281,62 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             float *out_f32 = p.out_f32 ? p.out_f32 + (size_t)t.z * p.split_stride : nullptr;
             const bool add_bias = bias != nullptr && t.z == 0;
             uint32_t r[16], rn[16];
-            if (!p.transposed) {
+            if constexpr (EPI == EPI_CONV) {
+                constexpr int CW = BN / NCG;
+                static_assert(CW % 64 == 0, "EPI_CONV: a warp owns whole 64-column groups");
+                const int c_lo = cg * CW;
+                // this lane's row of the warp's staging buffers ([32 rows][128 B] per tensor, 16-byte piece index ^ (row & 7))
+                const uint32_t row_s = smem_u32(smem) + (uint32_t)(p.stage_off + (warp - 2) * p.stage_stride + lane * 128);
+                const uint32_t x7 = (uint32_t)(lane & 7) << 4;
+                const bool raw = p.out_raw != nullptr, elu = act == ACT_ELU;
+                tmem_ld16(trow + c_lo, r);
+#pragma unroll 1
+                for (int g = 0; g < CW / 64; g++) {
+                    const int cb = c_lo + g * 64, nb0 = t.n0 + cb;
+                    const bool live = nb0 < n_total;
+                    if (g > 0) {   // the previous group's tensor stores have read the staging buffers
+                        if (lane == 0) bulk_wait_read0();
+                        __syncwarp();
+                    }
+                    const float4 *bp = (const float4 *)(bias + (bias_mask ? (nb0 & bias_mask) : nb0));
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        uint32_t(&cur)[16] = (q & 1) ? rn : r;
+                        uint32_t(&nxt)[16] = (q & 1) ? r : rn;
+                        tmem_ld_wait16(cur);
+                        if (q < 3 || g + 1 < CW / 64) tmem_ld16(trow + cb + (q + 1) * 16, nxt);   // in flight while this chunk is processed
+                        if (live) {
+                            float v[16];
+#pragma unroll
+                            for (int j = 0; j < 4; j++) {
+                                const float4 bb = bp[4 * q + j];
+                                v[4 * j] = __uint_as_float(cur[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(cur[4 * j + 1]) + bb.y;
+                                v[4 * j + 2] = __uint_as_float(cur[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(cur[4 * j + 3]) + bb.w;
+                            }
+                            const uint32_t o0 = (uint32_t)(q << 5) ^ x7, o1 = o0 ^ 16u;
+                            uint32_t hw[8], lw[8];
+                            if (raw) {
+                                act_pack16<ACT_NONE, true, false, false>(v, hw, lw);
+                                sts128(row_s + 4096 + o0, hw[0], hw[1], hw[2], hw[3]);
+                                sts128(row_s + 4096 + o1, hw[4], hw[5], hw[6], hw[7]);
+                            }
+                            if (elu) act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
+                            else act_pack16<ACT_NONE, true, false, false>(v, hw, lw);
+                            sts128(row_s + o0, hw[0], hw[1], hw[2], hw[3]);
+                            sts128(row_s + o1, hw[4], hw[5], hw[6], hw[7]);
+                        }
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && live) {
+                        const uint32_t stg_s = row_s;   // lane 0: the buffer's first row
+                        const int row0 = t.m0 + quad * 32;
+                        tma_store_3d_s(&mapOH, stg_s, nb0, row0, t.batch);
+                        if (raw) tma_store_3d_s(&mapOR, stg_s + 4096, nb0, row0, t.batch);
+                        bulk_commit();
+                    }
+                }
+            } else if (!p.transposed) {
                 // each warp owns a contiguous range of BN / NCG columns of its 32 rows
                 constexpr int CW = BN / NCG;
                 const int c_lo = cg * CW;
@@ -473,6 +536,7 @@ struct GemmOp {
     GemmParams p;
     int bn;        // N tile (B-operand box rows)
     int split;     // 0 none, 1 = A has lo, 2 = B has lo
+    int epi;       // EPI_GENERIC / EPI_CONV
     dim3 grid;       // persistent: min(total_tiles, max_ctas)
     int smem_bytes;
 };

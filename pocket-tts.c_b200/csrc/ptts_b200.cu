@@ -55,6 +55,8 @@ extern "C" const char *ptts_b200_last_error(void) { return g_last_error; }
 static int gemm_set_attrs() {
 #define SA(bn, sp) PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<bn, sp>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     SA(32, 0) SA(64, 0) SA(128, 0) SA(256, 0) SA(32, 1) SA(64, 1) SA(128, 1) SA(256, 1) SA(32, 2) SA(64, 2) SA(128, 2) SA(256, 2)
+    PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 0, EPI_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 0, EPI_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #undef SA
     return 0;
 }
