@@ -64,6 +64,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
              *d2_empty = w2_full + 4, *a3_full = w2_full + 5, *d3_full = w2_full + 6;
     uint32_t *tmem_slot = (uint32_t *)(w2_full + 7);
     float *dpart = (float *)(bars + 32);          // [2 buffers][128 rows][3]: per-row tap sums of the fused final conv
+    float *b1s = dpart + 768, *b2s = b1s + 128;   // biases (every lane reads the same address: one broadcast LDS instead of a global load)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool fuse_out = C2 == 64 && p.dw != nullptr;
     if (fuse_out) {
@@ -82,6 +83,8 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         fence_proxy_async();
     }
 
+    for (int i = threadIdx.x; i < p.chp; i += RB_THREADS) b1s[i] = p.b1[i];
+    for (int i = threadIdx.x; i < C2; i += RB_THREADS) b2s[i] = p.b2[i];
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&mapA); tma_prefetch_desc(&mapW1); tma_prefetch_desc(&mapW2);
         for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -202,7 +205,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     const bool more = c + 16 < c1_hi;
                     if (more) tmem_ld16(trow + c + 16, rn);
                     float v[16];
-                    const float4 *bp = (const float4 *)(p.b1 + c);
+                    const float4 *bp = (const float4 *)(b1s + c);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const float4 bb = bp[j];
@@ -227,38 +230,40 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             __syncwarp();
             if (lane == 0) mbar_arrive(a2_full);
             // ---- epilogue 2: D2 -> +b2 + u -> ELU -> fp16 -> HBM
-            mbar_wait(d2_full, lt & 1);
-            tc_fence_after();
+            // The residual rows do not depend on the contraction: the first two chunks' loads are issued BEFORE the wait for D2 (their
+            // latency hides behind the MMA round trip), later ones one chunk ahead. Chunks alternate between two register sets.
+            const bool m_ok = m < p.a_rows;
+            const size_t grow = (size_t)batch * p.a_rows + m;
             {
-                const bool m_ok = m < p.a_rows;
-                const size_t grow = (size_t)batch * p.a_rows + m;
-                const uint16_t *up = p.u + grow * C2;
-                uint16_t *op = p.out ? p.out + grow * C2 : nullptr;
-                uint32_t rr[16], rn[16];
-                tmem_ld16(trow + D2_COL + c2_lo, rr); tmem_ld_wait16(rr);
-#pragma unroll 1
-                for (int c = c2_lo; c < c2_hi; c += 16) {
-                    const bool more = c + 16 < c2_hi;
-                    if (more) tmem_ld16(trow + D2_COL + c + 16, rn);
+                constexpr int NU = (C2 / 2) / 16;   // chunks per warp: 2 / 4 / 8
+                const uint16_t *up = p.u + grow * C2 + c2_lo;
+                uint16_t *op = p.out ? p.out + grow * C2 + c2_lo : nullptr;
+                uint32_t u0[8], u1[8];
+                if (m_ok) { ld_global_v8u(up, u0); ld_global_v8u(up + 16, u1); }
+                mbar_wait(d2_full, lt & 1);
+                tc_fence_after();
+                uint32_t ra[16], rb[16];
+                tmem_ld16(trow + D2_COL + c2_lo, ra);
+                auto chunk = [&](int i, uint32_t(&acc)[16], uint32_t(&hr)[8]) {
+                    const int c = c2_lo + 16 * i;
                     if (m_ok) {
-                        uint32_t hr[8];
-                        ld_global_v8u(up + c, hr);
                         float v[16];
-                        const float4 *bp = (const float4 *)(p.b2 + c);
+                        const float4 *bp = (const float4 *)(b2s + c);
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
                             const float4 bb = bp[j];
-                            v[4 * j] = __uint_as_float(rr[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(rr[4 * j + 1]) + bb.y;
-                            v[4 * j + 2] = __uint_as_float(rr[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(rr[4 * j + 3]) + bb.w;
+                            v[4 * j] = __uint_as_float(acc[4 * j]) + bb.x; v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + bb.y;
+                            v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + bb.z; v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + bb.w;
                         }
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             const float2 f = __half22float2(*(const __half2 *)&hr[j]);
                             v[2 * j] += f.x; v[2 * j + 1] += f.y;
                         }
+                        if (i + 2 < NU) ld_global_v8u(up + 16 * (i + 2), hr);   // this register set's next chunk
                         uint32_t hw[8], lw[8];
                         act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
-                        if (op) st_global_v8(op + c, hw);
+                        if (op) st_global_v8(op + 16 * i, hw);
                         if (fuse_out) {   // final conv on the fp16-rounded block output (what the unfused path reads back): the tile goes
                                           // back into the operand buffer (contraction 2 is done with it) as the A operand of contraction 3
                             uint8_t *row = a2s + r * 128;
@@ -272,11 +277,15 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         *(uint4 *)(row + ((pc ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                         *(uint4 *)(row + (((pc + 1) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                     }
-                    if (more) {
-                        tmem_ld_wait16(rn);
-#pragma unroll
-                        for (int j = 0; j < 16; j++) rr[j] = rn[j];
-                    }
+                };
+#pragma unroll 1
+                for (int i = 0; i < NU; i += 2) {
+                    tmem_ld_wait16(ra);
+                    tmem_ld16(trow + D2_COL + c2_lo + 16 * (i + 1), rb);
+                    chunk(i, ra, u0);
+                    tmem_ld_wait16(rb);
+                    if (i + 2 < NU) tmem_ld16(trow + D2_COL + c2_lo + 16 * (i + 2), ra);
+                    chunk(i + 1, rb, u1);
                 }
                 if (fuse_out) {
                     fence_proxy_async();          // generic-proxy writes of the output tile -> visible to the tensor core
