@@ -163,9 +163,10 @@ static int resblock_launch_t(Engine *e, const ConvW &c1, const ConvW &c2, const 
     PTTS_CHECK(tiles < (1ll << 31), "resblock_launch: too many tiles");
     p.tiles_total = (int)tiles; p.a_rows = T; p.kb_per_tap = C2 / 64; p.chp = chp;
     const int stage = GEMM_BM * GEMM_BK * 2 + chp * 128, kb2 = chp / 64;
-    const int fixed = kb2 * C2 * 128 + kb2 * GEMM_BM * GEMM_BK * 2 + (C2 == 64 ? 2048 : 0) + 256 + (192 + 2 * 768) * 4 + 1024;
-    // C2 <= 128: two CTAs per SM (one's output epilogue overlaps the other's contractions) -> at most ~110 KB each
-    p.stages = std::min(C2 <= 128 ? 3 : GEMM_MAX_STAGES, (227 * 1024 - fixed) / stage);
+    // C2 == 64: + the output-tile operand buffer of the fused final conv (16 KB)
+    const int fixed = kb2 * C2 * 128 + kb2 * GEMM_BM * GEMM_BK * 2 + (C2 == 64 ? 2048 + GEMM_BM * GEMM_BK * 2 : 0) + 256 + (192 + 2 * 768) * 4 + 1024;
+    // C2 <= 128: two CTAs per SM (one's output epilogue overlaps the other's contractions) -> at most 113 KB each
+    p.stages = C2 <= 128 ? std::min(3, (113 * 1024 - fixed) / stage) : std::min(GEMM_MAX_STAGES, (227 * 1024 - fixed) / stage);
     PTTS_CHECK(p.stages >= 2, "resblock_launch: shared memory too small");
     p.idesc1 = umma_idesc_f16(GEMM_BM, std::min(chp, C2 / 2), false, false);   // N = the real middle channels (32 for the 64-channel block)
     p.idesc2 = umma_idesc_f16(GEMM_BM, C2, false, false);

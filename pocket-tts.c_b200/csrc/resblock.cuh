@@ -57,7 +57,8 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
     uint8_t *ring = smem;
     uint8_t *w2s = ring + p.stages * stage_bytes;                 // [kb2][C2 rows][128 B]
     uint8_t *a2s = w2s + kb2 * C2 * 128;                           // [kb2][128 rows][128 B]
-    uint8_t *w3s = a2s + kb2 * A_BYTES;                            // [16 rows][128 B]: taps of the fused final conv as a B operand (C2 == 64)
+    uint8_t *a3s = a2s + kb2 * A_BYTES;                            // [128 rows][128 B]: the block's output tile, A operand of the fused final conv (C2 == 64)
+    uint8_t *w3s = a3s + (C2 == 64 ? A_BYTES : 0);                 // [16 rows][128 B]: taps of the fused final conv as a B operand (C2 == 64)
     uint64_t *bars = (uint64_t *)(w3s + (C2 == 64 ? 2048 : 0));   // the wider blocks sit at the two-CTAs-per-SM limit: no room, no fused conv
     uint64_t *full = bars, *empty = bars + GEMM_MAX_STAGES;
     uint64_t *w2_full = bars + 2 * GEMM_MAX_STAGES, *d1_full = w2_full + 1, *a2_full = w2_full + 2, *d2_full = w2_full + 3,
@@ -149,7 +150,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 mbar_wait(a3_full, (lt - 1) & 1);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint64_t ad = umma_desc_sw128(smem_u32(a2s)), bd = umma_desc_sw128(smem_u32(w3s));
+                    const uint64_t ad = umma_desc_sw128(smem_u32(a3s)), bd = umma_desc_sw128(smem_u32(w3s));
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base + D3_COL, ad + 2 * k, bd + 2 * k, p.idesc3, k > 0 ? 1u : 0u);
                     umma_commit(d3_full);
@@ -175,7 +176,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
             mbar_wait(a3_full, (lt - 1) & 1);
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t ad = umma_desc_sw128(smem_u32(a2s)), bd = umma_desc_sw128(smem_u32(w3s));
+                const uint64_t ad = umma_desc_sw128(smem_u32(a3s)), bd = umma_desc_sw128(smem_u32(w3s));
 #pragma unroll
                 for (int k = 0; k < GEMM_BK / 16; k++) umma_f16(tmem_base + D3_COL, ad + 2 * k, bd + 2 * k, p.idesc3, k > 0 ? 1u : 0u);
                 umma_commit(d3_full);
@@ -190,10 +191,34 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
         const int c1_lo = cg * (CH / 2), c1_hi = c1_lo + CH / 2, c2_lo = cg * (C2 / 2), c2_hi = c2_lo + C2 / 2;
         pdl_wait();
         int lt = 0;
+        const int r = quad * 32 + lane;
+        const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+        // epilogue 3 of tile `tl` (the lt3-th of this CTA): D3 -> per-row tap sums -> pcm. Runs one tile LATE (between epilogue 1 and the
+        // wait for contraction 2 of the next tile), so neither the round trip of contraction 3 nor that of contraction 2 is idle time.
+        auto epilogue3 = [&](int tl, int lt3) {
+            mbar_wait(d3_full, lt3 & 1);   // every epilogue warp: the output-tile operand buffer is free again after this
+            tc_fence_after();
+            if (cg == 0) {
+                const int b3 = tl / p.tiles_per_batch, m3 = (tl - b3 * p.tiles_per_batch) * GEMM_BM + r;
+                uint32_t y3[16];
+                tmem_ld16(trow + D3_COL, y3); tmem_ld_wait16(y3);
+                float *pb = dpart + (lt3 & 1) * 384;               // double-buffered: one barrier per tile is enough
+                pb[r * 3 + 0] = __uint_as_float(y3[0]) + __uint_as_float(y3[3]);
+                pb[r * 3 + 1] = __uint_as_float(y3[1]) + __uint_as_float(y3[4]);
+                pb[r * 3 + 2] = __uint_as_float(y3[2]) + __uint_as_float(y3[5]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 warps that hold the 128 rows
+                auto D = [&](int row, int k) { return pb[row * 3 + k]; };
+                float y = p.dbias + D(r, 2);
+                if (r >= 1) y += D(r - 1, 1);
+                if (r >= 2) y += D(r - 2, 0);
+                if (m3 < p.a_rows) p.pcm[(size_t)b3 * p.a_rows + m3] = y;
+                if (r == 127) { float *e = p.edge + (size_t)tl * 4; e[0] = D(127, 1); e[1] = D(127, 0); e[2] = D(126, 0); }
+            }
+            tc_fence_before();
+        };
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, lt++) {
             const int batch = tile / p.tiles_per_batch, m0 = (tile - batch * p.tiles_per_batch) * GEMM_BM;
-            const int r = quad * 32 + lane, m = m0 + r;
-            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+            const int m = m0 + r;
             // ---- epilogue 1: D1 -> +b1 -> ELU -> fp16 -> shared memory (A operand of contraction 2)
             mbar_wait(d1_full, lt & 1);
             tc_fence_after();
@@ -240,6 +265,7 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                 uint16_t *op = p.out ? p.out + grow * C2 + c2_lo : nullptr;
                 uint32_t u0[8], u1[8];
                 if (m_ok) { ld_global_v8u(up, u0); ld_global_v8u(up + 16, u1); }
+                if (fuse_out && lt > 0) epilogue3(tile - (int)gridDim.x, lt - 1);
                 mbar_wait(d2_full, lt & 1);
                 tc_fence_after();
                 uint32_t ra[16], rb[16];
@@ -265,14 +291,14 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                         act_pack16<ACT_ELU, true, false, false>(v, hw, lw);
                         if (op) st_global_v8(op + 16 * i, hw);
                         if (fuse_out) {   // final conv on the fp16-rounded block output (what the unfused path reads back): the tile goes
-                                          // back into the operand buffer (contraction 2 is done with it) as the A operand of contraction 3
-                            uint8_t *row = a2s + r * 128;
+                                          // into its own operand buffer as the A operand of contraction 3
+                            uint8_t *row = a3s + r * 128;
                             const int pc = c >> 3;
                             *(uint4 *)(row + ((pc ^ (r & 7)) << 4)) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
                             *(uint4 *)(row + (((pc + 1) ^ (r & 7)) << 4)) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
                         }
                     } else if (fuse_out) {   // rows past the end of the utterance: finite operand rows
-                        uint8_t *row = a2s + r * 128;
+                        uint8_t *row = a3s + r * 128;
                         const int pc = c >> 3;
                         *(uint4 *)(row + ((pc ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
                         *(uint4 *)(row + (((pc + 1) ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
@@ -292,29 +318,13 @@ resblock_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant_
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(d2_empty); mbar_arrive(a3_full); }   // D2 is drained; the tile is staged
-                    mbar_wait(d3_full, lt & 1);   // every epilogue warp: the operand buffer is free again after this
-                    tc_fence_after();
-                    if (cg == 0) {
-                        uint32_t y3[16];
-                        tmem_ld16(trow + D3_COL, y3); tmem_ld_wait16(y3);
-                        float *pb = dpart + (lt & 1) * 384;               // double-buffered: one barrier per tile is enough
-                        pb[r * 3 + 0] = __uint_as_float(y3[0]) + __uint_as_float(y3[3]);
-                        pb[r * 3 + 1] = __uint_as_float(y3[1]) + __uint_as_float(y3[4]);
-                        pb[r * 3 + 2] = __uint_as_float(y3[2]) + __uint_as_float(y3[5]);
-                        asm volatile("bar.sync 1, 128;" ::: "memory");    // the 4 warps that hold the 128 rows
-                        auto D = [&](int row, int k) { return pb[row * 3 + k]; };
-                        float y = p.dbias + D(r, 2);
-                        if (r >= 1) y += D(r - 1, 1);
-                        if (r >= 2) y += D(r - 2, 0);
-                        if (m_ok) p.pcm[grow] = y;
-                        if (r == 127) { float *e = p.edge + (size_t)tile * 4; e[0] = D(127, 1); e[1] = D(127, 0); e[2] = D(126, 0); }
-                    }
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0 && !fuse_out) mbar_arrive(d2_empty);
         }
+        if (fuse_out && lt > 0) epilogue3(blockIdx.x + (lt - 1) * (int)gridDim.x, lt - 1);   // the last tile's samples
     }
     tc_fence_before();
     __syncthreads();
