@@ -147,6 +147,11 @@ int gemm_launch(const GemmOp &op, cudaStream_t st) {
         if (op.bn == 128) return gemm_launch_t<128, 0, EPI_CONV>(op, st);
         if (op.bn == 256) return gemm_launch_t<256, 0, EPI_CONV>(op, st);
     }
+    if (op.bn == 256 && op.split == 0) {
+        if (op.epi == EPI_RESID) return gemm_launch_t<256, 0, EPI_RESID>(op, st);
+        if (op.epi == EPI_GELU) return gemm_launch_t<256, 0, EPI_GELU>(op, st);
+        if (op.epi == EPI_ROPE) return gemm_launch_t<256, 0, EPI_ROPE>(op, st);
+    }
 #define GL(BN_, SP_) if (op.bn == BN_ && op.split == SP_) return gemm_launch_t<BN_, SP_>(op, st);
     GL(32, 0) GL(64, 0) GL(128, 0) GL(256, 0)
     GL(32, 1) GL(64, 1) GL(128, 1) GL(256, 1)
@@ -264,9 +269,21 @@ static int gemm_build(GemmOp &op, const GemmDesc &d) {
               p.fast_act && (p.act == ACT_ELU || p.act == ACT_NONE) && op.split == 0 && split_k == 1 && (d.bn == 128 || d.bn == 256) &&
               d.b_rows % 64 == 0 && (p.bias_mask == 0 || (p.bias_mask + 1) % 64 == 0) && getenv("PTTS_B200_NO_EPI_CONV") == nullptr)
                  ? EPI_CONV : EPI_GENERIC;
+    // the Mimi transformer linears (fp16 operands, N tile 256, no bias): EPI_RESID / EPI_GELU / EPI_ROPE
+    if (op.epi == EPI_GENERIC && !p.transposed && !p.tma_store && op.split == 0 && split_k == 1 && d.bn == 256 && !d.bf16 && !p.bias && !p.resid_h &&
+        !p.out_raw && !p.out_l && !p.out_bf16 && p.fast_act && d.b_rows % 16 == 0 && getenv("PTTS_B200_NO_EPI_SPECIAL") == nullptr) {
+        if (p.scale && p.resid && p.out_f32 && !p.rope_q && (p.act == ACT_NONE || !p.out_h) && d.b_rows <= 512 && p.ldo % 8 == 0 &&
+            (!p.out_h || p.ldh % 16 == 0))
+            op.epi = EPI_RESID;   // the scale table takes the (unused) staging area: 2 KB are always allocated behind the barriers
+        else if (!p.scale && !p.resid && !p.out_f32 && !p.rope_q && p.out_h && p.act == ACT_GELU_TANH && p.ldh % 16 == 0)
+            op.epi = EPI_GELU;
+        else if (p.rope_q && !p.scale && !p.resid && !p.out_f32 && !p.out_h && d.b_rows == 1536)
+            op.epi = EPI_ROPE;
+    }
     op.p = p;
     op.grid = dim3((unsigned)std::min<long long>(tiles, d.num_sms), 1, 1);
     op.smem_bytes = p.stages * stage_bytes(d.bn, op.split) + 1024 + 1024 + (p.tma_store ? GEMM_EPI_WARPS * p.stage_stride : 0);
+    if (op.epi == EPI_RESID) op.smem_bytes += 2048;   // layer-scale table at stage_off
     return 0;
 }
 

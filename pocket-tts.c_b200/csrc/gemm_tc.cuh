@@ -123,7 +123,12 @@ __device__ __forceinline__ TileCoord gemm_tile(const GemmParams &p, int tile, in
 //                 pre-activation value) -> ELU or identity -> fp16, both leaving through the staging buffers as TMA tensor stores.
 //                 Straight-line code per 64-column group, accumulator chunks in two alternating register sets, shared-space stores:
 //                 the generic path spends ~320 instructions per 16-column chunk on these GEMMs, which are bound by exactly that.
-constexpr int EPI_GENERIC = 0, EPI_CONV = 1;
+//   EPI_RESID   - Mimi out-projection / second feed-forward linear (ptts_mimi.c:343-375): x = resid + layer_scale * acc in fp32
+//                 (optional fp16 copy). The residual rows are loaded one chunk ahead, the first two before the wait for the
+//                 accumulator; the layer scale comes from a shared-memory table.
+//   EPI_GELU    - first feed-forward linear: tanh-GELU -> fp16.
+//   EPI_ROPE    - fused QKV epilogue (RoPE + 1/8 on q, head-major fp16 outputs), rotation tables loaded one chunk ahead.
+constexpr int EPI_GENERIC = 0, EPI_CONV = 1, EPI_RESID = 2, EPI_GELU = 3, EPI_ROPE = 4;
 
 template <int BN, int SPLIT, int EPI = EPI_GENERIC>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -170,6 +175,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (threadIdx.x == 0) pdl_trigger();   // the next kernel may start its own prologue now
     const bool tr = p.trace != nullptr && blockIdx.x == 0;
     if (tr && threadIdx.x == 0) p.trace[0] = clock64();
+    if constexpr (EPI == EPI_RESID) {   // layer scale (a constant tensor) -> shared memory at stage_off (host: n_total <= 512, no staging)
+        float *tab = (float *)(smem + p.stage_off);
+        for (int i = threadIdx.x; i < p.n_total; i += GEMM_THREADS) tab[i] = p.scale[i];
+        __syncthreads();
+    }
 
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
@@ -272,16 +282,145 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (lane == 0) bulk_wait_read0();
                 __syncwarp();
             }
-            mbar_wait(&tfull[acc], (lt / NACC) & 1);
-            tc_fence_after();
-            if (tr && lt == 0 && warp == 2 && lane == 0) p.trace[5] = clock64();
+            // (the specialised epilogues issue their first global loads before this wait)
+            auto wait_acc = [&]() {
+                mbar_wait(&tfull[acc], (lt / NACC) & 1);
+                tc_fence_after();
+                if (tr && lt == 0 && warp == 2 && lane == 0) p.trace[5] = clock64();
+            };
             const int m = t.m0 + quad * 32 + lane;
             const bool m_ok = m < p.a_rows;
             const uint32_t trow = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
             float *out_f32 = p.out_f32 ? p.out_f32 + (size_t)t.z * p.split_stride : nullptr;
             const bool add_bias = bias != nullptr && t.z == 0;
             uint32_t r[16], rn[16];
-            if constexpr (EPI == EPI_CONV) {
+            if constexpr (EPI == EPI_RESID) {
+                constexpr int CW = BN / NCG, NCH = CW / 16;
+                static_assert(NCH % 2 == 0, "EPI_RESID: chunks are processed in pairs");
+                const int c_lo = cg * CW, nb_lo = t.n0 + c_lo;
+                const size_t grow = (size_t)t.batch * p.a_rows + m;
+                const float *rs = resid + grow * ldo + nb_lo;
+                float *of = p.out_f32 + grow * ldo + nb_lo;
+                uint16_t *oh = out_h ? out_h + grow * ldh + nb_lo : nullptr;
+                const float *tab = (const float *)(smem + p.stage_off) + nb_lo;
+                float ta[16], tb[16];
+                auto ld_res = [&](int i, float(&tt)[16]) {
+                    if (m_ok && nb_lo + 16 * i < n_total) {
+                        float a0[8], a1[8];
+                        ld_global_v8(rs + 16 * i, a0); ld_global_v8(rs + 16 * i + 8, a1);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { tt[j] = a0[j]; tt[8 + j] = a1[j]; }
+                    }
+                };
+                auto step = [&](int i, uint32_t(&acc)[16], float(&tt)[16]) {
+                    if (m_ok && nb_lo + 16 * i < n_total) {
+                        float v[16];
+                        const float4 *sp = (const float4 *)(tab + 16 * i);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const float4 ss = sp[j];
+                            v[4 * j] = fmaf(__uint_as_float(acc[4 * j]), ss.x, tt[4 * j]); v[4 * j + 1] = fmaf(__uint_as_float(acc[4 * j + 1]), ss.y, tt[4 * j + 1]);
+                            v[4 * j + 2] = fmaf(__uint_as_float(acc[4 * j + 2]), ss.z, tt[4 * j + 2]); v[4 * j + 3] = fmaf(__uint_as_float(acc[4 * j + 3]), ss.w, tt[4 * j + 3]);
+                        }
+                        if (i + 2 < NCH) ld_res(i + 2, tt);   // this register set's next chunk
+                        uint32_t w0[8], w1[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) { w0[j] = __float_as_uint(v[j]); w1[j] = __float_as_uint(v[8 + j]); }
+                        st_global_v8(of + 16 * i, w0);
+                        st_global_v8(of + 16 * i + 8, w1);
+                        if (oh) {
+                            uint32_t hw[8], lw[8];
+                            act_pack16<ACT_NONE, true, false, false>(v, hw, lw);
+                            st_global_v8(oh + 16 * i, hw);
+                        }
+                    }
+                };
+                ld_res(0, ta); ld_res(1, tb);
+                wait_acc();
+                tmem_ld16(trow + c_lo, r);
+#pragma unroll 1
+                for (int i = 0; i < NCH; i += 2) {
+                    tmem_ld_wait16(r);
+                    tmem_ld16(trow + c_lo + 16 * (i + 1), rn);
+                    step(i, r, ta);
+                    tmem_ld_wait16(rn);
+                    if (i + 2 < NCH) tmem_ld16(trow + c_lo + 16 * (i + 2), r);
+                    step(i + 1, rn, tb);
+                }
+            } else if constexpr (EPI == EPI_GELU) {
+                constexpr int CW = BN / NCG, NCH = CW / 16;
+                const int c_lo = cg * CW, nb_lo = t.n0 + c_lo;
+                uint16_t *oh = out_h + ((size_t)t.batch * p.a_rows + m) * ldh + nb_lo;
+                auto step = [&](int i, uint32_t(&acc)[16]) {
+                    if (m_ok && nb_lo + 16 * i < n_total) {
+                        float v[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) v[j] = __uint_as_float(acc[j]);
+                        uint32_t hw[8], lw[8];
+                        act_pack16<ACT_GELU_TANH, true, false, false>(v, hw, lw);
+                        st_global_v8(oh + 16 * i, hw);
+                    }
+                };
+                wait_acc();
+                tmem_ld16(trow + c_lo, r);
+#pragma unroll 1
+                for (int i = 0; i < NCH; i += 2) {
+                    tmem_ld_wait16(r);
+                    tmem_ld16(trow + c_lo + 16 * (i + 1), rn);
+                    step(i, r);
+                    tmem_ld_wait16(rn);
+                    if (i + 2 < NCH) tmem_ld16(trow + c_lo + 16 * (i + 2), r);
+                    step(i + 1, rn);
+                }
+            } else if constexpr (EPI == EPI_ROPE) {
+                constexpr int CW = BN / NCG, NCH = CW / 16;
+                const int c_lo = cg * CW, nb_lo = t.n0 + c_lo;
+                const int which = nb_lo >> 9;                       // 0 q, 1 k, 2 v: uniform per warp (CW divides 512)
+                const float sc = which == 0 ? 0.125f : 1.0f;        // 1/sqrt(64) folded into q
+                const float *cp = p.rope_cos + (size_t)(m + p.rope_pos0) * 32, *sp = p.rope_sin + (size_t)(m + p.rope_pos0) * 32;
+                uint16_t *base = (which == 0 ? p.rope_q : which == 1 ? p.rope_k : p.rope_v);
+                const size_t hrows = (size_t)(p.rope_rows ? p.rope_rows : p.a_rows);
+                float ca[8], sa[8], cb[8], sb[8];
+                auto ld_tab = [&](int i, float(&cs)[8], float(&sn)[8]) {
+                    const int d0 = (nb_lo + 16 * i) & 63;
+                    if (which < 2 && m_ok) { ld_global_v8(cp + (d0 >> 1), cs); ld_global_v8(sp + (d0 >> 1), sn); }
+                };
+                auto step = [&](int i, uint32_t(&acc)[16], float(&cs)[8], float(&sn)[8]) {
+                    const int nb = nb_lo + 16 * i, within = nb & 511, head = within >> 6, d0 = within & 63;
+                    if (m_ok && nb < n_total) {
+                        uint32_t hw[8];
+                        if (which < 2) {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const float a0 = __uint_as_float(acc[2 * j]), a1 = __uint_as_float(acc[2 * j + 1]);
+                                const __half2 h2 = __floats2half2_rn((a0 * cs[j] - a1 * sn[j]) * sc, (a0 * sn[j] + a1 * cs[j]) * sc);
+                                hw[j] = *(const uint32_t *)&h2;
+                            }
+                            if (i + 2 < NCH) ld_tab(i + 2, cs, sn);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                const __half2 h2 = __floats2half2_rn(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+                                hw[j] = *(const uint32_t *)&h2;
+                            }
+                        }
+                        st_global_v8(base + (((size_t)t.batch * 8 + head) * hrows + m + p.rope_row0) * 64 + d0, hw);
+                    }
+                };
+                ld_tab(0, ca, sa); ld_tab(1, cb, sb);
+                wait_acc();
+                tmem_ld16(trow + c_lo, r);
+#pragma unroll 1
+                for (int i = 0; i < NCH; i += 2) {
+                    tmem_ld_wait16(r);
+                    tmem_ld16(trow + c_lo + 16 * (i + 1), rn);
+                    step(i, r, ca, sa);
+                    tmem_ld_wait16(rn);
+                    if (i + 2 < NCH) tmem_ld16(trow + c_lo + 16 * (i + 2), r);
+                    step(i + 1, rn, cb, sb);
+                }
+            } else if constexpr (EPI == EPI_CONV) {
+                wait_acc();
                 constexpr int CW = BN / NCG;
                 static_assert(CW % 64 == 0, "EPI_CONV: a warp owns whole 64-column groups");
                 const int c_lo = cg * CW;
@@ -337,6 +476,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                 }
             } else if (!p.transposed) {
+                wait_acc();
                 // each warp owns a contiguous range of BN / NCG columns of its 32 rows
                 constexpr int CW = BN / NCG;
                 const int c_lo = cg * CW;
@@ -458,6 +598,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                     }
                 }
             } else {
+                wait_acc();
                 // transposed: this thread owns output FEATURE m; columns are batch rows n. Stores are
                 // coalesced across the warp (32 consecutive features per batch row).
                 if (cg * 16 < BN) { tmem_ld16(trow + cg * 16, r); tmem_ld_wait16(r); }

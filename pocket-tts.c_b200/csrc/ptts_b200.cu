@@ -57,6 +57,9 @@ static int gemm_set_attrs() {
     SA(32, 0) SA(64, 0) SA(128, 0) SA(256, 0) SA(32, 1) SA(64, 1) SA(128, 1) SA(256, 1) SA(32, 2) SA(64, 2) SA(128, 2) SA(256, 2)
     PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<128, 0, EPI_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 0, EPI_CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 0, EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 0, EPI_GELU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTTS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<256, 0, EPI_ROPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 #undef SA
     return 0;
 }
