@@ -966,6 +966,15 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     const __half2 h = __floats2half2_rn(lo, hi);
     return *(const uint32_t *)&h;
 }
+// Four 8x8 b16 matrices from shared memory (lane i supplies the address of row i % 8 of matrix i / 8): register j of lane l holds
+// M_j[l / 4][2 (l % 4) .. +1] - the B-fragment layout of mma.m16n8k16 for a [n][k] operand; .trans gives M_j[2 (l % 4) .. +1][l / 4],
+// the layout for a [k][n] operand.
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
 // Streaming form: queries are rows [t_begin, T) of buffers that hold t_stride rows per head (the K / V caches of the utterance so
 // far); out row 0 = query t_begin. One-shot form: t_begin = 0, t_stride = T.
 __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __half *k, const __half *v, int T,
@@ -1020,25 +1029,35 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
         if (more) stage(kb + 64, buf ^ 1);          // the next block lands while this one is multiplied
         if (more) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
-        const __half *sK = sKb[buf], *sV = sVb[buf];
+        // fragment addresses for ldmatrix: K rows nt*8 + (lane & 7), 8-column block lane >> 3 (+ 4 for the second half of d);
+        // V rows ks*16 + ((lane >> 3) & 1) * 8 + (lane & 7), 8-column block 2*ndp + (lane >> 4)
+        const uint32_t sK_s = smem_u32(sKb[buf]) + (uint32_t)(((lane & 7) * FA_LD + (lane >> 3) * 8) * 2);
+        const uint32_t sV_s = smem_u32(sVb[buf]) + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * FA_LD + (lane >> 4) * 8) * 2);
         float sc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
             sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.0f;
-            const __half *kr = sK + (nt * 8 + g) * FA_LD + 2 * t;
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)
-                mma_f16_16816(sc[nt], qa[ks], *(const uint32_t *)(kr + ks * 16), *(const uint32_t *)(kr + ks * 16 + 8));
+            for (int hf = 0; hf < 2; hf++) {
+                uint32_t kf[4];
+                ldsm_x4(kf, sK_s + (uint32_t)((nt * 8 * FA_LD + hf * 32) * 2));
+                mma_f16_16816(sc[nt], qa[2 * hf], kf[0], kf[1]);
+                mma_f16_16816(sc[nt], qa[2 * hf + 1], kf[2], kf[3]);
+            }
         }
+        // blocks wholly inside every query's window need no mask (block-uniform test)
+        const bool need_mask = !(kb + 63 <= q0 && q0 + 63 - kb < MI_CTX);
         float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
+            if (need_mask) {
 #pragma unroll
-            for (int e = 0; e < 4; e++) {
-                const int key = kb + nt * 8 + 2 * t + (e & 1);
-                const int tq = e < 2 ? tq0 : tq1;
-                const bool ok = key <= tq && tq - key < MI_CTX;
-                if (!ok) sc[nt][e] = -INFINITY;
+                for (int e = 0; e < 4; e++) {
+                    const int key = kb + nt * 8 + 2 * t + (e & 1);
+                    const int tq = e < 2 ? tq0 : tq1;
+                    const bool ok = key <= tq && tq - key < MI_CTX;
+                    if (!ok) sc[nt][e] = -INFINITY;
+                }
             }
             bm0 = fmaxf(bm0, fmaxf(sc[nt][0], sc[nt][1]));
             bm1 = fmaxf(bm1, fmaxf(sc[nt][2], sc[nt][3]));
@@ -1067,12 +1086,12 @@ __global__ void __launch_bounds__(128) k_mimi_win_attn(const __half *q, const __
             pa[1] = pack_h2(sc[2 * ks][2], sc[2 * ks][3]);
             pa[2] = pack_h2(sc[2 * ks + 1][0], sc[2 * ks + 1][1]);
             pa[3] = pack_h2(sc[2 * ks + 1][2], sc[2 * ks + 1][3]);
-            const __half *v0 = sV + (ks * 16 + 2 * t) * FA_LD + g, *v1 = v0 + 8 * FA_LD;
 #pragma unroll
-            for (int nd = 0; nd < 8; nd++) {
-                const uint32_t b0 = (uint32_t)__half_as_ushort(v0[nd * 8]) | ((uint32_t)__half_as_ushort(v0[FA_LD + nd * 8]) << 16);
-                const uint32_t b1 = (uint32_t)__half_as_ushort(v1[nd * 8]) | ((uint32_t)__half_as_ushort(v1[FA_LD + nd * 8]) << 16);
-                mma_f16_16816(o[nd], pa, b0, b1);
+            for (int ndp = 0; ndp < 4; ndp++) {
+                uint32_t vf[4];
+                ldsm_x4_t(vf, sV_s + (uint32_t)((ks * 16 * FA_LD + ndp * 16) * 2));
+                mma_f16_16816(o[2 * ndp], pa, vf[0], vf[1]);
+                mma_f16_16816(o[2 * ndp + 1], pa, vf[2], vf[3]);
             }
         }
         __syncthreads();   // all warps are done with this buffer before the stage of the next iteration overwrites it
@@ -1183,16 +1202,21 @@ __global__ void __launch_bounds__(128) k_pf_attn_tc(const PrefillAttnParams p, c
         }
         __syncthreads();
         if (!warp_live) continue;   // padding rows only: nothing to compute (the barriers above are still reached)
+        // ldmatrix fragment addresses (see k_mimi_win_attn)
+        const uint32_t sK_s = smem_u32(sK) + (uint32_t)(((lane & 7) * FA_LD + (lane >> 3) * 8) * 2);
+        const uint32_t sV_s = smem_u32(sV) + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * FA_LD + (lane >> 4) * 8) * 2);
         float sc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
             sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.0f;
-            const __half *kr = sK + (nt * 8 + g) * FA_LD + 2 * t;
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++) {
-                const uint32_t b0 = *(const uint32_t *)(kr + ks * 16), b1 = *(const uint32_t *)(kr + ks * 16 + 8);
-                mma_f16_16816(sc[nt], qh[ks], b0, b1);
-                mma_f16_16816(sc[nt], ql[ks], b0, b1);
+            for (int hf = 0; hf < 2; hf++) {
+                uint32_t kf[4];
+                ldsm_x4(kf, sK_s + (uint32_t)((nt * 8 * FA_LD + hf * 32) * 2));
+                mma_f16_16816(sc[nt], qh[2 * hf], kf[0], kf[1]);
+                mma_f16_16816(sc[nt], ql[2 * hf], kf[0], kf[1]);
+                mma_f16_16816(sc[nt], qh[2 * hf + 1], kf[2], kf[3]);
+                mma_f16_16816(sc[nt], ql[2 * hf + 1], kf[2], kf[3]);
             }
         }
         float bm0 = -INFINITY, bm1 = -INFINITY;
@@ -1229,13 +1253,14 @@ __global__ void __launch_bounds__(128) k_pf_attn_tc(const PrefillAttnParams p, c
             split_h2(sc[2 * ks][2], sc[2 * ks][3], ph[1], pl[1]);
             split_h2(sc[2 * ks + 1][0], sc[2 * ks + 1][1], ph[2], pl[2]);
             split_h2(sc[2 * ks + 1][2], sc[2 * ks + 1][3], ph[3], pl[3]);
-            const __half *v0 = sV + (ks * 16 + 2 * t) * FA_LD + g, *v1 = v0 + 8 * FA_LD;
 #pragma unroll
-            for (int nd = 0; nd < 8; nd++) {
-                const uint32_t b0 = (uint32_t)__half_as_ushort(v0[nd * 8]) | ((uint32_t)__half_as_ushort(v0[FA_LD + nd * 8]) << 16);
-                const uint32_t b1 = (uint32_t)__half_as_ushort(v1[nd * 8]) | ((uint32_t)__half_as_ushort(v1[FA_LD + nd * 8]) << 16);
-                mma_f16_16816(o[nd], ph, b0, b1);
-                mma_f16_16816(o[nd], pl, b0, b1);
+            for (int ndp = 0; ndp < 4; ndp++) {
+                uint32_t vf[4];
+                ldsm_x4_t(vf, sV_s + (uint32_t)((ks * 16 * FA_LD + ndp * 16) * 2));
+                mma_f16_16816(o[2 * ndp], ph, vf[0], vf[1]);
+                mma_f16_16816(o[2 * ndp], pl, vf[0], vf[1]);
+                mma_f16_16816(o[2 * ndp + 1], ph, vf[2], vf[3]);
+                mma_f16_16816(o[2 * ndp + 1], pl, vf[2], vf[3]);
             }
         }
     }
