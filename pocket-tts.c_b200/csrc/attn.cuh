@@ -284,12 +284,17 @@ __device__ __forceinline__ void a6_issue(const A6Stream &S, int c, uint8_t *ring
 
 // (arguments by value: a reference to a struct built from kernel parameters would force that struct into local memory, and every field
 // access of the callee into an L1-cold local load)
-struct A6Out { uint16_t *out_h, *out_l; float *out_f32; const float *pk_far, *pv_far; };
+struct A6Out { uint16_t *out_h, *out_l; const float *pk_far, *pv_far; };
 __device__ __noinline__ void a6_own_stream(const A6Out p, const A6Stream S, int h, int b0, int u_first, int cond_len, int n_tile,
                                            uint8_t *sm, uint8_t *ring, uint64_t *bars, int lane, unsigned long long *tm) {
     const int k4 = lane >> 3, l8 = lane & 7, n_far = cond_len - n_tile;
+#ifdef PTTS_MEGA_ATTN_STAMPS   // per-stage cycle stamps of CTA 0 / warp 2 (tools/mega_trace.py prints them): a build option, not a run-time one
     long long c0 = tm ? clock64() : 0;
 #define A6_STAMP(i) if (tm) { const long long c1 = clock64(); if (lane == 0) tm[i] += (unsigned long long)(c1 - c0); c0 = c1; }
+#else
+    (void)tm;
+#define A6_STAMP(i)
+#endif
     A6Acc st;
     float q8[8];
     int c = 0;
@@ -360,11 +365,7 @@ __device__ __noinline__ void a6_own_stream(const A6Out p, const A6Stream S, int 
 #pragma unroll
             for (int d = 0; d < 8; d++) out[d] *= inv;
             const size_t oi = (size_t)(b0 + u) * FL_D + h * FL_HD + l8 * 8;
-            if (p.out_f32) {
-                *(float4 *)(p.out_f32 + oi) = make_float4(out[0], out[1], out[2], out[3]);
-                *(float4 *)(p.out_f32 + oi + 4) = make_float4(out[4], out[5], out[6], out[7]);
-            }
-            if (p.out_h) {
+            {   // bf16 hi + lo pair (the only output form of the persistent kernel)
                 uint4 hv, lv;
                 uint32_t *hp = (uint32_t *)&hv, *lw = (uint32_t *)&lv;
 #pragma unroll
@@ -375,11 +376,13 @@ __device__ __noinline__ void a6_own_stream(const A6Out p, const A6Stream S, int 
                     lw[d] = (uint32_t)l0 | ((uint32_t)l1 << 16);
                 }
                 *(uint4 *)(p.out_h + oi) = hv;
-                if (p.out_l) *(uint4 *)(p.out_l + oi) = lv;
+                *(uint4 *)(p.out_l + oi) = lv;
             }
         }
         A6_STAMP(4)
+#ifdef PTTS_MEGA_ATTN_STAMPS
         if (tm && lane == 0) tm[5] += 1;
+#endif
     }
 #undef A6_STAMP
 }
@@ -403,7 +406,12 @@ __device__ __forceinline__ void attn6_units(int B, int &u0, int &u1) {
 // (L2 prefetches of the rows - cp.async.bulk.prefetch.L2 at the start of the phase, or from the idle warps of the preceding GEMM
 // phases - were measured and lose: issuing them costs more than they save, profiles/r02_attention_experiments.txt.)
 __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, int cond_len, const int *ob_cache, uint8_t *sm, int tid,
-                                            unsigned long long *tmw = nullptr) {
+                                            unsigned long long *tmw_ = nullptr) {
+#ifdef PTTS_MEGA_ATTN_STAMPS
+    unsigned long long *const tmw = tmw_;
+#else
+    constexpr unsigned long long *tmw = nullptr; (void)tmw_;
+#endif
     const int w = tid >> 5, lane = tid & 31;
     uint8_t *ring = sm + A6_RING_A + w * A6_SLOT_BYTES;   // slot 0; slot 1 is the same offset inside ring B
     uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
@@ -480,7 +488,7 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
             }
             __syncwarp();
             if (S.n_old0 >= 0) {
-                const A6Out o = {p.out_h, p.out_l, p.out_f32, p.pk ? p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD : nullptr,
+                const A6Out o = {p.out_h, p.out_l, p.pk ? p.pk + ((size_t)h * p.pstride + n_tile) * FL_HD : nullptr,
                                  p.pv ? p.pv + ((size_t)h * p.pstride + n_tile) * FL_HD : nullptr};
                 a6_own_stream(o, S, h, b0, w, cond_len, n_tile, sm, ring, bars, lane, (tmw && w == 2) ? tmw : nullptr);
             }

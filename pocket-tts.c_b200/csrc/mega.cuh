@@ -60,11 +60,11 @@ __device__ __forceinline__ TileCoord mega_tile(const MegaGemmParams &p, int tile
     int r = tile / p.n_tiles;
     const int mt = r % p.m_tiles_total;
     t.z = r / p.m_tiles_total;
-    t.batch = mt / p.m_tiles_per_batch;
-    t.m0 = (mt - t.batch * p.m_tiles_per_batch) * GEMM_BM;
+    t.batch = 0;                       // mega_build only admits plain linears: one batch, one tap
+    t.m0 = mt * GEMM_BM;
     t.n0 = nt * BN;
     t.it0 = t.z * p.iters_per_split;
-    t.it1 = min(p.taps * p.kblocks_per_tap, t.it0 + p.iters_per_split);
+    t.it1 = min(p.kblocks_per_tap, t.it0 + p.iters_per_split);
     return t;
 }
 // Table capacities of the kernel parameter space (32 KB in all): lsd_steps <= 6 (the flow-head contractions and row programs of the
@@ -102,7 +102,6 @@ struct MegaProgram {
     unsigned int *bar;              // grid barrier counter, zeroed by the host before the launch
     int *done_count;                // utterances that reached their stop point, zeroed by the host
     int n_live, nsteps, first_gemm;
-    int flags;                      // experiment bits: 2 = light grid barrier
     int wrap_prefetch;              // 1: the last contraction of a frame may fetch weights of the next frame's first one
                                     // (only when the loop cannot stop early, i.e. EOS detection is off)
     unsigned long long *prof;       // optional [MP_COUNT][2]: ns and phase count per type (written by CTA 0)
@@ -136,27 +135,16 @@ __device__ __forceinline__ float group_sum(float v, float *red, int tid, int bar
 // Grid-wide barrier: every CTA arrives once on a monotonic counter; `epoch` is the value the counter
 // reaches when all CTAs have arrived. Global writes made before the barrier by any thread of any CTA
 // are visible after it to generic loads and to TMA (async proxy) loads.
-__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch, bool light = false, int bar_tid = 0) {
-    if (!light) asm volatile("fence.proxy.async.global;" ::: "memory");
+__device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch, int bar_tid = 0) {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
     epoch += gridDim.x;
     if ((int)threadIdx.x == bar_tid) {   // this thread's fence waits for ITS outstanding loads too: pick one that has none in flight
-        if (light) {
-            asm volatile("fence.proxy.async.global;" ::: "memory");
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
-        } else {
-            __threadfence();
-            atomicAdd(bar, 1u);
-        }
-        if (ld_acquire_u32(bar) < epoch) {
-            const long long t0 = clock64();
-            uint32_t spins = 0;
-            while (ld_acquire_u32(bar) < epoch) {
-                if ((++spins & 255u) == 0 && clock64() - t0 > 4000000000LL) {
-                    printf("ptts_b200: grid barrier timed out (block %d, epoch %u, counter %u)\n", blockIdx.x, epoch, ld_acquire_u32(bar));
-                    __trap();
-                }
-            }
+        __threadfence();
+        atomicAdd(bar, 1u);
+        uint32_t spins = 0;   // bounded: an L2 acquire load takes ~0.5 us, 2^23 of them several seconds
+        while (ld_acquire_u32(bar) < epoch) {
+            if (++spins == (1u << 23)) __trap();
         }
         __threadfence();
     }
@@ -229,10 +217,9 @@ __device__ __forceinline__ void row_ln_store(const RowNormParams &p, size_t row,
     if (p.out_h) {
         const uint2 hi = pack4_bf16(y);
         *(uint2 *)(p.out_h + row * p.D + i) = hi;
-        if (p.out_l) {
-            const float lo[4] = {y[0] - bf16lo(hi.x), y[1] - bf16hi(hi.x), y[2] - bf16lo(hi.y), y[3] - bf16hi(hi.y)};
-            *(uint2 *)(p.out_l + row * p.D + i) = pack4_bf16(lo);
-        }
+        // (the persistent kernel only runs with hi + lo activation pairs: out_l is always set with out_h)
+        const float lo[4] = {y[0] - bf16lo(hi.x), y[1] - bf16hi(hi.x), y[2] - bf16lo(hi.y), y[3] - bf16hi(hi.y)};
+        *(uint2 *)(p.out_l + row * p.D + i) = pack4_bf16(lo);
     }
 }
 
@@ -346,7 +333,7 @@ struct MegaPipe {
 };
 
 __device__ __forceinline__ uint32_t mg_stage_bytes(const MegaGemm &g) {
-    return (uint32_t)(MG_A_BYTES * (g.split == 1 ? 2 : 1) + g.bn * GEMM_BK * 2);
+    return (uint32_t)(MG_A_BYTES * 2 + g.bn * GEMM_BK * 2);   // A hi + A lo + B
 }
 
 __device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *next, MegaPipe &pipe, uint8_t *ring, uint64_t *full,
@@ -354,7 +341,6 @@ __device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *nex
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const MegaGemmParams &p = g.p;
     const int BN = g.bn;
-    const bool lo = g.split == 1;
     if (warp == 0) {
         // ------------------------------------------------ TMA producer
         if (lane == 0) {
@@ -370,7 +356,7 @@ __device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *nex
                         mbar_expect_tx(&full[pipe.s], sb);
                     }
                     tma_load_3d(st, &g.mapA, &full[pipe.s], it * GEMM_BK, t.m0, 0);
-                    if (lo) tma_load_3d(st + MG_A_BYTES, &g.mapAlo, &full[pipe.s], it * GEMM_BK, t.m0, 0);
+                    tma_load_3d(st + MG_A_BYTES, &g.mapAlo, &full[pipe.s], it * GEMM_BK, t.m0, 0);
                     if (n >= pipe.pre) tma_load_3d(st + 2 * MG_A_BYTES, &g.mapB, &full[pipe.s], it * GEMM_BK, t.n0, 0);
                     if (++pipe.s == MG_STAGES) { pipe.s = 0; pipe.ph ^= 1; }
                 }
@@ -409,7 +395,7 @@ __device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *nex
 #pragma unroll
                     for (int k = 0; k < GEMM_BK / 16; k++) {
                         umma_f16(d_tmem, ad + 2 * k, bd + 2 * k, p.idesc, (it > t.it0 || k > 0) ? 1u : 0u);
-                        if (lo) umma_f16(d_tmem, ald + 2 * k, bd + 2 * k, p.idesc, 1u);
+                        umma_f16(d_tmem, ald + 2 * k, bd + 2 * k, p.idesc, 1u);
                     }
                     umma_commit(&empty[pipe.s]);
                     if (it == t.it1 - 1) umma_commit(&tfull[acc]);
@@ -435,7 +421,7 @@ __device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *nex
             const uint32_t trow = tmem_base + acc * MG_MAX_BN + ((uint32_t)(quad * 32) << 16);
             float *of = p.out_f32 ? p.out_f32 + (size_t)t.z * p.split_stride + (size_t)m * ldo : nullptr;
             uint16_t *oh = out_h ? out_h + (size_t)m * ldh : nullptr;
-            uint16_t *ol = out_l ? out_l + (size_t)m * ldh : nullptr;
+            uint16_t *ol = out_l + (size_t)m * ldh;   // set whenever out_h is (hi + lo pairs only)
             const bool add_bias = bias != nullptr && t.z == 0;
             uint32_t r[16];
 #pragma unroll 1
@@ -461,9 +447,9 @@ __device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *nex
                     }
                     if (oh) {
                         uint32_t hw[8], lw[8];
-                        act_pack16_dispatch(act, false, true, ol != nullptr, v, hw, lw);
+                        act_pack16_dispatch(act, false, true, true, v, hw, lw);
                         st_global_v8(oh + nb, hw);
-                        if (ol) st_global_v8(ol + nb, lw);
+                        st_global_v8(ol + nb, lw);
                     }
                 }
             }
@@ -551,8 +537,9 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
         const int step = step0 + si;
         for (int pi = 0; pi < P.n_phases; pi++) {
             const MegaPhase ph = P.phases[pi];
-            unsigned long long t0 = 0;
-            if (prof) t0 = globaltimer_ns();
+            // phase start stamp of the profiling thread: parked in shared memory, not in two registers that would stay live (for
+            // every thread) across the whole phase
+            if (prof) *(volatile unsigned long long *)(sbase + 112) = globaltimer_ns();
             switch (ph.type) {
                 case MP_GEMM: {
                     // a fetch that wraps into the next frame must be consumed: never past the end of the launch
@@ -611,11 +598,11 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                     break;
                 default: break;
             }
-            unsigned long long t1 = 0;
-            if (prof && P.trace) t1 = globaltimer_ns();
-            grid_sync(P.bar, epoch, (P.flags & 2) != 0);
+            if (prof && P.trace) *(volatile unsigned long long *)(sbase + 120) = globaltimer_ns();
+            grid_sync(P.bar, epoch);
             if (prof) {
-                const unsigned long long t2 = globaltimer_ns();
+                const unsigned long long t2 = globaltimer_ns(), t0 = *(volatile unsigned long long *)(sbase + 112),
+                                         t1 = *(volatile unsigned long long *)(sbase + 120);
                 P.prof[2 * ph.type] += t2 - t0;
                 P.prof[2 * ph.type + 1] += 1;
                 if (P.trace) { P.trace[2 * pi] += t1 - t0; P.trace[2 * pi + 1] += t2 - t0; }
@@ -666,6 +653,8 @@ static AttnDecodeParams make_attn_params(Engine *e, int layer, bool out16, int q
 }
 
 // Returns 0 (M.fits tells whether the program can run as k_flow_mega) or -1 on error.
+// precise == 0 (single bf16 activations) is not a program of this kernel: M.fits = false and the caller takes the multi-kernel path
+// (the kernel carries one operand form only - every variant it does not have to hold is register-allocation headroom).
 static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd, int precise) {
     M = MegaHost();
     std::vector<RowNormParams> rows;
@@ -762,7 +751,7 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
                "attention score buffers of %zu bytes exceed the persistent kernel's shared memory (sequence too long)",
                attn6_smem_bytes(pcap));
     M.gen = e->gen; M.B = B; M.lsd = lsd; M.precise = precise;
-    M.fits = np <= MG_PHASES_C && (int)rows.size() <= MG_ROWS_C && (int)gm.size() <= MG_GEMMS_C;
+    M.fits = precise != 0 && np <= MG_PHASES_C && (int)rows.size() <= MG_ROWS_C && (int)gm.size() <= MG_GEMMS_C;
     if (!M.fits) return 0;
     MegaProgram &P = M.prog;
     for (int i = 0; i < np; i++) P.phases[i] = ph[i];

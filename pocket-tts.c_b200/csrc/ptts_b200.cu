@@ -203,7 +203,6 @@ static int run_mega(Engine *e, int B, int lsd, int precise, int nsteps) {
     P.done_count = (int *)(e->mega_ctl + 1);
     P.prof = e->prof.on ? e->mega_ctl + 8 : nullptr;
     P.nsteps = nsteps; P.n_live = e->st_n; P.wrap_prefetch = e->st_eos ? 0 : 1;
-    { const char *fl = getenv("PTTS_B200_MEGA_FLAGS"); P.flags = fl ? atoi(fl) : 0; }
     const bool want_trace = e->prof.on && getenv("PTTS_B200_MEGA_TRACE") != nullptr;
     unsigned long long *d_trace = nullptr;
     if (want_trace) {
