@@ -175,8 +175,8 @@ __device__ __forceinline__ void a6_prefix_slice(uint8_t *sm, int mt, int ke, int
         // key key0 is valid, so both maxima are finite
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
-            s[nt][0] = expf(s[nt][0] - m0); s[nt][1] = expf(s[nt][1] - m0);
-            s[nt][2] = expf(s[nt][2] - m1); s[nt][3] = expf(s[nt][3] - m1);
+            s[nt][0] = __expf(s[nt][0] - m0); s[nt][1] = __expf(s[nt][1] - m0);
+            s[nt][2] = __expf(s[nt][2] - m1); s[nt][3] = __expf(s[nt][3] - m1);
             l0 += s[nt][0] + s[nt][1];
             l1 += s[nt][2] + s[nt][3];
         }
@@ -230,14 +230,14 @@ __device__ __forceinline__ void a6_fold(A6Acc &st, const float (&q8)[8], const f
     cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 8));
     cm = fmaxf(cm, __shfl_xor_sync(0xffffffffu, cm, 16));
     const float mn = fmaxf(st.m, cm);               // finite whenever nvalid >= 1 (row 0 belongs to some lane group)
-    const float f = expf(st.m - mn);                // exp(-inf) = 0 on the first block
+    const float f = __expf(st.m - mn);                // exp(-inf) = 0 on the first block
     st.l *= f;
 #pragma unroll
     for (int d = 0; d < 8; d++) st.acc[d] *= f;
 #pragma unroll
     for (int it = 0; it < NIT; it++) {
         const bool ok = it * 4 + k4 < nvalid;
-        const float pw = ok ? expf(sc[it] - mn) : 0.0f;
+        const float pw = ok ? __expf(sc[it] - mn) : 0.0f;
         st.l += pw;
 #pragma unroll
         for (int d = 0; d < 8; d++) st.acc[d] += pw * (ok ? vf[it][d] : 0.0f);   // stale shared memory beyond nvalid may hold NaN patterns
@@ -347,21 +347,21 @@ __device__ __noinline__ void a6_own_stream(const A6Out p, const A6Stream S, int 
 #pragma unroll
                 for (int e = 0; e < A6_SLICES; e++) m = fmaxf(m, pml[2 * e]);
             }
-            const float wb = expf(st.m - m);
+            const float wb = __expf(st.m - m);
             float den = st.l * wb, out[8];
 #pragma unroll
             for (int d = 0; d < 8; d++) out[d] = st.acc[d] * wb;
             if (n_tile > 0) {
 #pragma unroll
                 for (int e = 0; e < A6_SLICES; e++) {
-                    const float we = expf(pml[2 * e] - m);   // exp(-inf) = 0 for slices past the end of the prefix
+                    const float we = __expf(pml[2 * e] - m);   // exp(-inf) = 0 for slices past the end of the prefix
                     den += pml[2 * e + 1] * we;
                     const float4 pa = *(const float4 *)(po + e * FL_HD), pb = *(const float4 *)(po + e * FL_HD + 4);
                     out[0] += pa.x * we; out[1] += pa.y * we; out[2] += pa.z * we; out[3] += pa.w * we;
                     out[4] += pb.x * we; out[5] += pb.y * we; out[6] += pb.z * we; out[7] += pb.w * we;
                 }
             }
-            const float inv = 1.0f / den;
+            const float inv = __fdividef(1.0f, den);
 #pragma unroll
             for (int d = 0; d < 8; d++) out[d] *= inv;
             const size_t oi = (size_t)(b0 + u) * FL_D + h * FL_HD + l8 * 8;

@@ -195,12 +195,15 @@ __device__ __forceinline__ void row_ln_store(const RowNormParams &p, size_t row,
         if (p.b) b4 = *(const float4 *)(p.b + i);
         if (p.scale) { sc4 = *(const float4 *)(p.scale + row * p.ldmod + i); sh4 = *(const float4 *)(p.shift + row * p.ldmod + i); }
     }
-    const float mean = group_sum(on ? v[0] + v[1] + v[2] + v[3] : 0.0f, red, tid, bar_id) / (float)p.D;
+    // (fast division / rsqrt / exp intrinsics throughout the persistent kernel: 1-2 ulp, far inside the bf16 hi + lo operand rounding,
+    // and none of the IEEE slow paths that cost instructions and registers)
+    const float inv_d = __fdividef(1.0f, (float)p.D);
+    const float mean = group_sum(on ? v[0] + v[1] + v[2] + v[3] : 0.0f, red, tid, bar_id) * inv_d;
     float q = 0.0f;
 #pragma unroll
     for (int j = 0; j < 4; j++) { const float d = v[j] - mean; q += d * d; }
-    const float var = group_sum(on ? q : 0.0f, red, tid, bar_id) / (float)p.D;
-    const float inv = 1.0f / sqrtf(var + p.eps);
+    const float var = group_sum(on ? q : 0.0f, red, tid, bar_id) * inv_d;
+    const float inv = rsqrtf(var + p.eps);
     y[0] = y[1] = y[2] = y[3] = 0.0f;
     if (!on) return;
     const float ww[4] = {w4.x, w4.y, w4.z, w4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {sc4.x, sc4.y, sc4.z, sc4.w},
@@ -276,7 +279,7 @@ __device__ __forceinline__ void mega_flow_update(const MegaProgram &P, int b, in
         const bool valid = step < st.max_frames[b] && !st.done[b];
         float f = 0.0f;
         for (int z = 0; z < P.flow_nsplit; z++) f += P.flow[z * P.flow_stride + (size_t)b * FL_LAT + tid];
-        const float v = st.latent[b * FL_LAT + tid] + f / (float)st.lsd_steps;
+        const float v = st.latent[b * FL_LAT + tid] + __fdividef(f, (float)st.lsd_steps);
         st.latent[b * FL_LAT + tid] = v;
         lat[tid] = v;
         if (valid) {
@@ -447,7 +450,9 @@ __device__ __forceinline__ void mega_gemm(const MegaGemm &g, const MegaGemm *nex
                     }
                     if (oh) {
                         uint32_t hw[8], lw[8];
-                        act_pack16_dispatch(act, false, true, true, v, hw, lw);
+                        if (act == ACT_GELU_ERF) act_pack16<ACT_GELU_ERF, false, true, true>(v, hw, lw);
+                        else if (act == ACT_SILU) act_pack16<ACT_SILU, true, true, true>(v, hw, lw);   // __expf / __fdividef
+                        else act_pack16<ACT_NONE, false, true, true>(v, hw, lw);
                         st_global_v8(oh + nb, hw);
                         st_global_v8(ol + nb, lw);
                     }
