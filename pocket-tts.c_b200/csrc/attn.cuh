@@ -370,10 +370,10 @@ __device__ __noinline__ void a6_own_stream(const A6Out p, const A6Stream S, int 
                 uint32_t *hp = (uint32_t *)&hv, *lw = (uint32_t *)&lv;
 #pragma unroll
                 for (int d = 0; d < 4; d++) {
-                    const uint16_t h0 = f2h16(out[2 * d], true), h1 = f2h16(out[2 * d + 1], true);
-                    hp[d] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                    const uint16_t l0 = f2h16(out[2 * d] - h162f(h0, true), true), l1 = f2h16(out[2 * d + 1] - h162f(h1, true), true);
-                    lw[d] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                    const __nv_bfloat162 hb = __floats2bfloat162_rn(out[2 * d], out[2 * d + 1]);
+                    hp[d] = *(const uint32_t *)&hb;
+                    const __nv_bfloat162 lb = __floats2bfloat162_rn(out[2 * d] - __low2float(hb), out[2 * d + 1] - __high2float(hb));
+                    lw[d] = *(const uint32_t *)&lb;
                 }
                 *(uint4 *)(p.out_h + oi) = hv;
                 *(uint4 *)(p.out_l + oi) = lv;
@@ -405,7 +405,7 @@ __device__ __forceinline__ void attn6_units(int B, int &u0, int &u1) {
 // ob_cache: own_base of this CTA's units [u0, u1) in shared memory (or NULL: read p.own_base), cond_len: the prefix length of the launch.
 // (L2 prefetches of the rows - cp.async.bulk.prefetch.L2 at the start of the phase, or from the idle warps of the preceding GEMM
 // phases - were measured and lose: issuing them costs more than they save, profiles/r02_attention_experiments.txt.)
-__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, int cond_len, const int *ob_cache, uint8_t *sm, int tid,
+__device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, int step, int cond_len, const int *ob_cache, const int *units, uint8_t *sm, int tid,
                                             unsigned long long *tmw_ = nullptr) {
 #ifdef PTTS_MEGA_ATTN_STAMPS
     unsigned long long *const tmw = tmw_;
@@ -416,11 +416,11 @@ __device__ __forceinline__ void attn6_phase(const AttnDecodeParams &p, int B, in
     uint8_t *ring = sm + A6_RING_A + w * A6_SLOT_BYTES;   // slot 0; slot 1 is the same offset inside ring B
     uint64_t *bars = (uint64_t *)(sm + A6_BARS) + w * A6_SLOTS;
     const int n_tile = min(cond_len, A6_TILE);
-    int u0, u1;
-    attn6_units(B, u0, u1);
+    const int u0 = units[0], u1 = units[1];   // launch constants, computed once by the kernel prologue (two 64-bit divisions)
     const long long t_entry = (tmw && w == 2) ? clock64() : 0;
-    for (int ua = u0; ua < u1;) {
-        const int h = ua / B, ub = min(u1, (h + 1) * B);   // sub-range of one head
+    int h = units[2];                         // head of unit u0; a CTA that crosses into the next head continues at its first unit
+    for (int ua = u0; ua < u1; h++) {
+        const int ub = min(u1, (h + 1) * B);   // sub-range of one head
         for (int c0 = ua; c0 < ub; c0 += A6_CHUNK) {
             const int nu = min(A6_CHUNK, ub - c0), b0 = c0 - h * B;
             __syncthreads();   // the previous chunk (or the previous phase's use of the ring memory) is over for every warp

@@ -44,6 +44,7 @@ struct MegaPhase {
 struct MegaGemmParams {
     int m_tiles_per_batch, m_tiles_total, n_tiles, iters_per_split, total_tiles, taps, kblocks_per_tap, a_rows, n_total, act, ldo, ldh, split_k;
     uint32_t idesc;
+    uint32_t n_magic, m_magic;   // ceil(2^32 / n_tiles), ceil(2^32 / m_tiles_total): x / d = umulhi(x, magic) for x * d < 2^32
     const float *bias;
     float *out_f32;
     size_t split_stride;
@@ -56,10 +57,10 @@ struct MegaGemm {
 };
 __device__ __forceinline__ TileCoord mega_tile(const MegaGemmParams &p, int tile, int BN) {   // gemm_tile() on the compact record
     TileCoord t;
-    const int nt = tile % p.n_tiles;
-    int r = tile / p.n_tiles;
-    const int mt = r % p.m_tiles_total;
-    t.z = r / p.m_tiles_total;
+    // (divisor 1 has no 32-bit reciprocal: magic == 0 marks it)
+    const int r = p.n_magic ? (int)__umulhi((uint32_t)tile, p.n_magic) : tile, nt = tile - r * p.n_tiles;
+    t.z = p.m_magic ? (int)__umulhi((uint32_t)r, p.m_magic) : r;
+    const int mt = r - t.z * p.m_tiles_total;
     t.batch = 0;                       // mega_build only admits plain linears: one batch, one tap
     t.m0 = mt * GEMM_BM;
     t.n0 = nt * BN;
@@ -178,9 +179,10 @@ __device__ __forceinline__ void row_load_fold(const RowNormParams &p, size_t row
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 __device__ __forceinline__ uint2 pack4_bf16(const float (&o)[4]) {
-    uint2 r;
-    r.x = (uint32_t)f2h16(o[0], true) | ((uint32_t)f2h16(o[1], true) << 16);
-    r.y = (uint32_t)f2h16(o[2], true) | ((uint32_t)f2h16(o[3], true) << 16);
+    uint2 r;   // one packed conversion per pair
+    const __nv_bfloat162 a = __floats2bfloat162_rn(o[0], o[1]), b = __floats2bfloat162_rn(o[2], o[3]);
+    r.x = *(const uint32_t *)&a;
+    r.y = *(const uint32_t *)&b;
     return r;
 }
 // LayerNorm (+ adaLN) of the row held in v (ptts_flowlm.c:159-181, 735-737); y returns the outputs.
@@ -513,14 +515,16 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
     // cached in shared memory - every grid barrier leaves the L1 cold, and a phase must not start with dependent L2 round trips
     const int cond_len0 = P.ctrl->cond_len;
     int *ob_cache = nullptr;
+    int *a_units = (int *)(sbase + 100);   // this CTA's unit range of the attention phases and the head of its first unit
     {
         int au0, au1;
         attn6_units(P.B, au0, au1);
+        if (tid == 0) { a_units[0] = au0; a_units[1] = au1; a_units[2] = au0 / P.B; }
         if (au1 - au0 <= 64 && au1 > au0 && au0 / P.B == (au1 - 1) / P.B) {
             ob_cache = (int *)(sbase + 768);
             if (tid < au1 - au0) ob_cache[tid] = P.attn[0].own_base[au0 - (au0 / P.B) * P.B + tid];
-            __syncthreads();
         }
+        __syncthreads();
     }
 
     // the first contraction's weight tiles can be requested right away
@@ -566,7 +570,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                     break;
                 }
                 case MP_ROW:
-                    if (tid < 512) {
+                    {   // (all MG_THREADS = 512 threads: two row groups of 256)
                         const RowNormParams &rp = P.rows[ph.idx];
                         for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
                             float v[4], y[4];
@@ -576,14 +580,12 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                     }
                     break;
                 case MP_HEAD:
-                    if (tid < 512)
                         for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
                             mega_head(P, b, gt, step, red, lat, 1 + grp);
                             group_bar(1 + grp);   // lat[] reusable
                         }
                     break;
                 case MP_MID:
-                    if (tid < 512)
                         for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
                             mega_flow_update(P, b, gt, step, ph.idx, lat);
                             group_bar(1 + grp);
@@ -592,14 +594,13 @@ __global__ void __launch_bounds__(MG_THREADS, 1) k_flow_mega(const __grid_consta
                         }
                     break;
                 case MP_TAIL:
-                    if (tid < 512)
                         for (int b = (int)blockIdx.x + grp * (int)gridDim.x; b < P.B; b += 2 * (int)gridDim.x) {
                             mega_tail(P, b, gt, step, red, lat, 1 + grp);
                             group_bar(1 + grp);
                         }
                     break;
                 case MP_ATTN:
-                    attn6_phase(P.attn[ph.idx], P.B, step, cond_len0, ob_cache, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
+                    attn6_phase(P.attn[ph.idx], P.B, step, cond_len0, ob_cache, a_units, ring, tid, (P.trace && blockIdx.x == 0) ? P.trace + 2 * P.n_phases : nullptr);
                     break;
                 default: break;
             }
@@ -768,6 +769,8 @@ static int mega_build(Engine *e, MegaHost &M, const FlowGemms &G, int B, int lsd
         g.p.m_tiles_per_batch = q.m_tiles_per_batch; g.p.m_tiles_total = q.m_tiles_total; g.p.n_tiles = q.n_tiles;
         g.p.iters_per_split = q.iters_per_split; g.p.total_tiles = q.total_tiles; g.p.taps = q.taps; g.p.kblocks_per_tap = q.kblocks_per_tap;
         g.p.a_rows = q.a_rows; g.p.n_total = q.n_total; g.p.act = q.act; g.p.ldo = q.ldo; g.p.ldh = q.ldh; g.p.split_k = q.split_k;
+        g.p.n_magic = q.n_tiles > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)q.n_tiles - 1) / (uint64_t)q.n_tiles) : 0u;
+        g.p.m_magic = q.m_tiles_total > 1 ? (uint32_t)(((1ull << 32) + (uint64_t)q.m_tiles_total - 1) / (uint64_t)q.m_tiles_total) : 0u;
         g.p.idesc = q.idesc; g.p.bias = q.bias; g.p.out_f32 = q.out_f32; g.p.split_stride = q.split_stride; g.p.out_h = q.out_h; g.p.out_l = q.out_l;
     }
     P.n_phases = np; P.n_gemm_phases = n_gp;
