@@ -1202,21 +1202,16 @@ __global__ void __launch_bounds__(128) k_pf_attn_tc(const PrefillAttnParams p, c
         }
         __syncthreads();
         if (!warp_live) continue;   // padding rows only: nothing to compute (the barriers above are still reached)
-        // ldmatrix fragment addresses (see k_mimi_win_attn)
-        const uint32_t sK_s = smem_u32(sK) + (uint32_t)(((lane & 7) * FA_LD + (lane >> 3) * 8) * 2);
-        const uint32_t sV_s = smem_u32(sV) + (uint32_t)(((((lane >> 3) & 1) * 8 + (lane & 7)) * FA_LD + (lane >> 4) * 8) * 2);
         float sc[8][4];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
             sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.0f;
+            const __half *kr = sK + (nt * 8 + g) * FA_LD + 2 * t;
 #pragma unroll
-            for (int hf = 0; hf < 2; hf++) {
-                uint32_t kf[4];
-                ldsm_x4(kf, sK_s + (uint32_t)((nt * 8 * FA_LD + hf * 32) * 2));
-                mma_f16_16816(sc[nt], qh[2 * hf], kf[0], kf[1]);
-                mma_f16_16816(sc[nt], ql[2 * hf], kf[0], kf[1]);
-                mma_f16_16816(sc[nt], qh[2 * hf + 1], kf[2], kf[3]);
-                mma_f16_16816(sc[nt], ql[2 * hf + 1], kf[2], kf[3]);
+            for (int ks = 0; ks < 4; ks++) {
+                const uint32_t b0 = *(const uint32_t *)(kr + ks * 16), b1 = *(const uint32_t *)(kr + ks * 16 + 8);
+                mma_f16_16816(sc[nt], qh[ks], b0, b1);
+                mma_f16_16816(sc[nt], ql[ks], b0, b1);
             }
         }
         float bm0 = -INFINITY, bm1 = -INFINITY;
@@ -1253,14 +1248,13 @@ __global__ void __launch_bounds__(128) k_pf_attn_tc(const PrefillAttnParams p, c
             split_h2(sc[2 * ks][2], sc[2 * ks][3], ph[1], pl[1]);
             split_h2(sc[2 * ks + 1][0], sc[2 * ks + 1][1], ph[2], pl[2]);
             split_h2(sc[2 * ks + 1][2], sc[2 * ks + 1][3], ph[3], pl[3]);
+            const __half *v0 = sV + (ks * 16 + 2 * t) * FA_LD + g, *v1 = v0 + 8 * FA_LD;
 #pragma unroll
-            for (int ndp = 0; ndp < 4; ndp++) {
-                uint32_t vf[4];
-                ldsm_x4_t(vf, sV_s + (uint32_t)((ks * 16 * FA_LD + ndp * 16) * 2));
-                mma_f16_16816(o[2 * ndp], ph, vf[0], vf[1]);
-                mma_f16_16816(o[2 * ndp], pl, vf[0], vf[1]);
-                mma_f16_16816(o[2 * ndp + 1], ph, vf[2], vf[3]);
-                mma_f16_16816(o[2 * ndp + 1], pl, vf[2], vf[3]);
+            for (int nd = 0; nd < 8; nd++) {
+                const uint32_t b0 = (uint32_t)__half_as_ushort(v0[nd * 8]) | ((uint32_t)__half_as_ushort(v0[FA_LD + nd * 8]) << 16);
+                const uint32_t b1 = (uint32_t)__half_as_ushort(v1[nd * 8]) | ((uint32_t)__half_as_ushort(v1[FA_LD + nd * 8]) << 16);
+                mma_f16_16816(o[nd], ph, b0, b1);
+                mma_f16_16816(o[nd], pl, b0, b1);
             }
         }
     }
