@@ -147,7 +147,8 @@ __device__ __forceinline__ void grid_sync(unsigned int *bar, unsigned int &epoch
         while (ld_acquire_u32(bar) < epoch) {
             if (++spins == (1u << 23)) __trap();
         }
-        __threadfence();
+        // no fence here: the acquire load synchronises with the other CTAs' releases and the CTA barrier below extends that to this
+        // CTA's threads (an explicit fence.acq_rel.gpu after the loop costs 0.3 us per barrier: 604 vs 583 us per frame)
     }
     __syncthreads();
 }
