@@ -105,11 +105,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 // says so) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    // a failed try_wait comes back after ~0.1 us: 2^24 of them are more than a second. Counting them keeps the loop at five
-    // instructions and holds no 64-bit clock value in registers (these loops are 20-30 % of the instructions the GEMM kernels execute)
+    // a failed try_wait comes back after ~0.1 us (measured: 11 iterations per ~1 us wait); 2^26 of them are several seconds, and at
+    // least 0.7 s even if every attempt returned at once - longer than any legitimate wait (the longest: a kernel launched early by
+    // programmatic dependent launch behind a predecessor of tens of milliseconds). Counting keeps the loop at five instructions and
+    // holds no 64-bit clock value in registers (these loops are 20-30 % of the instructions the GEMM kernels execute)
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins == (1u << 24)) __trap();   // no device printf here: the call alone costs k_flow_mega 8 us per frame in register allocation
+        if (++spins == (1u << 26)) __trap();   // no device printf here: the call alone costs k_flow_mega 8 us per frame in register allocation
     }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
