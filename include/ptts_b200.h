@@ -98,7 +98,9 @@ typedef struct {
     float eos_threshold;
     int eos_min_frames;
     int eos_after;        /* used when per-utterance eos_after[] is NULL */
-    int precise;          /* 1: activations fed to the tensor cores as bf16 hi+lo pairs (default); 0: hi only */
+    int precise;          /* 1: activations fed to the tensor cores as bf16 hi+lo pairs (default, the parity-tested form, runs in the
+                             persistent step kernel); 0: hi only - a diagnostic form (3e-2 against the oracle) that runs on the
+                             multi-kernel graph path */
 } ptts_b200_gen_params;
 
 /* Batched generation, tokens -> latents -> PCM, n utterances sharing one voice prefix.

@@ -49,6 +49,24 @@ def test_batched_decode_equals_single(eng, oracle):
         assert np.abs(one - out[i]).max() < 1e-5       # batch items are independent
 
 
+def test_specialised_epilogues_match_the_generic_one(eng, monkeypatch):
+    """The Mimi launches take compile-time epilogues (gemm_tc.cuh EPI_CONV / EPI_RESID / EPI_GELU / EPI_ROPE); the same decode
+    through the generic run-time-dispatched epilogue (the round-1 path, PTTS_B200_NO_EPI_* read at every launch) must give the
+    same samples bit for bit: the specialised forms re-order instructions, not arithmetic."""
+    rng = np.random.default_rng(11)
+    lat = rng.standard_normal((3, 21, 32)).astype(np.float32)
+    fast = eng.mimi_decode_batch(lat).copy()
+    monkeypatch.setenv("PTTS_B200_NO_EPI_CONV", "1")
+    monkeypatch.setenv("PTTS_B200_NO_EPI_SPECIAL", "1")
+    generic = eng.mimi_decode_batch(lat).copy()
+    monkeypatch.delenv("PTTS_B200_NO_EPI_CONV")
+    monkeypatch.delenv("PTTS_B200_NO_EPI_SPECIAL")
+    assert np.isfinite(fast).all() and np.abs(generic).max() > 1e-3
+    assert np.array_equal(fast, generic)
+    again = eng.mimi_decode_batch(lat)
+    assert np.array_equal(again, fast)
+
+
 def test_causal_prefix_property_full_size(eng):
     """Size-independent property at a size the oracle cannot reach quickly: decoding a prefix
     gives the prefix of the full decode (all convs causal, attention causal + windowed)."""
